@@ -1,0 +1,793 @@
+// C ABI (include/gpss.h) and host-side drivers of the sm_100a exact-GP path: blocked potrf, trsv, trtri,
+// lauum, gradient reductions and batched prediction, each a fixed sequence of launches of the kernels in
+// gpss_kernels.cuh / gpss_gemm.cuh on one stream.  No cuBLAS / cuSOLVER, no CPU fallback.
+// File:line citations are into /root/reference.
+#include "../../include/gpss.h"
+#include "gpss_gemm.cuh"
+#include "gpss_kernels.cuh"
+#include "gpss_params.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <limits>
+
+using namespace gpss;
+
+static thread_local std::string g_last_error;
+
+static int fail_cuda(cudaError_t e, const char* what, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error '%s' in %s (gpss_capi.cu:%d)", cudaGetErrorString(e), what, line);
+  g_last_error = buf;
+  return GPSS_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail_cuda(e__, #x, __LINE__); } while (0)
+#define RET(x) do { int r__ = (x); if (r__ < 0) return r__; } while (0)
+
+static int fail_arg(const char* msg) { g_last_error = msg; return GPSS_ERR_ARG; }
+
+constexpr int NBO = 512;      // outer block (k-depth of the big trailing updates)
+constexpr int PRED_BATCH = 8192;
+
+enum QState { Q_NONE = 0, Q_IS_BINV = 1, Q_IS_W = 2 };
+
+struct gpss_ctx {
+  int device = 0;
+  int n = 0, n_pad = 0, nblk = 0;
+  cudaStream_t st = nullptr;
+  // data
+  double *xs = nullptr, *y = nullptr, *zs = nullptr;           // 3 x n_pad, n_pad, 4 x n_pad
+  double *Lm = nullptr, *Um = nullptr, *Qm = nullptr;          // n_pad^2 each (Um, Qm lazily)
+  double *Winv = nullptr;                                      // nblk x 128 x 128
+  double *logdet_parts = nullptr;                              // nblk
+  double *rvec = nullptr, *zvec = nullptr, *alpha = nullptr, *fvec = nullptr;   // n_pad each
+  double *Tpanel = nullptr, *Wjj = nullptr;                    // n_pad x NBO, NBO x NBO (lazily)
+  double *partial = nullptr; long partial_blocks = 0;          // gradient partial sums
+  double *red = nullptr;                                       // 32 doubles of reduced scalars
+  DevParams* dP = nullptr;                                     // [0] training, [1] prediction
+  int* dflag = nullptr;
+  // prediction scratch (lazily)
+  double *xt = nullptr, *zt = nullptr, *zsp = nullptr, *Bm = nullptr, *Vm = nullptr, *mu_part = nullptr, *dmu = nullptr, *dvar = nullptr;
+  int pred_cap = 0;
+  // host state
+  double theta[GPSS_NPAR];
+  double sums_train[3];
+  bool have_factor = false, have_alpha = false, have_U = false;
+  int qstate = Q_NONE;
+  int chol_fail = 0;
+  double nlml = std::numeric_limits<double>::quiet_NaN();
+  double s3 = 0.0;
+  // instrumentation
+  bool profiling = false;
+  double phase_ms[16];
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  long launches = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------
+static int configure_kernels()
+{
+  CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTileWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWide::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTilePanel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTilePanel::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(potrf_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  return GPSS_OK;
+}
+
+template <class T>
+static int gemm(gpss_ctx* c, const GemmArgs& g)
+{
+  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
+  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
+  dim3 grid(g.M / T::BM, g.N / T::BN);
+  gemm_nt_kernel<T><<<grid, T::THREADS, T::SMEM_BYTES, c->st>>>(g);
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K)
+{
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+struct PhaseTimer {
+  gpss_ctx* c; int idx;
+  PhaseTimer(gpss_ctx* c_, int idx_) : c(c_), idx(idx_) { if (c->profiling) cudaEventRecord(c->ev[0], c->st); }
+  ~PhaseTimer()
+  {
+    if (c->profiling) {
+      cudaEventRecord(c->ev[1], c->st);
+      cudaEventSynchronize(c->ev[1]);
+      float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      c->phase_ms[idx] += ms;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// parameters -> device
+// ---------------------------------------------------------------------------------------------------
+static void fill_params(const double theta[GPSS_NPAR], const double centre[3], DevParams& P)
+{
+  sig_inv(theta, P.S);
+  for (int j = 0; j < 3; j++) P.c[j] = centre[j];
+  P.var2 = theta[6] * theta[6];
+  P.bias = theta[8];
+  P.sn2 = theta[9];
+  P.inv_sn2 = 1 / theta[9];
+  P.sw = std::sqrt(P.inv_sn2);
+  P.sww = P.sw * P.sw;
+  P.lp_const = std::log(2.0 * M_PI * theta[9]) / 2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// blocked right-looking Cholesky, two-level (outer NBO = 512 for deep-k trailing updates, inner 128)
+// A: n_pad x n_pad lower, in place.  Replaces arma::chol -> dpotrf (GP_Utils.cpp:881,903).
+// ---------------------------------------------------------------------------------------------------
+static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Winv, double* logdet_parts, int* dflag)
+{
+  for (int K0 = 0; K0 < n_pad; K0 += NBO) {
+    const int nbk = (n_pad - K0 < NBO) ? (n_pad - K0) : NBO;
+    for (int k = K0; k < K0 + nbk; k += NB) {
+      double* Akk = A + (long)k * ld + k;
+      double* Wk = Winv + (long)(k / NB) * NB * NB;
+      potrf_diag_inv_kernel<<<1, NB, DIAG_SMEM, c->st>>>(Akk, ld, Wk, logdet_parts + k / NB, dflag);
+      c->launches++;
+      CU(cudaGetLastError());
+      const int m = n_pad - k - NB;
+      if (m <= 0) continue;
+      double* A21 = A + (long)k * ld + (k + NB);
+      {  // panel solve, in place: A21 <- A21 * inv(L11)^T
+        GemmArgs g = gemm_args(A21, ld, Wk, NB, A21, ld, m, NB, NB);
+        RET(gemm<GemmTilePanel>(c, g));
+      }
+      const int ncols = K0 + nbk - (k + NB);
+      if (ncols > 0) {  // update of the remaining columns of the outer panel
+        double* A22 = A + (long)(k + NB) * ld + (k + NB);
+        GemmArgs g = gemm_args(A21, ld, A21, ld, A22, ld, m, ncols, NB);
+        g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = k + NB; g.gcol0 = k + NB;
+        RET(gemm<GemmTileWide>(c, g));
+      }
+    }
+    const int m2 = n_pad - (K0 + nbk);
+    if (m2 > 0) {  // deep trailing update: A22 -= P P^T, k-depth nbk
+      const double* Pn = A + (long)K0 * ld + (K0 + nbk);
+      double* A22 = A + (long)(K0 + nbk) * ld + (K0 + nbk);
+      GemmArgs g = gemm_args(Pn, ld, Pn, ld, A22, ld, m2, m2, nbk);
+      g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = K0 + nbk; g.gcol0 = K0 + nbk;
+      RET(gemm<GemmTileWide>(c, g));
+    }
+  }
+  return GPSS_OK;
+}
+
+// U = L^-T (upper), block-column left-looking; only NT products (see gpss_gemm.cuh header).
+static int trtri_upper(gpss_ctx* c)
+{
+  const long ld = c->n_pad;
+  const int n_pad = c->n_pad;
+  double *L = c->Lm, *U = c->Um;
+  for (int J0 = 0; J0 < n_pad; J0 += NBO) {
+    const int nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
+    // (1) the diagonal NBO-block of U in 128-steps
+    for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
+      const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
+      put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, c->st>>>(U + (long)i0 * ld + i0, ld, Wi);
+      c->launches++;
+      CU(cudaGetLastError());
+      const int mr = i0 - J0;
+      if (mr > 0) {
+        double* Uc = U + (long)i0 * ld + J0;                 // U[J0:i0, i0:i0+128]
+        GemmArgs g = gemm_args(U + (long)J0 * ld + J0, ld, L + (long)J0 * ld + i0, ld, Uc, ld, mr, NB, mr);
+        g.kbeg_row = 1;
+        RET(gemm<GemmTilePanel>(c, g));
+        GemmArgs g2 = gemm_args(Uc, ld, Wi, NB, Uc, ld, mr, NB, NB);
+        g2.negate_out = 1;
+        RET(gemm<GemmTilePanel>(c, g2));
+      }
+    }
+    if (J0 > 0) {
+      // (2) W_JJ = U_JJ^T into scratch
+      transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(c->Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
+      c->launches++;
+      CU(cudaGetLastError());
+      // (3) T = U[0:J0,0:J0] * L[Jblk,0:J0]^T
+      GemmArgs g = gemm_args(U, ld, L + J0, ld, c->Tpanel, ld, J0, nbj, J0);
+      g.kbeg_row = 1;
+      RET(gemm<GemmTileWide>(c, g));
+      // (4) U[0:J0, Jblk] = -T * W_JJ^T
+      GemmArgs g2 = gemm_args(c->Tpanel, ld, c->Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
+      g2.negate_out = 1; g2.kend_col = 1;
+      RET(gemm<GemmTileWide>(c, g2));
+    }
+  }
+  return GPSS_OK;
+}
+
+// Q (lower) = U U^T = B^-1
+static int lauum_lower(gpss_ctx* c)
+{
+  const long ld = c->n_pad;
+  GemmArgs g = gemm_args(c->Um, ld, c->Um, ld, c->Qm, ld, c->n_pad, c->n_pad, c->n_pad);
+  g.lower_only = 1; g.kbeg_row = 1;
+  return gemm<GemmTileWide>(c, g);
+}
+
+// x = L^-T L^-1 rhs through the stored diagonal inverses; rhs in c->rvec (destroyed), result in c->alpha
+static int potrs_vec(gpss_ctx* c)
+{
+  const long ld = c->n_pad;
+  for (int k = 0; k < c->nblk; k++) {
+    const int k0 = k * NB;
+    const int grid = 1 + (c->n_pad - k0 - NB) / NB;
+    trsv_fwd_step_kernel<<<grid, NB, 0, c->st>>>(c->Lm, ld, c->Winv + (long)k * NB * NB, c->rvec, c->zvec, k0);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  for (int k = c->nblk - 1; k >= 0; k--) {
+    const int k0 = k * NB;
+    const int grid = 1 + k;
+    trsv_bwd_step_kernel<<<grid, NB, 0, c->st>>>(c->Lm, ld, c->Winv + (long)k * NB * NB, c->zvec, c->alpha, k0);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+__global__ void scale_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, double s, int n, int n_pad)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (i < n) ? src[i] * s : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// objective pieces
+// ---------------------------------------------------------------------------------------------------
+static int upload_params(gpss_ctx* c, int slot, const double centre[3])
+{
+  DevParams P;
+  fill_params(c->theta, centre, P);
+  CU(cudaMemcpyAsync(c->dP + slot, &P, sizeof P, cudaMemcpyHostToDevice, c->st));
+  CU(cudaStreamSynchronize(c->st));   // P is a stack object
+  return GPSS_OK;
+}
+
+static int ensure_factor(gpss_ctx* c)
+{
+  if (c->have_factor) return GPSS_OK;
+  const int n_pad = c->n_pad;
+  const long ld = n_pad;
+  double centre[3];
+  maha_centre(c->n, c->sums_train, c->n, c->sums_train, centre);
+  RET(upload_params(c, 0, centre));
+  CU(cudaMemsetAsync(c->dflag, 0, sizeof(int), c->st));
+  {
+    PhaseTimer t(c, 0);
+    transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs, ld, c->n, n_pad, c->dP);
+    kbuild_lower_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0);
+    c->launches += 2;
+    CU(cudaGetLastError());
+  }
+  {
+    PhaseTimer t(c, 1);
+    RET(potrf_blocked(c, c->Lm, ld, n_pad, c->Winv, c->logdet_parts, c->dflag));
+  }
+  c->have_factor = true;
+  c->have_alpha = false;
+  c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+// alpha, f = K alpha, and the scalar terms; sets c->nlml (GP_Utils.cpp:1138-1162)
+static int ensure_objective(gpss_ctx* c)
+{
+  RET(ensure_factor(c));
+  if (c->have_alpha) return GPSS_OK;
+  const int n_pad = c->n_pad;
+  {
+    PhaseTimer t(c, 2);
+    // rhs = y / sn2: the IRLS fixed point alpha = B^-1 (y/sn2) = (K + sn2 I)^-1 y (GP_Utils.cpp:214-223)
+    scale_copy_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->rvec, c->y, 1 / c->theta[9], c->n, n_pad);
+    c->launches++;
+    RET(potrs_vec(c));
+    kmatvec_kernel<<<(c->n + 63) / 64, 256, 0, c->st>>>(c->zs, n_pad, c->alpha, c->fvec, c->n, c->dP);
+    lml_terms_kernel<<<1, 256, 0, c->st>>>(c->y, c->alpha, c->fvec, c->n, c->dP, c->logdet_parts, c->nblk, c->red);
+    c->launches += 2;
+    CU(cudaGetLastError());
+  }
+  double red[4];
+  int flag = 0;
+  CU(cudaMemcpyAsync(red, c->red, sizeof red, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaMemcpyAsync(&flag, c->dflag, sizeof flag, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->chol_fail = flag;
+  if (flag) {
+    c->nlml = std::numeric_limits<double>::quiet_NaN();
+  } else {
+    // L = Alpha' * ydif - accu(lp) + Lchol_db2 (GP_Utils.cpp:1159)
+    c->nlml = red[0] - red[1] + red[3];
+    c->s3 = red[2];
+  }
+  c->have_alpha = true;
+  return GPSS_OK;
+}
+
+static int ensure_lazy(double** p, size_t count)
+{
+  if (*p) return GPSS_OK;
+  CU(cudaMalloc(p, count * sizeof(double)));
+  return GPSS_OK;
+}
+
+static int ensure_U(gpss_ctx* c)
+{
+  if (c->have_U) return GPSS_OK;
+  const size_t nn = (size_t)c->n_pad * c->n_pad;
+  RET(ensure_lazy(&c->Um, nn));
+  RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
+  RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO));
+  {
+    PhaseTimer t(c, 3);
+    RET(trtri_upper(c));
+  }
+  c->have_U = true;
+  return GPSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpss_version(void) { return 100; }
+
+const char* gpss_last_error(void) { return g_last_error.c_str(); }
+
+int gpss_device_count(int* count)
+{
+  if (!count) return fail_arg("gpss_device_count: null");
+  CU(cudaGetDeviceCount(count));
+  return GPSS_OK;
+}
+
+int gpss_destroy(gpss_handle c)
+{
+  if (!c) return GPSS_OK;
+  cudaSetDevice(c->device);
+  double** bufs[] = {&c->xs, &c->y, &c->zs, &c->Lm, &c->Um, &c->Qm, &c->Winv, &c->logdet_parts, &c->rvec, &c->zvec, &c->alpha,
+                     &c->fvec, &c->Tpanel, &c->Wjj, &c->partial, &c->red, &c->xt, &c->zt, &c->zsp, &c->Bm, &c->Vm, &c->mu_part,
+                     &c->dmu, &c->dvar};
+  for (auto b : bufs) if (*b) cudaFree(*b);
+  if (c->dP) cudaFree(c->dP);
+  if (c->dflag) cudaFree(c->dflag);
+  if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+  if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+  return GPSS_OK;
+}
+
+int gpss_set_data(gpss_handle c, const double* X, const double* y)
+{
+  if (!c || !X || !y) return fail_arg("gpss_set_data: null argument");
+  CU(cudaSetDevice(c->device));
+  const int n = c->n, n_pad = c->n_pad;
+  seq_colsums(X, n, c->sums_train);
+  CU(cudaMemsetAsync(c->xs, 0, sizeof(double) * 3 * n_pad, c->st));
+  for (int j = 0; j < 3; j++)
+    CU(cudaMemcpyAsync(c->xs + (long)j * n_pad, X + (long)j * n, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->y, 0, sizeof(double) * n_pad, c->st));
+  CU(cudaMemcpyAsync(c->y, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->have_factor = c->have_alpha = c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_create(int device, int n, int d, const double* X, const double* y, gpss_handle* out)
+{
+  if (!out || !X || !y) return fail_arg("gpss_create: null argument");
+  if (d != 3) return fail_arg("gpss_create: only the 3-D ExpAns path is implemented (d must be 3)");
+  if (n < 2) return fail_arg("gpss_create: n must be >= 2");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail_arg("gpss_create: no such CUDA device");
+  CU(cudaSetDevice(device));
+  RET(configure_kernels());
+  gpss_ctx* c = new gpss_ctx();
+  c->device = device;
+  c->n = n;
+  c->n_pad = ((n + NB - 1) / NB) * NB;
+  c->nblk = c->n_pad / NB;
+  memset(c->phase_ms, 0, sizeof c->phase_ms);
+  const size_t np = c->n_pad;
+  auto fail = [&](int code) { gpss_destroy(c); return code; };
+#define CUF(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(fail_cuda(e__, #x, __LINE__)); } while (0)
+  CUF(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CUF(cudaEventCreate(&c->ev[0]));
+  CUF(cudaEventCreate(&c->ev[1]));
+  CUF(cudaMalloc(&c->xs, sizeof(double) * 3 * np));
+  CUF(cudaMalloc(&c->y, sizeof(double) * np));
+  CUF(cudaMalloc(&c->zs, sizeof(double) * 4 * np));
+  CUF(cudaMalloc(&c->Lm, sizeof(double) * np * np));
+  CUF(cudaMalloc(&c->Winv, sizeof(double) * (size_t)c->nblk * NB * NB));
+  CUF(cudaMalloc(&c->logdet_parts, sizeof(double) * c->nblk));
+  CUF(cudaMalloc(&c->rvec, sizeof(double) * np));
+  CUF(cudaMalloc(&c->zvec, sizeof(double) * np));
+  CUF(cudaMalloc(&c->alpha, sizeof(double) * np));
+  CUF(cudaMalloc(&c->fvec, sizeof(double) * np));
+  CUF(cudaMalloc(&c->red, sizeof(double) * 32));
+  CUF(cudaMalloc(&c->dP, sizeof(DevParams) * 2));
+  CUF(cudaMalloc(&c->dflag, sizeof(int)));
+  CUF(cudaMemsetAsync(c->alpha, 0, sizeof(double) * np, c->st));
+  CUF(cudaMemsetAsync(c->fvec, 0, sizeof(double) * np, c->st));
+#undef CUF
+  for (int i = 0; i < GPSS_NPAR; i++) c->theta[i] = 0;
+  int r = gpss_set_data(c, X, y);
+  if (r != GPSS_OK) return fail(r);
+  *out = c;
+  return GPSS_OK;
+}
+
+int gpss_set_theta(gpss_handle c, const double theta[GPSS_NPAR])
+{
+  if (!c || !theta) return fail_arg("gpss_set_theta: null argument");
+  memcpy(c->theta, theta, sizeof c->theta);
+  c->have_factor = c->have_alpha = c->have_U = false;   // setKUpdateStat(false) (GP_Utils.cpp:132)
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_get_theta(gpss_handle c, double theta[GPSS_NPAR])
+{
+  if (!c || !theta) return fail_arg("gpss_get_theta: null argument");
+  memcpy(theta, c->theta, sizeof c->theta);
+  return GPSS_OK;
+}
+
+int gpss_nlml(gpss_handle c, double* nlml)
+{
+  if (!c || !nlml) return fail_arg("gpss_nlml: null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  RET(ensure_objective(c));
+  *nlml = c->nlml;
+  return c->chol_fail ? GPSS_NOT_POSDEF : GPSS_OK;
+}
+
+int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
+{
+  if (!c || !nlml || !g) return fail_arg("gpss_nlml_grad: null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  RET(ensure_objective(c));
+  *nlml = c->nlml;
+  if (c->chol_fail) {
+    for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
+    return GPSS_NOT_POSDEF;
+  }
+  RET(ensure_U(c));
+  const size_t nn = (size_t)c->n_pad * c->n_pad;
+  RET(ensure_lazy(&c->Qm, nn));
+  if (c->qstate != Q_IS_BINV) {
+    PhaseTimer t(c, 4);
+    RET(lauum_lower(c));
+    c->qstate = Q_IS_BINV;
+  }
+  const long nblocks = (long)c->nblk * c->nblk;
+  if (c->partial_blocks < nblocks) {
+    if (c->partial) cudaFree(c->partial);
+    c->partial = nullptr;
+    CU(cudaMalloc(&c->partial, sizeof(double) * nblocks * NGRAD));
+    c->partial_blocks = nblocks;
+  }
+  {
+    PhaseTimer t(c, 5);
+    grad_pass_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Qm, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
+                                                              c->dP, c->partial);
+    sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);
+    c->launches += 2;
+    CU(cudaGetLastError());
+  }
+  double red[NGRAD];
+  CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  combine_gradient(c->theta, red, c->s3, g);
+  return GPSS_OK;
+}
+
+int gpss_get_alpha(gpss_handle c, double* alpha)
+{
+  if (!c || !alpha) return fail_arg("gpss_get_alpha: null argument");
+  CU(cudaSetDevice(c->device));
+  RET(ensure_objective(c));
+  CU(cudaMemcpyAsync(alpha, c->alpha, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return c->chol_fail ? GPSS_NOT_POSDEF : GPSS_OK;
+}
+
+int gpss_get_yhat(gpss_handle c, double* yhat)
+{
+  if (!c || !yhat) return fail_arg("gpss_get_yhat: null argument");
+  CU(cudaSetDevice(c->device));
+  RET(ensure_objective(c));
+  CU(cudaMemcpyAsync(yhat, c->fvec, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return c->chol_fail ? GPSS_NOT_POSDEF : GPSS_OK;
+}
+
+// --- prediction ---------------------------------------------------------------------------------
+static int ensure_W(gpss_ctx* c)
+{
+  RET(ensure_U(c));
+  if (c->qstate == Q_IS_W) return GPSS_OK;
+  const size_t nn = (size_t)c->n_pad * c->n_pad;
+  RET(ensure_lazy(&c->Qm, nn));
+  PhaseTimer t(c, 3);
+  transpose_kernel<<<dim3(c->n_pad / 32, c->n_pad / 32), 256, 0, c->st>>>(c->Qm, c->n_pad, c->Um, c->n_pad, 1);
+  c->launches++;
+  CU(cudaGetLastError());
+  c->qstate = Q_IS_W;
+  return GPSS_OK;
+}
+
+int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
+{
+  if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
+  if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
+  CU(cudaSetDevice(c->device));
+  if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  RET(ensure_objective(c));          // _postMean -> updateAlpha (GP_Utils.cpp:961)
+  if (c->chol_fail) return GPSS_NOT_POSDEF;
+  if (var) RET(ensure_W(c));
+  const int n_pad = c->n_pad;
+  const int cap = PRED_BATCH;
+  if (!c->pred_cap) {
+    RET(ensure_lazy(&c->xt, (size_t)3 * cap));
+    RET(ensure_lazy(&c->zt, (size_t)4 * cap));
+    RET(ensure_lazy(&c->zsp, (size_t)4 * n_pad));
+    RET(ensure_lazy(&c->mu_part, (size_t)c->nblk * cap));
+    RET(ensure_lazy(&c->dmu, cap));
+    RET(ensure_lazy(&c->dvar, cap));
+    c->pred_cap = cap;
+  }
+  if (var) {
+    RET(ensure_lazy(&c->Bm, (size_t)cap * n_pad));
+    RET(ensure_lazy(&c->Vm, (size_t)cap * n_pad));
+  }
+  // centre over the training set and ALL test points (Kernel.cpp:1391-1392)
+  double centre[3];
+  maha_centre(c->n, c->sums_train, m_total, sums_total, centre);
+  RET(upload_params(c, 1, centre));
+  transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
+  c->launches++;
+  const double kD = c->theta[6] * c->theta[6] + c->theta[8];   // diag_Compute (Kernel.cpp:782, 331, 127-136)
+  const int add_noise = (c->theta[9] != 1.0);                  // GP_Utils.cpp:1036-1040
+  for (long off = 0; off < count; off += cap) {
+    const int mb = (int)((count - off < cap) ? (count - off) : cap);
+    const int m_pad = ((mb + NB - 1) / NB) * NB;
+    CU(cudaMemsetAsync(c->xt, 0, sizeof(double) * 3 * cap, c->st));
+    for (int j = 0; j < 3; j++)
+      CU(cudaMemcpyAsync(c->xt + (long)j * cap, Xs + (long)j * count + off, sizeof(double) * mb, cudaMemcpyHostToDevice, c->st));
+    transform_kernel<<<(m_pad + 255) / 256, 256, 0, c->st>>>(c->xt, cap, c->zt, cap, mb, m_pad, c->dP + 1);
+    {
+      PhaseTimer t(c, 6);
+      cross_build_kernel<<<dim3(m_pad / NB, c->nblk), 256, 0, c->st>>>(c->Bm, m_pad, c->zt, cap, c->zsp, n_pad, c->alpha, mb, c->n,
+                                                                    c->dP + 1, c->mu_part, cap, var ? 1 : 0);
+      mean_finish_kernel<<<(mb + 255) / 256, 256, 0, c->st>>>(c->mu_part, cap, c->nblk, mb, c->dmu);
+      c->launches += 3;
+      CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(mu + off, c->dmu, sizeof(double) * mb, cudaMemcpyDeviceToHost, c->st));
+    if (var) {
+      PhaseTimer t(c, 7);
+      // V = L^-1 (Sw o kX): A = W (lower), B = Bm (test index contiguous)
+      GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
+      g.kend_row = 1; g.rev_order = 1;
+      RET(gemm<GemmTileWide>(c, g));
+      var_finish_kernel<<<(mb + 7) / 8, 256, 0, c->st>>>(c->Vm, n_pad, n_pad, mb, kD, c->theta[9], add_noise, c->dvar);
+      c->launches++;
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(var + off, c->dvar, sizeof(double) * mb, cudaMemcpyDeviceToHost, c->st));
+    }
+    CU(cudaStreamSynchronize(c->st));
+  }
+  CU(cudaStreamSynchronize(c->st));
+  return GPSS_OK;
+}
+
+int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* var)
+{
+  if (!c || !Xs || !mu) return fail_arg("gpss_predict: null argument");
+  if (m < 1) return fail_arg("gpss_predict: m must be >= 1");
+  double sums[3];
+  seq_colsums(Xs, m, sums);
+  return gpss_predict_shard(c, m, sums, m, Xs, mu, var);
+}
+
+// --- Kernels::computeK compatibility ----------------------------------------------------------
+__global__ void __launch_bounds__(256) full_K_kernel(double* __restrict__ Km, double* __restrict__ D2m, long ld, const double* __restrict__ z1,
+                                                     long ld1, const double* __restrict__ z2, long ld2, int n1, int n2,
+                                                     const DevParams* __restrict__ Pp)
+{
+  const DevParams P = *Pp;
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int jb = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
+  if (i >= n1) return;
+  const double a0 = z1[i], a1 = z1[ld1 + i], a2 = z1[2 * ld1 + i], aa = z1[3 * ld1 + i];
+  for (int j = jb; j < jb + 16 && j < n2; j++) {
+    const double d2 = pair_d2(a0, a1, a2, aa, z2[j], z2[ld2 + j], z2[2 * ld2 + j], z2[3 * ld2 + j]);
+    if (Km) Km[(long)j * ld + i] = kern_val(d2, P);
+    if (D2m) D2m[(long)j * ld + i] = d2;
+  }
+}
+
+int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const double* X1, int n2, const double* X2, double* K, double* D2)
+{
+  if (!theta || !X1 || !X2 || n1 < 1 || n2 < 1) return fail_arg("gpss_compute_K: bad argument");
+  CU(cudaSetDevice(device));
+  double s1[3], s2[3], centre[3];
+  seq_colsums(X1, n1, s1);
+  seq_colsums(X2, n2, s2);
+  maha_centre(n1, s1, n2, s2, centre);
+  DevParams P;
+  fill_params(theta, centre, P);
+  double *dx1 = nullptr, *dx2 = nullptr, *dz1 = nullptr, *dz2 = nullptr, *dK = nullptr, *dD = nullptr;
+  DevParams* dP = nullptr;
+  int rc = GPSS_OK;
+  auto cleanup = [&]() { cudaFree(dx1); cudaFree(dx2); cudaFree(dz1); cudaFree(dz2); cudaFree(dK); cudaFree(dD); cudaFree(dP); };
+#define CUK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
+  CUK(cudaMalloc(&dx1, sizeof(double) * 3 * n1));
+  CUK(cudaMalloc(&dx2, sizeof(double) * 3 * n2));
+  CUK(cudaMalloc(&dz1, sizeof(double) * 4 * n1));
+  CUK(cudaMalloc(&dz2, sizeof(double) * 4 * n2));
+  CUK(cudaMalloc(&dP, sizeof(DevParams)));
+  if (K) CUK(cudaMalloc(&dK, sizeof(double) * (size_t)n1 * n2));
+  if (D2) CUK(cudaMalloc(&dD, sizeof(double) * (size_t)n1 * n2));
+  CUK(cudaMemcpy(dx1, X1, sizeof(double) * 3 * n1, cudaMemcpyHostToDevice));
+  CUK(cudaMemcpy(dx2, X2, sizeof(double) * 3 * n2, cudaMemcpyHostToDevice));
+  CUK(cudaMemcpy(dP, &P, sizeof P, cudaMemcpyHostToDevice));
+  transform_kernel<<<(n1 + 255) / 256, 256>>>(dx1, n1, dz1, n1, n1, n1, dP);
+  transform_kernel<<<(n2 + 255) / 256, 256>>>(dx2, n2, dz2, n2, n2, n2, dP);
+  full_K_kernel<<<dim3((n1 + 63) / 64, (n2 + 63) / 64), 256>>>(dK, dD, n1, dz1, n1, dz2, n2, n1, n2, dP);
+  CUK(cudaGetLastError());
+  if (K) CUK(cudaMemcpy(K, dK, sizeof(double) * (size_t)n1 * n2, cudaMemcpyDeviceToHost));
+  if (D2) CUK(cudaMemcpy(D2, dD, sizeof(double) * (size_t)n1 * n2, cudaMemcpyDeviceToHost));
+#undef CUK
+  cleanup();
+  return GPSS_OK;
+}
+
+// --- instrumentation ------------------------------------------------------------------------------
+int gpss_set_profiling(gpss_handle c, int on)
+{
+  if (!c) return fail_arg("gpss_set_profiling: null");
+  c->profiling = on != 0;
+  return GPSS_OK;
+}
+
+int gpss_get_phase_ms(gpss_handle c, double ms[16])
+{
+  if (!c || !ms) return fail_arg("gpss_get_phase_ms: null");
+  memcpy(ms, c->phase_ms, sizeof c->phase_ms);
+  return GPSS_OK;
+}
+
+int gpss_get_launch_count(gpss_handle c, long* launches)
+{
+  if (!c || !launches) return fail_arg("gpss_get_launch_count: null");
+  *launches = c->launches;
+  return GPSS_OK;
+}
+
+int gpss_padded_n(gpss_handle c, int* n_pad)
+{
+  if (!c || !n_pad) return fail_arg("gpss_padded_n: null");
+  *n_pad = c->n_pad;
+  return GPSS_OK;
+}
+
+// which: 0 = L factor, 1 = U, 2 = Q/W buffer, 3 = zs (4 x n_pad)
+int gpss_debug_fetch(gpss_handle c, int which, double* host_out, long count)
+{
+  if (!c || !host_out) return fail_arg("gpss_debug_fetch: null");
+  CU(cudaSetDevice(c->device));
+  const double* src = which == 0 ? c->Lm : which == 1 ? c->Um : which == 2 ? c->Qm : c->zs;
+  if (!src) return fail_arg("gpss_debug_fetch: buffer not allocated");
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpy(host_out, src, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  return GPSS_OK;
+}
+
+// --- kernel-level test hooks --------------------------------------------------------------------------
+int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C, int subtract_from_C,
+                      double* ms_out)
+{
+  if (!A || !B || !C) return fail_arg("gpss_test_gemm_nt: null");
+  CU(cudaSetDevice(device));
+  RET(configure_kernels());
+  gpss_ctx tmp;
+  tmp.st = nullptr;
+  double *dA, *dB, *dC;
+  CU(cudaMalloc(&dA, sizeof(double) * (size_t)M * K));
+  CU(cudaMalloc(&dB, sizeof(double) * (size_t)N * K));
+  CU(cudaMalloc(&dC, sizeof(double) * (size_t)M * N));
+  CU(cudaMemcpy(dA, A, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dB, B, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dC, C, sizeof(double) * (size_t)M * N, cudaMemcpyHostToDevice));
+  GemmArgs g = gemm_args(dA, M, dB, N, dC, M, M, N, K);
+  if (subtract_from_C) { g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  int rc;
+  CU(cudaEventRecord(e0, 0));
+  if (tile == 0) rc = gemm<GemmTileWide>(&tmp, g); else rc = gemm<GemmTilePanel>(&tmp, g);
+  CU(cudaEventRecord(e1, 0));
+  if (rc < 0) return rc;
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms;
+  CU(cudaMemcpy(C, dC, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return GPSS_OK;
+}
+
+int gpss_test_potrf(int device, int n, double* A, double* logdet_half, double* ms_out)
+{
+  if (!A || n < 1) return fail_arg("gpss_test_potrf: bad argument");
+  CU(cudaSetDevice(device));
+  RET(configure_kernels());
+  gpss_ctx tmp;
+  const int n_pad = ((n + NB - 1) / NB) * NB;
+  const int nblk = n_pad / NB;
+  double *dA, *dW, *dl;
+  int* dflag;
+  CU(cudaMalloc(&dA, sizeof(double) * (size_t)n_pad * n_pad));
+  CU(cudaMalloc(&dW, sizeof(double) * (size_t)nblk * NB * NB));
+  CU(cudaMalloc(&dl, sizeof(double) * nblk));
+  CU(cudaMalloc(&dflag, sizeof(int)));
+  CU(cudaMemset(dflag, 0, sizeof(int)));
+  // identity padding
+  std::vector<double> pad((size_t)n_pad * n_pad, 0.0);
+  for (int j = 0; j < n_pad; j++)
+    for (int i = 0; i < n_pad; i++) pad[(size_t)j * n_pad + i] = (i < n && j < n) ? A[(size_t)j * n + i] : (i == j ? 1.0 : 0.0);
+  CU(cudaMemcpy(dA, pad.data(), sizeof(double) * pad.size(), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, 0));
+  int rc = potrf_blocked(&tmp, dA, n_pad, n_pad, dW, dl, dflag);
+  CU(cudaEventRecord(e1, 0));
+  if (rc < 0) return rc;
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms;
+  CU(cudaMemcpy(pad.data(), dA, sizeof(double) * pad.size(), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) A[(size_t)j * n + i] = (i >= j) ? pad[(size_t)j * n_pad + i] : 0.0;
+  std::vector<double> ld(nblk);
+  int flag = 0;
+  CU(cudaMemcpy(ld.data(), dl, sizeof(double) * nblk, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  double s = 0;
+  for (double v : ld) s += v;
+  if (logdet_half) *logdet_half = s;
+  cudaFree(dA); cudaFree(dW); cudaFree(dl); cudaFree(dflag);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return flag ? GPSS_NOT_POSDEF : GPSS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+// Hand-written sm_100a kernels for the exact-GP hot path of GP_SS_AK (everything except the DMMA GEMM,
+// which lives in gpss_gemm.cuh).  File:line citations are into /root/reference.
+//
+// Data layout in HBM (all FP64, column-major like arma::mat):
+//   xs[3][n_pad]   standardised, UNcentred coordinates (the reference's Xinp), SoA
+//   zs[4][n_pad]   z = (x - c) * sigInv (3 rows) and a = |z|^2 (4th row), SoA
+//   Lm[n_pad^2]    B = I + (Sw Sw') o K  -> overwritten by its Cholesky factor L (lower)
+//   Um[n_pad^2]    U = L^-T (upper)
+//   Qm[n_pad^2]    Q = B^-1 (lower triangle)  (also W = L^-1 for prediction)
+//   Winv[nblk][128*128]  inverses of the 128x128 diagonal blocks of L
+// n_pad = n rounded up to 128; the padding rows/cols carry the identity so no kernel needs edge handling.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace gpss {
+
+constexpr int NB = 128;          // diagonal / tile block
+
+struct DevParams {
+  double S[9];        // sigInv = Rot*diag(l)*Rot' (Kernel.cpp:1425), S[k*3+j]
+  double c[3];        // MahaDist centre (Kernel.cpp:1391-1392)
+  double var2;        // Sigma_ExpAns^2 (Kernel.cpp:861)
+  double bias;        // Sigma_Bias (Kernel.cpp:366)
+  double sn2;         // hyperlf(0) (GP_Utils.cpp:406)
+  double inv_sn2;     // 1/sn2 = d2lp (GP_Utils.cpp:412-413)
+  double sw;          // Sw = sqrt(d2lp) (GP_Utils.cpp:897)
+  double sww;         // fl(Sw*Sw), the element of Sw*Sw.t() (GP_Utils.cpp:900)
+  double lp_const;    // log(2*pi*sn2)/2 (GP_Utils.cpp:810)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// defined-order Mahalanobis pieces (SURVEY.md section 7 hard part 1; mirrors oracle maha_dist_defined)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pair_d2(double zi0, double zi1, double zi2, double ai,
+                                          double zj0, double zj1, double zj2, double aj)
+{
+  const double cij = fma(zi2, zj2, fma(zi1, zj1, __dmul_rn(zi0, zj0)));
+  const double d2 = __dadd_rn(__dadd_rn(ai, aj), __dmul_rn(-2.0, cij));
+  return d2 < 0.0 ? 0.0 : d2;     // find(D2<0) -> 0 (Kernel.cpp:1433-1434)
+}
+
+// z = (x - c) * S, a = fl(fl(z0^2+z1^2)+z2^2)   (Kernel.cpp:1393-1397, 1426-1432)
+__global__ void transform_kernel(const double* __restrict__ xs, long ldx, double* __restrict__ zs, long ldz,
+                                 int n, int n_pad, const DevParams* __restrict__ P)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i >= n) { zs[i] = 0; zs[ldz + i] = 0; zs[2 * ldz + i] = 0; zs[3 * ldz + i] = 0; return; }
+  const double d0 = __dsub_rn(xs[i], P->c[0]);
+  const double d1 = __dsub_rn(xs[ldx + i], P->c[1]);
+  const double d2 = __dsub_rn(xs[2 * ldx + i], P->c[2]);
+  double z[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) z[j] = fma(d2, P->S[6 + j], fma(d1, P->S[3 + j], __dmul_rn(d0, P->S[j])));
+  zs[i] = z[0]; zs[ldz + i] = z[1]; zs[2 * ldz + i] = z[2];
+  zs[3 * ldz + i] = __dadd_rn(__dadd_rn(__dmul_rn(z[0], z[0]), __dmul_rn(z[1], z[1])), __dmul_rn(z[2], z[2]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: lower-triangle tiles of B = I + (Sw Sw') o K,  K = var2*exp(-sqrt(D2)) + bias
+//     (Kernel.cpp:881, 366, 140-154; GP_Utils.cpp:898-902).  One 128x128 tile per CTA, 256 threads,
+//     each thread owns 2 consecutive rows (16-byte coalesced stores down a column) x 32 columns.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double kern_val(double d2, const DevParams& P)
+{
+  return __dadd_rn(__dmul_rn(P.var2, exp(-sqrt(d2))), P.bias);
+}
+
+__global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ Bm, long ld, const double* __restrict__ zs, long ldz,
+                                                           int n, const DevParams* __restrict__ Pp, int raw_K)
+{
+  const int tm = blockIdx.x, tn = blockIdx.y;
+  if (tn > tm) return;
+  __shared__ double cz[4][NB];
+  __shared__ DevParams P;
+  const int tid = threadIdx.x;
+  if (tid == 0) P = *Pp;
+  const int r0 = tm * NB, c0 = tn * NB;
+  for (int idx = tid; idx < 4 * NB; idx += 256) cz[idx / NB][idx % NB] = zs[(long)(idx / NB) * ldz + c0 + idx % NB];
+  const int tx = tid & 63, ty = tid >> 6;
+  const int i0 = r0 + 2 * tx;
+  double zi[2][4];
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+  __syncthreads();
+#pragma unroll 4
+  for (int jj = ty; jj < NB; jj += 4) {
+    const int j = c0 + jj;
+    double2 out;
+    double* o = &out.x;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = i0 + e;
+      double v;
+      if (i < n && j < n) {
+        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj]);
+        v = kern_val(d2, P);
+        if (!raw_K) {
+          v = __dmul_rn(P.sww, v);
+          if (i == j) v = __dadd_rn(v, 1.0);
+        }
+      } else {
+        v = (i == j) ? 1.0 : 0.0;
+      }
+      o[e] = v;
+    }
+    *reinterpret_cast<double2*>(Bm + (long)j * ld + i0) = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: Cholesky of one 128x128 diagonal block in shared memory + its triangular inverse.
+//     Replaces the diagonal-block dpotf2 inside arma::chol (GP_Utils.cpp:881,903) and supplies
+//     inv(L11) so that every panel solve becomes a DMMA GEMM.  Also accumulates sum(log(diag))
+//     (GP_Utils.cpp:913) and raises *flag when a pivot is not positive (chol() == false, :882-886).
+// ---------------------------------------------------------------------------------------------------
+constexpr int LDS_D = NB + 1;
+constexpr size_t DIAG_SMEM = (size_t)(NB * LDS_D + 2 * NB) * sizeof(double);
+
+__global__ void __launch_bounds__(NB) potrf_diag_inv_kernel(double* __restrict__ A, long ld, double* __restrict__ Winv,
+                                                            double* __restrict__ logdet_part, int* __restrict__ flag)
+{
+  extern __shared__ double sm[];
+  double* Ls = sm;                 // Ls[k*LDS_D + i] = element (row i, col k)
+  double* colv = sm + NB * LDS_D;  // scratch vector
+  double* red = colv + NB;
+  const int i = threadIdx.x;
+  for (int k = 0; k < NB; k++) Ls[k * LDS_D + i] = (i >= k) ? A[(long)k * ld + i] : 0.0;
+  __syncthreads();
+  double logsum = 0.0;
+  // left-looking, column by column
+  for (int j = 0; j < NB; j++) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (i >= j) {
+      int k = 0;
+      for (; k + 3 < j; k += 4) {
+        s0 = fma(Ls[k * LDS_D + i], Ls[k * LDS_D + j], s0);
+        s1 = fma(Ls[(k + 1) * LDS_D + i], Ls[(k + 1) * LDS_D + j], s1);
+        s2 = fma(Ls[(k + 2) * LDS_D + i], Ls[(k + 2) * LDS_D + j], s2);
+        s3 = fma(Ls[(k + 3) * LDS_D + i], Ls[(k + 3) * LDS_D + j], s3);
+      }
+      for (; k < j; k++) s0 = fma(Ls[k * LDS_D + i], Ls[k * LDS_D + j], s0);
+    }
+    const double v = Ls[j * LDS_D + i] - ((s0 + s1) + (s2 + s3));
+    if (i == j) {
+      double d;
+      if (!(v > 0.0)) { atomicExch(flag, 1); d = nan(""); }
+      else d = sqrt(v);
+      Ls[j * LDS_D + j] = d;
+      colv[0] = 1.0 / d;
+      logsum += log(d);
+    }
+    __syncthreads();
+    if (i > j) Ls[j * LDS_D + i] = v * colv[0];
+    __syncthreads();
+  }
+  // factor back to global (lower part; the strict upper part of the tile is zeroed)
+  for (int k = 0; k < NB; k++) A[(long)k * ld + i] = Ls[k * LDS_D + i];
+  // sum of log-diagonal: each thread added its own diagonal entry's log
+  red[i] = logsum;
+  __syncthreads();
+  if (i == 0) {
+    double s = 0;
+    for (int q = 0; q < NB; q++) s += red[q];
+    *logdet_part = s;
+  }
+  // in-place inverse of the lower-triangular block, last column first (dtrti2, lower, non-unit)
+  for (int j = NB - 1; j >= 0; j--) {
+    colv[i] = Ls[j * LDS_D + i];         // column j of L (rows >= j are meaningful)
+    __syncthreads();
+    const double wjj = 1.0 / colv[j];
+    if (i == j) Ls[j * LDS_D + j] = wjj;
+    if (i > j) {
+      double s0 = 0, s1 = 0;
+      int k = j + 1;
+      for (; k + 1 <= i; k += 2) {
+        s0 = fma(Ls[k * LDS_D + i], colv[k], s0);
+        s1 = fma(Ls[(k + 1) * LDS_D + i], colv[k + 1], s1);
+      }
+      for (; k <= i; k++) s0 = fma(Ls[k * LDS_D + i], colv[k], s0);
+      Ls[j * LDS_D + i] = -(s0 + s1) * wjj;
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < NB; k++) Winv[k * NB + i] = Ls[k * LDS_D + i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4 (vector right-hand side): blocked triangular solves with the stored diagonal-block inverses.
+//     Replaces solve_chol's two dtrtrs for alpha (GP_Utils.cpp:841-845 via :893).
+// ---------------------------------------------------------------------------------------------------
+// forward step k:  z_k = Winv_k r_k ;  r[i] -= L[i, kblk] z_k  for rows below.   grid = 1 + #row tiles below
+__global__ void __launch_bounds__(NB) trsv_fwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
+                                                           double* __restrict__ r, double* __restrict__ z, int k0)
+{
+  __shared__ double rk[NB], zk[NB];
+  const int t = threadIdx.x;
+  rk[t] = r[k0 + t];
+  __syncthreads();
+  double s = 0;
+  for (int c = 0; c <= t; c++) s = fma(Winv[c * NB + t], rk[c], s);
+  zk[t] = s;
+  __syncthreads();
+  if (blockIdx.x == 0) { z[k0 + t] = s; return; }
+  const long i = (long)k0 + (long)blockIdx.x * NB + t;
+  const double* Lp = L + (long)k0 * ld + i;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+  for (int c = 0; c < NB; c += 4) {
+    a0 = fma(Lp[(long)c * ld], zk[c], a0);
+    a1 = fma(Lp[(long)(c + 1) * ld], zk[c + 1], a1);
+    a2 = fma(Lp[(long)(c + 2) * ld], zk[c + 2], a2);
+    a3 = fma(Lp[(long)(c + 3) * ld], zk[c + 3], a3);
+  }
+  r[i] -= (a0 + a1) + (a2 + a3);
+}
+
+// backward step k:  x_k = Winv_k^T r_k ;  r[j] -= L[kblk, j]^T x_k  for column tiles to the left.
+__global__ void __launch_bounds__(NB) trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
+                                                           double* __restrict__ r, double* __restrict__ x, int k0)
+{
+  __shared__ double rk[NB], xk[NB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  rk[t] = r[k0 + t];
+  __syncthreads();
+  // x_k[c] = sum_{c' >= c} Winv[c'][c] r[c'] : one warp per output column
+  for (int c = warp; c < NB; c += NB / 32) {
+    double s = 0;
+    for (int q = lane; q < NB; q += 32) s = fma(Winv[c * NB + q], rk[q], s);   // Winv(q,c), zero for q<c
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) xk[c] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) { x[k0 + t] = xk[t]; return; }
+  const int j0 = (blockIdx.x - 1) * NB;
+  for (int c = warp; c < NB; c += NB / 32) {
+    const double* Lp = L + (long)(j0 + c) * ld + k0;
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < NB; q += 32) s = fma(Lp[q + lane], xk[q + lane], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) r[j0 + c] -= s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// f = K * alpha with K regenerated from coordinates (mvmK_exact, GP_Utils.cpp:394-397, used at :1147).
+// 64 rows per CTA, 256 threads: thread (row, part) strides over columns, partials combined in smem.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
+                                                      double* __restrict__ f, int n, const DevParams* __restrict__ Pp)
+{
+  __shared__ double cz[5][256];
+  __shared__ double part[4][64];
+  __shared__ DevParams P;
+  const int tid = threadIdx.x, rr = tid & 63, pp = tid >> 6;
+  if (tid == 0) P = *Pp;
+  const int i = blockIdx.x * 64 + rr;
+  const bool vi = i < n;
+  const int ic = vi ? i : 0;
+  const double z0 = zs[ic], z1 = zs[ldz + ic], z2 = zs[2 * ldz + ic], ai = zs[3 * ldz + ic];
+  double acc = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    __syncthreads();
+    const int j = j0 + tid;
+    if (j < n) {
+      cz[0][tid] = zs[j]; cz[1][tid] = zs[ldz + j]; cz[2][tid] = zs[2 * ldz + j]; cz[3][tid] = zs[3 * ldz + j];
+      cz[4][tid] = alpha[j];
+    } else { cz[0][tid] = cz[1][tid] = cz[2][tid] = cz[3][tid] = 0; cz[4][tid] = 0; }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = pp; q < 256; q += 4) {
+      const double d2 = pair_d2(z0, z1, z2, ai, cz[0][q], cz[1][q], cz[2][q], cz[3][q]);
+      acc = fma(kern_val(d2, P), cz[4][q], acc);
+    }
+  }
+  part[pp][rr] = acc;
+  __syncthreads();
+  if (pp == 0 && vi) f[i] = (part[0][rr] + part[1][rr]) + (part[2][rr] + part[3][rr]);
+}
+
+// block-wide sum of NV values per thread -> out[blockIdx][NV]; 256 threads
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out)
+{
+  __shared__ double red[8][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double s = v[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) red[warp][q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scalar pieces of the objective (GP_Utils.cpp:1147-1159, 810, 858-862):
+//   out[0] = sum alpha_i * 0.5 f_i ;  out[1] = sum lp_i ;  out[2] = sum ((y_i-f_i)^2/sn2 - 1)
+// single CTA, fixed summation tree -> bitwise reproducible.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lml_terms_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
+                                                        const double* __restrict__ f, int n, const DevParams* __restrict__ Pp,
+                                                        const double* __restrict__ logdet_parts, int nblk, double* __restrict__ out)
+{
+  const DevParams P = *Pp;
+  double v[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double ymmu = y[i] - f[i];
+    v[0] = fma(alpha[i], 0.5 * f[i], v[0]);
+    v[1] += ymmu * ymmu * (-1.0 / (2.0 * P.sn2)) - P.lp_const;
+    v[2] += P.inv_sn2 * (ymmu * ymmu) - 1.0;
+  }
+  for (int b = threadIdx.x; b < nblk; b += 256) v[3] += logdet_parts[b];
+  block_reduce_store<4>(v, out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7: one pass over the lower triangle of Q = B^-1 accumulating every reduction GradLL needs
+//     (GP_Utils.cpp:1164-1169, 1206, 1222-1235; Kernel.cpp:1176-1242, 370-377):
+//       QW_ij = Q_ij*d2lp - alpha_i alpha_j
+//       w_ij  = var2*QW_ij*exp(-s_ij)*(-0.5/s_ij)   (0 on the diagonal and where s_ij == 0)
+//       T_kl  = sum_ij w_ij x_ik x_jl ; V_k = sum_ij w_ij x_ik^2 ; G6 = sum_ij QW_ij exp(-s_ij)
+//       TR    = sum_i QW_ii ; QK = sum_ij Q_ij K_ij
+//     partial[block][16] = {T00,T01,T02,T11,T12,T22, V0,V1,V2, G6, TR, QK}; combined on the host into g[0..9].
+// ---------------------------------------------------------------------------------------------------
+constexpr int NGRAD = 12;
+
+__global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict__ Qm, long ld, const double* __restrict__ zs, long ldz,
+                                                        const double* __restrict__ xs, long ldx, const double* __restrict__ alpha,
+                                                        int n, const DevParams* __restrict__ Pp, double* __restrict__ partial)
+{
+  const int tm = blockIdx.x, tn = blockIdx.y;
+  double* out = partial + ((long)tn * gridDim.x + tm) * NGRAD;
+  if (tn > tm) { if (threadIdx.x < NGRAD) out[threadIdx.x] = 0.0; return; }
+  __shared__ double cz[4][NB], cx[3][NB], ca[NB];
+  __shared__ DevParams P;
+  const int tid = threadIdx.x;
+  if (tid == 0) P = *Pp;
+  const int r0 = tm * NB, c0 = tn * NB;
+  for (int idx = tid; idx < NB; idx += 256) {
+    const int j = c0 + idx;
+#pragma unroll
+    for (int q = 0; q < 4; q++) cz[q][idx] = zs[(long)q * ldz + j];
+#pragma unroll
+    for (int q = 0; q < 3; q++) cx[q][idx] = xs[(long)q * ldx + j];
+    ca[idx] = alpha[j];
+  }
+  const int tx = tid & 63, ty = tid >> 6;
+  const int i0 = r0 + 2 * tx;
+  double zi[2][4], xi[2][3], al[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+#pragma unroll
+    for (int q = 0; q < 3; q++) xi[e][q] = xs[(long)q * ldx + i0 + e];
+    al[e] = alpha[i0 + e];
+  }
+  __syncthreads();
+  double om[2] = {0, 0}, u[2][3] = {{0, 0, 0}, {0, 0, 0}}, pq[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  double g6 = 0, tr = 0, qk = 0;
+  for (int jj = ty; jj < NB; jj += 4) {
+    const int j = c0 + jj;
+    const double2 qv = *reinterpret_cast<const double2*>(Qm + (long)j * ld + i0);
+    const double qe[2] = {qv.x, qv.y};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = i0 + e;
+      if (i < n && j < n && i >= j) {
+        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj]);
+        const double s = sqrt(d2);
+        const double es = exp(-s);
+        const double QWij = qe[e] * P.inv_sn2 - al[e] * ca[jj];
+        const double Kij = __dadd_rn(__dmul_rn(P.var2, es), P.bias);
+        if (i == j) {
+          g6 += QWij * es;
+          tr += QWij;
+          qk += qe[e] * Kij;
+        } else {
+          g6 += 2.0 * (QWij * es);
+          qk += 2.0 * (qe[e] * Kij);
+          if (s != 0.0) {
+            const double w = (P.var2 * QWij) * (es * (-0.5 / s));
+            om[e] += w;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              u[e][q] = fma(w, cx[q][jj], u[e][q]);
+              pq[e][q] = fma(w, cx[q][jj] * cx[q][jj], pq[e][q]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ordered-pair sums from the unordered (i>j) traversal:
+  //   V_k  = sum_{i>j} w (x_ik^2 + x_jk^2) ;  T_kl = sum_{i>j} w (x_ik x_jl + x_jk x_il)
+  double v[NGRAD];
+#pragma unroll
+  for (int q = 0; q < NGRAD; q++) v[q] = 0;
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    v[0] += 2.0 * xi[e][0] * u[e][0];
+    v[1] += xi[e][0] * u[e][1] + xi[e][1] * u[e][0];
+    v[2] += xi[e][0] * u[e][2] + xi[e][2] * u[e][0];
+    v[3] += 2.0 * xi[e][1] * u[e][1];
+    v[4] += xi[e][1] * u[e][2] + xi[e][2] * u[e][1];
+    v[5] += 2.0 * xi[e][2] * u[e][2];
+#pragma unroll
+    for (int q = 0; q < 3; q++) v[6 + q] += xi[e][q] * xi[e][q] * om[e] + pq[e][q];
+  }
+  v[9] = g6; v[10] = tr; v[11] = qk;
+  block_reduce_store<NGRAD>(v, out);
+}
+
+// deterministic final sum of per-CTA partials: out[q] = sum_b partial[b][q]
+template <int NV>
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partial, long nblocks, double* __restrict__ out)
+{
+  double v[NV];
+#pragma unroll
+  for (int q = 0; q < NV; q++) v[q] = 0;
+  for (long b = threadIdx.x; b < nblocks; b += 256)
+#pragma unroll
+    for (int q = 0; q < NV; q++) v[q] += partial[b * NV + q];
+  block_reduce_store<NV>(v, out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small data-movement helpers
+// ---------------------------------------------------------------------------------------------------
+// dst(128x128 tile, upper) = transpose of Winv block (lower); dst is column-major with leading dimension ld
+__global__ void __launch_bounds__(256) put_transposed_block_kernel(double* __restrict__ dst, long ld, const double* __restrict__ Winv)
+{
+  __shared__ double t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) t[r][tx] = Winv[(long)(by + r) * NB + bx + tx];   // Winv(row bx+tx, col by+r)
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) dst[(long)(bx + r) * ld + by + tx] = t[tx][r];     // dst(row by+tx, col bx+r) = Winv(bx+r, by+tx)
+}
+
+// out(r x c region) = in^T : out(i,j) = in(j,i); generic tiled transpose, dims multiples of 32
+__global__ void __launch_bounds__(256) transpose_kernel(double* __restrict__ out, long ldo, const double* __restrict__ in, long ldi,
+                                                        int upper_src_only)
+{
+  __shared__ double t[32][33];
+  const int bi = blockIdx.x * 32, bj = blockIdx.y * 32;     // block of the SOURCE: rows bi.., cols bj..
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool zero = upper_src_only && (bi > bj + 31);       // strictly below the diagonal of an upper-triangular source
+  for (int r = ty; r < 32; r += 8) t[r][tx] = zero ? 0.0 : in[(long)(bj + r) * ldi + bi + tx];   // in(bi+tx, bj+r)
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) out[(long)(bi + r) * ldo + bj + tx] = t[tx][r];               // out(bj+tx, bi+r) = in(bi+r, bj+tx)
+}
+
+__global__ void fill_kernel(double* __restrict__ p, long count, double v)
+{
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// zero a rectangular region of a column-major matrix
+__global__ void zero_region_kernel(double* __restrict__ p, long ld, int rows, int cols)
+{
+  const long total = (long)rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    p[(idx / rows) * ld + (idx % rows)] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2/K8: scaled cross-covariance tile  Bm(j,i) = Sw * K(x*_j, x_i)  (test index j contiguous) with the
+//        predictive-mean partial sums fused in:  mu_part[tile_i][j] = sum_{i in tile} alpha_i K(x*_j,x_i)
+//        (GP_Utils.cpp:943-949, 958-972, 985-990).  grid = (m_pad/128, n_pad/128), 256 threads.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ Bm, long ldb, const double* __restrict__ zt, long ldzt,
+                                                          const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
+                                                          int m, int n, const DevParams* __restrict__ Pp,
+                                                          double* __restrict__ mu_part, long ldmu, int write_B)
+{
+  __shared__ double cz[4][NB], ca[NB];
+  __shared__ double mred[4][NB];
+  __shared__ DevParams P;
+  const int tid = threadIdx.x;
+  if (tid == 0) P = *Pp;
+  const int j0t = blockIdx.x * NB, i0t = blockIdx.y * NB;
+  for (int idx = tid; idx < NB; idx += 256) {
+    const int i = i0t + idx;
+#pragma unroll
+    for (int q = 0; q < 4; q++) cz[q][idx] = zs[(long)q * ldz + i];
+    ca[idx] = (i < n) ? alpha[i] : 0.0;
+  }
+  const int tx = tid & 63, ty = tid >> 6;
+  const int j0 = j0t + 2 * tx;
+  double zj[2][4];
+#pragma unroll
+  for (int e = 0; e < 2; e++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) zj[e][q] = zt[(long)q * ldzt + j0 + e];
+  __syncthreads();
+  double mu[2] = {0, 0};
+  for (int ii = ty; ii < NB; ii += 4) {
+    const int i = i0t + ii;
+    double2 out;
+    double* o = &out.x;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double v = 0.0;
+      if (i < n && (j0 + e) < m) {
+        // K(X_train, X_test)(i,j): first argument is the training point (GP_Utils.cpp:946-947)
+        const double d2 = pair_d2(cz[0][ii], cz[1][ii], cz[2][ii], cz[3][ii], zj[e][0], zj[e][1], zj[e][2], zj[e][3]);
+        const double k = kern_val(d2, P);
+        mu[e] = fma(ca[ii], k, mu[e]);
+        v = __dmul_rn(k, P.sw);
+      }
+      o[e] = v;
+    }
+    if (write_B) *reinterpret_cast<double2*>(Bm + (long)i * ldb + j0) = out;
+  }
+  mred[ty][2 * tx] = mu[0];
+  mred[ty][2 * tx + 1] = mu[1];
+  __syncthreads();
+  if (tid < NB) mu_part[(long)blockIdx.y * ldmu + j0t + tid] = (mred[0][tid] + mred[1][tid]) + (mred[2][tid] + mred[3][tid]);
+}
+
+// mu[j] = sum_t mu_part[t][j]  (fixed order)
+__global__ void mean_finish_kernel(const double* __restrict__ mu_part, long ldmu, int ntiles, int m, double* __restrict__ mu)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s = 0;
+  for (int t = 0; t < ntiles; t++) s += mu_part[(long)t * ldmu + j];
+  mu[j] = s;
+}
+
+// var[j] = max(0, kD - sum_i V(i,j)^2) + sn2   (GP_Utils.cpp:997-1003, 1033-1040); V is n_pad x m_pad, one warp per column
+__global__ void __launch_bounds__(256) var_finish_kernel(const double* __restrict__ V, long ldv, int n_pad, int m, double kD, double sn2,
+                                                         int add_noise, double* __restrict__ var)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= m) return;
+  const double* col = V + (long)j * ldv;
+  double s0 = 0, s1 = 0;
+  for (int i = lane * 2; i < n_pad; i += 64) {
+    const double2 v = *reinterpret_cast<const double2*>(col + i);
+    s0 = fma(v.x, v.x, s0);
+    s1 = fma(v.y, v.y, s1);
+  }
+  double s = s0 + s1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    double v = kD - s;
+    if (v < 0) v = 0.0;
+    if (add_noise) v += sn2;
+    var[j] = v;
+  }
+}
+
+}  // namespace gpss

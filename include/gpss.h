@@ -1,0 +1,104 @@
+/* gpss.h -- C ABI of the B200-native exact-GP hot path of GP_SS_AK.
+ *
+ * This is the ONLY boundary between host code (the C++ classes that mirror the reference's
+ * Kernels / Opt_Algs / GP_utils surface, the ctypes test harness, bench.py) and the CUDA
+ * implementation in gp_ss_ak_b200/csrc.  Plain pointers and sizes, no C++/torch types.
+ *
+ * The reference has no FFI of its own (single C++ process, Armadillo); each entry point below
+ * replaces the body of one reference member function -- the file:line it stands in for is cited.
+ * INTEGRATION.md shows the few lines a maintainer of the reference adds to route GP_utils through
+ * this library.
+ *
+ * Conventions
+ *   - matrices are column-major like arma::mat: X(i,d) at X[i + d*n]
+ *   - theta[10] = {AngleX, iWx, AngleY, iWy, AngleZ, iWz, Sigma, iWR, Sigma_Bias, sn2}: the order
+ *     GP_utils::get_GP_Pars produces (GP_Utils.cpp:101-128, Kernel.cpp:803-838, 350-360)
+ *   - every function returns an int status: GPSS_OK, GPSS_NOT_POSDEF (the reference's Chol_fail ->
+ *     quiet-NaN path, GP_Utils.cpp:881-888,1145-1146) or a negative error; gpss_last_error() gives text
+ *   - a handle is bound to one CUDA device and is not thread-safe (the reference is single-threaded)
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is available every call fails loudly
+ */
+#ifndef GPSS_H
+#define GPSS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPSS_OK 0
+#define GPSS_NOT_POSDEF 1
+#define GPSS_ERR_CUDA (-1)
+#define GPSS_ERR_ARG (-2)
+#define GPSS_ERR_NCCL (-3)
+#define GPSS_ERR_STATE (-4)
+
+#define GPSS_NPAR 10
+
+typedef struct gpss_ctx* gpss_handle;
+
+/* library / device ------------------------------------------------------------------------------ */
+int gpss_version(void);
+int gpss_device_count(int* count);
+const char* gpss_last_error(void);
+
+/* model state ------------------------------------------------------------------------------------ */
+/* Replaces GP_utils::GP_utils + initialize_vars (GP_Utils.cpp:9-86): takes the standardised training
+ * inputs X (n x d, d == 3) and targets y (n) and makes them device resident. */
+int gpss_create(int device, int n, int d, const double* X_colmajor, const double* y, gpss_handle* out);
+int gpss_destroy(gpss_handle h);
+/* Re-upload training data of the same shape (test() assigns Xinp / yTarg, gp_ss_ak.cpp:389-395). */
+int gpss_set_data(gpss_handle h, const double* X_colmajor, const double* y);
+/* GP_utils::set_GP_Pars (GP_Utils.cpp:130-157): stores theta and invalidates the caches; no GPU work. */
+int gpss_set_theta(gpss_handle h, const double theta[GPSS_NPAR]);
+int gpss_get_theta(gpss_handle h, double theta[GPSS_NPAR]);
+
+/* objective ---------------------------------------------------------------------------------------- */
+/* Opt_Algs::ObjVal -> GP_utils::logLikelihood (Opt_pars.h:248-251, GP_Utils.cpp:1138-1162):
+ * negative log marginal likelihood.  On GPSS_NOT_POSDEF *nlml is NaN. */
+int gpss_nlml(gpss_handle h, double* nlml);
+/* Opt_Algs::Grad_Values -> GP_utils::GradLL (Opt_pars.h:242-246, GP_Utils.cpp:1171-1262 +
+ * Kernel.cpp:886-1263, 370-377): value and the reference's 10-vector g (quirks included). */
+int gpss_nlml_grad(gpss_handle h, double* nlml, double g[GPSS_NPAR]);
+/* GP_utils::Alpha after updateAlpha (GP_Utils.cpp:383-393): alpha = (K + sn2 I)^-1 y, n doubles. */
+int gpss_get_alpha(gpss_handle h, double* alpha);
+/* yhat = K*alpha as logLikelihood leaves it (GP_Utils.cpp:1147-1148), n doubles. */
+int gpss_get_yhat(gpss_handle h, double* yhat);
+
+/* prediction --------------------------------------------------------------------------------------- */
+/* GP_utils::Calc_Out / posteriorMeanVar (GP_Utils.cpp:159-178, 1016-1041): predictive mean and variance
+ * (noise included) of m standardised test points; var may be NULL (posteriorMean, :1005-1015).
+ * The Mahalanobis centre uses the training set and ALL m test points as MahaDist does (Kernel.cpp:1391). */
+int gpss_predict(gpss_handle h, long m, const double* Xs_colmajor, double* mu, double* var);
+/* Same, for one shard [first, first+count) of a test set of m_total points whose column sums are
+ * sums_total[3]: lets ranks split the test points (L and alpha replicated) yet use the global centre. */
+int gpss_predict_shard(gpss_handle h, long m_total, const double sums_total[3], long count,
+                       const double* Xs_shard_colmajor, double* mu, double* var);
+
+/* Kernels::computeK compatibility (host matrices; Kernel.cpp:140-154, 856-882, 362-367) ---------- */
+/* K and D2 are n1 x n2 column-major host buffers (either may be NULL). */
+int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const double* X1, int n2, const double* X2,
+                   double* K, double* D2);
+
+/* instrumentation ---------------------------------------------------------------------------------- */
+/* Device time in ms of the phases of the last gpss_nlml / gpss_nlml_grad / gpss_predict on this handle:
+ * [0] K build, [1] potrf, [2] solves+objective terms, [3] trtri, [4] lauum, [5] gradient pass,
+ * [6] cross-covariance+mean, [7] variance GEMM, [8..15] reserved.  Requires gpss_set_profiling(h,1). */
+int gpss_set_profiling(gpss_handle h, int on);
+int gpss_get_phase_ms(gpss_handle h, double ms[16]);
+/* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+int gpss_get_launch_count(gpss_handle h, long* launches);
+/* Raw device pointer to the n_pad x n_pad factor / inverse and the padded size (tests only). */
+int gpss_debug_fetch(gpss_handle h, int which, double* host_out, long count);
+int gpss_padded_n(gpss_handle h, int* n_pad);
+
+/* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
+/* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = 128x64, 1 = 128x128. */
+int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C,
+                      int subtract_from_C, double* ms_out);
+/* In-place blocked Cholesky of a host n x n SPD matrix (lower), through the full potrf driver. */
+int gpss_test_potrf(int device, int n, double* A_colmajor, double* logdet_half, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSS_H */

@@ -1,0 +1,670 @@
+"""CPU oracle for the exact-GP hot path of GP_SS_AK  --  TEST INFRASTRUCTURE ONLY.
+
+This file restates, step by step, the arithmetic the reference performs on the path
+named by BASELINE.json:north_star.  It is imported only by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.  The
+product (gp_ss_ak_b200/) never imports it and has no CPU fallback.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ and cannot be compiled in this image (every translation unit
+includes <armadillo>, which is absent).  The restatement below is therefore pinned
+only by (a) line-by-line citation of the reference sources, (b) self-consistency
+checks in tests/test_oracle.py (IRLS fixed point == direct solve, matrix-form gradient
+== fused form, etc.) and (c) where available, oracle/_ref (the unmodified reference
+sources compiled against the in-repo Armadillo API stand-in, see oracle/README.md).
+
+All file:line citations are into /root/reference.
+
+LAPACK/BLAS: numpy / scipy dispatch to the bundled OpenBLAS (dpotrf, dtrtrs, dgemm,
+dgemv) -- the same routines Armadillo forwards chol(), solve(trimatl/trimatu()), and
+operator* to.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+import scipy.linalg as sla
+
+# ----------------------------------------------------------------------------------
+# parameter vector (GP_Utils.cpp:101-128, Kernel.cpp:741-773, Kernel.cpp:317-320)
+#   theta = [AngleX, iWx, AngleY, iWy, AngleZ, iWz, Sigma, iWR, Sigma_Bias, sn2]
+# ----------------------------------------------------------------------------------
+THETA0 = np.array([math.pi / 3.1, 1.5, math.pi / 3.1, 1.5, math.pi / 3.1, 1.3, 0.9, 0.6, 0.2, 0.016])
+NPAR = 10
+
+
+# ----------------------------------------------------------------------------------
+# A. symmetric standardisation  (Control.h:46-73, Control.cpp:299-324)
+# ----------------------------------------------------------------------------------
+def statistics_calc(X, y):
+    """Control::StatisticsCalc (Control.h:46-73): row 0 = y, rows 1..D = X columns."""
+    n, D = X.shape
+    st = {
+        "MaxTotalin": float(X.max()), "MinTotalin": float(X.min()),
+        "MaxTotalo": float(y.max()), "MinTotalo": float(y.min()),
+        "Min": np.zeros(D + 1), "Max": np.zeros(D + 1), "Mean": np.zeros(D + 1), "Std": np.zeros(D + 1),
+    }
+    cols = [y.reshape(-1)] + [X[:, j] for j in range(D)]
+    for i, c in enumerate(cols):
+        st["Min"][i] = c.min()
+        st["Max"][i] = c.max()
+        st["Mean"][i] = c.sum() / n
+        st["Std"][i] = math.sqrt(((c - st["Mean"][i]) ** 2).sum() / (n - 1))
+    return st
+
+
+def prep_symmetric_params(st, D):
+    """Control::prep_symmetric, train mode (Control.cpp:301-316): params[:,0]=centre, [:,1]=half-range.
+    The first THREE X columns share one centre/half-range from the global X min/max."""
+    params = np.zeros((D + 1, 2))
+    params[0, 0] = 0.5 * (st["MaxTotalo"] + st["MinTotalo"])
+    params[0, 1] = 0.5 * (st["MaxTotalo"] - st["MinTotalo"])
+    for j in range(3):
+        params[j + 1, 0] = 0.5 * (st["MaxTotalin"] + st["MinTotalin"])
+        params[j + 1, 1] = 0.5 * (st["MaxTotalin"] - st["MinTotalin"])
+    for j in range(3, D):
+        params[j + 1, 0] = 0.5 * (st["Max"][j + 1] + st["Min"][j + 1])
+        params[j + 1, 1] = 0.5 * (st["Max"][j + 1] - st["Min"][j + 1])
+    return params
+
+
+def apply_standardise(X, y, params):
+    """Control.cpp:318-323."""
+    Xs = np.empty_like(X)
+    for j in range(X.shape[1]):
+        Xs[:, j] = (X[:, j] - params[j + 1, 0]) / params[j + 1, 1]
+    ys = (y - params[0, 0]) / params[0, 1]
+    return Xs, ys
+
+
+def standardise_train(X, y):
+    st = statistics_calc(X, y)
+    params = prep_symmetric_params(st, X.shape[1])
+    Xs, ys = apply_standardise(X, y, params)
+    return Xs, ys, params, st
+
+
+def post_mean(mu, params):
+    """Control::postData (Control.cpp:218): y = mu*half + centre."""
+    return mu * params[0, 1] + params[0, 0]
+
+
+def post_std(var, params):
+    """Control::postData_var (Control.cpp:253-254): sqrt(var*half^2)."""
+    return np.sqrt(var * params[0, 1] ** 2)
+
+
+# ----------------------------------------------------------------------------------
+# B. rotation / anisotropy matrix  (Kernel.cpp:1402-1425)
+# ----------------------------------------------------------------------------------
+def rot_matrix(alpha, beta, teta):
+    """Rot (Kernel.cpp:1402-1410); libm sin/cos (math.*), the same routines the C++ host calls."""
+    sa, ca = math.sin(alpha), math.cos(alpha)
+    sb, cb = math.sin(beta), math.cos(beta)
+    st, ct = math.sin(teta), math.cos(teta)
+    R = np.zeros((3, 3))
+    R[0, 0] = ca * ct + sa * sb * st
+    R[0, 1] = -sa * ct + ca * sb * st
+    R[0, 2] = -cb * st
+    R[1, 0] = sa * cb
+    R[1, 1] = ca * cb
+    R[1, 2] = sb
+    R[2, 0] = ca * st - sa * sb * ct
+    R[2, 1] = -sa * st - ca * sb * ct
+    R[2, 2] = cb * ct
+    return R
+
+
+def sig_inv(theta):
+    """sigInv = Rot*lambda*Rot.t() (Kernel.cpp:1417-1425).  Evaluated in a DEFINED order shared with the
+    product's host code (gp_ss_ak_b200/host/gpss_params.h): T = Rot*diag(l) element-wise, then
+    S(i,j) = (T(i,0)*Rot(j,0) + T(i,1)*Rot(j,1)) + T(i,2)*Rot(j,2), every operation individually rounded."""
+    R = rot_matrix(theta[0], theta[2], theta[4])
+    lam = (theta[1], theta[3], theta[5])
+    S = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            t0 = R[i, 0] * lam[0]
+            t1 = R[i, 1] * lam[1]
+            t2 = R[i, 2] * lam[2]
+            S[i, j] = (t0 * R[j, 0] + t1 * R[j, 1]) + t2 * R[j, 2]
+    return S
+
+
+def seq_colsum(X):
+    """Column sums accumulated strictly in row order (defined order shared with the product host code)."""
+    s = np.zeros(X.shape[1])
+    for j in range(X.shape[1]):
+        acc = 0.0
+        col = X[:, j]
+        for v in col.tolist():
+            acc += v
+        s[j] = acc
+    return s
+
+
+def centre(X1, X2, sums1=None, sums2=None):
+    """mX2 of MahaDist (Kernel.cpp:1391-1392): n/(n+m)*sum(X1)/n + m/(n+m)*sum(X2)/m."""
+    n, m = X1.shape[0], X2.shape[0]
+    s1 = seq_colsum(X1) if sums1 is None else sums1
+    s2 = seq_colsum(X2) if sums2 is None else sums2
+    mX1 = (float(n) / (n + m)) * s1 / n
+    return (float(m) / (n + m)) * s2 / m + mX1
+
+
+# ----------------------------------------------------------------------------------
+# B/C/D. covariance, literal (BLAS) form  (Kernel.cpp:1370-1435, 856-882, 362-367, 140-154)
+# ----------------------------------------------------------------------------------
+def maha_dist_blas(X1, X2, theta):
+    """MahaDist exactly as written: centred copies, X*sigInv via dgemm, expansion-form D2 via dgemm, clamp."""
+    c = centre(X1, X2)
+    S = sig_inv(theta)
+    Z1 = (X1 - c) @ S
+    Z2 = (X2 - c) @ S
+    a1 = (Z1 * Z1)
+    a1 = (a1[:, 0] + a1[:, 1]) + a1[:, 2]
+    a2 = (Z2 * Z2)
+    a2 = (a2[:, 0] + a2[:, 1]) + a2[:, 2]
+    D2 = (a1[:, None] + a2[None, :]) - 2.0 * (Z1 @ Z2.T)
+    D2[D2 < 0] = 0.0
+    return D2
+
+
+def _fma_emul(a, b, c):
+    """Exact fused multiply-add on float64 arrays via Dekker/Veltkamp error-free transformations
+    (round(a*b+c) with one rounding).  Used when the C helper is unavailable."""
+    # two-product (Veltkamp split)
+    p = a * b
+    SPL = 134217729.0
+    ta = SPL * a
+    ah = ta - (ta - a)
+    al = a - ah
+    tb = SPL * b
+    bh = tb - (tb - b)
+    bl = b - bh
+    e = ((ah * bh - p) + ah * bl + al * bh) + al * bl  # a*b = p + e exactly
+    # two-sum p + c
+    s = p + c
+    bb = s - p
+    err = (p - (s - bb)) + (c - bb)
+    # s + (err + e): correct to 1 rounding except in rare double-rounding ties (not hit for these magnitudes;
+    # the C helper oracle/c/oracle_kernels.c uses a hardware fma and is the authoritative path).
+    return s + (err + e)
+
+
+def transform_defined(X, c, S):
+    """Z = (X - c) * S in the defined order: z_j = fma(d2, S[2,j], fma(d1, S[1,j], d0*S[0,j])), d = x - c."""
+    d0 = X[:, 0] - c[0]
+    d1 = X[:, 1] - c[1]
+    d2 = X[:, 2] - c[2]
+    Z = np.empty((X.shape[0], 3))
+    for j in range(3):
+        Z[:, j] = _fma_emul(d2, S[2, j], _fma_emul(d1, S[1, j], d0 * S[0, j]))
+    return Z
+
+
+def sqnorm_defined(Z):
+    """a_i = fl(fl(z0^2 + z1^2) + z2^2) (sum(X%X,1), Kernel.cpp:1431)."""
+    return (Z[:, 0] * Z[:, 0] + Z[:, 1] * Z[:, 1]) + Z[:, 2] * Z[:, 2]
+
+
+def maha_dist_defined(X1, X2, theta, c=None):
+    """Defined-operation-order D2 (SURVEY.md section 7 hard part 1), the order the CUDA kernels use:
+       c_ij = fma(z_i2, z_j2, fma(z_i1, z_j1, z_i0*z_j0));  D2 = max(0, fl(fl(a_i + a_j) - 2 c_ij))."""
+    if c is None:
+        c = centre(X1, X2)
+    S = sig_inv(theta)
+    Z1 = transform_defined(X1, c, S)
+    Z2 = transform_defined(X2, c, S)
+    a1 = sqnorm_defined(Z1)
+    a2 = sqnorm_defined(Z2)
+    cij = _fma_emul(Z1[:, 2][:, None], Z2[:, 2][None, :],
+                    _fma_emul(Z1[:, 1][:, None], Z2[:, 1][None, :], Z1[:, 0][:, None] * Z2[:, 0][None, :]))
+    D2 = (a1[:, None] + a2[None, :]) - 2.0 * cij
+    D2[D2 < 0] = 0.0
+    return D2
+
+
+def compute_K(X1, X2, theta, dist="defined", c=None):
+    """HybKerns::computeK = ExpAns + Bias (Kernel.cpp:140-154, 856-882, 362-367):
+       K = Sigma^2 * exp(-sqrt(D2)) + Sigma_Bias  (bias added to EVERY element)."""
+    if dist == "blas":
+        D2 = maha_dist_blas(X1, X2, theta)
+    else:
+        D2 = maha_dist_defined(X1, X2, theta, c)
+    var2 = theta[6] * theta[6]
+    K = var2 * np.exp(-1 * np.sqrt(D2))
+    K += theta[8]
+    return K, D2
+
+
+# ----------------------------------------------------------------------------------
+# F/G. Laplace/IRLS alpha, log-likelihood  (GP_Utils.cpp:180-416, 795-915, 1138-1162)
+# ----------------------------------------------------------------------------------
+def sign_ref(v):
+    """ModelInf.h:14-20: sign(0) = -1."""
+    return -1.0 if v <= 0 else 1.0
+
+
+class OracleGP:
+    """State-carrying restatement of GP_utils for Gaussian likelihood, zero mean (GP_Utils.cpp)."""
+
+    def __init__(self, X, y, theta=None, dist="defined", literal=True):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        self.n = self.X.shape[0]
+        self.theta = np.array(THETA0 if theta is None else theta, dtype=np.float64)
+        self.dist = dist
+        self.literal = literal          # True: IRLS + Brent + 3 Cholesky (reference-literal); False: direct solve
+        # Alpha starts at zero only because arma::Mat::resize zero-fills (GP_Utils.cpp:69)
+        self.Alpha = np.zeros(self.n)
+        self.K_ok = False
+        self.alpha_ok = False
+        self.chol_fail = False
+        self.n_chol = 0
+        self.n_psi = 0
+
+    # -- parameter protocol (GP_Utils.cpp:101-157) --
+    def get_pars(self):
+        return self.theta.copy()
+
+    def set_pars(self, th):
+        self.K_ok = False           # setKUpdateStat(false) also clears AlphaUpStatus (GP_Utils.h:262-268)
+        self.alpha_ok = False
+        self.theta = np.array(th, dtype=np.float64).reshape(-1).copy()
+
+    @property
+    def sn2(self):
+        return self.theta[9]
+
+    # -- kernel (GP_Utils.cpp:1100-1113) --
+    def update_kernel(self):
+        if not self.K_ok:
+            self.K, self.D2 = compute_K(self.X, self.X, self.theta, self.dist)
+            self.K_ok = True
+
+    # -- likelihood terms (GP_Utils.cpp:398-416 and 795-839) --
+    def _lik(self, f):
+        sn2 = self.sn2
+        ymmu = self.y - f
+        self.lp = ymmu ** 2 * (-1 / (2 * sn2)) - math.log(2 * math.pi * sn2) / 2
+        self.dlp = (1 / sn2) * ymmu
+        self.d2lp = np.full(self.n, 1 / sn2)
+
+    def _psi(self, alp):
+        """PSI (GP_Utils.cpp:180-190); returns (psi, fval=K*alp)."""
+        self.n_psi += 1
+        f = self.K @ alp
+        self._lik(f)
+        return float(alp @ (0.5 * f) - self.lp.sum()), f
+
+    def _chol_B(self):
+        """chol(Sw Sw' % K + I) -> upper R (GP_Utils.cpp:876-888 / 898-910)."""
+        self.n_chol += 1
+        Sw = np.sqrt(self.d2lp)
+        B = (Sw[:, None] * Sw[None, :]) * self.K + np.eye(self.n)
+        try:
+            R = sla.cholesky(B, lower=False, check_finite=False)
+        except np.linalg.LinAlgError:
+            self.chol_fail = True
+            return None, Sw
+        if not np.all(np.isfinite(np.diag(R))):
+            self.chol_fail = True
+            return None, Sw
+        self.chol_fail = False
+        return R, Sw
+
+    @staticmethod
+    def _solve_chol(R, b):
+        """solve_chol (GP_Utils.cpp:841-845): solve(trimatl(R'), b) then solve(trimatu(R), .)."""
+        t = sla.solve_triangular(R, b, trans="T", lower=False, check_finite=False)
+        return sla.solve_triangular(R, t, trans="N", lower=False, check_finite=False)
+
+    def _brentmin(self, dalpha):
+        """brentmin (GP_Utils.cpp:229-381)."""
+        Alpha = self.Alpha
+        smin, smax, nmax, thr = 0.0, 2.0, 10, 1e-4
+        counters = 0
+        fa, _ = self._psi(Alpha + smin * dalpha); counters += 1
+        fb, _ = self._psi(dalpha * smax + Alpha); counters += 1
+        seps = math.sqrt(2.220446049250313e-16)
+        c = 0.5 * (3.0 - math.sqrt(5.0))
+        a, b = smin, smax
+        v = a + c * (b - a)
+        w = v
+        xf = v
+        d = 0.0
+        e = 0.0
+        x = xf
+        fc, _ = self._psi(Alpha + x * dalpha); counters += 1
+        fv = fc
+        fw = fc
+        xm = 0.5 * (a + b)
+        tol1 = seps * abs(xf) + thr / 3.0
+        tol2 = 2.0 * tol1
+        while abs(xf - xm) > (tol2 - 0.5 * (b - a)):
+            gs = 1
+            if abs(e) > tol1:
+                gs = 0
+                r = (xf - w) * (fc - fv)
+                q = (xf - v) * (fc - fw)
+                p = (xf - v) * q - (xf - w) * r
+                q = 2.0 * (q - r)
+                if q > 0.0:
+                    p = -p
+                q = abs(q)
+                r = e
+                e = d
+                if (abs(p) < abs(0.5 * q * r)) and (p > q * (a - xf)) and (p < q * (b - xf)):
+                    d = p / q
+                    x = xf + d
+                    if ((x - a) < tol2) or ((b - x) < tol2):
+                        si = sign_ref(xm - xf) + (1.0 if (xm - xf) == 0 else 0.0)
+                        d = tol1 * si
+                else:
+                    gs = 1
+            if gs == 1:
+                if xf >= xm:
+                    e = a - xf
+                else:
+                    e = b - xf
+                d = c * e
+            si = sign_ref(d) + (1.0 if d == 0 else 0.0)
+            sd = tol1 if abs(d) < tol1 else abs(d)
+            x = xf + si * sd
+            fu, _ = self._psi(dalpha * x + Alpha); counters += 1
+            if fu <= fc:
+                if x >= xf:
+                    a = xf
+                else:
+                    b = xf
+                v = w; fv = fw
+                w = xf; fw = fc
+                xf = x
+                fc = fu
+            else:
+                if x < xf:
+                    a = x
+                else:
+                    b = x
+                if (fu <= fw) or (w == xf):
+                    v = w; fv = fw
+                    w = x; fw = fu
+                elif (fu <= fv) or (v == xf) or (v == w):
+                    v = x; fv = fu
+            xm = 0.5 * (a + b)
+            tol1 = seps * abs(xf) + thr / 3.0
+            tol2 = 2.0 * tol1
+            if counters >= nmax:
+                break
+        if (fa < fc) and (fa <= fb):
+            xf = smin; fc = fa
+        elif fb < fc:
+            xf = smax; fc = fb
+        fmin = fc
+        Xc = dalpha * xf + Alpha
+        self.Alpha = Xc
+        _, Fv = self._psi(Xc)
+        self.last_step = xf
+        return fmin, Fv
+
+    def _irls(self):
+        """irls (GP_Utils.cpp:191-228)."""
+        maxit, tol = 20, 1e-6
+        psi_new, Fv = self._psi(self.Alpha)
+        psi_old = math.inf
+        it = 0
+        self.irls_steps = []
+        while (psi_old - psi_new) > tol and it < maxit:
+            psi_old = psi_new
+            it += 1
+            B = Fv * self.d2lp + self.dlp
+            r = self.K @ B
+            R, Sw = self._chol_B()
+            if self.chol_fail:
+                return
+            self.Lchol = R
+            dalpha = self._solve_chol(R, Sw * r) * Sw
+            dalpha = -1 * dalpha - self.Alpha + B
+            psi_new, Fv = self._brentmin(dalpha)
+            self.irls_steps.append(self.last_step)
+        self.irls_its = it
+
+    def update_alpha(self):
+        if not self.alpha_ok:
+            self.update_kernel()
+            if self.literal:
+                self._irls()
+                if self.chol_fail:
+                    return
+            else:
+                # the fixed point the IRLS converges to: alpha = (K + sn2 I)^-1 y
+                self._lik(np.zeros(self.n))
+                R, Sw = self._chol_B()
+                if self.chol_fail:
+                    return
+                self.Lchol = R
+                self.Alpha = self._solve_chol(R, self.y / self.sn2)
+            self.alpha_ok = True
+
+    def log_likelihood(self):
+        """logLikelihood (GP_Utils.cpp:1138-1162): the NEGATIVE log marginal likelihood."""
+        self.update_kernel()
+        self.update_alpha()
+        if self.chol_fail:
+            return math.nan
+        self.yhat = self.K @ self.Alpha
+        self._lik(self.yhat)
+        ydif = 0.5 * self.yhat
+        if self.literal:
+            R, Sw = self._chol_B()          # the reference factorises the same matrix again (GP_Utils.cpp:894-915)
+            if self.chol_fail:
+                return math.nan
+            self.Lchol = R
+        self.Sw = np.sqrt(self.d2lp)
+        self.Lchol_db2 = float(np.log(np.diag(self.Lchol)).sum())
+        self.L = float(self.Alpha @ ydif - self.lp.sum() + self.Lchol_db2)
+        return self.L
+
+    # -- H/I/J. gradient (GP_Utils.cpp:1164-1284, Kernel.cpp:886-1263, 370-377) --
+    def grad_ll(self):
+        L = self.log_likelihood()
+        if self.chol_fail:
+            return math.nan, np.full(NPAR, math.nan)
+        n = self.n
+        Sw = self.Sw
+        R = self.Lchol
+        # Q = B^-1 through two triangular solves with an n x n right-hand side (GP_Utils.cpp:1202-1205)
+        Q = self._solve_chol(R, np.diag(Sw))
+        Q = Q * ((1 / Sw)[:, None] * np.ones((1, n)))
+        dW = 0.5 * (Q * self.K).sum(axis=1)
+        d3lp = np.zeros(n)
+        dfhat = dW * d3lp
+        kmvm = (self.K @ dfhat) * Sw
+        dahat = self._solve_chol(R, kmvm)
+        dahat = -1 * dahat * Sw + dfhat
+        # dhyp (GP_Utils.cpp:1164-1169)
+        QW = Q * (self.d2lp[:, None] * np.ones((1, n))) - np.outer(self.Alpha, self.Alpha) \
+            + np.outer(self.dlp, dahat) * 2.0
+        self.QW = QW
+        g = np.zeros(NPAR)
+        g[0:8] = expans_gradients_literal(self.X, self.theta, QW, self.dist)
+        g[8] = bias_gradient_literal(QW)
+        # likelihood hyper-parameter (GP_Utils.cpp:1222-1235, 846-871)
+        sn2 = self.sn2
+        ymmu = self.y - self.yhat
+        lp_dhyp = (1 / sn2) * ymmu ** 2 - 1
+        dlp_dhyp = (-2 / sn2) * ymmu
+        d2lp_dhyp = np.full(n, 2 / sn2)
+        g_tmp0 = -1 * (dW @ d2lp_dhyp) - lp_dhyp.sum()
+        B = self.K @ dlp_dhyp
+        B0 = B.copy()
+        B = self._solve_chol(R, B * Sw) * Sw
+        B = -1 * B + B0
+        g_tmp0 += -1.0 * (dfhat @ B)
+        g[9] = g_tmp0
+        self.dW = dW
+        return L, g
+
+    # -- K. prediction (GP_Utils.cpp:943-1041) --
+    def predict(self, Xs):
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+        kX, _ = compute_K(self.X, Xs, self.theta, self.dist)      # n x m, centre uses BOTH sets (Kernel.cpp:1391)
+        self.update_alpha()
+        mu = kX.T @ self.Alpha
+        kD = np.full(Xs.shape[0], self.theta[6] * self.theta[6] + self.theta[8])   # diag_Compute (Kernel.cpp:782,331)
+        self.log_likelihood()                                         # GP_Utils.cpp:980
+        Wh = np.sqrt(self.d2lp)
+        LKs = kX * Wh[:, None]
+        LKs = self._solve_chol(self.Lchol, LKs)
+        LKs = LKs * Wh[:, None]
+        LKs *= kX
+        var = kD - LKs.sum(axis=0)
+        var[var < 0] = 0.0
+        if self.sn2 != 1.0:
+            var = var + self.sn2
+        return mu, var
+
+
+def s_matrices(theta):
+    """S and the six S_p of Kern_ExpAnisotropic::getGradients, entry by entry (Kernel.cpp:946-1166),
+    including the quirk that S_angle(0,0) carries no factor 2 on its z term (Kernel.cpp:1003-1011)."""
+    al, be, te = theta[0], theta[2], theta[4]
+    l = (theta[1], theta[3], theta[5])
+    sa, ca, sb, cb, st, ct = math.sin(al), math.cos(al), math.sin(be), math.cos(be), math.sin(te), math.cos(te)
+    Rot = rot_matrix(al, be, te)
+    Ra = np.zeros((3, 3)); Rb = np.zeros((3, 3)); Rt = np.zeros((3, 3))
+    Ra[0, 0] = -sa * ct + ca * sb * st
+    Rb[0, 0] = sa * cb * st
+    Rt[0, 0] = -ca * st + sa * sb * ct
+    Ra[0, 1] = -ca * ct - sa * sb * st
+    Rb[0, 1] = ca * cb * st
+    Rt[0, 1] = sa * st + ca * sb * ct
+    Ra[0, 2] = 0.0
+    Rb[0, 2] = sb * st
+    Rt[0, 2] = -cb * ct
+    Ra[1, 0] = ca * cb
+    Rb[1, 0] = -sa * sb
+    Rt[1, 0] = 0.0
+    Ra[1, 1] = -sa * cb
+    Rb[1, 1] = -ca * sb
+    Rt[1, 1] = 0.0
+    Ra[1, 2] = 0.0
+    Rb[1, 2] = cb
+    Rt[1, 2] = 0.0
+    Ra[2, 0] = -sa * st - ca * sb * ct
+    Rb[2, 0] = -sa * cb * ct
+    Rt[2, 0] = ca * ct + sa * sb * st
+    Ra[2, 1] = -ca * st + sa * sb * ct
+    Rb[2, 1] = -ca * cb * ct
+    Rt[2, 1] = -sa * ct + ca * sb * st
+    Ra[2, 2] = 0.0
+    Rb[2, 2] = -sb * ct
+    Rt[2, 2] = -cb * st
+
+    S = np.zeros((3, 3))
+    Sd = {k: np.zeros((3, 3)) for k in ("a", "b", "t")}
+    SL = [np.zeros((3, 3)) for _ in range(3)]
+    dR = {"a": Ra, "b": Rb, "t": Rt}
+    # (0,0): the quirk
+    S[0, 0] = l[0] * Rot[0, 0] ** 2 + l[1] * Rot[0, 1] ** 2 + l[2] * Rot[0, 2] ** 2
+    for k, D in dR.items():
+        Sd[k][0, 0] = l[0] * 2 * Rot[0, 0] * D[0, 0] + l[1] * 2 * Rot[0, 1] * D[0, 1] + l[2] * Rot[0, 2] * D[0, 2]
+    for q in range(3):
+        SL[q][0, 0] = Rot[0, q] ** 2
+    # remaining upper-triangle entries: the regular product rule
+    for (i, j) in ((0, 1), (0, 2), (1, 1), (1, 2), (2, 2)):
+        S[i, j] = l[0] * Rot[i, 0] * Rot[j, 0] + l[1] * Rot[i, 1] * Rot[j, 1] + l[2] * Rot[i, 2] * Rot[j, 2]
+        for k, D in dR.items():
+            Sd[k][i, j] = (l[0] * D[i, 0] * Rot[j, 0] + l[0] * Rot[i, 0] * D[j, 0]
+                           + l[1] * D[i, 1] * Rot[j, 1] + l[1] * Rot[i, 1] * D[j, 1]
+                           + l[2] * D[i, 2] * Rot[j, 2] + l[2] * Rot[i, 2] * D[j, 2])
+        for q in range(3):
+            SL[q][i, j] = Rot[i, q] * Rot[j, q]
+    for (i, j) in ((1, 0), (2, 0), (2, 1)):
+        S[i, j] = S[j, i]
+        for k in Sd:
+            Sd[k][i, j] = Sd[k][j, i]
+        for q in range(3):
+            SL[q][i, j] = SL[q][j, i]
+    # parameter order: AngleX, iWx, AngleY, iWy, AngleZ, iWz  (Kernel.cpp:1192-1233)
+    return S, [Sd["a"], SL[0], Sd["b"], SL[1], Sd["t"], SL[2]]
+
+
+def expans_gradients_literal(X, theta, QW, dist="defined"):
+    """Kern_ExpAnisotropic::getGradients in its matrix form (Kernel.cpp:886-1263), 3-D branch."""
+    n = X.shape[0]
+    var2 = theta[6] * theta[6]
+    if dist == "blas":
+        DD2 = maha_dist_blas(X, X, theta)
+    else:
+        DD2 = maha_dist_defined(X, X, theta)
+    S, Sp = s_matrices(theta)
+    Qs = var2 * QW
+    SD2 = np.sqrt(DD2)
+    KD2 = np.exp(-1 * SD2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dk_tmp = -0.5 / SD2
+    dk_tmp[SD2 == 0] = 0
+    dk = np.exp(-1.0 * SD2) * dk_tmp
+    np.fill_diagonal(dk, 0.0)
+    Rm = Qs * dk
+    g = np.zeros(8)
+    XX = X * X
+    for p in range(6):
+        M = S * Sp[p]                                   # Hadamard product S % S_p (Kernel.cpp:1192)
+        rowq = (2.0 * XX @ M).sum(axis=1)
+        Di2 = rowq[:, None] + rowq[None, :] - 4.0 * ((X @ M) @ X.T)
+        g[p] = float((Rm * Di2).sum())
+    g[6] = 2.0 * float((KD2 * QW).sum()) * theta[6]     # Kernel.cpp:1239-1242
+    g[7] = 0.0                                          # Kernel.cpp:1256-1257
+    return g
+
+
+def bias_gradient_literal(QW):
+    """Kern_Bias::getGradients (Kernel.cpp:370-377): vec(QW) . vec(eye) = trace(QW)."""
+    return float(np.trace(QW))
+
+
+def expans_gradients_fused(X, theta, QW, DD2):
+    """Algebraically identical one-pass form used by the CUDA kernel:
+       g[p] = 4 sum_i q_p(x_i) omega_i - 4 <M_p, T>,  omega = w 1,  T = X' w X,  q_p(x) = sum_k x_k^2 rho_pk."""
+    var2 = theta[6] * theta[6]
+    S, Sp = s_matrices(theta)
+    SD2 = np.sqrt(DD2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = var2 * QW * np.exp(-SD2) * (-0.5 / SD2)
+    w[SD2 == 0] = 0
+    np.fill_diagonal(w, 0.0)
+    omega_r = w.sum(axis=1)
+    omega_c = w.sum(axis=0)
+    T = X.T @ w @ X
+    g = np.zeros(8)
+    XX = X * X
+    for p in range(6):
+        M = S * Sp[p]
+        rho = M.sum(axis=0)        # (XX @ M).sum(axis=1) = XX @ (M 1)
+        q = XX @ M.sum(axis=1)
+        g[p] = 2.0 * float(q @ omega_r) + 2.0 * float(q @ omega_c) - 4.0 * float((M * T).sum())
+    g[6] = 2.0 * theta[6] * float((QW * np.exp(-SD2)).sum())
+    return g
+
+
+# ----------------------------------------------------------------------------------
+# convenience entry points used by tests / bench
+# ----------------------------------------------------------------------------------
+def nlml_and_grad(X, y, theta, dist="defined", literal=True):
+    gp = OracleGP(X, y, theta, dist=dist, literal=literal)
+    L, g = gp.grad_ll()
+    return L, g, gp
+
+
+def nlml_direct(X, y, theta, dist="defined"):
+    """Textbook value the reference's objective equals at the IRLS fixed point:
+       0.5 y' alpha + 0.5 log det(K + sn2 I) + n/2 log(2 pi)."""
+    K, _ = compute_K(X, X, theta, dist)
+    n = X.shape[0]
+    sn2 = theta[9]
+    Lc = sla.cholesky(K + sn2 * np.eye(n), lower=True, check_finite=False)
+    alpha = sla.cho_solve((Lc, True), y, check_finite=False)
+    return 0.5 * float(y @ alpha) + float(np.log(np.diag(Lc)).sum()) + 0.5 * n * math.log(2 * math.pi), alpha
