@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the exact-GP hot path: ExpAns LML+gradient evaluations/s at n=50,000.
+
+One "step" = set_GP_Pars(theta_k) followed by Grad_Values(g) (GP_Utils.cpp:130,1171) on synthetic 3-D
+drillhole-style data, i.e. K build + FP64 Cholesky + alpha + objective + B^-1 (trtri+lauum) + fused gradient
+reductions.  Every step uses a different theta, so nothing is cached between steps; K (20 GB), L and B^-1 do
+not fit in the 126 MB L2, so no L2 flush is needed between iterations.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 50000] [--impl reference]
+
+N > 1 (launched by torchrun, one rank per GPU): the evaluation is not yet partitioned across GPUs in this
+round, so every rank runs an independent replica on its own theta probes ("replicas only", DESIGN.md
+section 6); value = evaluations of all ranks / max-over-ranks time, scaling "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HEADLINE = 50000
+FP64_PEAK_FALLBACK_TFLOPS = 37.13   # profiles/r01_fp64_peak_microbench.txt (DMMA.8x8x4 register loop on this pool's B200)
+
+
+def theta_probe(k):
+    """Deterministic theta probes around the reference's initial vector (Kernel.cpp:763-773, GP_Utils.cpp:43)."""
+    base = np.array([np.pi / 3.1, 1.5, np.pi / 3.1, 1.5, np.pi / 3.1, 1.3, 0.9, 0.6, 0.2, 0.016])
+    rng = np.random.default_rng(1000 + k)
+    th = base * rng.uniform(0.9, 1.1, size=10)
+    return np.clip(th, 1e-4, 6.0)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_eval(n_sample, seed=0):
+    """One reference-literal LML+gradient evaluation of the oracle port on the host cores (all BLAS threads):
+    3 dpotrf of the same matrix + two n x n dtrtrs + the matrix-form gradients."""
+    from gp_ss_ak_b200 import datagen
+    from oracle import gpss_oracle as O
+    X, y = datagen.drillholes(n_sample, seed)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    t0 = time.perf_counter()
+    L, g, _ = O.nlml_and_grad(Xs, ys, O.THETA0.copy(), dist="blas", literal=True)
+    return time.perf_counter() - t0, L
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n_sample = args.cpu_n
+    cores = os.cpu_count()
+    times = []
+    for k in range(args.warmup + args.steps):
+        dt, L = cpu_reference_eval(n_sample, seed=k)
+        if k >= args.warmup:
+            times.append(dt)
+    t_step = float(np.mean(times))
+    scale = (args.n / n_sample) ** 3
+    value = 1.0 / (t_step * scale)
+    sample = ("oracle port (numpy/scipy -> OpenBLAS dpotrf/dtrtrs/dgemm), reference-literal evaluation at n=%d "
+              "timed on %d host threads and scaled by (n/n_sample)^3 = %.1f to n=%d (the reference keeps ~34 dense "
+              "n x n buffers and cannot hold n=%d)" % (n_sample, cores, scale, args.n, args.n))
+    line = {
+        "impl": "reference", "metric": "ExpAns LML+grad evals/s at n=%dk" % (args.n // 1000), "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * scale * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LML+gradient evaluation, ExpAns+Bias 3-D, n=%d (cubic extrapolation from n=%d)" % (args.n, n_sample)},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=N_HEADLINE)
+    ap.add_argument("--impl", default="gpss")
+    ap.add_argument("--cpu-n", type=int, default=4000, help="sample size of the CPU baseline evaluation")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gp_ss_ak_b200 as G
+    from gp_ss_ak_b200 import datagen
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    X, y = datagen.drillholes(n, seed=rank)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    Xf = np.asfortranarray(Xs)
+    model = G.GpssModel(Xf, ys, device=local_rank)
+    n_pad = model.padded_n()
+
+    # ---- warm-up (>= 3): also allocates U / Q and pages the kernels in ----
+    for k in range(args.warmup):
+        model.set_theta(theta_probe(rank * 7919 + k))
+        model.nlml_grad()
+
+    # ---- timed region 1: device-resident (`value`) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = model.launch_count()
+    barrier()
+    dev_ms = []
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        model.set_theta(theta_probe(rank * 7919 + 100 + k))
+        L, g = model.nlml_grad()
+        dev_ms.append(model.last_call_ms())      # CUDA events on the stream the kernels are launched on
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = model.launch_count() - l0
+    t_dev = float(np.sum(dev_ms)) * 1e-3
+
+    # ---- timed region 2: end to end through the C ABI with HOST buffers (`e2e`) ----
+    barrier()
+    t1 = time.perf_counter()
+    for k in range(args.steps):
+        model.set_data(Xf, ys)                    # host -> device copy of this step's inputs
+        model.set_theta(theta_probe(rank * 7919 + 200 + k))
+        L, g = model.nlml_grad()                  # device -> host read of value + g[10]
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel (DMMA GEMM-NT) from a profiled evaluation ----
+    model.set_profiling(True)
+    model.set_theta(theta_probe(rank * 7919 + 300))
+    model.nlml_grad()
+    ph = model.phase_ms()
+    model.set_profiling(False)
+    gemm_ms = float(ph[1] + ph[3] + ph[4])        # potrf + trtri + lauum phases: >99% of it inside gemm_nt_kernel
+    alg_flops = float(n_pad) ** 3                 # n^3/3 each
+    try:
+        peak = G.measure_fp64_peak(local_rank)
+        peak_src = "DMMA.8x8x4 register-loop micro-peak measured live by gpss_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)"
+    except Exception:
+        peak = FP64_PEAK_FALLBACK_TFLOPS
+        peak_src = "profiles/r01_fp64_peak_microbench.txt"
+    achieved = alg_flops / (gemm_ms * 1e-3) * 1e-12
+
+    # ---- max over ranks ----
+    if world > 1:
+        t = torch.tensor([t_dev, wall, wall_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, wall, wall_e2e = (float(v) for v in t.cpu())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        total_evals = args.steps * world
+        value = total_evals / t_dev
+        e2e_value = total_evals / wall_e2e
+        line = {
+            "metric": "ExpAns LML+grad evals/s at n=%dk" % (n // 1000), "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d, theta differs every step"
+                                   % n, "n": n, "n_pad": n_pad, "l2_policy": "inputs larger than L2 (K, L, B^-1 = %.1f GB each)"
+                                   % (n_pad * n_pad * 8 / 1e9), "parallelism": "replicas x%d" % world if world > 1 else "single GPU"},
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(n * 4 * 8 + 80),
+                    "d2h_bytes_per_step": 88},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gemm_nt_kernel<GemmTile<128,64,2,2,2>> (FP64 DMMA)",
+                         "peak_source": peak_src,
+                         "note": "achieved = n_pad^3 algorithmic flops (potrf+trtri+lauum) / device time of those phases"},
+            "phases_ms": {"kbuild": ph[0], "potrf": ph[1], "solve_objective": ph[2], "trtri": ph[3], "lauum": ph[4], "grad_pass": ph[5]},
+            "cholesky_tflops": (float(n_pad) ** 3 / 3) / (ph[1] * 1e-3) * 1e-12,
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            t_cpu, _ = cpu_reference_eval(args.cpu_n, seed=0)
+            scale = (n / args.cpu_n) ** 3
+            line["cpu_baseline"] = {
+                "value": 1.0 / (t_cpu * scale), "unit": "evals/s", "cores": cores, "kind": "port",
+                "sample": "one reference-literal oracle evaluation at n=%d (%.2f s on %d threads), scaled by (n/%d)^3 = %.1f"
+                          % (args.cpu_n, t_cpu, cores, args.cpu_n, scale)}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,8 @@ def load_library():
         "gpss_compute_K": (I, [I, P, I, P, I, P, P, P]),
         "gpss_set_profiling": (I, [H, I]),
         "gpss_get_phase_ms": (I, [H, P]),
+        "gpss_get_last_call_ms": (I, [H, P]),
+        "gpss_measure_fp64_peak": (I, [I, P]),
         "gpss_get_launch_count": (I, [H, ctypes.POINTER(L)]),
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
@@ -180,6 +182,11 @@ class GpssModel:
         _check(self._lib.gpss_get_phase_ms(self._h, _dp(ms)))
         return ms
 
+    def last_call_ms(self):
+        v = ctypes.c_double(0.0)
+        _check(self._lib.gpss_get_last_call_ms(self._h, ctypes.byref(v)))
+        return v.value
+
     def launch_count(self):
         v = ctypes.c_long(0)
         _check(self._lib.gpss_get_launch_count(self._h, ctypes.byref(v)))
@@ -195,6 +202,12 @@ class GpssModel:
         out = np.zeros((npad, npad), order="F")
         _check(self._lib.gpss_debug_fetch(self._h, which, _dp(out), npad * npad))
         return out
+
+
+def measure_fp64_peak(device=0):
+    v = ctypes.c_double(0.0)
+    _check(load_library().gpss_measure_fp64_peak(device, ctypes.byref(v)))
+    return v.value
 
 
 def compute_K(theta, X1, X2, want_K=True, want_D2=True, device=0):

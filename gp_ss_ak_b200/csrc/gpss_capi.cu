@@ -66,6 +66,8 @@ struct gpss_ctx {
   bool profiling = false;
   double phase_ms[16];
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};   // bracket the device work of the last objective / predict call
+  double last_call_ms = 0.0;
   long launches = 0;
 };
 
@@ -97,6 +99,19 @@ static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, 
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   return g;
 }
+
+// CUDA-event bracket of a whole C-ABI call on the handle's stream (always on; read with gpss_get_last_call_ms)
+struct CallTimer {
+  gpss_ctx* c;
+  explicit CallTimer(gpss_ctx* c_) : c(c_) { cudaEventRecord(c->ev_call[0], c->st); }
+  ~CallTimer()
+  {
+    cudaEventRecord(c->ev_call[1], c->st);
+    cudaEventSynchronize(c->ev_call[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]);
+    c->last_call_ms = ms;
+  }
+};
 
 struct PhaseTimer {
   gpss_ctx* c; int idx;
@@ -371,6 +386,8 @@ int gpss_destroy(gpss_handle c)
   if (c->dflag) cudaFree(c->dflag);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->ev_call[0]) cudaEventDestroy(c->ev_call[0]);
+  if (c->ev_call[1]) cudaEventDestroy(c->ev_call[1]);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
   return GPSS_OK;
@@ -415,6 +432,8 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   CUF(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   CUF(cudaEventCreate(&c->ev[0]));
   CUF(cudaEventCreate(&c->ev[1]));
+  CUF(cudaEventCreate(&c->ev_call[0]));
+  CUF(cudaEventCreate(&c->ev_call[1]));
   CUF(cudaMalloc(&c->xs, sizeof(double) * 3 * np));
   CUF(cudaMalloc(&c->y, sizeof(double) * np));
   CUF(cudaMalloc(&c->zs, sizeof(double) * 4 * np));
@@ -459,6 +478,7 @@ int gpss_nlml(gpss_handle c, double* nlml)
   if (!c || !nlml) return fail_arg("gpss_nlml: null argument");
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  CallTimer ct(c);
   RET(ensure_objective(c));
   *nlml = c->nlml;
   return c->chol_fail ? GPSS_NOT_POSDEF : GPSS_OK;
@@ -469,6 +489,7 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   if (!c || !nlml || !g) return fail_arg("gpss_nlml_grad: null argument");
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  CallTimer ct(c);
   RET(ensure_objective(c));
   *nlml = c->nlml;
   if (c->chol_fail) {
@@ -546,6 +567,7 @@ int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], 
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
+  CallTimer ct(c);
   RET(ensure_objective(c));          // _postMean -> updateAlpha (GP_Utils.cpp:961)
   if (c->chol_fail) return GPSS_NOT_POSDEF;
   if (var) RET(ensure_W(c));
@@ -679,6 +701,60 @@ int gpss_get_phase_ms(gpss_handle c, double ms[16])
 {
   if (!c || !ms) return fail_arg("gpss_get_phase_ms: null");
   memcpy(ms, c->phase_ms, sizeof c->phase_ms);
+  return GPSS_OK;
+}
+
+int gpss_get_last_call_ms(gpss_handle c, double* ms)
+{
+  if (!c || !ms) return fail_arg("gpss_get_last_call_ms: null");
+  *ms = c->last_call_ms;
+  return GPSS_OK;
+}
+
+// Register-only DMMA.8x8x4 loop: the FP64 tensor-pipe peak used as the roofline denominator
+// (MEASURED_PEAKS.json carries no FP64 figure).  Same loop as bench_micro/fp64_peak.cu.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b)
+{
+  double c0[32], c1[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) { c0[i] = 0; c1[i] = 0; }
+  const double fa = a + threadIdx.x * 1e-9, fb = b;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) dmma884(c0[i], c1[i], fa, fb);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) s += c0[i] + c1[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int gpss_measure_fp64_peak(int device, double* tflops)
+{
+  if (!tflops) return fail_arg("gpss_measure_fp64_peak: null");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  const int grid = p.multiProcessorCount * 2, iters = 20000;
+  double* out;
+  CU(cudaMalloc(&out, sizeof(double) * grid * 256));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(e0, 0));
+    dmma_peak_kernel<<<grid, 256>>>(out, iters, 0.999999, 1e-7);
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * grid * 8.0 * 256 * 32 * (double)iters / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaFree(out);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
   return GPSS_OK;
 }
 

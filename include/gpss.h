@@ -85,6 +85,10 @@ int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const doub
  * [6] cross-covariance+mean, [7] variance GEMM, [8..15] reserved.  Requires gpss_set_profiling(h,1). */
 int gpss_set_profiling(gpss_handle h, int on);
 int gpss_get_phase_ms(gpss_handle h, double ms[16]);
+/* Device time (CUDA events on the handle's stream) of the last gpss_nlml / gpss_nlml_grad / gpss_predict*. */
+int gpss_get_last_call_ms(gpss_handle h, double* ms);
+/* FP64 tensor-pipe (DMMA.8x8x4) micro-peak in TFLOP/s, measured live: the roofline denominator. */
+int gpss_measure_fp64_peak(int device, double* tflops);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int gpss_get_launch_count(gpss_handle h, long* launches);
 /* Raw device pointer to the n_pad x n_pad factor / inverse and the padded size (tests only). */

@@ -1,0 +1,193 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the golden
+fixtures.  Tolerances (FP64, stated per north_star):
+   nlml      |d|/|L|          <= 1e-9   (n <= 20k)
+   g[p]      |d|/max|g|       <= 1e-7
+   alpha     ||d||/||alpha||  <= 1e-8
+   mu        abs              <= 1e-8   (standardised units)
+   var       abs              <= 1e-7
+   D2        bit-exact (defined operation order), K to 2 ulp (exp differs between libdevice and glibc)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from gp_ss_ak_b200 import datagen
+from oracle import gpss_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TOL_NLML, TOL_G, TOL_ALPHA, TOL_MU, TOL_VAR = 1e-9, 1e-7, 1e-8, 1e-8, 1e-7
+
+
+def _check_against_oracle(G, Xs, ys, th, Xt=None):
+    Lo, go, gp = O.nlml_and_grad(Xs, ys, th, literal=True)
+    m = G.GpssModel(Xs, ys)
+    m.set_theta(th)
+    L = m.nlml()
+    L2, g = m.nlml_grad()
+    assert L == L2
+    assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+    a = m.alpha()
+    assert np.linalg.norm(a - gp.Alpha) <= TOL_ALPHA * np.linalg.norm(gp.Alpha)
+    if Xt is not None:
+        mu_o, var_o = gp.predict(Xt)
+        mu, var = m.predict(Xt)
+        assert np.abs(mu - mu_o).max() <= TOL_MU
+        assert np.abs(var - var_o).max() <= TOL_VAR
+    m.close()
+
+
+def test_gemm_nt_kernel_exact(gpss):
+    rng = np.random.default_rng(0)
+    for tile in (0, 1):
+        A = rng.integers(-8, 9, (256, 96)).astype(float)
+        B = rng.integers(-8, 9, (384, 96)).astype(float)
+        C0 = rng.integers(-8, 9, (256, 384)).astype(float)
+        C, _ = gpss.test_gemm_nt(A, B, tile=tile)
+        assert np.array_equal(C, A @ B.T)              # small integers: exact in FP64
+        C, _ = gpss.test_gemm_nt(A, B, C=C0, tile=tile)
+        assert np.array_equal(C, C0 - A @ B.T)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 700, 1537])
+def test_potrf_driver(gpss, n):
+    import scipy.linalg as sla
+    rng = np.random.default_rng(n)
+    Am = rng.standard_normal((n, n))
+    S = Am @ Am.T + n * np.eye(n)
+    L, half_logdet, ms, rc = gpss.test_potrf(S)
+    assert rc == 0
+    Lr = sla.cholesky(S, lower=True)
+    assert np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
+    assert abs(half_logdet - np.log(np.diag(Lr)).sum()) <= 1e-11 * max(1.0, abs(half_logdet))
+
+
+def test_potrf_not_positive_definite(gpss):
+    S = np.eye(200)
+    S[150, 150] = -1.0
+    L, _, _, rc = gpss.test_potrf(S)
+    assert rc == gpss.GPSS_NOT_POSDEF
+
+
+def test_kernel_matrix_bit_exact_distance(gpss):
+    X, y = datagen.drillholes(600, 11)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    th = O.THETA0
+    K, D2 = gpss.compute_K(th, Xs, Xs)
+    Ko, D2o = O.compute_K(Xs, Xs, th, dist="defined")
+    assert np.array_equal(D2, D2o)                                 # defined-order distance: bit-exact
+    assert np.abs(K - Ko).max() <= 4 * np.finfo(float).eps         # exp(): libdevice vs glibc, <= 2 ulp of ~1
+    Xt = Xs[:77] + 0.01
+    K2, D22 = gpss.compute_K(th, Xs, Xt)
+    K2o, D22o = O.compute_K(Xs, Xt, th, dist="defined")
+    assert np.array_equal(D22, D22o)
+
+
+@pytest.mark.parametrize("name,nth", [("gp_n300.npz", 3), ("gp_n1000.npz", 2)])
+def test_golden_fixtures(gpss, name, nth):
+    z = np.load(os.path.join(GOLD, name))
+    m = gpss.GpssModel(z["Xs"], z["ys"])
+    for k in range(nth):
+        m.set_theta(z["thetas"][k])
+        L, g = m.nlml_grad()
+        Lo, go = float(z["nlml_%d" % k]), z["g_%d" % k]
+        assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+        assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+        a = m.alpha()
+        assert np.linalg.norm(a - z["alpha_%d" % k]) <= TOL_ALPHA * np.linalg.norm(a)
+        mu, var = m.predict(z["Xt"])
+        assert np.abs(mu - z["mu_%d" % k]).max() <= TOL_MU      # includes 10 test points coincident with training points
+        assert np.abs(var - z["var_%d" % k]).max() <= TOL_VAR
+    m.close()
+
+
+@pytest.mark.parametrize("n,seed", [(64, 1), (129, 2), (500, 3), (2000, 0)])
+def test_parity_with_oracle(gpss, n, seed):
+    X, y = datagen.drillholes(n, seed)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt_raw, _ = datagen.drillholes(150, seed + 100)
+    Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
+    _check_against_oracle(gpss, Xs, ys, O.THETA0.copy(), Xt)
+
+
+def test_parity_perturbed_thetas(gpss):
+    X, y = datagen.drillholes(800, 4)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    rng = np.random.default_rng(9)
+    for _ in range(5):
+        th = np.clip(O.THETA0 * rng.uniform(0.8, 1.25, 10), 1e-4, 6.0)
+        _check_against_oracle(gpss, Xs, ys, th)
+
+
+def test_duplicate_points_zero_distance(gpss):
+    """Coincident training points: s_ij == 0 off the diagonal -> w_ij = 0 (Kernel.cpp:1178-1180)."""
+    X, y = datagen.drillholes(300, 6)
+    X[10] = X[200]
+    X[11] = X[201]
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    _check_against_oracle(gpss, Xs, ys, O.THETA0.copy(), Xs[:32])
+
+
+def test_cholesky_failure_returns_nan(gpss):
+    """Chol_fail -> quiet NaN (GP_Utils.cpp:881-888, 1145-1146): force it with a negative noise variance."""
+    X, y = datagen.drillholes(300, 8)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    m = gpss.GpssModel(Xs, ys)
+    th = O.THETA0.copy()
+    th[6] = 3.0
+    th[9] = -0.5
+    m.set_theta(th)
+    assert np.isnan(m.nlml())
+    L, g = m.nlml_grad()
+    assert np.isnan(L) and np.all(np.isnan(g))
+    m.set_theta(O.THETA0)          # and the handle recovers
+    assert np.isfinite(m.nlml())
+    m.close()
+
+
+def test_caching_protocol(gpss):
+    """set_GP_Pars invalidates; ObjVal after Grad_Values at the same theta is free and identical."""
+    X, y = datagen.drillholes(400, 9)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    m = gpss.GpssModel(Xs, ys)
+    m.set_theta(O.THETA0)
+    L1, g1 = m.nlml_grad()
+    n1 = m.launch_count()
+    assert m.nlml() == L1 and m.launch_count() == n1
+    m.set_theta(O.THETA0)
+    L2, g2 = m.nlml_grad()
+    assert m.launch_count() > n1
+    assert L2 == L1 and np.array_equal(g1, g2)          # deterministic reductions: bitwise reproducible
+    m.close()
+
+
+def test_large_n_properties(gpss):
+    """n = 20,000 (BASELINE configs[1]): too large for the oracle in seconds, so size-independent properties:
+    (K + sn2 I) alpha = y round trip, sigma-gradient == 2 x central difference, prediction bounds."""
+    n = 20000
+    X, y = datagen.drillholes(n, 1)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    th = O.THETA0.copy()
+    m = gpss.GpssModel(Xs, ys)
+    m.set_theta(th)
+    L, g = m.nlml_grad()
+    a, f = m.alpha(), m.yhat()
+    resid = f + th[9] * a - ys
+    assert np.abs(resid).max() <= 1e-9 * max(1.0, np.abs(a).max())
+    mu, var = m.predict(Xs[:256])
+    assert np.all(var >= th[9]) and np.all(var <= th[6] ** 2 + th[8] + th[9] + 1e-12)
+    assert np.abs(mu - f[:256]).max() < 1e-6            # mean at training points == K alpha rows (centre differs: not bitwise)
+    h = 1e-5
+    tp, tm = th.copy(), th.copy()
+    tp[6] += h
+    tm[6] -= h
+    m.set_theta(tp)
+    Lp = m.nlml()
+    m.set_theta(tm)
+    Lm = m.nlml()
+    fd = (Lp - Lm) / (2 * h)
+    assert abs(g[6] / fd - 2.0) < 1e-4
+    m.close()

@@ -1,0 +1,115 @@
+"""CPU tests of the oracle itself (no GPU): self-consistency of the restatement and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from gp_ss_ak_b200 import datagen
+from oracle import gpss_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def small():
+    X, y = datagen.drillholes(400, 5)
+    Xs, ys, params, st = O.standardise_train(X, y)
+    return Xs, ys, params
+
+
+def test_standardise_matches_reference_rule(small):
+    Xs, ys, params = small
+    # the three spatial columns share ONE centre / half-range (Control.cpp:306-310)
+    assert np.all(params[1:4, 0] == params[1, 0]) and np.all(params[1:4, 1] == params[1, 1])
+    assert abs(ys.max() - 1.0) < 1e-15 and abs(ys.min() + 1.0) < 1e-15
+    assert Xs.max() <= 1.0 and Xs.min() >= -1.0
+    X, y = datagen.drillholes(400, 5)
+    Xs2, ys2, p2 = datagen.standardise_symmetric(X, y)
+    assert np.array_equal(Xs, Xs2) and np.array_equal(ys, ys2)
+
+
+def test_irls_converges_to_direct_solve(small):
+    """the Newton/Brent loop's fixed point is alpha = (K + sn2 I)^-1 y."""
+    Xs, ys, _ = small
+    L, g, gp = O.nlml_and_grad(Xs, ys, O.THETA0, literal=True)
+    Ld, alpha = O.nlml_direct(Xs, ys, O.THETA0)
+    assert gp.n_chol == 3 and gp.irls_its == 2         # 3 factorisations of the same matrix per evaluation
+    assert abs(gp.irls_steps[0] - 1.0) < 1e-9          # first Brent step is the exact Newton step
+    assert abs(L - Ld) / abs(Ld) < 1e-12
+    assert np.linalg.norm(gp.Alpha - alpha) / np.linalg.norm(alpha) < 1e-9
+    L2, g2, _ = O.nlml_and_grad(Xs, ys, O.THETA0, literal=False)
+    assert abs(L - L2) / abs(L) < 1e-11
+    assert np.abs(g - g2).max() / np.abs(g).max() < 1e-9
+
+
+def test_fused_gradient_equals_matrix_form(small):
+    Xs, ys, _ = small
+    rng = np.random.default_rng(3)
+    th = np.clip(O.THETA0 * rng.uniform(0.8, 1.25, 10), 1e-4, 6.0)
+    L, g, gp = O.nlml_and_grad(Xs, ys, th, literal=True)
+    gf = O.expans_gradients_fused(Xs, th, gp.QW, gp.D2)
+    assert np.abs(gf[:7] - g[:7]).max() / np.abs(g[:7]).max() < 1e-12
+    assert g[7] == 0.0
+    assert abs(g[8] - np.trace(gp.QW)) == 0.0
+
+
+def test_sigma_gradient_is_twice_the_true_derivative(small):
+    """the reference's g[6] is exactly 2 x dL/dSigma; the other kernel entries are not gradients."""
+    Xs, ys, _ = small
+    th = O.THETA0.copy()
+    L, g, _ = O.nlml_and_grad(Xs, ys, th, literal=False)
+    h = 1e-6
+    tp, tm = th.copy(), th.copy()
+    tp[6] += h
+    tm[6] -= h
+    fd = (O.nlml_direct(Xs, ys, tp)[0] - O.nlml_direct(Xs, ys, tm)[0]) / (2 * h)
+    assert abs(g[6] / fd - 2.0) < 1e-5
+
+
+def test_diagonal_residue_of_expansion_distance(small):
+    """SURVEY section 7 hard part 1: D2_ii is rounding residue, not 0, and K_ii is therefore slightly below Sigma^2+b."""
+    Xs, ys, _ = small
+    K, D2 = O.compute_K(Xs, Xs, O.THETA0)
+    d = np.diag(D2)
+    assert d.min() >= 0.0 and d.max() < 1e-14
+    assert (d != 0).sum() > 0
+    top = O.THETA0[6] ** 2 + O.THETA0[8]
+    assert np.all(np.diag(K) <= top) and (top - np.diag(K)).max() < 1e-6
+
+
+def test_defined_order_matches_blas_order(small):
+    Xs, ys, _ = small
+    Kd, Dd = O.compute_K(Xs, Xs, O.THETA0, dist="defined")
+    Kb, Db = O.compute_K(Xs, Xs, O.THETA0, dist="blas")
+    assert (Dd == Db).mean() > 0.98                      # bit-identical on (nearly) every entry
+    assert np.abs(Kd - Kb).max() < 1e-7                  # the rest differ by sqrt(rounding residue) at most
+
+
+def test_prediction_properties(small):
+    Xs, ys, _ = small
+    gp = O.OracleGP(Xs, ys, O.THETA0, literal=True)
+    mu, var = gp.predict(Xs[:60])
+    sn2 = O.THETA0[9]
+    assert np.all(var >= sn2)
+    assert np.all(var <= O.THETA0[6] ** 2 + O.THETA0[8] + sn2 + 1e-12)
+    far = np.array([[50.0, 50.0, 50.0]])
+    mu_f, var_f = gp.predict(far)
+    # far from the data only the bias term correlates: mean -> b * sum(alpha)
+    assert abs(mu_f[0] - O.THETA0[8] * gp.Alpha.sum()) < 1e-9
+
+
+@pytest.mark.parametrize("name,nth", [("gp_n300.npz", 3), ("gp_n1000.npz", 2)])
+def test_oracle_reproduces_golden(name, nth):
+    z = np.load(os.path.join(GOLD, name))
+    Xs0, ys0, params, _ = O.standardise_train(z["X_raw"], z["y_raw"])
+    assert np.array_equal(Xs0, z["Xs"]) and np.array_equal(ys0, z["ys"])
+    for k in range(nth):
+        th = z["thetas"][k]
+        L, g, gp = O.nlml_and_grad(z["Xs"], z["ys"], th, dist="defined", literal=True)
+        assert abs(L - float(z["nlml_%d" % k])) <= 1e-11 * abs(L)
+        assert np.abs(g - z["g_%d" % k]).max() <= 1e-9 * np.abs(g).max()
+        ii, jj = z["K_idx_%d" % k]
+        assert np.array_equal(gp.K[ii, jj], z["K_val_%d" % k])
+        assert np.array_equal(np.diag(gp.D2), z["D2_diag_%d" % k])
+        mu, var = gp.predict(z["Xt"])
+        assert np.abs(mu - z["mu_%d" % k]).max() < 1e-10 and np.abs(var - z["var_%d" % k]).max() < 1e-10
