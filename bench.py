@@ -155,10 +155,17 @@ def main():
     model = G.GpssModel(Xf, ys, device=local_rank)
     n_pad = model.padded_n()
 
+    def checked_eval():
+        """One Grad_Values; a NaN (Cholesky failure path) would skip trtri/lauum and fake the timing, so it is fatal."""
+        L, g = model.nlml_grad()
+        if not (np.isfinite(L) and np.all(np.isfinite(g))):
+            raise SystemExit("bench.py: evaluation returned a non-finite objective/gradient (L=%r) -- refusing to time it" % L)
+        return L, g
+
     # ---- warm-up (>= 3): also allocates U / Q and pages the kernels in ----
     for k in range(args.warmup):
         model.set_theta(theta_probe(rank * 7919 + k))
-        model.nlml_grad()
+        checked_eval()
 
     # ---- timed region 1: device-resident (`value`) ----
     sampler = ClockSampler(local_rank)
@@ -169,7 +176,7 @@ def main():
     t0 = time.perf_counter()
     for k in range(args.steps):
         model.set_theta(theta_probe(rank * 7919 + 100 + k))
-        L, g = model.nlml_grad()
+        L, g = checked_eval()
         dev_ms.append(model.last_call_ms())      # CUDA events on the stream the kernels are launched on
     barrier()
     wall = time.perf_counter() - t0
@@ -182,7 +189,7 @@ def main():
     for k in range(args.steps):
         model.set_data(Xf, ys)                    # host -> device copy of this step's inputs
         model.set_theta(theta_probe(rank * 7919 + 200 + k))
-        L, g = model.nlml_grad()                  # device -> host read of value + g[10]
+        L, g = checked_eval()                     # device -> host read of value + g[10]
     barrier()
     wall_e2e = time.perf_counter() - t1
     sampler.stop_flag = True
@@ -191,7 +198,7 @@ def main():
     # ---- roofline of the dominant kernel (DMMA GEMM-NT) from a profiled evaluation ----
     model.set_profiling(True)
     model.set_theta(theta_probe(rank * 7919 + 300))
-    model.nlml_grad()
+    checked_eval()
     ph = model.phase_ms()
     model.set_profiling(False)
     gemm_ms = float(ph[1] + ph[3] + ph[4])        # potrf + trtri + lauum phases: >99% of it inside gemm_nt_kernel
@@ -230,7 +237,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_nt_kernel<GemmTile<128,64,2,2,2>> (FP64 DMMA)",
+                         "traffic": None, "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
                          "peak_source": peak_src,
                          "note": "achieved = n_pad^3 algorithmic flops (potrf+trtri+lauum) / device time of those phases"},
             "phases_ms": {"kbuild": ph[0], "potrf": ph[1], "solve_objective": ph[2], "trtri": ph[3], "lauum": ph[4], "grad_pass": ph[5]},

@@ -39,7 +39,12 @@ enum QState { Q_NONE = 0, Q_IS_BINV = 1, Q_IS_W = 2 };
 struct gpss_ctx {
   int device = 0;
   int n = 0, n_pad = 0, nblk = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;                                  // main stream (highest priority): critical-path kernels
+  cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
+  cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
+                                                              // the tail wave of one is filled by the head of the next
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
+  std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
   // data
   double *xs = nullptr, *y = nullptr, *zs = nullptr;           // 3 x n_pad, n_pad, 4 x n_pad
   double *Lm = nullptr, *Um = nullptr, *Qm = nullptr;          // n_pad^2 each (Um, Qm lazily)
@@ -74,24 +79,43 @@ struct gpss_ctx {
 // ---------------------------------------------------------------------------------------------------
 static int configure_kernels()
 {
+  CU(cudaFuncSetAttribute(gemm_nt_ws_kernel<GemmTileWideWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWideWS::SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTileWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWide::SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTilePanel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTilePanel::SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   return GPSS_OK;
 }
 
-template <class T>
-static int gemm(gpss_ctx* c, const GemmArgs& g)
+// Every O(n^3) product of the path goes through the warp-specialised 128x64 DMMA kernel (gemm_nt_ws_kernel).
+static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
 {
+  using T = GemmTileWideWS;
   if (g.M <= 0 || g.N <= 0) return GPSS_OK;
   if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
-  dim3 grid(g.M / T::BM, g.N / T::BN);
-  gemm_nt_kernel<T><<<grid, T::THREADS, T::SMEM_BYTES, c->st>>>(g);
+  GemmArgs ga = g;
+  ga.mt = g.M / T::BM;
+  ga.nt = g.N / T::BN;
+  gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
   c->launches++;
   CU(cudaGetLastError());
   return GPSS_OK;
 }
 
+// legacy cp.async kernel (kept as the A/B baseline of bench_micro/gemm_bench.cu and for the tile=1 test hook)
+static int gemm_legacy_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
+{
+  using T = GemmTileWide;
+  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
+  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
+  GemmArgs ga = g;
+  ga.mt = g.M / T::BM;
+  ga.nt = g.N / T::BN;
+  gemm_nt_kernel<T><<<(unsigned)(ga.mt * ga.nt), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st); }
 static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K)
 {
   GemmArgs g;
@@ -147,51 +171,138 @@ static void fill_params(const double theta[GPSS_NPAR], const double centre[3], D
 // blocked right-looking Cholesky, two-level (outer NBO = 512 for deep-k trailing updates, inner 128)
 // A: n_pad x n_pad lower, in place.  Replaces arma::chol -> dpotrf (GP_Utils.cpp:881,903).
 // ---------------------------------------------------------------------------------------------------
-static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Winv, double* logdet_parts, int* dflag)
+// One outer panel: factor the NBO-wide block column starting at K0 (all rows below), 128 columns at a time.
+static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
 {
-  for (int K0 = 0; K0 < n_pad; K0 += NBO) {
-    const int nbk = (n_pad - K0 < NBO) ? (n_pad - K0) : NBO;
-    for (int k = K0; k < K0 + nbk; k += NB) {
-      double* Akk = A + (long)k * ld + k;
-      double* Wk = Winv + (long)(k / NB) * NB * NB;
-      potrf_diag_inv_kernel<<<1, NB, DIAG_SMEM, c->st>>>(Akk, ld, Wk, logdet_parts + k / NB, dflag);
-      c->launches++;
-      CU(cudaGetLastError());
-      const int m = n_pad - k - NB;
-      if (m <= 0) continue;
-      double* A21 = A + (long)k * ld + (k + NB);
-      {  // panel solve, in place: A21 <- A21 * inv(L11)^T
-        GemmArgs g = gemm_args(A21, ld, Wk, NB, A21, ld, m, NB, NB);
-        RET(gemm<GemmTilePanel>(c, g));
-      }
-      const int ncols = K0 + nbk - (k + NB);
-      if (ncols > 0) {  // update of the remaining columns of the outer panel
-        double* A22 = A + (long)(k + NB) * ld + (k + NB);
-        GemmArgs g = gemm_args(A21, ld, A21, ld, A22, ld, m, ncols, NB);
-        g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = k + NB; g.gcol0 = k + NB;
-        RET(gemm<GemmTileWide>(c, g));
-      }
+  for (int k = K0; k < K0 + nbk; k += NB) {
+    double* Akk = A + (long)k * ld + k;
+    double* Wk = Winv + (long)(k / NB) * NB * NB;
+    potrf_diag_inv_kernel<<<1, DIAG_THREADS, DIAG_SMEM, c->st>>>(Akk, ld, Wk, logdet_parts + k / NB, dflag);
+    c->launches++;
+    CU(cudaGetLastError());
+    const int m = n_pad - k - NB;
+    if (m <= 0) continue;
+    double* A21 = A + (long)k * ld + (k + NB);
+    {  // panel solve, in place: A21 <- A21 * inv(L11)^T, with the 128x64 tile (it shares an SM with a resident
+       // trailing-update CTA, which the 128x128 tile cannot).  Columns 64..127 first: they read all 128 input
+       // columns; columns 0..63 then need only inputs 0..63 because inv(L11) is lower triangular.
+      GemmArgs g1 = gemm_args(A21, ld, Wk + 64, NB, A21 + 64 * ld, ld, m, 64, NB);
+      RET(gemm(c, g1));
+      GemmArgs g2 = gemm_args(A21, ld, Wk, NB, A21, ld, m, 64, 64);
+      RET(gemm(c, g2));
     }
-    const int m2 = n_pad - (K0 + nbk);
-    if (m2 > 0) {  // deep trailing update: A22 -= P P^T, k-depth nbk
-      const double* Pn = A + (long)K0 * ld + (K0 + nbk);
-      double* A22 = A + (long)(K0 + nbk) * ld + (K0 + nbk);
-      GemmArgs g = gemm_args(Pn, ld, Pn, ld, A22, ld, m2, m2, nbk);
-      g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = K0 + nbk; g.gcol0 = K0 + nbk;
-      RET(gemm<GemmTileWide>(c, g));
+    const int ncols = K0 + nbk - (k + NB);
+    if (ncols > 0) {  // update of the remaining columns of the outer panel
+      double* A22 = A + (long)(k + NB) * ld + (k + NB);
+      GemmArgs g = gemm_args(A21, ld, A21, ld, A22, ld, m, ncols, NB);
+      g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = k + NB; g.gcol0 = k + NB;
+      RET(gemm(c, g));
     }
   }
   return GPSS_OK;
 }
 
-// U = L^-T (upper), block-column left-looking; only NT products (see gpss_gemm.cuh header).
+// LEFT-looking blocked Cholesky with look-ahead.  Block column T (width NBO) receives
+//     U1(T):  A[T:, T] -= L[T:, 0:T-1] L[T, 0:T-1]^T     (panels 0..T-2: one long-k DMMA GEMM, side stream)
+//     U2(T):  A[T:, T] -= L[T:, T-1]   L[T, T-1]^T       (panel T-1, k = NBO, main stream)
+// and is then factored by potrf_panel on the main stream.  U1(T+1) only needs panels <= T-1, so it runs on the
+// side stream WHILE the main stream does U2(T) and the latency-bound panel T: the DMMA pipe never waits for a
+// panel, every output tile is written once per update instead of once per outer step (the right-looking form
+// re-read and re-wrote the whole trailing matrix n/NBO times), and nearly all flops run in long-k GEMMs.
+static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Winv, double* logdet_parts, int* dflag)
+{
+  const bool la = c->st2 != nullptr && !getenv("GPSS_NO_LOOKAHEAD");
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  if (la && (int)c->ev_pool.size() < 2 * nblk_o + 2) {
+    const size_t want = 2 * nblk_o + 2;
+    while (c->ev_pool.size() < want) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->ev_pool.push_back(e);
+    }
+  }
+  auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
+    // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
+    const double* Lp = A + (long)kbeg * ld + T0;
+    GemmArgs g = gemm_args(Lp, ld, Lp, ld, A + (long)T0 * ld + T0, ld, n_pad - T0, nbT, klen);
+    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
+    return gemm_ws_on(c, g, stream);
+  };
+  for (int t = 0; t < nblk_o; t++) {
+    const int T0 = t * NBO;
+    const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+    if (!la) {
+      if (t >= 1) RET(update(T0, nbT, 0, T0, c->st));
+      RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+      continue;
+    }
+    cudaEvent_t evP = c->ev_pool[2 * t], evU = c->ev_pool[2 * t + 1];
+    if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
+    if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
+    RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+    CU(cudaEventRecord(evP, c->st));
+    // issue U1(t+1) = panels 0..t-1 applied to block column t+1; needs panel t-1 (complete: main stream order) --
+    // here, right after panel t was ENQUEUED, the side stream must only wait for panel t-1.
+    if (t + 1 < nblk_o && t >= 1) {
+      const int T1 = T0 + NBO;
+      const int nb1 = (n_pad - T1 < NBO) ? (n_pad - T1) : NBO;
+      cudaStream_t side = (t & 1) ? c->st2 : c->st3;
+      CU(cudaStreamWaitEvent(side, c->ev_pool[2 * (t - 1)], 0));
+      RET(update(T1, nb1, 0, T0, side));
+      CU(cudaEventRecord(c->ev_pool[2 * (t + 1) + 1], side));
+    }
+  }
+  return GPSS_OK;
+}
+
+static int create_streams(gpss_ctx* c)
+{
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (largest number), hi = greatest
+  CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, lo));
+  CU(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, lo));
+  CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  return GPSS_OK;
+}
+
+static void destroy_streams(gpss_ctx* c)
+{
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  c->ev_pool.clear();
+  if (c->st2) cudaStreamDestroy(c->st2);
+  if (c->st3) cudaStreamDestroy(c->st3);
+  if (c->st) cudaStreamDestroy(c->st);
+  c->ev_main = c->ev_side = nullptr;
+  c->st = c->st2 = c->st3 = nullptr;
+}
+
+// U = L^-T (upper), block-column left-looking; only NT products (see gpss_gemm.cuh header):
+//     U[J,J]   = inv(L[J,J])^T                       built from the stored 128x128 inverses      (main stream)
+//     U[0:J,J] = -(U[0:J,0:J] L[J,0:J]^T) U[J,J]     one long-k GEMM + one k = NBO GEMM           (side stream)
+// The diagonal blocks depend only on L, so the main stream produces them (latency-bound small launches) ahead of
+// the side stream, which runs the bulk GEMMs back to back.
 static int trtri_upper(gpss_ctx* c)
 {
   const long ld = c->n_pad;
   const int n_pad = c->n_pad;
   double *L = c->Lm, *U = c->Um;
-  for (int J0 = 0; J0 < n_pad; J0 += NBO) {
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  // the side stream must not start before the factor is complete on the main stream
+  CU(cudaEventRecord(c->ev_main, c->st));
+  CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
+  for (int t = 0; t < nblk_o; t++) {
+    const int J0 = t * NBO;
     const int nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
+    double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
     // (1) the diagonal NBO-block of U in 128-steps
     for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
       const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
@@ -203,27 +314,34 @@ static int trtri_upper(gpss_ctx* c)
         double* Uc = U + (long)i0 * ld + J0;                 // U[J0:i0, i0:i0+128]
         GemmArgs g = gemm_args(U + (long)J0 * ld + J0, ld, L + (long)J0 * ld + i0, ld, Uc, ld, mr, NB, mr);
         g.kbeg_row = 1;
-        RET(gemm<GemmTilePanel>(c, g));
-        GemmArgs g2 = gemm_args(Uc, ld, Wi, NB, Uc, ld, mr, NB, NB);
+        RET(gemm(c, g));
+        // Uc <- -Uc Wi^T in place: columns 64..127 first (all 128 inputs), then 0..63 (inputs 0..63 only)
+        GemmArgs g1 = gemm_args(Uc, ld, Wi + 64, NB, Uc + 64 * ld, ld, mr, 64, NB);
+        g1.negate_out = 1;
+        RET(gemm(c, g1));
+        GemmArgs g2 = gemm_args(Uc, ld, Wi, NB, Uc, ld, mr, 64, 64);
         g2.negate_out = 1;
-        RET(gemm<GemmTilePanel>(c, g2));
+        RET(gemm(c, g2));
       }
     }
-    if (J0 > 0) {
-      // (2) W_JJ = U_JJ^T into scratch
-      transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(c->Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
-      c->launches++;
-      CU(cudaGetLastError());
-      // (3) T = U[0:J0,0:J0] * L[Jblk,0:J0]^T
-      GemmArgs g = gemm_args(U, ld, L + J0, ld, c->Tpanel, ld, J0, nbj, J0);
-      g.kbeg_row = 1;
-      RET(gemm<GemmTileWide>(c, g));
-      // (4) U[0:J0, Jblk] = -T * W_JJ^T
-      GemmArgs g2 = gemm_args(c->Tpanel, ld, c->Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
-      g2.negate_out = 1; g2.kend_col = 1;
-      RET(gemm<GemmTileWide>(c, g2));
-    }
+    if (t == 0) continue;
+    // (2) W_JJ = U_JJ^T into this block's scratch
+    transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
+    CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
+    // (3) T = U[0:J0,0:J0] * L[Jblk,0:J0]^T
+    GemmArgs g = gemm_args(U, ld, L + J0, ld, c->Tpanel, ld, J0, nbj, J0);
+    g.kbeg_row = 1;
+    RET(gemm_ws_on(c, g, c->st2));
+    // (4) U[0:J0, Jblk] = -T * W_JJ^T
+    GemmArgs g2 = gemm_args(c->Tpanel, ld, Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
+    g2.negate_out = 1; g2.kend_col = 1;
+    RET(gemm_ws_on(c, g2, c->st2));
   }
+  CU(cudaEventRecord(c->ev_side, c->st2));
+  CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
   return GPSS_OK;
 }
 
@@ -233,7 +351,7 @@ static int lauum_lower(gpss_ctx* c)
   const long ld = c->n_pad;
   GemmArgs g = gemm_args(c->Um, ld, c->Um, ld, c->Qm, ld, c->n_pad, c->n_pad, c->n_pad);
   g.lower_only = 1; g.kbeg_row = 1;
-  return gemm<GemmTileWide>(c, g);
+  return gemm(c, g);
 }
 
 // x = L^-T L^-1 rhs through the stored diagonal inverses; rhs in c->rvec (destroyed), result in c->alpha
@@ -349,7 +467,7 @@ static int ensure_U(gpss_ctx* c)
   const size_t nn = (size_t)c->n_pad * c->n_pad;
   RET(ensure_lazy(&c->Um, nn));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
-  RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO));
+  RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
   {
     PhaseTimer t(c, 3);
     RET(trtri_upper(c));
@@ -388,7 +506,7 @@ int gpss_destroy(gpss_handle c)
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
   if (c->ev_call[0]) cudaEventDestroy(c->ev_call[0]);
   if (c->ev_call[1]) cudaEventDestroy(c->ev_call[1]);
-  if (c->st) cudaStreamDestroy(c->st);
+  destroy_streams(c);
   delete c;
   return GPSS_OK;
 }
@@ -429,7 +547,7 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   const size_t np = c->n_pad;
   auto fail = [&](int code) { gpss_destroy(c); return code; };
 #define CUF(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(fail_cuda(e__, #x, __LINE__)); } while (0)
-  CUF(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  { int r__ = create_streams(c); if (r__ != GPSS_OK) return fail(r__); }
   CUF(cudaEventCreate(&c->ev[0]));
   CUF(cudaEventCreate(&c->ev[1]));
   CUF(cudaEventCreate(&c->ev_call[0]));
@@ -615,7 +733,7 @@ int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], 
       // V = L^-1 (Sw o kX): A = W (lower), B = Bm (test index contiguous)
       GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
       g.kend_row = 1; g.rev_order = 1;
-      RET(gemm<GemmTileWide>(c, g));
+      RET(gemm(c, g));
       var_finish_kernel<<<(mb + 7) / 8, 256, 0, c->st>>>(c->Vm, n_pad, n_pad, mb, kD, c->theta[9], add_noise, c->dvar);
       c->launches++;
       CU(cudaGetLastError());
@@ -807,7 +925,7 @@ int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A
   CU(cudaEventCreate(&e1));
   int rc;
   CU(cudaEventRecord(e0, 0));
-  if (tile == 0) rc = gemm<GemmTileWide>(&tmp, g); else rc = gemm<GemmTilePanel>(&tmp, g);
+  if (tile == 0) rc = gemm_ws_on(&tmp, g, tmp.st); else rc = gemm_legacy_on(&tmp, g, tmp.st);
   CU(cudaEventRecord(e1, 0));
   if (rc < 0) return rc;
   CU(cudaEventSynchronize(e1));
@@ -826,6 +944,7 @@ int gpss_test_potrf(int device, int n, double* A, double* logdet_half, double* m
   CU(cudaSetDevice(device));
   RET(configure_kernels());
   gpss_ctx tmp;
+  RET(create_streams(&tmp));
   const int n_pad = ((n + NB - 1) / NB) * NB;
   const int nblk = n_pad / NB;
   double *dA, *dW, *dl;
@@ -843,9 +962,10 @@ int gpss_test_potrf(int device, int n, double* A, double* logdet_half, double* m
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaEventRecord(e0, tmp.st));
   int rc = potrf_blocked(&tmp, dA, n_pad, n_pad, dW, dl, dflag);
-  CU(cudaEventRecord(e1, 0));
+  CU(cudaEventRecord(e1, tmp.st));
   if (rc < 0) return rc;
   CU(cudaEventSynchronize(e1));
   float ms = 0;
@@ -863,6 +983,7 @@ int gpss_test_potrf(int device, int n, double* A, double* logdet_half, double* m
   if (logdet_half) *logdet_half = s;
   cudaFree(dA); cudaFree(dW); cudaFree(dl); cudaFree(dflag);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  destroy_streams(&tmp);
   return flag ? GPSS_NOT_POSDEF : GPSS_OK;
 }
 

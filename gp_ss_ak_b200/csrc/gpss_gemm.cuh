@@ -35,7 +35,14 @@ struct GemmArgs {
   int kend_row;                  // k ends   at the tile's last row+1  (A lower-triangular in (row,k))
   int kend_col;                  // k ends   at the tile's last col+1  (B lower-triangular in (col,k))
   int rev_order;                 // schedule tiles with the longest k-range first
+  int mt, nt;                    // tile counts M/BM, N/BN (filled by the launcher)
 };
+
+// CTA rasterisation: the grid is 1-D and walks the output in super-columns of GEMM_RASTER_W tile columns,
+// tile-column fastest.  A wave of 2 x 148 CTAs then covers ~37 tile rows x 8 tile columns, so each operand
+// k-slab is fetched from DRAM once per wave and shared through the 126 MB L2 (the row-fastest order it
+// replaces streamed the whole A panel once per tile column: ~2 TB/s of DRAM reads in the big updates).
+constexpr int GEMM_RASTER_W = 8;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 {
@@ -76,8 +83,15 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_kernel(const 
   double* As = smem;
   double* Bs = smem + STAGES * BK * LDAS;
 
-  int tm = blockIdx.x, tn = blockIdx.y;
-  if (g.rev_order) { tm = gridDim.x - 1 - tm; }
+  int tm, tn;
+  {
+    const int per_group = GEMM_RASTER_W * g.mt;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
+    const int w = min(GEMM_RASTER_W, g.nt - grp * GEMM_RASTER_W);
+    tm = rem / w;
+    tn = grp * GEMM_RASTER_W + (rem - tm * w);
+  }
+  if (g.rev_order) { tm = g.mt - 1 - tm; }
   const int row0 = tm * BM, col0 = tn * BN;
   if (g.lower_only && (g.gcol0 + col0) > (g.grow0 + row0 + BM - 1)) return;
 
@@ -171,25 +185,182 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_kernel(const 
     }
 }
 
-// 128x64 tile, 4 warps (64x32 each), 2 CTAs per SM: one CTA's prologue/epilogue hides behind the other's DMMA loop.
-using GemmTileWide = GemmTile<128, 64, 2, 2, 2>;
-// 128x128 tile, 8 warps, 1 CTA per SM: a single CTA owns the full 128-wide panel row, which makes the
-// in-place panel solve  A21 <- A21 inv(L11)^T  hazard free.
-using GemmTilePanel = GemmTile<128, 128, 2, 4, 1>;
+// ---------------------------------------------------------------------------------------------------
+// Warp-specialised variant: one PRODUCER warp feeds the operand ring with bulk asynchronous copies
+// (cp.async.bulk global->shared, 1 KB / 512 B rows, completion counted on an mbarrier), the consumer
+// warps only wait on the stage's "full" mbarrier, load fragments and issue DMMA, then release the stage
+// on its "empty" mbarrier.  Compared with gemm_nt_kernel this removes from the DMMA warps all the
+// per-stage work the ncu source view charged ~10% of the issue time to: the 64-bit address arithmetic of
+// 12 LDGSTS per thread, LDGDEPBAR/DEPBAR and the CTA-wide BAR.SYNC (profiles/r01_gemm_wide_source.txt).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int MIN_CTAS_, int STAGES_ = 4>
+struct GemmTileWS {
+  static constexpr int BM = BM_, BN = BN_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
+  static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+  static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;      // + the producer warp
+  static constexpr int MIN_CTAS = MIN_CTAS_;
+  static constexpr int BK = 16;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int LDAS = BM + 4;
+  static constexpr int LDBS = BN + 4;
+  static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
+  static constexpr int MI = WTM / 8, NI = WTN / 8;
+  static constexpr uint32_t STAGE_TX_BYTES = (uint32_t)BK * (BM + BN) * sizeof(double);
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * BK * (LDAS + LDBS) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+};
 
 template <class T>
-inline cudaError_t gemm_nt_launch(const GemmArgs& g, cudaStream_t st)
+__global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(const GemmArgs g)
 {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
+  constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES;
+  constexpr int LDAS = T::LDAS, LDBS = T::LDBS, MI = T::MI, NI = T::NI;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * BK * LDAS;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * BK * (LDAS + LDBS));
+  uint64_t* empty_bar = full_bar + STAGES;
+
+  int tm, tn;
+  {
+    const int per_group = GEMM_RASTER_W * g.mt;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
+    const int w = min(GEMM_RASTER_W, g.nt - grp * GEMM_RASTER_W);
+    tm = rem / w;
+    tn = grp * GEMM_RASTER_W + (rem - tm * w);
   }
-  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  dim3 grid(g.M / T::BM, g.N / T::BN);
-  gemm_nt_kernel<T><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(g);
-  return cudaGetLastError();
+  if (g.rev_order) { tm = g.mt - 1 - tm; }
+  const int row0 = tm * BM, col0 = tn * BN;
+  if (g.lower_only && (g.gcol0 + col0) > (g.grow0 + row0 + BM - 1)) return;
+
+  int kbeg = 0, kend = g.K;
+  if (g.kbeg_row) kbeg = row0;
+  if (g.kend_row) kend = min(kend, row0 + BM);
+  if (g.kend_col) kend = min(kend, col0 + BN);
+  kbeg = (kbeg / BK) * BK;
+  const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, T::CONSUMER_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == T::CONSUMER_WARPS) {
+    // ---------------- producer warp: lanes 0..15 copy the A rows, lanes 16..31 the B rows of each stage ----------------
+    const int kk = lane & 15;
+    const bool isA = lane < 16;
+    const double* src = isA ? (g.A + row0 + (long)(kbeg + kk) * g.lda) : (g.B + col0 + (long)(kbeg + kk) * g.ldb);
+    const long src_step = (long)BK * (isA ? g.lda : g.ldb);
+    double* dst0 = isA ? (As + kk * LDAS) : (Bs + kk * LDBS);
+    const int dst_step = BK * (isA ? LDAS : LDBS);
+    const uint32_t bytes = (uint32_t)((isA ? BM : BN) * sizeof(double));
+    for (int it = 0; it < nk; it++) {
+      const int slot = it % STAGES;
+      if (it >= STAGES) mbar_wait(empty_bar + slot, ((it / STAGES) - 1) & 1);
+      if (lane == 0) mbar_arrive_expect_tx(full_bar + slot, T::STAGE_TX_BYTES);
+      __syncwarp();
+      bulk_g2s(dst0 + slot * dst_step, src, bytes, full_bar + slot);
+      src += src_step;
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const int wm0 = (warp % T::WARPS_M) * T::WTM;
+  const int wn0 = (warp / T::WARPS_M) * T::WTN;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double acc[MI][NI][2];
+  double* Cg = g.C + (long)(col0 + wn0 + 2 * lc) * g.ldc + (row0 + wm0 + lr);
+  if (g.init_mode == GEMM_INIT_NEGC) {
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) {
+        acc[i][j][0] = -Cg[(long)(j * 8) * g.ldc + i * 8];
+        acc[i][j][1] = -Cg[(long)(j * 8 + 1) * g.ldc + i * 8];
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  }
+
+  for (int it = 0; it < nk; it++) {
+    const int slot = it % STAGES;
+    mbar_wait(full_bar + slot, (it / STAGES) & 1);
+    if (it > 0) {
+      // Release the PREVIOUS stage here, not right after its last LDS: SYNCS.ARRIVE is not held back by LDS that
+      // are still in flight (ptxas also hoists it above the DMMAs), and with a second, out-of-phase CTA on the SM
+      // the producer's refill was observed to overtake them (bench_micro/gemm_stress.cu, "concurrent" cases).
+      // At this point every DMMA of the previous stage has been issued, hence all its LDS have delivered.
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + (it - 1) % STAGES);
+    }
+    const double* as = As + slot * BK * LDAS + wm0 + lr;
+    const double* bs = Bs + slot * BK * LDBS + wn0 + lr;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; k4++) {
+      double a[MI], b[NI];
+      const int kq = k4 * 4 + lc;
+#pragma unroll
+      for (int i = 0; i < MI; i++) a[i] = as[kq * LDAS + i * 8];
+#pragma unroll
+      for (int j = 0; j < NI; j++) b[j] = bs[kq * LDBS + j * 8];
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+
+  const double sgn = g.negate_out ? -1.0 : 1.0;
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+      Cg[(long)(j * 8) * g.ldc + i * 8] = sgn * acc[i][j][0];
+      Cg[(long)(j * 8 + 1) * g.ldc + i * 8] = sgn * acc[i][j][1];
+    }
 }
+
+using GemmTileWideWS = GemmTileWS<128, 64, 2, 2, 2>;
+
+// 128x64 tile, 4 warps (64x32 each), 2 CTAs per SM: one CTA's prologue/epilogue hides behind the other's DMMA loop.
+using GemmTileWide = GemmTile<128, 64, 2, 2, 2>;
 
 }  // namespace gpss

@@ -116,76 +116,220 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
 //     Replaces the diagonal-block dpotf2 inside arma::chol (GP_Utils.cpp:881,903) and supplies
 //     inv(L11) so that every panel solve becomes a DMMA GEMM.  Also accumulates sum(log(diag))
 //     (GP_Utils.cpp:913) and raises *flag when a pivot is not positive (chol() == false, :882-886).
+//
+//     One CTA of 256 threads.  The lower triangle lives in shared memory as ten packed 32x32 blocks
+//     (column-major, leading dimension 33: row- and column-walks are bank-conflict free) plus the four
+//     diagonal-block inverses: 119 KB and <= 144 registers/thread, so the kernel fits on an SM NEXT TO a
+//     resident trailing-update CTA -- the look-ahead in potrf_blocked depends on that.
+//     Blocked right-looking with 32-wide steps:
+//       (a) warp 0 factors the 32x32 diagonal block entirely in registers (lane = row) with warp-shuffle
+//           broadcasts of the pivot column, then inverts it (lane = column, forward substitution);
+//       (b) panel blocks are multiplied by inv(L_kk)^T and (c) the rank-32 trailing update is applied, one
+//           32x32 output block per 64-thread group (row-per-thread, the other operand broadcast from smem).
+//     The 128x128 inverse is then assembled recursively:  W = [[W11,0],[-W22 L21 W11, W22]]
+//     at block size 32 -> 64 -> 128.
 // ---------------------------------------------------------------------------------------------------
-constexpr int LDS_D = NB + 1;
-constexpr size_t DIAG_SMEM = (size_t)(NB * LDS_D + 2 * NB) * sizeof(double);
+constexpr int DIAG_THREADS = 256;
+constexpr int BLD = 33;                      // leading dimension of a packed 32x32 block
+constexpr int BSZ = 32 * BLD;                // doubles per block
+constexpr size_t DIAG_SMEM = (size_t)(14 * BSZ + NB) * sizeof(double);
 
-__global__ void __launch_bounds__(NB) potrf_diag_inv_kernel(double* __restrict__ A, long ld, double* __restrict__ Winv,
-                                                            double* __restrict__ logdet_part, int* __restrict__ flag)
+__device__ __forceinline__ int blk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }   // bi >= bj
+
+// out[q] += sum_k A(r,k) * B(k, 16g+q)   with A(r,k) at Ab[k*BLD + r] and
+//   TRANSB = false: B(k,c) at Bb[c*BLD + k] ;  TRANSB = true: B(k,c) = Bt(c,k) at Bb[k*BLD + c]
+template <bool TRANSB>
+__device__ __forceinline__ void blk_acc(double (&out)[16], const double* __restrict__ Ab, const double* __restrict__ Bb, int r, int g)
+{
+  const double* bq = Bb + (TRANSB ? 16 * g : 16 * g * BLD);
+#pragma unroll 4
+  for (int k = 0; k < 32; k++) {
+    const double a = Ab[k * BLD + r];
+#pragma unroll
+    for (int q = 0; q < 16; q++) out[q] = fma(a, TRANSB ? bq[k * BLD + q] : bq[q * BLD + k], out[q]);
+  }
+}
+
+__device__ __forceinline__ void blk_zero(double (&out)[16])
+{
+#pragma unroll
+  for (int q = 0; q < 16; q++) out[q] = 0.0;
+}
+
+// 32x32 Cholesky in registers: lane = row.  Lb = packed block (leading dimension BLD).
+__device__ __forceinline__ void warp_chol32(double* Lb, double* invd, double& my_diag, int* flag, int lane)
+{
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) a[c] = Lb[c * BLD + lane];
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double ajj = __shfl_sync(0xffffffffu, a[j], j);
+    double d;
+    if (!(ajj > 0.0)) { if (lane == 0) atomicExch(flag, 1); d = nan(""); }
+    else d = sqrt(ajj);
+    const double inv = 1.0 / d;
+    const double l = a[j] * inv;            // column j of L for rows (lanes) > j
+    if (lane == j) { a[j] = d; my_diag = d; invd[j] = inv; }
+    else a[j] = l;
+#pragma unroll
+    for (int c = j + 1; c < 32; c++) {
+      const double lc = __shfl_sync(0xffffffffu, l, c);
+      a[c] = fma(-l, lc, a[c]);             // meaningful for rows >= c only
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) Lb[c * BLD + lane] = (lane >= c) ? a[c] : 0.0;
+}
+
+// inverse of the 32x32 lower-triangular block Lb: lane = column of W, forward substitution with the
+// matrix entries broadcast from shared memory.  W(r,c) -> Wb[c*BLD + r] (zeros above the diagonal).
+__device__ __forceinline__ void warp_inv32(const double* Lb, const double* invd, double* Wb, int lane)
+{
+  double s[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) s[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    const double wk = s[k] * invd[k];
+    s[k] = wk;
+#pragma unroll
+    for (int r = k + 1; r < 32; r++) s[r] = fma(-Lb[k * BLD + r], wk, s[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 32; r++) Wb[lane * BLD + r] = s[r];
+}
+
+__global__ void __maxnreg__(144)
+potrf_diag_inv_kernel(double* __restrict__ A, long ld, double* __restrict__ Winv, double* __restrict__ logdet_part, int* __restrict__ flag)
 {
   extern __shared__ double sm[];
-  double* Ls = sm;                 // Ls[k*LDS_D + i] = element (row i, col k)
-  double* colv = sm + NB * LDS_D;  // scratch vector
-  double* red = colv + NB;
-  const int i = threadIdx.x;
-  for (int k = 0; k < NB; k++) Ls[k * LDS_D + i] = (i >= k) ? A[(long)k * ld + i] : 0.0;
+  double* Lb = sm;                       // ten packed lower blocks, blk_index(bi,bj)
+  double* Wd = sm + 10 * BSZ;            // four diagonal-block inverses
+  double* invd = Wd + 4 * BSZ;           // reciprocal pivots
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid >> 6, r = tid & 31, g = (tid >> 5) & 1;      // 64-thread groups: row r, column half g
+  {
+    const int i = tid & (NB - 1), bi = i >> 5;
+    for (int k = tid >> 7; k < NB; k += DIAG_THREADS / NB) {
+      const int bk = k >> 5;
+      if (bk <= bi) Lb[blk_index(bi, bk) * BSZ + (k & 31) * BLD + (i & 31)] = A[(long)k * ld + i];
+    }
+  }
   __syncthreads();
   double logsum = 0.0;
-  // left-looking, column by column
-  for (int j = 0; j < NB; j++) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    if (i >= j) {
-      int k = 0;
-      for (; k + 3 < j; k += 4) {
-        s0 = fma(Ls[k * LDS_D + i], Ls[k * LDS_D + j], s0);
-        s1 = fma(Ls[(k + 1) * LDS_D + i], Ls[(k + 1) * LDS_D + j], s1);
-        s2 = fma(Ls[(k + 2) * LDS_D + i], Ls[(k + 2) * LDS_D + j], s2);
-        s3 = fma(Ls[(k + 3) * LDS_D + i], Ls[(k + 3) * LDS_D + j], s3);
+  for (int kb = 0; kb < 4; kb++) {
+    if (warp == 0) {
+      double my_diag = 1.0;
+      double* Lkk = Lb + blk_index(kb, kb) * BSZ;
+      warp_chol32(Lkk, invd + 32 * kb, my_diag, flag, lane);
+      __syncwarp();
+      warp_inv32(Lkk, invd + 32 * kb, Wd + kb * BSZ, lane);
+      logsum += log(my_diag);
+    }
+    __syncthreads();
+    if (kb == 3) break;
+    // (b) panel blocks P_bi <- P_bi * inv(L_kk)^T, one block per group (in place: barrier between read and write)
+    {
+      const int bi = kb + 1 + grp;
+      double out[16];
+      blk_zero(out);
+      double* Pb = Lb + blk_index(bi <= 3 ? bi : 3, kb) * BSZ;
+      if (bi <= 3) blk_acc<true>(out, Pb, Wd + kb * BSZ, r, g);
+      __syncthreads();
+      if (bi <= 3) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) Pb[(16 * g + q) * BLD + r] = out[q];
       }
-      for (; k < j; k++) s0 = fma(Ls[k * LDS_D + i], Ls[k * LDS_D + j], s0);
+      __syncthreads();
     }
-    const double v = Ls[j * LDS_D + i] - ((s0 + s1) + (s2 + s3));
-    if (i == j) {
-      double d;
-      if (!(v > 0.0)) { atomicExch(flag, 1); d = nan(""); }
-      else d = sqrt(v);
-      Ls[j * LDS_D + j] = d;
-      colv[0] = 1.0 / d;
-      logsum += log(d);
+    // (c) trailing blocks (bi >= bj > kb):  C -= P_bi P_bj^T
+    {
+      const int nrem = 3 - kb, nout = nrem * (nrem + 1) / 2;
+      for (int o = grp; o < nout; o += 4) {
+        int bi = kb + 1, bj = kb + 1, cnt = o;
+        while (cnt > bi - (kb + 1)) { cnt -= bi - kb; bi++; }      // row-by-row enumeration of the lower blocks
+        bj = kb + 1 + cnt;
+        double out[16];
+        blk_zero(out);
+        blk_acc<true>(out, Lb + blk_index(bi, kb) * BSZ, Lb + blk_index(bj, kb) * BSZ, r, g);
+        double* Cb = Lb + blk_index(bi, bj) * BSZ;
+#pragma unroll
+        for (int q = 0; q < 16; q++) Cb[(16 * g + q) * BLD + r] -= out[q];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (i > j) Ls[j * LDS_D + i] = v * colv[0];
-    __syncthreads();
   }
-  // factor back to global (lower part; the strict upper part of the tile is zeroed)
-  for (int k = 0; k < NB; k++) A[(long)k * ld + i] = Ls[k * LDS_D + i];
-  // sum of log-diagonal: each thread added its own diagonal entry's log
-  red[i] = logsum;
+  // factor back to global (the strict upper part of the tile is zeroed)
+  {
+    const int i = tid & (NB - 1), bi = i >> 5;
+    for (int k = tid >> 7; k < NB; k += DIAG_THREADS / NB) {
+      const int bk = k >> 5;
+      A[(long)k * ld + i] = (bk <= bi) ? Lb[blk_index(bi, bk) * BSZ + (k & 31) * BLD + (i & 31)] : 0.0;
+    }
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
+    if (lane == 0) *logdet_part = logsum;
+  }
   __syncthreads();
-  if (i == 0) {
-    double s = 0;
-    for (int q = 0; q < NB; q++) s += red[q];
-    *logdet_part = s;
-  }
-  // in-place inverse of the lower-triangular block, last column first (dtrti2, lower, non-unit)
-  for (int j = NB - 1; j >= 0; j--) {
-    colv[i] = Ls[j * LDS_D + i];         // column j of L (rows >= j are meaningful)
+  // ---- inverse: W(b,b) = Wd[b]; off-diagonal blocks overwrite the packed L blocks ----
+  {
+    // level 1: X(1,0) = -W11 (L10 W00) [groups 0,1 idle in pairs: group 0 -> (1,0), group 1 -> (3,2)]
+    const int b = 2 * grp;                                   // grp 0 -> b=0, grp 1 -> b=2
+    const bool on = grp < 2;
+    double* Xb = Lb + blk_index(on ? b + 1 : 1, on ? b : 0) * BSZ;
+    double out[16];
+    blk_zero(out);
+    if (on) blk_acc<false>(out, Xb, Wd + b * BSZ, r, g);     // T = L10 * W00
     __syncthreads();
-    const double wjj = 1.0 / colv[j];
-    if (i == j) Ls[j * LDS_D + j] = wjj;
-    if (i > j) {
-      double s0 = 0, s1 = 0;
-      int k = j + 1;
-      for (; k + 1 <= i; k += 2) {
-        s0 = fma(Ls[k * LDS_D + i], colv[k], s0);
-        s1 = fma(Ls[(k + 1) * LDS_D + i], colv[k + 1], s1);
-      }
-      for (; k <= i; k++) s0 = fma(Ls[k * LDS_D + i], colv[k], s0);
-      Ls[j * LDS_D + i] = -(s0 + s1) * wjj;
+    if (on) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) Xb[(16 * g + q) * BLD + r] = out[q];
+    }
+    __syncthreads();
+    blk_zero(out);
+    if (on) blk_acc<false>(out, Wd + (b + 1) * BSZ, Xb, r, g);   // W11 * T
+    __syncthreads();
+    if (on) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) Xb[(16 * g + q) * BLD + r] = -out[q];
     }
     __syncthreads();
   }
-  for (int k = 0; k < NB; k++) Winv[k * NB + i] = Ls[k * LDS_D + i];
+  {
+    // level 2: blocks (2+bi, bj), bi,bj in {0,1}, one per group:  X = -W22' (L21 W11')
+    const int bi = grp >> 1, bj = grp & 1;
+    double* Xb = Lb + blk_index(2 + bi, bj) * BSZ;
+    double out[16];
+    blk_zero(out);
+    // T(bi,bj) = sum_{kb >= bj} L(2+bi, kb) W11'(kb, bj)
+    blk_acc<false>(out, Lb + blk_index(2 + bi, bj) * BSZ, Wd + bj * BSZ, r, g);
+    if (bj == 0) blk_acc<false>(out, Lb + blk_index(2 + bi, 1) * BSZ, Lb + blk_index(1, 0) * BSZ, r, g);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; q++) Xb[(16 * g + q) * BLD + r] = out[q];
+    __syncthreads();
+    // X(bi,bj) = - sum_{kb <= bi} W22'(bi, kb) T(kb, bj)
+    blk_zero(out);
+    blk_acc<false>(out, Wd + (2 + bi) * BSZ, Lb + blk_index(2 + bi, bj) * BSZ, r, g);
+    if (bi == 1) blk_acc<false>(out, Lb + blk_index(3, 2) * BSZ, Lb + blk_index(2, bj) * BSZ, r, g);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; q++) Xb[(16 * g + q) * BLD + r] = -out[q];
+    __syncthreads();
+  }
+  {
+    const int i = tid & (NB - 1), bi = i >> 5;
+    for (int k = tid >> 7; k < NB; k += DIAG_THREADS / NB) {
+      const int bk = k >> 5;
+      double v = 0.0;
+      if (bk == bi) v = Wd[bi * BSZ + (k & 31) * BLD + (i & 31)];
+      else if (bk < bi) v = Lb[blk_index(bi, bk) * BSZ + (k & 31) * BLD + (i & 31)];
+      Winv[k * NB + i] = v;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -96,7 +96,8 @@ int gpss_debug_fetch(gpss_handle h, int which, double* host_out, long count);
 int gpss_padded_n(gpss_handle h, int* n_pad);
 
 /* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
-/* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = 128x64, 1 = 128x128. */
+/* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised
+ * bulk-copy/mbarrier kernel every product of the path uses, 1 = the legacy cp.async kernel (A/B baseline). */
 int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C,
                       int subtract_from_C, double* ms_out);
 /* In-place blocked Cholesky of a host n x n SPD matrix (lower), through the full potrf driver. */
