@@ -59,7 +59,9 @@ def load_library():
         "gpss_get_yhat": (I, [H, P]),
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
+        "gpss_var_postprocess": (I, [L, D, P]),
         "gpss_compute_K": (I, [I, P, I, P, I, P, P, P]),
+        "gpss_expans_gradients": (I, [I, P, I, P, P, P]),
         "gpss_set_profiling": (I, [H, I]),
         "gpss_get_phase_ms": (I, [H, P]),
         "gpss_get_last_call_ms": (I, [H, P]),
@@ -204,6 +206,13 @@ class GpssModel:
         return out
 
 
+def var_postprocess(var_raw, sn2):
+    """The reference's post-processing of the gathered raw variance vector (include/gpss.h)."""
+    v = np.ascontiguousarray(np.asarray(var_raw, dtype=np.float64).reshape(-1)).copy()
+    _check(load_library().gpss_var_postprocess(v.shape[0], float(sn2), _dp(v)))
+    return v
+
+
 def measure_fp64_peak(device=0):
     v = ctypes.c_double(0.0)
     _check(load_library().gpss_measure_fp64_peak(device, ctypes.byref(v)))
@@ -219,6 +228,16 @@ def compute_K(theta, X1, X2, want_K=True, want_D2=True, device=0):
     D2 = np.zeros((X1.shape[0], X2.shape[0]), order="F") if want_D2 else None
     _check(lib.gpss_compute_K(device, _dp(th), X1.shape[0], _dp(X1), X2.shape[0], _dp(X2), _dp(K), _dp(D2)))
     return K, D2
+
+
+def expans_gradients(theta, X, QW, device=0):
+    """Kern_ExpAnisotropic::getGradients for a host QW (compatibility entry point); returns g[0..7]."""
+    X = _colmajor(X)
+    QW = _colmajor(QW)
+    th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+    g = np.zeros(8)
+    _check(load_library().gpss_expans_gradients(device, _dp(th), X.shape[0], _dp(X), _dp(QW), _dp(g)))
+    return g
 
 
 def test_gemm_nt(A, B, C=None, tile=0, device=0):

@@ -679,7 +679,8 @@ static int ensure_W(gpss_ctx* c)
   return GPSS_OK;
 }
 
-int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
+// mean and RAW variance (kD - k*' A k*, no post-processing) of one shard
+static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
@@ -711,7 +712,6 @@ int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], 
   transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
   c->launches++;
   const double kD = c->theta[6] * c->theta[6] + c->theta[8];   // diag_Compute (Kernel.cpp:782, 331, 127-136)
-  const int add_noise = (c->theta[9] != 1.0);                  // GP_Utils.cpp:1036-1040
   for (long off = 0; off < count; off += cap) {
     const int mb = (int)((count - off < cap) ? (count - off) : cap);
     const int m_pad = ((mb + NB - 1) / NB) * NB;
@@ -734,7 +734,7 @@ int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], 
       GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
       g.kend_row = 1; g.rev_order = 1;
       RET(gemm(c, g));
-      var_finish_kernel<<<(mb + 7) / 8, 256, 0, c->st>>>(c->Vm, n_pad, n_pad, mb, kD, c->theta[9], add_noise, c->dvar);
+      var_finish_kernel<<<(mb + 7) / 8, 256, 0, c->st>>>(c->Vm, n_pad, n_pad, mb, kD, c->dvar);
       c->launches++;
       CU(cudaGetLastError());
       CU(cudaMemcpyAsync(var + off, c->dvar, sizeof(double) * mb, cudaMemcpyDeviceToHost, c->st));
@@ -745,13 +745,38 @@ int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], 
   return GPSS_OK;
 }
 
+int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
+{
+  RET(predict_core(c, m_total, sums_total, count, Xs, mu, var));
+  return GPSS_OK;
+}
+
+// The reference's treatment of the variance vector, literally (GP_Utils.cpp:1001-1003, 1033-1040):
+//     uvec ind = varSigma < 0;  varSigma.elem(ind) = zeros(...);      ind holds 0/1 FLAGS but is used as INDICES, so
+// element 0 is zeroed when any entry is non-negative, element 1 when any entry is negative, and negative entries
+// themselves are NOT clamped; then sn2 is added to every element unless sn2 == 1.0.  Reproduced as is (verified
+// against the compiled reference: tests/golden/ref_*.npz has var[0] == sn2 for every theta).
+int gpss_var_postprocess(long m, double sn2, double* var)
+{
+  if (!var || m < 1) return fail_arg("gpss_var_postprocess: bad argument");
+  bool any_neg = false, any_nonneg = false;
+  for (long i = 0; i < m; i++) { if (var[i] < 0) any_neg = true; else any_nonneg = true; }
+  if (any_neg && m < 2) { g_last_error = "gpss_var_postprocess: the reference aborts here (Mat::elem(): index out of bounds)"; return GPSS_ERR_STATE; }
+  if (any_nonneg) var[0] = 0.0;
+  if (any_neg) var[1] = 0.0;
+  if (sn2 != 1.0) for (long i = 0; i < m; i++) var[i] += sn2;
+  return GPSS_OK;
+}
+
 int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* var)
 {
   if (!c || !Xs || !mu) return fail_arg("gpss_predict: null argument");
   if (m < 1) return fail_arg("gpss_predict: m must be >= 1");
   double sums[3];
   seq_colsums(Xs, m, sums);
-  return gpss_predict_shard(c, m, sums, m, Xs, mu, var);
+  RET(predict_core(c, m, sums, m, Xs, mu, var));
+  if (var) return gpss_var_postprocess(m, c->theta[9], var);
+  return GPSS_OK;
 }
 
 // --- Kernels::computeK compatibility ----------------------------------------------------------
@@ -804,6 +829,95 @@ int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const doub
   if (D2) CUK(cudaMemcpy(D2, dD, sizeof(double) * (size_t)n1 * n2, cudaMemcpyDeviceToHost));
 #undef CUK
   cleanup();
+  return GPSS_OK;
+}
+
+// --- Kernels::getGradients compatibility -------------------------------------------------------------
+// Kern_ExpAnisotropic::getGradients with a HOST n x n matrix QW (Kernel.cpp:886-1263), for callers of the Kernels
+// interface that do not go through the device-resident GradLL.  One pass over ALL (i, j) pairs (QW need not be
+// symmetric) accumulating  T = X' w X (3x3),  V1_k = sum w x_ik^2,  V2_k = sum w x_jk^2,  G6 = sum QW e^{-s}  with
+// w_ij = Sigma^2 QW_ij e^{-s_ij} (-0.5 / s_ij), zero on the diagonal and where s_ij == 0 (Kernel.cpp:1176-1185).
+constexpr int NGFULL = 16;
+__global__ void __launch_bounds__(256) grad_full_kernel(const double* __restrict__ QW, long ldq, const double* __restrict__ z, long ldz,
+                                                        const double* __restrict__ x, long ldx, int n, const DevParams* __restrict__ Pp,
+                                                        double* __restrict__ partial)
+{
+  const DevParams P = *Pp;
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int jb = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
+  double v[NGFULL];
+#pragma unroll
+  for (int q = 0; q < NGFULL; q++) v[q] = 0.0;
+  if (i < n) {
+    const double zi0 = z[i], zi1 = z[ldz + i], zi2 = z[2 * ldz + i], ai = z[3 * ldz + i];
+    const double xi[3] = {x[i], x[ldx + i], x[2 * ldx + i]};
+    for (int j = jb; j < jb + 16 && j < n; j++) {
+      const double d2 = pair_d2(zi0, zi1, zi2, ai, z[j], z[ldz + j], z[2 * ldz + j], z[3 * ldz + j]);
+      const double s = sqrt(d2), es = exp(-s);
+      const double q = QW[(long)j * ldq + i];
+      v[15] += q * es;
+      if (i != j && s != 0.0) {
+        const double w = (P.var2 * q) * (es * (-0.5 / s));
+        const double xj[3] = {x[j], x[ldx + j], x[2 * ldx + j]};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+          for (int l = 0; l < 3; l++) v[k * 3 + l] = fma(w * xi[k], xj[l], v[k * 3 + l]);
+          v[9 + k] = fma(w, xi[k] * xi[k], v[9 + k]);
+          v[12 + k] = fma(w, xj[k] * xj[k], v[12 + k]);
+        }
+      }
+    }
+  }
+  block_reduce_store<NGFULL>(v, partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * NGFULL);
+}
+
+int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, const double* X, const double* QW, double g8[8])
+{
+  if (!theta || !X || !QW || !g8 || n < 1) return fail_arg("gpss_expans_gradients: bad argument");
+  CU(cudaSetDevice(device));
+  double s1[3], centre[3];
+  seq_colsums(X, n, s1);
+  maha_centre(n, s1, n, s1, centre);
+  DevParams P;
+  fill_params(theta, centre, P);
+  const dim3 grid((n + 63) / 64, (n + 63) / 64);
+  const long nblocks = (long)grid.x * grid.y;
+  double *dx = nullptr, *dz = nullptr, *dQ = nullptr, *dpart = nullptr, *dred = nullptr;
+  DevParams* dP = nullptr;
+  int rc = GPSS_OK;
+  auto cleanup = [&]() { cudaFree(dx); cudaFree(dz); cudaFree(dQ); cudaFree(dpart); cudaFree(dred); cudaFree(dP); };
+#define CUG(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
+  CUG(cudaMalloc(&dx, sizeof(double) * 3 * n));
+  CUG(cudaMalloc(&dz, sizeof(double) * 4 * n));
+  CUG(cudaMalloc(&dQ, sizeof(double) * (size_t)n * n));
+  CUG(cudaMalloc(&dpart, sizeof(double) * nblocks * NGFULL));
+  CUG(cudaMalloc(&dred, sizeof(double) * NGFULL));
+  CUG(cudaMalloc(&dP, sizeof(DevParams)));
+  CUG(cudaMemcpy(dx, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  CUG(cudaMemcpy(dQ, QW, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+  CUG(cudaMemcpy(dP, &P, sizeof P, cudaMemcpyHostToDevice));
+  transform_kernel<<<(n + 255) / 256, 256>>>(dx, n, dz, n, n, n, dP);
+  grad_full_kernel<<<grid, 256>>>(dQ, n, dz, n, dx, n, n, dP, dpart);
+  sum_partials_kernel<NGFULL><<<1, 256>>>(dpart, nblocks, dred);
+  CUG(cudaGetLastError());
+  double red[NGFULL];
+  CUG(cudaMemcpy(red, dred, sizeof red, cudaMemcpyDeviceToHost));
+#undef CUG
+  cleanup();
+  double M[6][9];
+  grad_M_matrices(theta, M);
+  for (int p = 0; p < 6; p++) {
+    double qv = 0.0, mt = 0.0;
+    for (int k = 0; k < 3; k++) {
+      const double rho = (M[p][k * 3 + 0] + M[p][k * 3 + 1]) + M[p][k * 3 + 2];
+      qv += rho * (red[9 + k] + red[12 + k]);
+      for (int l = 0; l < 3; l++) mt += M[p][k * 3 + l] * red[k * 3 + l];
+    }
+    g8[p] = 2.0 * qv - 4.0 * mt;               // sum_ij w_ij (2 q_p(x_i) + 2 q_p(x_j) - 4 x_i' M_p x_j), Kernel.cpp:1192-1233
+  }
+  g8[6] = 2.0 * red[15] * theta[6];            // Kernel.cpp:1239-1242
+  g8[7] = 0.0;                                 // Kernel.cpp:1256-1257 (3-D)
   return GPSS_OK;
 }
 

@@ -686,9 +686,11 @@ __global__ void mean_finish_kernel(const double* __restrict__ mu_part, long ldmu
   mu[j] = s;
 }
 
-// var[j] = max(0, kD - sum_i V(i,j)^2) + sn2   (GP_Utils.cpp:997-1003, 1033-1040); V is n_pad x m_pad, one warp per column
-__global__ void __launch_bounds__(256) var_finish_kernel(const double* __restrict__ V, long ldv, int n_pad, int m, double kD, double sn2,
-                                                         int add_noise, double* __restrict__ var)
+// raw predictive variance  var[j] = kD - sum_i V(i,j)^2  (GP_Utils.cpp:997-998); V is n_pad x m_pad, one warp per column.
+// The reference's post-processing of this vector (GP_Utils.cpp:1001-1003 and 1033-1040) is index arithmetic over the
+// WHOLE test set and is applied on the host (gpss_capi.cu: apply_reference_var_postprocessing).
+__global__ void __launch_bounds__(256) var_finish_kernel(const double* __restrict__ V, long ldv, int n_pad, int m, double kD,
+                                                         double* __restrict__ var)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 8 + warp;
@@ -703,12 +705,7 @@ __global__ void __launch_bounds__(256) var_finish_kernel(const double* __restric
   double s = s0 + s1;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) {
-    double v = kD - s;
-    if (v < 0) v = 0.0;
-    if (add_noise) v += sn2;
-    var[j] = v;
-  }
+  if (lane == 0) var[j] = kD - s;
 }
 
 }  // namespace gpss

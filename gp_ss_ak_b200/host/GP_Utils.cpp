@@ -1,0 +1,373 @@
+// See GP_Utils.h.  File:line citations are into /root/reference.
+#include "GP_Utils.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+
+using namespace arma;
+using std::cout;
+using std::endl;
+using std::string;
+
+GP_utils::GP_utils() : Modeling(), Main_Opt_Algs(), KerenlW(0) { _init(); }
+
+GP_utils::GP_utils(Kernels* kernel, mat Xin, mat Yin, int Inf_type, int likeLtype, int mean_type, unsigned int numhyper,
+                   unsigned int numlik_par, unsigned int numMF_par, int verbos)
+    : Modeling(), Main_Opt_Algs(), Xinp(Xin), yTarg(Yin), KerenlW(kernel)
+{
+  setNumMFpar(numMF_par);
+  setNumlikfpar(numlik_par);
+  setNumCovpar(numhyper);
+  _init();
+  setInferenceType(Inf_type);
+  setLikelihoodType(likeLtype);
+  setMeanType(mean_type);
+  setVerbose(verbos);
+  g_param.resize(1, KerenlW->getNPars());
+  setOutDim(yTarg.n_cols);
+  setInpDim(Xin.n_cols);
+  setNumData(yTarg.n_rows);
+  initialize_vars();
+  // hard-coded starting values of the reference (GP_Utils.cpp:33-44)
+  if (numMF_par > 0) { hypermf.resize(numMF_par, 1); hypermf.fill(0.12); }
+  if (numlik_par > 0) { hyperlf.resize(numlik_par, 1); hyperlf.fill(0.016); }
+}
+
+GP_utils::~GP_utils()
+{
+  if (handle) gpss_destroy(handle);
+}
+
+void GP_utils::_init()
+{
+  setName("Gaussian process");
+  setInf("Lapalce");            // sic: this spelling is part of the model-file format (GP_Utils.cpp:50)
+  setlik("Gaussian");
+  setMean("Zero");
+  likelihoodType_ = likeL_Gaussian;
+  InferenceType_ = inf_laplace;
+  MeanType_ = mean_zero;
+  handle = 0;
+  handle_n = -1;
+  data_stale = true;
+  dirty = true;
+  Chol_fail = false;
+  const char* dev = std::getenv("GPSS_DEVICE");
+  device = dev ? std::atoi(dev) : 0;
+  L.zeros(1, 1);
+}
+
+void GP_utils::initialize_vars()
+{
+  const unsigned int n = getNumData();
+  Alpha.resize(n, getOutDim());     // zero-filled growth, like arma::Mat::resize in the reference (GP_Utils.cpp:69)
+  yhat.resize(n, getOutDim());
+  data_stale = true;
+  dirty = true;
+}
+
+string GP_utils::getLiklihoodStr() const
+{
+  if (likelihoodType_ == likeL_Gaussian) return "likeL_Gaussian";
+  if (likelihoodType_ == likeL_WarpGauss) return "likeL_WarpGauss";
+  cout << "Unknown approximation type \n";
+  exit(1);
+}
+string GP_utils::getInferenceStr() const
+{
+  if (InferenceType_ == inf_laplace) return "inf_laplace";
+  if (InferenceType_ == inf_EP) return "inf_EP";
+  cout << "Unknown approximation type \n";
+  exit(1);
+}
+string GP_utils::getMeanTypeStr() const
+{
+  if (MeanType_ == mean_zero) return "mean_zero";
+  if (MeanType_ == mean_sum) return "mean_sum";
+  cout << "Unknown approximation type \n";
+  exit(1);
+}
+void GP_utils::setLikelihoodType(const int val)
+{
+  likelihoodType_ = val;
+  if (val == likeL_Gaussian) {
+    hyperlf.zeros(1, 1);
+    g_hyperlf.zeros(1, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parameter vector: kernel parameters, then likelihood, then mean-function parameters (GP_Utils.cpp:101-157)
+// ---------------------------------------------------------------------------------------------------
+unsigned int GP_utils::getNumPars() const { return KerenlW->getNPars() + getNumMFpar() + getNumlikfpar(); }
+
+void GP_utils::get_GP_Pars(mat& param) const
+{
+  unsigned int c = 0;
+  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) param(c++) = KerenlW->getParam(i);
+  for (unsigned int i = 0; i < getNumlikfpar(); i++) param(c++) = hyperlf(i);
+  for (unsigned int i = 0; i < getNumMFpar(); i++) param(c++) = hypermf(i);
+}
+
+void GP_utils::set_GP_Pars(mat& param) const
+{
+  unsigned int c = 0;
+  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) KerenlW->setParam(param(c++), i);
+  for (unsigned int i = 0; i < getNumlikfpar(); i++) hyperlf(i) = param(c++);
+  for (unsigned int i = 0; i < getNumMFpar(); i++) hypermf(i) = param(c++);
+  dirty = true;                    // setKUpdateStat(false): everything is recomputed at the next evaluation
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device plumbing
+// ---------------------------------------------------------------------------------------------------
+void GP_utils::device_failure(const char* what) const
+{
+  cout << what << " failed: " << gpss_last_error() << "\n";
+  exit(1);
+}
+
+void GP_utils::check_supported() const
+{
+  const char* why = 0;
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+  if (!KerenlW) why = "no kernel";
+  else if (!hyb || KerenlW->getKerName() != "Hyb" || hyb->getNumKerns() != 2 || hyb->getKern(0)->getKerName() != "ExpAns" ||
+           hyb->getKern(1)->getKerName() != "Bias")
+    why = "the kernel must be Hyb{ExpAns, Bias} (train with -k ExpAns -kn 1)";
+  else if (Xinp.n_cols != 3) why = "inputs must have 3 columns";
+  else if (yTarg.n_cols != 1 || getOutDim() != 1) why = "exactly one output column is supported";
+  else if (likelihoodType_ != likeL_Gaussian || getNumlikfpar() != 1) why = "only the Gaussian likelihood is supported";
+  else if (MeanType_ != mean_zero || getNumMFpar() != 0) why = "only the zero mean function is supported";
+  else if (Xinp.n_rows != yTarg.n_rows || Xinp.n_rows < 2) why = "inconsistent training data";
+  if (why) {
+    cout << "GP_utils: configuration outside the B200 hot path (" << why << "); there is no CPU fallback.\n";
+    exit(1);
+  }
+}
+
+void GP_utils::theta_now(double theta[GPSS_NPAR]) const
+{
+  for (unsigned int i = 0; i < 9; i++) theta[i] = KerenlW->getParam(i);
+  theta[9] = hyperlf(0);
+}
+
+void GP_utils::sync_device() const
+{
+  check_supported();
+  const int n = (int)Xinp.n_rows;
+  if (handle && handle_n != n) {
+    gpss_destroy(handle);
+    handle = 0;
+  }
+  if (!handle) {
+    if (gpss_create(device, n, 3, Xinp.memptr(), yTarg.memptr(), &handle) != GPSS_OK) device_failure("gpss_create");
+    handle_n = n;
+    data_stale = false;
+    dirty = true;
+  } else if (data_stale) {
+    if (gpss_set_data(handle, Xinp.memptr(), yTarg.memptr()) != GPSS_OK) device_failure("gpss_set_data");
+    data_stale = false;
+    dirty = true;
+  }
+  double theta[GPSS_NPAR];
+  theta_now(theta);
+  if (dirty || std::memcmp(theta, theta_dev, sizeof theta) != 0) {
+    if (gpss_set_theta(handle, theta) != GPSS_OK) device_failure("gpss_set_theta");
+    std::memcpy(theta_dev, theta, sizeof theta);
+    dirty = false;
+  }
+}
+
+double GP_utils::lastDeviceMs() const
+{
+  double ms = 0.0;
+  if (handle) gpss_get_last_call_ms(handle, &ms);
+  return ms;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// objective and gradient
+// ---------------------------------------------------------------------------------------------------
+double GP_utils::logLikelihood() const
+{
+  sync_device();
+  double nlml = 0.0;
+  const int rc = gpss_nlml(handle, &nlml);
+  if (rc < 0) device_failure("gpss_nlml");
+  Chol_fail = (rc == GPSS_NOT_POSDEF);
+  if (Chol_fail) return std::numeric_limits<double>::quiet_NaN();       // GP_Utils.cpp:1145-1146, 1155-1158
+  L.zeros(1, 1);
+  L[0] = nlml;
+  return nlml;
+}
+
+void GP_utils::updateAlpha() const
+{
+  sync_device();
+  Alpha.set_size(Xinp.n_rows, 1);
+  yhat.set_size(Xinp.n_rows, 1);
+  const int rc = gpss_get_alpha(handle, Alpha.memptr());
+  if (rc < 0) device_failure("gpss_get_alpha");
+  Chol_fail = (rc == GPSS_NOT_POSDEF);
+  if (!Chol_fail && gpss_get_yhat(handle, yhat.memptr()) < 0) device_failure("gpss_get_yhat");
+}
+
+double GP_utils::GradLL(mat& g) const
+{
+  sync_device();
+  double nlml = 0.0, gv[GPSS_NPAR];
+  const int rc = gpss_nlml_grad(handle, &nlml, gv);
+  if (rc < 0) device_failure("gpss_nlml_grad");
+  Chol_fail = (rc == GPSS_NOT_POSDEF);
+  if (Chol_fail) return std::numeric_limits<double>::quiet_NaN();       // g is left untouched, as in the reference (:1175-1176)
+  L.zeros(1, 1);
+  L[0] = nlml;
+  // same packing as GP_Utils.cpp:1243-1260: kernel entries, likelihood entry, mean entries
+  g_param.set_size(1, KerenlW->getNPars());
+  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g_param(i) = gv[i];
+  g_hyperlf.zeros(1, 1);
+  g_hyperlf(0) = gv[9];
+  unsigned int c = 0;
+  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g(0, c++) = g_param(0, i);
+  for (unsigned int i = 0; i < getNumlikfpar(); i++) g(0, c++) = g_hyperlf(0, i);
+  return nlml;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prediction
+// ---------------------------------------------------------------------------------------------------
+void GP_utils::posteriorMeanVar(mat& mu, mat& varSigma, const mat& X) const
+{
+  if (X.n_cols != 3) { cout << "GP_utils: test inputs must have 3 columns\n"; exit(1); }
+  sync_device();
+  mu.set_size(X.n_rows, 1);
+  varSigma.set_size(X.n_rows, 1);
+  const int rc = gpss_predict(handle, (long)X.n_rows, X.memptr(), mu.memptr(), varSigma.memptr());
+  if (rc == GPSS_NOT_POSDEF) {                     // the reference carries NaN through here
+    mu.fill(std::numeric_limits<double>::quiet_NaN());
+    varSigma.fill(std::numeric_limits<double>::quiet_NaN());
+  } else if (rc != GPSS_OK) {
+    device_failure("gpss_predict");
+  }
+}
+
+void GP_utils::posteriorMean(mat& mu, const mat& X) const
+{
+  if (X.n_cols != 3) { cout << "GP_utils: test inputs must have 3 columns\n"; exit(1); }
+  sync_device();
+  mu.set_size(X.n_rows, 1);
+  const int rc = gpss_predict(handle, (long)X.n_rows, X.memptr(), mu.memptr(), 0);
+  if (rc == GPSS_NOT_POSDEF) mu.fill(std::numeric_limits<double>::quiet_NaN());
+  else if (rc != GPSS_OK) device_failure("gpss_predict");
+}
+
+// [quirk kept] the one-output overload also computes the variance and throws it away (GP_Utils.cpp:159-165)
+void GP_utils::Calc_Out(mat& yPred, const mat& Xin) const
+{
+  mat var;
+  posteriorMeanVar(yPred, var, Xin);
+}
+void GP_utils::Calc_Out(mat& yPred, mat& yVar, const mat& Xin) const { posteriorMeanVar(yPred, yVar, Xin); }
+void GP_utils::Calc_Out(mat& yPred, mat& /*probPred*/, mat& yVar, const mat& Xin) const { posteriorMeanVar(yPred, yVar, Xin); }
+
+// ---------------------------------------------------------------------------------------------------
+// optimisation entry point and report (GP_Utils.cpp:1288-1322)
+// ---------------------------------------------------------------------------------------------------
+void GP_utils::OptimisePars(unsigned int iters)
+{
+  if (getVerbose() > 2) {
+    cout << "Initial model:" << endl;
+    ShowKernelPars(cout);
+  }
+  // [quirk] the iteration count only takes effect at verbosity > 2: a dangling `if` guards setMaxIters (GP_Utils.cpp:1295-1296)
+  if (getVerbose() > 2 && getNumPars() < 40) setMaxIters(iters);
+  Optimise();
+  if (getVerbose() > 0) ShowKernelPars(cout);
+}
+
+void GP_utils::ShowKernelPars(std::ostream& os) const
+{
+  cout << "Standard GP Model: " << endl;
+  cout << "Optimiser: " << getDefaultOptimiserStr() << endl;
+  cout << "Inference: " << getInferenceStr() << endl;
+  cout << "likelihood function: " << getLiklihoodStr() << endl;
+  cout << "Mean function: " << getMeanTypeStr() << endl;
+  cout << "Data Set Size: " << getNumData() << endl;
+  cout << "Kernel Type: " << endl;
+  KerenlW->ShowKernelPars(os);
+  for (unsigned int i = 0; i < getNumlikfpar(); i++) cout << "likelihood hyperparmeters : " << hyperlf(i) << endl;
+  for (unsigned int i = 0; i < getNumMFpar(); i++) cout << "likelihood hyperparmeters : " << std::exp(hypermf(i)) << endl;
+  if (getVerbose()) cout << "Log likelihood: " << logLikelihood() << endl;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// train_model file (GP_Utils.cpp:1324-1425): key=value lines, default stream precision (6 significant digits)
+// ---------------------------------------------------------------------------------------------------
+void GP_utils::ToFile_GP_Params(std::ostream& out) const
+{
+  out << "Inference=" << getInf() << endl;
+  out << "likelihood=" << getLikelihoodType() << endl;
+  out << "MeanFunction=" << getMean() << endl;
+  out << "numData=" << getNumData() << endl;
+  out << "outputDim=" << getOutDim() << endl;
+  out << "inputDim=" << getInpDim() << endl;
+  out << "NumHyperKernel=" << KerenlW->getNPars() << endl;
+  out << "NumHyperLik=" << getNumlikfpar() << endl;
+  out << "NumHyperMean=" << getNumMFpar() << endl;
+  KerenlW->StrmOut(out);
+  for (unsigned int i = 0; i < getNumlikfpar(); i++) out << "Hyperparams_likelihood=" << getHyperlfVal(i) << endl;
+  for (unsigned int i = 0; i < getNumMFpar(); i++) out << "Hyperparams_meanfunction=" << std::exp(getHypermfVal(i)) << endl;
+}
+
+void GP_utils::FromFile_GP_Params(std::istream& in)
+{
+  setInf(ReadStrStrm(in, "Inference"));
+  setLikelihoodType(ReadIntStrm(in, "likelihood"));
+  setMean(ReadStrStrm(in, "MeanFunction"));
+  setNumData(ReadIntStrm(in, "numData"));
+  setOutDim(ReadIntStrm(in, "outputDim"));
+  setInpDim(ReadIntStrm(in, "inputDim"));
+  setNumCovpar(ReadIntStrm(in, "NumHyperKernel"));
+  setNumlikfpar(ReadIntStrm(in, "NumHyperLik"));
+  setNumMFpar(ReadIntStrm(in, "NumHyperMean"));
+  initialize_vars();
+  KerenlW = ReadKerFromFile(in);       // owned by nobody, as in the reference (GP_Utils.cpp:1336)
+  g_param.resize(1, KerenlW->getNPars());
+  if (getNumlikfpar() > 0) {
+    hyperlf.resize(getNumlikfpar(), 1);
+    for (unsigned int i = 0; i < getNumlikfpar(); i++) setHyperlfVal(ReadDoubleStrm(in, "Hyperparams_likelihood"), i);
+  }
+  if (getNumMFpar() > 0) {
+    hypermf.resize(getNumMFpar(), 1);
+    for (unsigned int i = 0; i < getNumMFpar(); i++) setHypermfVal(std::log((double)ReadIntStrm(in, "Hyperparams_meanfunction")), i);
+  }
+}
+
+void writeGpToStream(const GP_utils& model, std::ostream& out) { model.StrmOut(out); }
+void writeGPFile(const GP_utils& model, const string modelFileName, const string comment) { model.WFile(modelFileName, comment); }
+
+GP_utils* readGpFromStream(std::istream& in)
+{
+  GP_utils* m = new GP_utils();
+  m->StrmIn(in);
+  return m;
+}
+
+GP_utils* readGpFromFile(const string modelFileName, int verbosity)
+{
+  if (verbosity > 0) cout << "Loading model file." << endl;
+  std::ifstream in(modelFileName.c_str());
+  if (!in.is_open()) {
+    cout << "Error in reading file name. \n";
+    exit(1);
+  }
+  GP_utils* m = readGpFromStream(in);
+  if (verbosity > 0) cout << "Model Info has been read.\n";
+  in.close();
+  m->setVerbose(verbosity);
+  return m;
+}

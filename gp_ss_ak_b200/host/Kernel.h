@@ -1,0 +1,183 @@
+// Covariance-function classes of the B200 exact-GP path, mirroring the reference's Kernel.h (/root/reference):
+// abstract `Kernels`, the additive container `mainKernel` / `HybKerns`, the anisotropic exponential kernel
+// `Kern_ExpAnisotropic` (3 rotation angles + 3 inverse widths + Sigma [+ the 4-th column width]) and `Kern_Bias`.
+// They own parameters, names and the text (de)serialisation of the train_model file.  The matrix-valued members
+// computeK / getGradients are COMPATIBILITY wrappers: they move host matrices through the C ABI
+// (gpss_compute_K / gpss_expans_gradients); GP_utils never uses them on the hot path -- it hands the parameter
+// vector to the device-resident handle instead.
+// Kernels outside the scope table (RBF, Exponential, White) are not provided by this build.
+#ifndef GPSS_HOST_KERNEL_H
+#define GPSS_HOST_KERNEL_H
+
+#include <armadillo>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "ModelInf.h"
+
+using arma::mat;
+
+class Kernels : public StreamIntfce {
+ public:
+  Kernels() : nParams(0), inputDim(0) {}
+  explicit Kernels(const mat&) : nParams(0), inputDim(0) {}
+  explicit Kernels(unsigned int) : nParams(0), inputDim(0) {}
+  virtual ~Kernels() {}
+
+  virtual Kernels* clone() const = 0;
+  virtual void setInitPars() = 0;
+  virtual double Diag_Kernel(const mat& X, unsigned int index) const = 0;
+  virtual void diag_Compute(mat& d, const mat& X) const
+  {
+    for (unsigned int i = 0; i < X.n_rows; i++) d(i) = Diag_Kernel(X, i);
+  }
+  virtual void setParam(double, unsigned int) = 0;
+  virtual double getParam(unsigned int) const = 0;
+  // K (n1 x n2) and the squared Mahalanobis distance D2 between the rows of X1 and X2
+  virtual void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const = 0;
+  // g (1 x nParams) = sum_ij QW_ij dK_ij/dparam in the reference's own (non-textbook) form
+  virtual void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const = 0;
+  virtual unsigned int addNewKernel(const Kernels*)
+  {
+    std::cerr << "Error in adding new kernel." << std::endl;
+    return 0;
+  }
+
+  void setParams(const mat& v) { for (unsigned int i = 0; i < nParams; i++) setParam(v(i), i); }
+  void getParams(mat& v) const { for (unsigned int i = 0; i < nParams; i++) v(i) = getParam(i); }
+  std::string getKerName() const { return kernName; }
+  void setKerName(const std::string name) { kernName = name; }
+  void setInputDim(unsigned int dim) { inputDim = dim; }
+  unsigned getInputDim() const { return inputDim; }
+  unsigned int getNPars() const { return nParams; }
+  void setNPars(unsigned int np) { nParams = np; }
+  void setParamName(const std::string name, unsigned int index)
+  {
+    if (paramNames.size() <= index) paramNames.resize(index + 1, "no name");
+    paramNames[index] = name;
+  }
+  virtual std::string getParamName(unsigned int index) const { return paramNames[index]; }
+
+  virtual void ToFile_GP_Params(std::ostream& out) const;
+  virtual void FromFile_GP_Params(std::istream& in);
+  virtual std::ostream& ShowKernelPars(std::ostream& os) const;
+  void GetGrads(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const { getGradients(g, X, X2, D2, QW); }
+
+ protected:
+  unsigned int nParams;
+  std::string kernName;
+  std::vector<std::string> paramNames;
+
+ private:
+  unsigned int inputDim;
+};
+
+// container that concatenates the parameter vectors of its members
+class mainKernel : public Kernels {
+ public:
+  mainKernel() : Kernels() {}
+  explicit mainKernel(unsigned int inDim) : Kernels(inDim) {}
+  explicit mainKernel(const mat& X) : Kernels(X) {}
+  virtual unsigned int addNewKernel(const Kernels* kern)
+  {
+    MainKEl.push_back(kern->clone());
+    nParams += kern->getNPars();
+    return MainKEl.size() - 1;
+  }
+  virtual void setParam(double val, unsigned int paramNo);
+  virtual double getParam(unsigned int paramNo) const;
+  virtual std::string getParamName(unsigned int paramNo) const;
+  virtual void FromFile_GP_Params(std::istream& in);
+  virtual void ToFile_GP_Params(std::ostream& out) const;
+  virtual unsigned int getNumKerns() const { return MainKEl.size(); }
+  const Kernels* getKern(unsigned int i) const { return MainKEl[i]; }
+
+ protected:
+  // member index and local parameter index of global parameter `paramNo`; false when out of range
+  bool locate(unsigned int paramNo, size_t& member, unsigned int& local) const;
+  std::vector<Kernels*> MainKEl;
+};
+
+// additive ("hybrid") kernel: K = sum of the members' K
+class HybKerns : public mainKernel {
+ public:
+  HybKerns();
+  explicit HybKerns(unsigned int inDim);
+  explicit HybKerns(const mat& X);
+  HybKerns(const HybKerns&);          // deep copy (the reference's copy constructor appends to the list it iterates)
+  ~HybKerns();
+  HybKerns* clone() const { return new HybKerns(*this); }
+
+  void setInitPars() {}
+  double Diag_Kernel(const mat& X, unsigned int index) const;
+  void diag_Compute(mat& d, const mat& X) const;
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const;
+
+ private:
+  HybKerns& operator=(const HybKerns&);
+  void _init();
+};
+
+// constant kernel K_ij = Sigma_Bias on EVERY element (reference Kernel.cpp:285-377)
+class Kern_Bias : public Kernels {
+ public:
+  Kern_Bias() : Kernels() { _init(); }
+  explicit Kern_Bias(unsigned int inDim) : Kernels(inDim) { _init(); setInputDim(inDim); }
+  explicit Kern_Bias(const mat& X) : Kernels(X) { _init(); setInputDim(X.n_cols); }
+  Kern_Bias* clone() const { return new Kern_Bias(*this); }
+
+  void setInitPars() { Sigma_Bias = 0.2; }
+  double Diag_Kernel(const mat&, unsigned int) const { return Sigma_Bias; }
+  void diag_Compute(mat& d, const mat&) const { d.fill(Sigma_Bias); }
+  void setParam(double val, unsigned int paramNo);
+  double getParam(unsigned int paramNo) const;
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const;
+
+ private:
+  void _init();
+  double Sigma_Bias;
+};
+
+// K_ij = Sigma^2 exp(-sqrt(D2_ij)),  D2 = (x - x')' S^2 (x - x'),  S = Rot(AngleX, AngleY, AngleZ) diag(iWx, iWy, iWz) Rot'
+// (reference Kernel.cpp:700-1263, 1370-1435)
+class Kern_ExpAnisotropic : public Kernels {
+ public:
+  Kern_ExpAnisotropic() : Kernels() { _init(); }
+  explicit Kern_ExpAnisotropic(unsigned int inDim) : Kernels(inDim) { _init(); setInputDim(inDim); }
+  explicit Kern_ExpAnisotropic(const mat& X) : Kernels(X) { _init(); setInputDim(X.n_cols); }
+  Kern_ExpAnisotropic* clone() const { return new Kern_ExpAnisotropic(*this); }
+
+  void setAngleX(double v) { par[0] = v; }
+  double getAngleX() const { return par[0]; }
+  void setInverseWidthx(double v) { par[1] = v; }
+  double getInverseWidthx() const { return par[1]; }
+  void setAngleY(double v) { par[2] = v; }
+  double getAngleY() const { return par[2]; }
+  void setInverseWidthy(double v) { par[3] = v; }
+  double getInverseWidthy() const { return par[3]; }
+  void setAngleZ(double v) { par[4] = v; }
+  double getAngleZ() const { return par[4]; }
+  void setInverseWidthz(double v) { par[5] = v; }
+  double getInverseWidthz() const { return par[5]; }
+
+  void setInitPars();
+  double Diag_Kernel(const mat&, unsigned int) const { return par[6] * par[6]; }
+  void diag_Compute(mat& d, const mat&) const { d.fill(par[6] * par[6]); }
+  void setParam(double val, unsigned int paramNo);
+  double getParam(unsigned int paramNo) const;
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const;
+
+ private:
+  void _init();
+  // AngleX, iWx, AngleY, iWy, AngleZ, iWz, Sigma, iWR -- the order of the parameter vector (Kernel.cpp:803-838)
+  double par[8];
+};
+
+void WriteKernelPas(const Kernels& kern, std::ostream& out);
+Kernels* ReadKerFromFile(std::istream& in);
+
+#endif

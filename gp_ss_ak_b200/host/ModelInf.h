@@ -8,7 +8,8 @@
 #include <string>
 
 #include "StreamInt.h"
-#include "gpss_mat.h"
+#include <armadillo>
+using arma::mat;
 
 inline double sign(double val) { return (val <= 0) ? -1.0 : 1.0; }
 

@@ -66,18 +66,30 @@ int gpss_get_yhat(gpss_handle h, double* yhat);
 
 /* prediction --------------------------------------------------------------------------------------- */
 /* GP_utils::Calc_Out / posteriorMeanVar (GP_Utils.cpp:159-178, 1016-1041): predictive mean and variance
- * (noise included) of m standardised test points; var may be NULL (posteriorMean, :1005-1015).
+ * of m standardised test points EXACTLY as the reference returns them, i.e. including its post-processing of the
+ * variance vector (gpss_var_postprocess below); var may be NULL (posteriorMean, :1005-1015).
  * The Mahalanobis centre uses the training set and ALL m test points as MahaDist does (Kernel.cpp:1391). */
 int gpss_predict(gpss_handle h, long m, const double* Xs_colmajor, double* mu, double* var);
-/* Same, for one shard [first, first+count) of a test set of m_total points whose column sums are
- * sums_total[3]: lets ranks split the test points (L and alpha replicated) yet use the global centre. */
+/* One shard [first, first+count) of a test set of m_total points whose column sums are sums_total[3]: lets ranks
+ * split the test points (L and alpha replicated) yet use the global centre.  var receives the RAW variance
+ * kD - k*' (K + sn2 I)^-1 k* (GP_Utils.cpp:997-998) with no post-processing: the reference's next step is index
+ * arithmetic over the whole vector, so the caller gathers the shards and calls gpss_var_postprocess once. */
 int gpss_predict_shard(gpss_handle h, long m_total, const double sums_total[3], long count,
                        const double* Xs_shard_colmajor, double* mu, double* var);
+/* GP_Utils.cpp:1001-1003 + 1033-1040, literally: `uvec ind = varSigma < 0; varSigma.elem(ind) = 0` uses the 0/1
+ * comparison flags AS INDICES (element 0 is zeroed if any entry is >= 0, element 1 if any entry is < 0, negative
+ * entries are left as they are), then sn2 is added unless sn2 == 1.0.  Host-side, O(m). */
+int gpss_var_postprocess(long m, double sn2, double* var_inout);
 
 /* Kernels::computeK compatibility (host matrices; Kernel.cpp:140-154, 856-882, 362-367) ---------- */
 /* K and D2 are n1 x n2 column-major host buffers (either may be NULL). */
 int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const double* X1, int n2, const double* X2,
                    double* K, double* D2);
+
+/* Kern_ExpAnisotropic::getGradients compatibility (Kernel.cpp:886-1263): the 8 kernel-parameter entries of the
+ * reference's gradient for a HOST n x n matrix QW (column-major, need not be symmetric) and X1 == X2 == X (n x 3). */
+int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, const double* X_colmajor,
+                          const double* QW_colmajor, double g8[8]);
 
 /* instrumentation ---------------------------------------------------------------------------------- */
 /* Device time in ms of the phases of the last gpss_nlml / gpss_nlml_grad / gpss_predict on this handle:

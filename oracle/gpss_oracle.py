@@ -5,13 +5,21 @@ named by BASELINE.json:north_star.  It is imported only by tests/, by
 __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.  The
 product (gp_ss_ak_b200/) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- and cannot be compiled in this image (every translation unit
-includes <armadillo>, which is absent).  The restatement below is therefore pinned
-only by (a) line-by-line citation of the reference sources, (b) self-consistency
-checks in tests/test_oracle.py (IRLS fixed point == direct solve, matrix-form gradient
-== fused form, etc.) and (c) where available, oracle/_ref (the unmodified reference
-sources compiled against the in-repo Armadillo API stand-in, see oracle/README.md).
+PARITY PINNED AGAINST THE REFERENCE ITSELF.  The reference ships no tests, golden vectors or
+fixtures and real Armadillo is absent from this image, but its sources
+compile UNMODIFIED against the in-repo Armadillo stand-in (gp_ss_ak_b200/host/armadillo_standin,
+dense kernels forwarded to scipy's OpenBLAS): oracle/Makefile builds oracle/_ref/gp_ss_ak and
+oracle/_ref/ref_driver from the files where they lie under /root/reference, and
+tests/golden/make_ref_golden.py stores what the reference's own classes compute
+(tests/golden/ref_n300.npz, ref_n1000.npz: standardisation, nlml, g[10], Alpha, K samples,
+predictions incl. the variance post-processing quirk, a 30-iteration LBFGS probe trace).
+tests/test_oracle.py::test_oracle_matches_compiled_reference holds this restatement to those
+numbers: standardisation bit-exact; nlml 2e-7, g 5e-7, alpha 5e-7 relative, mu 5e-7 / var 1e-7
+absolute.  Those are NOT tolerances of the restatement but the reference's own reproducibility
+floor: sqrt() of the O(1e-16) rounding residue that MahaDist's expansion-form distance leaves on
+~5% of the diagonal of D2 moves K_ii by ~3e-8, and which entries carry a residue depends on the
+BLAS dgemm micro-kernel (hard part 1).  Against this oracle's own
+defined-operation-order distance the CUDA path is held to 1e-9 (tests/test_gpu_parity.py).
 
 All file:line citations are into /root/reference.
 
@@ -520,10 +528,26 @@ class OracleGP:
         LKs = LKs * Wh[:, None]
         LKs *= kX
         var = kD - LKs.sum(axis=0)
-        var[var < 0] = 0.0
-        if self.sn2 != 1.0:
-            var = var + self.sn2
+        self.var_raw = var.copy()
+        var = var_postprocess(var, self.sn2)
         return mu, var
+
+
+def var_postprocess(var_raw, sn2):
+    """GP_Utils.cpp:1001-1003 then 1033-1040, literally:
+           uvec ind = varSigma < 0;                          // 0/1 FLAGS ...
+           varSigma.elem(ind) = zeros<mat>(ind.n_rows, ind.n_cols);   // ... used as INDICES
+       so element 0 is zeroed when any entry is non-negative, element 1 when any entry is negative, negative entries
+       are not clamped; then `varSigma += sn2` unless sn2 == 1.0.  (The compiled reference confirms it: var[0] == sn2
+       in every tests/golden/ref_*.npz record.)"""
+    var = np.array(var_raw, dtype=np.float64).reshape(-1).copy()
+    ind = (var < 0).astype(np.int64)
+    if ind.max(initial=0) >= var.shape[0]:
+        raise IndexError("Mat::elem(): index out of bounds")      # the reference aborts here
+    var[ind] = 0.0
+    if sn2 != 1.0:
+        var = var + sn2
+    return var
 
 
 def s_matrices(theta):

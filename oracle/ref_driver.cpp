@@ -1,0 +1,147 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+// Drives the UNMODIFIED reference classes (GP_utils, HybKerns, Kern_ExpAnisotropic, Kern_Bias, Control, Opt_Algs;
+// compiled from /root/reference by oracle/Makefile, never copied) exactly the way gp_ss_ak.cpp:train()/test() do
+// (gp_ss_ak.cpp:134-190, 230, 288-306, 384-409) and dumps what the CLI only prints to 6 digits -- the objective,
+// the 10-vector gradient, Alpha, samples of K and D2, predictions, and the full LBFGS probe trace -- with 17
+// significant digits, so tests/golden/make_ref_golden.py can turn them into fixtures that pin oracle/gpss_oracle.py
+// and the CUDA path to the reference's own numbers.
+//
+//   ref_driver <train.txt> <test.txt> <thetas.txt> <lbfgs_iters> <workdir> > dump.txt
+#include "gp_ss_ak.h"
+#include <cstdio>
+#include <new>
+
+static void dump(const char* key, const mat& m)
+{
+  printf("%s %llu %llu", key, (unsigned long long)m.n_rows, (unsigned long long)m.n_cols);
+  for (uword i = 0; i < m.n_elem; i++) printf(" %.17g", m[i]);
+  printf("\n");
+}
+static void dump(const char* key, double v) { printf("%s 1 1 %.17g\n", key, v); }
+
+// logs every probe the optimiser makes through the reference's own callback surface (Opt_pars.h:51-55, 236-253)
+class TraceGP : public GP_utils {
+ public:
+  TraceGP(Kernels* k, mat X, mat y) : GP_utils(k, X, y, inf_laplace, likeL_Gaussian, mean_zero, 8, 1, 0, 0), on(false), count(0) {}
+  virtual double ObjVal() const
+  {
+    const double f = GP_utils::ObjVal();
+    if (on) { mat th(1, getNumPars()); get_GP_Pars(th); printf("probe %d O", count++); for (uword i = 0; i < th.n_elem; i++) printf(" %.17g", th[i]); printf(" f %.17g\n", f); }
+    return f;
+  }
+  virtual double Grad_Values(mat& g) const
+  {
+    const double f = GP_utils::Grad_Values(g);
+    if (on) {
+      mat th(1, getNumPars()); get_GP_Pars(th);
+      printf("probe %d G", count++); for (uword i = 0; i < th.n_elem; i++) printf(" %.17g", th[i]);
+      printf(" f %.17g g", f); for (uword i = 0; i < g.n_elem; i++) printf(" %.17g", g[i]); printf("\n");
+    }
+    return f;
+  }
+  mutable bool on;
+  mutable int count;
+};
+
+int main(int argc, char** argv)
+{
+  if (argc < 6) { fprintf(stderr, "usage: ref_driver train.txt test.txt thetas.txt lbfgs_iters workdir\n"); return 2; }
+  const string trainFile = argv[1], testFile = argv[2], thetaFile = argv[3];
+  const int iters = atoi(argv[4]);
+  const string model = string(argv[5]) + "/ref_model";
+  char* fake[] = {argv[0], 0};
+  int Data_mode = 0;
+  bool yscale = true;
+
+  // ---- train-mode data path (gp_ss_ak.cpp:137-142) ----
+  Control ctl(1, fake);
+  ctl.setMode("train");
+  ctl.setprepM(1);
+  int* sz = ctl.readDataSize(trainFile);
+  mat X(sz[0], sz[1]), y(sz[0], 1);
+  ctl.readDataFile(X, y, sz, trainFile);
+  dump("X_raw", X);
+  dump("y_raw", y);
+  ctl.prepareData(X, y, Data_mode, yscale, model);
+  dump("Xs", X);
+  dump("ys", y);
+  dump("params", ctl.params);
+
+  // ---- kernels and model (gp_ss_ak.cpp:146-190, 230) ----
+  HybKerns Kerns(X);
+  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
+  Kerns.addNewKernel(new Kern_Bias(X));
+  TraceGP gp(&Kerns, X, y);
+  const unsigned np = gp.getNumPars();
+
+  // ---- test-mode data path (gp_ss_ak.cpp:379-388) ----
+  Control ctl2(1, fake);
+  ctl2.setMode("test");
+  ctl2.setprepM(1);
+  int* szt = ctl2.readDataSize(testFile);
+  mat Xt(szt[0], szt[1]), yt(szt[0], 1);
+  ctl2.readDataFile(Xt, yt, szt, testFile);
+  int Data_mode_t = 1;
+  ctl2.prepareData(Xt, yt, Data_mode_t, yscale, model);
+  dump("Xt", Xt);
+
+  // ---- evaluations at the given thetas ----
+  std::ifstream tf(thetaFile.c_str());
+  int nth = 0;
+  while (true) {
+    mat th(1, np);
+    bool ok = true;
+    for (unsigned i = 0; i < np; i++) { double v; if (!(tf >> v)) { ok = false; break; } th[i] = v; }
+    if (!ok) break;
+    char key[64];
+    gp.set_GP_Pars(th);
+    const double L = gp.logLikelihood();
+    mat g(1, np);
+    gp.set_GP_Pars(th);                    // the optimiser always calls set_GP_Pars before Grad_Values (Opt_pars.cpp:266-267)
+    const double L2 = gp.Grad_Values(g);
+    snprintf(key, sizeof key, "theta_%d", nth); dump(key, th);
+    snprintf(key, sizeof key, "nlml_%d", nth); dump(key, L);
+    snprintf(key, sizeof key, "nlml_grad_%d", nth); dump(key, L2);
+    snprintf(key, sizeof key, "g_%d", nth); dump(key, g);
+    snprintf(key, sizeof key, "alpha_%d", nth); dump(key, gp.Alpha);
+    snprintf(key, sizeof key, "K_diag_%d", nth); dump(key, mat(gp.K.diag()));
+    snprintf(key, sizeof key, "D2_diag_%d", nth); dump(key, mat(gp.D2.diag()));
+    snprintf(key, sizeof key, "K_col0_%d", nth); dump(key, mat(gp.K.col(0)));
+    snprintf(key, sizeof key, "K_col17_%d", nth); dump(key, mat(gp.K.col(17)));
+    mat mu(Xt.n_rows, 1), var(Xt.n_rows, 1);
+    gp.Calc_Out(mu, var, Xt);
+    snprintf(key, sizeof key, "mu_%d", nth); dump(key, mu);
+    snprintf(key, sizeof key, "var_%d", nth); dump(key, var);
+    // back-transformed outputs as the CLI reports them (gp_ss_ak.cpp:410-412, Control.cpp:197-255)
+    mat Xc = Xt, muc = mu, varc = var;
+    ctl2.postData(Xc, muc, yscale, model);
+    ctl2.postData_var(varc, yscale, model);
+    snprintf(key, sizeof key, "yhat_raw_%d", nth); dump(key, muc);
+    snprintf(key, sizeof key, "std_raw_%d", nth); dump(key, varc);        // postData_var already takes the square root (Control.cpp:253-254)
+    nth++;
+  }
+  dump("n_theta", (double)nth);
+
+  // ---- LBFGS fit with the probe trace (gp_ss_ak.cpp:288-296; Opt_pars.cpp:179-332) ----
+  if (iters > 0) {
+    HybKerns Kerns2(X);
+    Kerns2.addNewKernel(new Kern_ExpAnisotropic(X));
+    Kerns2.addNewKernel(new Kern_Bias(X));
+    // Opt_Algs never initialises fail_pre_bfgs (Opt_pars.h:218, read at Opt_pars.cpp:577): construct the object in
+    // zero-filled storage so the flag starts false, which is what a fresh heap page gives the CLI's `new GP_utils`
+    void* raw = calloc(1, sizeof(TraceGP));
+    TraceGP& gp2 = *new (raw) TraceGP(&Kerns2, X, y);
+    gp2.setOptimiser(GP_utils::LBFGS);
+    gp2.setMaxIters(iters);
+    gp2.on = true;
+    gp2.Optimise();
+    gp2.on = false;
+    mat th(1, np);
+    gp2.get_GP_Pars(th);
+    dump("theta_fit", th);
+    dump("nlml_fit", gp2.logLikelihood());
+    dump("n_probes", (double)gp2.count);
+    writeGPFile(gp2, model, "# GP_SS_AK Model File ");
+  }
+  return 0;
+}

@@ -113,3 +113,52 @@ def test_oracle_reproduces_golden(name, nth):
         assert np.array_equal(np.diag(gp.D2), z["D2_diag_%d" % k])
         mu, var = gp.predict(z["Xt"])
         assert np.abs(mu - z["mu_%d" % k]).max() < 1e-10 and np.abs(var - z["var_%d" % k]).max() < 1e-10
+
+
+# tolerances against the COMPILED REFERENCE = its own BLAS-dependent reproducibility floor (oracle header)
+REF_TOL_NLML, REF_TOL_G, REF_TOL_ALPHA, REF_TOL_MU, REF_TOL_VAR = 2e-7, 5e-7, 5e-7, 5e-7, 1e-7
+
+
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz"])
+def test_oracle_matches_compiled_reference(name):
+    """The restatement against numbers produced by the unmodified reference classes (tests/golden/make_ref_golden.py)."""
+    z = np.load(os.path.join(GOLD, name))
+    Xs0, ys0, params, _ = O.standardise_train(z["X_raw"], z["y_raw"].reshape(-1))
+    assert np.array_equal(Xs0, z["Xs"]) and np.array_equal(ys0, z["ys"].reshape(-1))        # Control.cpp:299-324 bit-exact
+    assert np.array_equal(params, z["params"])
+    Xt, _ = O.apply_standardise(z["Xt_raw"], np.zeros(z["Xt_raw"].shape[0]), params)
+    assert np.array_equal(Xt, z["Xt"])                                                      # test-mode standardisation
+    for k in range(int(z["n_theta"])):
+        th = z["theta_%d" % k].reshape(-1)
+        L, g, gp = O.nlml_and_grad(z["Xs"], z["ys"].reshape(-1), th, dist="defined", literal=True)
+        Lr, gr = float(z["nlml_%d" % k]), z["g_%d" % k].reshape(-1)
+        assert abs(float(z["nlml_grad_%d" % k]) - Lr) <= 1e-12 * abs(Lr)                   # GradLL re-evaluates from a warm Alpha
+        assert abs(L - Lr) <= REF_TOL_NLML * abs(Lr)
+        assert np.abs(g - gr).max() <= REF_TOL_G * np.abs(gr).max()
+        assert gr[7] == 0.0                                                                 # Kernel.cpp:1256-1257
+        ar = z["alpha_%d" % k].reshape(-1)
+        assert np.linalg.norm(gp.Alpha - ar) <= REF_TOL_ALPHA * np.linalg.norm(ar)
+        assert np.abs(np.diag(gp.K) - z["K_diag_%d" % k].reshape(-1)).max() < 1e-7
+        assert np.abs(gp.K[:, 17] - z["K_col17_%d" % k].reshape(-1)).max() < 1e-12        # off the diagonal: rounding only
+        mu, var = gp.predict(z["Xt"])
+        assert np.abs(mu - z["mu_%d" % k].reshape(-1)).max() <= REF_TOL_MU
+        assert np.abs(var - z["var_%d" % k].reshape(-1)).max() <= REF_TOL_VAR
+        # the variance post-processing quirk (GP_Utils.cpp:1001-1003): element 0 is zeroed, then sn2 is added
+        assert z["var_%d" % k].reshape(-1)[0] == th[9] and var[0] == th[9]
+        # CLI back-transform (Control.cpp:218, 253-254)
+        assert np.abs(O.post_mean(mu, params) - z["yhat_raw_%d" % k].reshape(-1)).max() <= 1e-6 * params[0, 1]
+        assert np.abs(O.post_std(var, params) - z["std_raw_%d" % k].reshape(-1)).max() <= 1e-6 * params[0, 1]
+
+
+def test_var_postprocess_is_index_arithmetic():
+    """uvec ind = varSigma < 0; varSigma.elem(ind) = 0  (flags used as indices)."""
+    v = O.var_postprocess(np.array([0.5, 0.25, 0.125]), 0.01)
+    assert np.allclose(v, [0.01, 0.26, 0.135])
+    v = O.var_postprocess(np.array([0.5, 0.25, -0.125]), 0.01)          # a negative entry zeroes element 1, stays negative itself
+    assert np.allclose(v, [0.01, 0.01, -0.115])
+    v = O.var_postprocess(np.array([-0.5, -0.25]), 0.01)                # all negative: only element 1
+    assert np.allclose(v, [-0.49, 0.01])
+    v = O.var_postprocess(np.array([0.5, 0.25]), 1.0)                   # sn2 == 1.0 is not added (GP_Utils.cpp:1037)
+    assert np.allclose(v, [0.0, 0.25])
+    with pytest.raises(IndexError):
+        O.var_postprocess(np.array([-0.5]), 0.01)
