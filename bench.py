@@ -74,16 +74,41 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference_eval(n_sample, seed=0):
-    """One reference-literal LML+gradient evaluation of the oracle port on the host cores (all BLAS threads):
-    3 dpotrf of the same matrix + two n x n dtrtrs + the matrix-form gradients."""
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def cpu_reference_times(n_sample, warmup, steps):
+    """Seconds per LML+gradient evaluation (set_GP_Pars + Grad_Values, a new theta every step) of the reference's own
+    CPU implementation on the host cores.  kind "reference": the UNMODIFIED reference classes, built by oracle/Makefile
+    into oracle/_ref/ref_driver with the reference's own flags (no optimisation, make_linux:19) and OpenBLAS on all
+    cores; kind "port": the numpy/scipy restatement (oracle/gpss_oracle.py) when that binary is not present."""
     from gp_ss_ak_b200 import datagen
+    X, y = datagen.drillholes(n_sample, 0)
+    if os.path.exists(REF_DRIVER):
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            datagen.write_data_file(os.path.join(d, "train.txt"), X, y)
+            out = subprocess.run([REF_DRIVER, "--time", os.path.join(d, "train.txt"), d, str(warmup), str(steps)],
+                                 capture_output=True, text=True, check=True)
+        secs = [float(l.split()[4]) for l in out.stdout.splitlines() if l.startswith("eval") and " timed " in l]
+        return secs, "reference"
     from oracle import gpss_oracle as O
-    X, y = datagen.drillholes(n_sample, seed)
     Xs, ys, _ = datagen.standardise_symmetric(X, y)
-    t0 = time.perf_counter()
-    L, g, _ = O.nlml_and_grad(Xs, ys, O.THETA0.copy(), dist="blas", literal=True)
-    return time.perf_counter() - t0, L
+    secs = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.nlml_and_grad(Xs, ys, O.THETA0 * (1.0 + 0.01 * ((k % 7) - 3)), dist="blas", literal=True)
+        if k >= warmup:
+            secs.append(time.perf_counter() - t0)
+    return secs, "port"
+
+
+def cpu_sample_text(kind, n_sample, n, t_step, cores):
+    what = ("the unmodified reference (oracle/_ref/ref_driver: reference sources + Armadillo stand-in + OpenBLAS, built -O0 like "
+            "make_linux)" if kind == "reference" else "the numpy/scipy port of the reference (oracle/gpss_oracle.py, literal path)")
+    return ("%s: set_GP_Pars + Grad_Values at n=%d took %.2f s per evaluation on %d host threads; scaled by (n/n_sample)^3 = %.0f to "
+            "n=%d (the reference keeps ~34 dense n x n buffers, ~680 GB at n=%d, and cannot run the full size)"
+            % (what, n_sample, t_step, cores, (n / n_sample) ** 3, n, n))
 
 
 def run_reference_arm(args, rank, world):
@@ -91,23 +116,19 @@ def run_reference_arm(args, rank, world):
         return
     n_sample = args.cpu_n
     cores = os.cpu_count()
-    times = []
-    for k in range(args.warmup + args.steps):
-        dt, L = cpu_reference_eval(n_sample, seed=k)
-        if k >= args.warmup:
-            times.append(dt)
-    t_step = float(np.mean(times))
+    secs, kind = cpu_reference_times(n_sample, args.warmup, args.steps)
+    t_step = float(np.mean(secs))
     scale = (args.n / n_sample) ** 3
     value = 1.0 / (t_step * scale)
-    sample = ("oracle port (numpy/scipy -> OpenBLAS dpotrf/dtrtrs/dgemm), reference-literal evaluation at n=%d "
-              "timed on %d host threads and scaled by (n/n_sample)^3 = %.1f to n=%d (the reference keeps ~34 dense "
-              "n x n buffers and cannot hold n=%d)" % (n_sample, cores, scale, args.n, args.n))
     line = {
         "impl": "reference", "metric": "ExpAns LML+grad evals/s at n=%dk" % (args.n // 1000), "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * scale * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LML+gradient evaluation, ExpAns+Bias 3-D, n=%d (cubic extrapolation from n=%d)" % (args.n, n_sample)},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d; each step is a bounded "
+                               "sample: one evaluation at n=%d, scaled by (n/n_sample)^3" % (args.n, n_sample), "n": args.n,
+                   "n_sample": n_sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(kind, n_sample, args.n, t_step, cores)},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -120,7 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=N_HEADLINE)
     ap.add_argument("--impl", default="gpss")
-    ap.add_argument("--cpu-n", type=int, default=4000, help="sample size of the CPU baseline evaluation")
+    ap.add_argument("--cpu-n", type=int, default=1500, help="sample size of the CPU baseline / reference-arm evaluation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -245,12 +266,10 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count()
-            t_cpu, _ = cpu_reference_eval(args.cpu_n, seed=0)
-            scale = (n / args.cpu_n) ** 3
-            line["cpu_baseline"] = {
-                "value": 1.0 / (t_cpu * scale), "unit": "evals/s", "cores": cores, "kind": "port",
-                "sample": "one reference-literal oracle evaluation at n=%d (%.2f s on %d threads), scaled by (n/%d)^3 = %.1f"
-                          % (args.cpu_n, t_cpu, cores, args.cpu_n, scale)}
+            secs, kind = cpu_reference_times(args.cpu_n, 1, 3)
+            t_cpu = float(np.mean(secs))
+            line["cpu_baseline"] = {"value": 1.0 / (t_cpu * (n / args.cpu_n) ** 3), "unit": "evals/s", "cores": cores, "kind": kind,
+                                    "sample": cpu_sample_text(kind, args.cpu_n, n, t_cpu, cores)}
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:

@@ -7,6 +7,7 @@
 // and the CUDA path to the reference's own numbers.
 //
 //   ref_driver <train.txt> <test.txt> <thetas.txt> <lbfgs_iters> <workdir> > dump.txt
+//   ref_driver --time <train.txt> <workdir> <warmup> <steps>     one line per timed set_GP_Pars + Grad_Values (bench.py)
 #include "gp_ss_ak.h"
 #include <cstdio>
 #include <new>
@@ -43,8 +44,47 @@ class TraceGP : public GP_utils {
   mutable int count;
 };
 
+#include <chrono>
+// bench.py --impl reference: W untimed + K timed LML+gradient evaluations (set_GP_Pars(theta_k); Grad_Values(g)) by the
+// unmodified reference, a different theta every step so nothing is cached (GP_Utils.cpp:130-133)
+static int time_mode(int argc, char** argv)
+{
+  if (argc < 6) { fprintf(stderr, "usage: ref_driver --time train.txt workdir warmup steps\n"); return 2; }
+  const string trainFile = argv[2];
+  const string model = string(argv[3]) + "/ref_time_model";
+  const int warm = atoi(argv[4]), steps = atoi(argv[5]);
+  char* fake[] = {argv[0], 0};
+  int Data_mode = 0;
+  bool yscale = true;
+  Control ctl(1, fake);
+  ctl.setMode("train");
+  ctl.setprepM(1);
+  int* sz = ctl.readDataSize(trainFile);
+  mat X(sz[0], sz[1]), y(sz[0], 1);
+  ctl.readDataFile(X, y, sz, trainFile);
+  ctl.prepareData(X, y, Data_mode, yscale, model);
+  HybKerns Kerns(X);
+  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
+  Kerns.addNewKernel(new Kern_Bias(X));
+  GP_utils gp(&Kerns, X, y, GP_utils::inf_laplace, GP_utils::likeL_Gaussian, GP_utils::mean_zero, 8, 1, 0, 0);
+  const unsigned np = gp.getNumPars();
+  mat th0(1, np), g(1, np);
+  gp.get_GP_Pars(th0);
+  for (int k = 0; k < warm + steps; k++) {
+    mat th = th0 * (1.0 + 0.01 * ((k % 7) - 3));
+    const auto t0 = std::chrono::steady_clock::now();
+    gp.set_GP_Pars(th);
+    const double L = gp.Grad_Values(g);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("eval %d %s seconds %.6f nlml %.12g\n", k, k < warm ? "warmup" : "timed", sec, L);
+    fflush(stdout);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc > 1 && string(argv[1]) == "--time") return time_mode(argc, argv);
   if (argc < 6) { fprintf(stderr, "usage: ref_driver train.txt test.txt thetas.txt lbfgs_iters workdir\n"); return 2; }
   const string trainFile = argv[1], testFile = argv[2], thetaFile = argv[3];
   const int iters = atoi(argv[4]);
