@@ -358,17 +358,18 @@ static int lauum_lower(gpss_ctx* c)
 static int potrs_vec(gpss_ctx* c)
 {
   const long ld = c->n_pad;
-  for (int k = 0; k < c->nblk; k++) {
-    const int k0 = k * NB;
-    const int grid = 1 + (c->n_pad - k0 - NB) / NB;
-    trsv_fwd_step_kernel<<<grid, NB, 0, c->st>>>(c->Lm, ld, c->Winv + (long)k * NB * NB, c->rvec, c->zvec, k0);
+  const int nblk = c->nblk;
+  trsv_fwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv, c->rvec, c->zvec);
+  c->launches++;
+  for (int k = 0; k + 1 < nblk; k++) {
+    trsv_fwd_step_kernel<<<nblk - 1 - k, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->rvec, c->zvec, k * NB);
     c->launches++;
   }
   CU(cudaGetLastError());
-  for (int k = c->nblk - 1; k >= 0; k--) {
-    const int k0 = k * NB;
-    const int grid = 1 + k;
-    trsv_bwd_step_kernel<<<grid, NB, 0, c->st>>>(c->Lm, ld, c->Winv + (long)k * NB * NB, c->zvec, c->alpha, k0);
+  trsv_bwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv + (long)(nblk - 1) * NB * NB, c->zvec, c->alpha, (nblk - 1) * NB);
+  c->launches++;
+  for (int k = nblk - 1; k >= 1; k--) {
+    trsv_bwd_step_kernel<<<k, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->zvec, c->alpha, k * NB);
     c->launches++;
   }
   CU(cudaGetLastError());

@@ -335,61 +335,124 @@ potrf_diag_inv_kernel(double* __restrict__ A, long ld, double* __restrict__ Winv
 // ---------------------------------------------------------------------------------------------------
 // K4 (vector right-hand side): blocked triangular solves with the stored diagonal-block inverses.
 //     Replaces solve_chol's two dtrtrs for alpha (GP_Utils.cpp:841-845 via :893).
+//     One launch per 128-block step; a launch streams the 128-column panel of L exactly once (HBM-bound: the two
+//     sweeps read 8 n^2 bytes in total).  Every CTA applies the current block solution to its 128 rows (columns);
+//     the CTA that owns the NEXT diagonal block then produces that block's solution, so consecutive launches need
+//     no extra kernel in between.
 // ---------------------------------------------------------------------------------------------------
-// forward step k:  z_k = Winv_k r_k ;  r[i] -= L[i, kblk] z_k  for rows below.   grid = 1 + #row tiles below
-__global__ void __launch_bounds__(NB) trsv_fwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
-                                                           double* __restrict__ r, double* __restrict__ z, int k0)
+constexpr int TRSV_THREADS = 256;
+
+// s[0..127] = Winv(128x128 lower, column-major ld 128) * v   (TRANS = false)   or   Winv^T * v   (TRANS = true); v, s in smem
+template <bool TRANS>
+__device__ __forceinline__ void block_tri_matvec(const double* __restrict__ Winv, const double* v, double* s_out, double* scratch)
 {
-  __shared__ double rk[NB], zk[NB];
-  const int t = threadIdx.x;
-  rk[t] = r[k0 + t];
-  __syncthreads();
-  double s = 0;
-  for (int c = 0; c <= t; c++) s = fma(Winv[c * NB + t], rk[c], s);
-  zk[t] = s;
-  __syncthreads();
-  if (blockIdx.x == 0) { z[k0 + t] = s; return; }
-  const long i = (long)k0 + (long)blockIdx.x * NB + t;
-  const double* Lp = L + (long)k0 * ld + i;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 4
-  for (int c = 0; c < NB; c += 4) {
-    a0 = fma(Lp[(long)c * ld], zk[c], a0);
-    a1 = fma(Lp[(long)(c + 1) * ld], zk[c + 1], a1);
-    a2 = fma(Lp[(long)(c + 2) * ld], zk[c + 2], a2);
-    a3 = fma(Lp[(long)(c + 3) * ld], zk[c + 3], a3);
+  const int t = threadIdx.x, r = t & 127, h = t >> 7;
+  double acc = 0.0;
+  if (!TRANS) {
+    // s[r] = sum_{c <= r} W(r,c) v[c]; the two halves of the CTA split the columns
+    for (int c = h * 64; c < h * 64 + 64 && c <= r; c++) acc = fma(Winv[c * NB + r], v[c], acc);
+  } else {
+    // s[r] = sum_{q >= r} W(q,r) v[q]; column r is contiguous
+    for (int q = max(r, h * 64); q < h * 64 + 64; q++) acc = fma(Winv[r * NB + q], v[q], acc);
   }
-  r[i] -= (a0 + a1) + (a2 + a3);
+  scratch[h * NB + r] = acc;
+  __syncthreads();
+  if (t < NB) s_out[t] = scratch[t] + scratch[NB + t];
+  __syncthreads();
 }
 
-// backward step k:  x_k = Winv_k^T r_k ;  r[j] -= L[kblk, j]^T x_k  for column tiles to the left.
-__global__ void __launch_bounds__(NB) trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
-                                                           double* __restrict__ r, double* __restrict__ x, int k0)
+// first block of the forward sweep: z_0 = Winv_0 r_0
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_first_kernel(const double* __restrict__ Winv, const double* __restrict__ r,
+                                                                       double* __restrict__ z)
 {
-  __shared__ double rk[NB], xk[NB];
+  __shared__ double v[NB], s[NB], scratch[2 * NB];
+  if (threadIdx.x < NB) v[threadIdx.x] = r[threadIdx.x];
+  __syncthreads();
+  block_tri_matvec<false>(Winv, v, s, scratch);
+  if (threadIdx.x < NB) z[threadIdx.x] = s[threadIdx.x];
+}
+
+// forward step k: rows below block k get  r[i] -= L[i, kblk] z_k ;  the CTA of block k+1 then stores z_{k+1} = Winv_{k+1} r_{k+1}.
+// grid = number of 128-row tiles below block k.
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
+                                                                      double* __restrict__ r, double* __restrict__ z, int k0)
+{
+  __shared__ double zk[NB], rn[NB], s[NB], scratch[2 * NB];
+  const int t = threadIdx.x, row = t & 127, h = t >> 7;
+  if (t < NB) zk[t] = z[k0 + t];
+  __syncthreads();
+  const long i = (long)k0 + NB + (long)blockIdx.x * NB + row;
+  const double* Lp = L + (long)(k0 + h * 64) * ld + i;
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 64; c += 8) {
+    double l[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) l[q] = Lp[(long)(c + q) * ld];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = fma(l[q], zk[h * 64 + c + q], a[q]);
+  }
+  scratch[h * NB + row] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (t < NB) {
+    const double v = r[i] - (scratch[t] + scratch[NB + t]);
+    r[i] = v;
+    rn[t] = v;
+  }
+  if (blockIdx.x != 0) return;
+  __syncthreads();
+  block_tri_matvec<false>(Winv + (long)(k0 / NB + 1) * NB * NB, rn, s, scratch);
+  if (t < NB) z[k0 + NB + t] = s[t];
+}
+
+// last block of the backward sweep's start: x_last = Winv_last^T r_last
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_first_kernel(const double* __restrict__ Winv_last, const double* __restrict__ r,
+                                                                       double* __restrict__ x, int k0)
+{
+  __shared__ double v[NB], s[NB], scratch[2 * NB];
+  if (threadIdx.x < NB) v[threadIdx.x] = r[k0 + threadIdx.x];
+  __syncthreads();
+  block_tri_matvec<true>(Winv_last, v, s, scratch);
+  if (threadIdx.x < NB) x[k0 + threadIdx.x] = s[threadIdx.x];
+}
+
+// backward step k: column tiles left of block k get  r[j] -= L[kblk, j]^T x_k ;  the CTA of block k-1 then stores
+// x_{k-1} = Winv_{k-1}^T r_{k-1}.  grid = k (number of 128-column tiles left of block k); tile b covers columns 128 b.
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Winv,
+                                                                      double* __restrict__ r, double* __restrict__ x, int k0)
+{
+  __shared__ double xk[NB], rn[NB], s[NB], scratch[2 * NB];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  rk[t] = r[k0 + t];
+  if (t < NB) xk[t] = x[k0 + t];
   __syncthreads();
-  // x_k[c] = sum_{c' >= c} Winv[c'][c] r[c'] : one warp per output column
-  for (int c = warp; c < NB; c += NB / 32) {
-    double s = 0;
-    for (int q = lane; q < NB; q += 32) s = fma(Winv[c * NB + q], rk[q], s);   // Winv(q,c), zero for q<c
+  const int j0 = blockIdx.x * NB;
+  // warp w owns columns j0 + 16 w .. + 15; lanes run down the 128 rows of the tile (4 each), then a shuffle reduction
+  double acc[16];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) xk[c] = s;
+  for (int c = 0; c < 16; c++) {
+    const double* Lp = L + (long)(j0 + warp * 16 + c) * ld + k0 + lane;
+    acc[c] = fma(Lp[0], xk[lane], fma(Lp[32], xk[lane + 32], fma(Lp[64], xk[lane + 64], Lp[96] * xk[lane + 96])));
   }
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    double v = acc[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    acc[c] = v;
+  }
+  if (lane < 16) {
+    double mine = acc[0];
+#pragma unroll
+    for (int c = 1; c < 16; c++) if (lane == c) mine = acc[c];
+    const int j = j0 + warp * 16 + lane;
+    const double v = r[j] - mine;
+    r[j] = v;
+    rn[warp * 16 + lane] = v;
+  }
+  if ((int)blockIdx.x != k0 / NB - 1) return;
   __syncthreads();
-  if (blockIdx.x == 0) { x[k0 + t] = xk[t]; return; }
-  const int j0 = (blockIdx.x - 1) * NB;
-  for (int c = warp; c < NB; c += NB / 32) {
-    const double* Lp = L + (long)(j0 + c) * ld + k0;
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < NB; q += 32) s = fma(Lp[q + lane], xk[q + lane], s);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) r[j0 + c] -= s;
-  }
+  block_tri_matvec<true>(Winv + (long)(k0 / NB - 1) * NB * NB, rn, s, scratch);
+  if (t < NB) x[k0 - NB + t] = s[t];
 }
 
 // ---------------------------------------------------------------------------------------------------
