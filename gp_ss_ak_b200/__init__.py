@@ -57,6 +57,9 @@ def load_library():
         "gpss_nlml_grad": (I, [H, P, P]),
         "gpss_get_alpha": (I, [H, P]),
         "gpss_get_yhat": (I, [H, P]),
+        "gpss_nccl_unique_id": (I, [ctypes.c_void_p]),
+        "gpss_dist_init": (I, [H, I, I, ctypes.c_void_p]),
+        "gpss_dist_partition": (I, [I, I, I, ctypes.POINTER(I)]),
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
         "gpss_var_postprocess": (I, [L, D, P]),
@@ -126,6 +129,11 @@ class GpssModel:
             self.close()
         except Exception:
             pass
+
+    def dist_init(self, rank, world, unique_id):
+        """Collective: joins this handle to an NCCL communicator of `world` ranks (unique_id: 128 bytes from rank 0)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        _check(self._lib.gpss_dist_init(self._h, rank, world, ctypes.cast(buf, ctypes.c_void_p)))
 
     def set_data(self, X, y):
         X = _colmajor(X)
@@ -211,6 +219,18 @@ def var_postprocess(var_raw, sn2):
     v = np.ascontiguousarray(np.asarray(var_raw, dtype=np.float64).reshape(-1)).copy()
     _check(load_library().gpss_var_postprocess(v.shape[0], float(sn2), _dp(v)))
     return v
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    _check(load_library().gpss_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return bytes(buf.raw)
+
+
+def dist_partition(n_pad, world, kind):
+    b = (ctypes.c_int * (world + 1))()
+    _check(load_library().gpss_dist_partition(n_pad, world, kind, b))
+    return list(b)
 
 
 def measure_fp64_peak(device=0):

@@ -7,6 +7,9 @@
 #include "gpss_kernels.cuh"
 #include "gpss_params.h"
 
+#include <dlfcn.h>
+#include <nccl.h>       // types and prototypes only: the library is dlopen'ed when a communicator is first needed
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +33,46 @@ static int fail_cuda(cudaError_t e, const char* what, int line)
 #define RET(x) do { int r__ = (x); if (r__ < 0) return r__; } while (0)
 
 static int fail_arg(const char* msg) { g_last_error = msg; return GPSS_ERR_ARG; }
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (libnccl.so.2: the copy torch has already loaded, else the system one), so that the
+// single-GPU library has no hard dependency on it.
+// ---------------------------------------------------------------------------------------------------
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+  if (g_nccl.ok) return GPSS_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_last_error = std::string("cannot load libnccl.so.2: ") + dlerror(); return GPSS_ERR_NCCL; }
+#define NCCL_SYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) { g_last_error = "libnccl.so.2 lacks " name; return GPSS_ERR_NCCL; }
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  NCCL_SYM(Broadcast, "ncclBroadcast")
+  NCCL_SYM(AllReduce, "ncclAllReduce")
+  NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+  g_nccl.ok = true;
+  return GPSS_OK;
+}
+static int fail_nccl(ncclResult_t r, const char* what, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "NCCL error '%s' in %s (gpss_capi.cu:%d)", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what, line);
+  g_last_error = buf;
+  return GPSS_ERR_NCCL;
+}
+#define NC(x) do { ncclResult_t r__ = (x); if (r__ != ncclSuccess) return fail_nccl(r__, #x, __LINE__); } while (0)
 
 constexpr int NBO = 512;      // outer block (k-depth of the big trailing updates)
 constexpr int PRED_BATCH = 8192;
@@ -59,6 +102,12 @@ struct gpss_ctx {
   // prediction scratch (lazily)
   double *xt = nullptr, *zt = nullptr, *zsp = nullptr, *Bm = nullptr, *Vm = nullptr, *mu_part = nullptr, *dmu = nullptr, *dvar = nullptr;
   int pred_cap = 0;
+  // distributed evaluation (one process per GPU; rank/world = 0/1 when not initialised)
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
+  int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
+  int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
   // host state
   double theta[GPSS_NPAR];
   double sums_train[3];
@@ -171,6 +220,49 @@ static void fill_params(const double theta[GPSS_NPAR], const double centre[3], D
 // blocked right-looking Cholesky, two-level (outer NBO = 512 for deep-k trailing updates, inner 128)
 // A: n_pad x n_pad lower, in place.  Replaces arma::chol -> dpotrf (GP_Utils.cpp:881,903).
 // ---------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// distributed evaluation helpers (world > 1): staging buffer, balanced row partitions
+// ---------------------------------------------------------------------------------------------------
+static int ensure_stage(gpss_ctx* c, size_t count)
+{
+  if (c->stage_count >= count) return GPSS_OK;
+  if (c->stage) cudaFree(c->stage);
+  c->stage = nullptr;
+  c->stage_count = 0;
+  CU(cudaMalloc(&c->stage, count * sizeof(double)));
+  c->stage_count = count;
+  return GPSS_OK;
+}
+
+// Row boundaries (multiples of 128) that give every rank the same share of work:
+//   kind 0: rows of U = L^-T in the block-column inverse, cost(row i) ~ (n - i)^2 / 2   -> (n - r_k)^3 = n^3 (1 - k/P)
+//   kind 1: rows of B^-1 = U U^T (lower),                 cost(row i) ~ (i + 1)(n - i)  -> n x^2/2 - x^3/3 = (k/P) n^3/6
+static void balanced_rows(int n_pad, int world, int kind, std::vector<int>& bounds)
+{
+  bounds.assign(world + 1, 0);
+  bounds[world] = n_pad;
+  const double n = n_pad;
+  for (int k = 1; k < world; k++) {
+    const double f = (double)k / world;
+    double x;
+    if (kind == 0) {
+      x = n * (1.0 - std::cbrt(1.0 - f));
+    } else {
+      double lo = 0.0, hi = n;
+      const double target = f * n * n * n / 6.0;
+      for (int it = 0; it < 100; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (n * mid * mid / 2.0 - mid * mid * mid / 3.0 < target) lo = mid; else hi = mid;
+      }
+      x = 0.5 * (lo + hi);
+    }
+    int b = (int)std::lround(x / NB) * NB;
+    if (b < bounds[k - 1]) b = bounds[k - 1];
+    if (b > n_pad) b = n_pad;
+    bounds[k] = b;
+  }
+}
+
 // One outer panel: factor the NBO-wide block column starting at K0 (all rows below), 128 columns at a time.
 static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
 {
@@ -211,7 +303,9 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
 // re-read and re-wrote the whole trailing matrix n/NBO times), and nearly all flops run in long-k GEMMs.
 static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Winv, double* logdet_parts, int* dflag)
 {
+  const int P = c->world, me = c->rank;
   const bool la = c->st2 != nullptr && !getenv("GPSS_NO_LOOKAHEAD");
+  if (P > 1 && !la) return fail_arg("the distributed factorisation needs the look-ahead streams");
   const int nblk_o = (n_pad + NBO - 1) / NBO;
   if (la && (int)c->ev_pool.size() < 2 * nblk_o + 2) {
     const size_t want = 2 * nblk_o + 2;
@@ -221,6 +315,9 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
       c->ev_pool.push_back(e);
     }
   }
+  // staging layout of one broadcast: [panel rows T0.. x nbT | the panel's 128x128 diagonal inverses | their log-dets]
+  const size_t stage_need = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
+  if (P > 1) RET(ensure_stage(c, stage_need));
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
     const double* Lp = A + (long)kbeg * ld + T0;
@@ -231,19 +328,41 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   for (int t = 0; t < nblk_o; t++) {
     const int T0 = t * NBO;
     const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+    const bool mine = (t % P) == me;
     if (!la) {
       if (t >= 1) RET(update(T0, nbT, 0, T0, c->st));
       RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
       continue;
     }
     cudaEvent_t evP = c->ev_pool[2 * t], evU = c->ev_pool[2 * t + 1];
-    if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
-    if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
-    RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
-    CU(cudaEventRecord(evP, c->st));
-    // issue U1(t+1) = panels 0..t-1 applied to block column t+1; needs panel t-1 (complete: main stream order) --
-    // here, right after panel t was ENQUEUED, the side stream must only wait for panel t-1.
-    if (t + 1 < nblk_o && t >= 1) {
+    if (mine) {
+      if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));             // U1(t) was issued on a side stream below
+      if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));         // U2(t)
+      RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+    }
+    if (P > 1) {
+      // the owner's finished block column (+ its diagonal inverses and log-dets) goes to every rank: after the loop L,
+      // Winv and logdet_parts are replicated.  One NCCL broadcast per panel (<= 205 MB at n = 50k), on the main stream.
+      const long rows = n_pad - T0;
+      const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
+      double* Wt = Winv + (size_t)(T0 / NB) * NB * NB;
+      if (mine) {
+        pack_kernel<<<592, 256, 0, c->st>>>(c->stage, A + (long)T0 * ld + T0, ld, rows, nbT);
+        CU(cudaMemcpyAsync(c->stage + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        c->launches++;
+      }
+      NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, t % P, c->comm, c->st));
+      if (!mine) {
+        unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
+        CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        c->launches++;
+      }
+    }
+    CU(cudaEventRecord(evP, c->st));                                   // panel t is complete on this rank
+    // issue U1(t+1) = panels 0..t-1 applied to block column t+1 if it is mine; it must only wait for panel t-1
+    if (t + 1 < nblk_o && t >= 1 && ((t + 1) % P) == me) {
       const int T1 = T0 + NBO;
       const int nb1 = (n_pad - T1 < NBO) ? (n_pad - T1) : NBO;
       cudaStream_t side = (t & 1) ? c->st2 : c->st3;
@@ -251,6 +370,9 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
       RET(update(T1, nb1, 0, T0, side));
       CU(cudaEventRecord(c->ev_pool[2 * (t + 1) + 1], side));
     }
+  }
+  if (P > 1) {   // a failed pivot anywhere must be seen everywhere
+    NC(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMax, c->comm, c->st));
   }
   return GPSS_OK;
 }
@@ -296,6 +418,10 @@ static int trtri_upper(gpss_ctx* c)
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->ev_pool.push_back(e);
   }
+  // Distributed: every row of U depends only on L and on the SAME row of earlier block columns, so a rank computes
+  // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
+  // rank needs as right factors, are cheap and computed redundantly).
+  const int R0 = c->urow0, R1 = c->urow1;
   // the side stream must not start before the factor is complete on the main stream
   CU(cudaEventRecord(c->ev_main, c->st));
   CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
@@ -331,12 +457,14 @@ static int trtri_upper(gpss_ctx* c)
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
     CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
-    // (3) T = U[0:J0,0:J0] * L[Jblk,0:J0]^T
-    GemmArgs g = gemm_args(U, ld, L + J0, ld, c->Tpanel, ld, J0, nbj, J0);
-    g.kbeg_row = 1;
+    const int ra = R0, rb = (R1 < J0) ? R1 : J0;             // my rows above this block column
+    if (rb <= ra) continue;
+    // (3) T[ra:rb] = U[ra:rb, 0:J0] * L[Jblk, 0:J0]^T      (k starts at each tile's own row: U is upper triangular)
+    GemmArgs g = gemm_args(U + ra, ld, L + J0, ld, c->Tpanel + ra, ld, rb - ra, nbj, J0);
+    g.kbeg_row = 1; g.krow_off = ra;
     RET(gemm_ws_on(c, g, c->st2));
-    // (4) U[0:J0, Jblk] = -T * W_JJ^T
-    GemmArgs g2 = gemm_args(c->Tpanel, ld, Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
+    // (4) U[ra:rb, Jblk] = -T * W_JJ^T
+    GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
     g2.negate_out = 1; g2.kend_col = 1;
     RET(gemm_ws_on(c, g2, c->st2));
   }
@@ -345,12 +473,37 @@ static int trtri_upper(gpss_ctx* c)
   return GPSS_OK;
 }
 
-// Q (lower) = U U^T = B^-1
+// Distributed: every rank has computed its rows of U; B^-1 = U U^T and W = U^T need all of them.  Each rank's slice
+// (rows [b_k, b_k+1) x columns b_k..n, a strided region of the column-major buffer) is packed, broadcast and unpacked.
+static int allgather_U(gpss_ctx* c)
+{
+  if (c->world == 1) return GPSS_OK;
+  const long ld = c->n_pad;
+  std::vector<int> b;
+  balanced_rows(c->n_pad, c->world, 0, b);
+  size_t need = 0;
+  for (int k = 0; k < c->world; k++) need = std::max(need, (size_t)(b[k + 1] - b[k]) * (size_t)(c->n_pad - b[k]));
+  RET(ensure_stage(c, need));
+  for (int k = 0; k < c->world; k++) {
+    const long rows = b[k + 1] - b[k], cols = c->n_pad - b[k];
+    if (rows <= 0) continue;
+    double* slice = c->Um + (long)b[k] * ld + b[k];
+    if (k == c->rank) { pack_kernel<<<1184, 256, 0, c->st>>>(c->stage, slice, ld, rows, cols); c->launches++; }
+    NC(g_nccl.Broadcast(c->stage, c->stage, (size_t)rows * cols, ncclDouble, k, c->comm, c->st));
+    if (k != c->rank) { unpack_kernel<<<1184, 256, 0, c->st>>>(slice, ld, c->stage, rows, cols); c->launches++; }
+  }
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+// Q (lower) = U U^T = B^-1; a rank computes the rows [qrow0, qrow1) of its balanced slice (all rows when alone)
 static int lauum_lower(gpss_ctx* c)
 {
   const long ld = c->n_pad;
-  GemmArgs g = gemm_args(c->Um, ld, c->Um, ld, c->Qm, ld, c->n_pad, c->n_pad, c->n_pad);
-  g.lower_only = 1; g.kbeg_row = 1;
+  const int q0 = c->qrow0, q1 = c->qrow1;
+  if (q1 <= q0) return GPSS_OK;
+  GemmArgs g = gemm_args(c->Um + q0, ld, c->Um, ld, c->Qm + q0, ld, q1 - q0, q1, c->n_pad);
+  g.lower_only = 1; g.kbeg_row = 1; g.krow_off = q0; g.grow0 = q0; g.gcol0 = 0;
   return gemm(c, g);
 }
 
@@ -473,6 +626,10 @@ static int ensure_U(gpss_ctx* c)
     PhaseTimer t(c, 3);
     RET(trtri_upper(c));
   }
+  {
+    PhaseTimer t(c, 8);
+    RET(allgather_U(c));
+  }
   c->have_U = true;
   return GPSS_OK;
 }
@@ -503,6 +660,8 @@ int gpss_destroy(gpss_handle c)
   for (auto b : bufs) if (*b) cudaFree(*b);
   if (c->dP) cudaFree(c->dP);
   if (c->dflag) cudaFree(c->dflag);
+  if (c->stage) cudaFree(c->stage);
+  if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
   if (c->ev_call[0]) cudaEventDestroy(c->ev_call[0]);
@@ -544,6 +703,8 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   c->n = n;
   c->n_pad = ((n + NB - 1) / NB) * NB;
   c->nblk = c->n_pad / NB;
+  c->urow0 = c->qrow0 = 0;
+  c->urow1 = c->qrow1 = c->n_pad;
   memset(c->phase_ms, 0, sizeof c->phase_ms);
   const size_t np = c->n_pad;
   auto fail = [&](int code) { gpss_destroy(c); return code; };
@@ -623,20 +784,25 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
     RET(lauum_lower(c));
     c->qstate = Q_IS_BINV;
   }
-  const long nblocks = (long)c->nblk * c->nblk;
+  const int tm0 = c->qrow0 / NB, ntm = (c->qrow1 - c->qrow0) / NB;
+  const long nblocks = (long)ntm * c->nblk;
   if (c->partial_blocks < nblocks) {
     if (c->partial) cudaFree(c->partial);
     c->partial = nullptr;
-    CU(cudaMalloc(&c->partial, sizeof(double) * nblocks * NGRAD));
+    CU(cudaMalloc(&c->partial, sizeof(double) * (nblocks > 0 ? nblocks : 1) * NGRAD));
     c->partial_blocks = nblocks;
   }
   {
     PhaseTimer t(c, 5);
-    grad_pass_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Qm, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
-                                                              c->dP, c->partial);
+    if (ntm > 0) {
+      grad_pass_kernel<<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
+                                                             c->dP, c->partial, tm0);
+      c->launches++;
+    }
     sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);
-    c->launches += 2;
+    c->launches++;
     CU(cudaGetLastError());
+    if (c->world > 1) NC(g_nccl.AllReduce(c->red + 8, c->red + 8, NGRAD, ncclDouble, ncclSum, c->comm, c->st));
   }
   double red[NGRAD];
   CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
@@ -663,6 +829,49 @@ int gpss_get_yhat(gpss_handle c, double* yhat)
   CU(cudaMemcpyAsync(yhat, c->fvec, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   return c->chol_fail ? GPSS_NOT_POSDEF : GPSS_OK;
+}
+
+// --- distributed evaluation: one process per GPU, NCCL over NVLink ----------------------------------------------
+int gpss_nccl_unique_id(void* id128)
+{
+  if (!id128) return fail_arg("gpss_nccl_unique_id: null");
+  RET(nccl_load());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return GPSS_OK;
+}
+
+int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
+{
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail_arg("gpss_dist_init: bad argument");
+  if (c->comm) return fail_arg("gpss_dist_init: already initialised");
+  CU(cudaSetDevice(c->device));
+  if (world == 1) return GPSS_OK;
+  RET(nccl_load());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  std::vector<int> b;
+  balanced_rows(c->n_pad, world, 0, b);
+  c->urow0 = b[rank]; c->urow1 = b[rank + 1];
+  balanced_rows(c->n_pad, world, 1, b);
+  c->qrow0 = b[rank]; c->qrow1 = b[rank + 1];
+  c->have_factor = c->have_alpha = c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_dist_partition(int n_pad, int world, int kind, int* bounds)
+{
+  if (!bounds || world < 1 || n_pad < NB || n_pad % NB || (kind != 0 && kind != 1)) return fail_arg("gpss_dist_partition: bad argument");
+  std::vector<int> b;
+  balanced_rows(n_pad, world, kind, b);
+  for (int k = 0; k <= world; k++) bounds[k] = b[k];
+  return GPSS_OK;
 }
 
 // --- prediction ---------------------------------------------------------------------------------

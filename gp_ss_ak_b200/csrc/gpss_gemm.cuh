@@ -32,6 +32,7 @@ struct GemmArgs {
   int lower_only;                // skip tiles that lie entirely above the diagonal of the GLOBAL matrix
   int grow0, gcol0;              // global (row, col) of C(0,0), used by lower_only
   int kbeg_row;                  // k starts at the tile's first row   (A upper-triangular in (row,k))
+  int krow_off;                  // global row of A(0,.) / C(0,.) when the operands are a row slice (added to the tile row for kbeg_row / kend_row)
   int kend_row;                  // k ends   at the tile's last row+1  (A lower-triangular in (row,k))
   int kend_col;                  // k ends   at the tile's last col+1  (B lower-triangular in (col,k))
   int rev_order;                 // schedule tiles with the longest k-range first
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_kernel(const 
   if (g.lower_only && (g.gcol0 + col0) > (g.grow0 + row0 + BM - 1)) return;
 
   int kbeg = 0, kend = g.K;
-  if (g.kbeg_row) kbeg = row0;
-  if (g.kend_row) kend = min(kend, row0 + BM);
+  if (g.kbeg_row) kbeg = g.krow_off + row0;
+  if (g.kend_row) kend = min(kend, g.krow_off + row0 + BM);
   if (g.kend_col) kend = min(kend, col0 + BN);
   kbeg = (kbeg / BK) * BK;
   const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   if (g.lower_only && (g.gcol0 + col0) > (g.grow0 + row0 + BM - 1)) return;
 
   int kbeg = 0, kend = g.K;
-  if (g.kbeg_row) kbeg = row0;
-  if (g.kend_row) kend = min(kend, row0 + BM);
+  if (g.kbeg_row) kbeg = g.krow_off + row0;
+  if (g.kend_row) kend = min(kend, g.krow_off + row0 + BM);
   if (g.kend_col) kend = min(kend, col0 + BN);
   kbeg = (kbeg / BK) * BK;
   const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;

@@ -546,10 +546,11 @@ constexpr int NGRAD = 12;
 
 __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict__ Qm, long ld, const double* __restrict__ zs, long ldz,
                                                         const double* __restrict__ xs, long ldx, const double* __restrict__ alpha,
-                                                        int n, const DevParams* __restrict__ Pp, double* __restrict__ partial)
+                                                        int n, const DevParams* __restrict__ Pp, double* __restrict__ partial, int tm0)
 {
-  const int tm = blockIdx.x, tn = blockIdx.y;
-  double* out = partial + ((long)tn * gridDim.x + tm) * NGRAD;
+  // tile rows tm0 .. tm0 + gridDim.x - 1 (a rank's slice of B^-1 when the evaluation is distributed), all tile columns
+  const int tm = tm0 + blockIdx.x, tn = blockIdx.y;
+  double* out = partial + ((long)tn * gridDim.x + blockIdx.x) * NGRAD;
   if (tn > tm) { if (threadIdx.x < NGRAD) out[threadIdx.x] = 0.0; return; }
   __shared__ double cz[4][NB], cx[3][NB], ca[NB];
   __shared__ DevParams P;
@@ -669,6 +670,20 @@ __global__ void __launch_bounds__(256) transpose_kernel(double* __restrict__ out
   for (int r = ty; r < 32; r += 8) t[r][tx] = zero ? 0.0 : in[(long)(bj + r) * ldi + bi + tx];   // in(bi+tx, bj+r)
   __syncthreads();
   for (int r = ty; r < 32; r += 8) out[(long)(bi + r) * ldo + bj + tx] = t[tx][r];               // out(bj+tx, bi+r) = in(bi+r, bj+tx)
+}
+
+// dst (rows x cols, contiguous) <- src (leading dimension ld), and back: staging of strided sub-matrices for NCCL
+__global__ void pack_kernel(double* __restrict__ dst, const double* __restrict__ src, long ld, long rows, long cols)
+{
+  const long total = rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    dst[idx] = src[(idx / rows) * ld + (idx % rows)];
+}
+__global__ void unpack_kernel(double* __restrict__ dst, long ld, const double* __restrict__ src, long rows, long cols)
+{
+  const long total = rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    dst[(idx / rows) * ld + (idx % rows)] = src[idx];
 }
 
 __global__ void fill_kernel(double* __restrict__ p, long count, double v)

@@ -64,6 +64,19 @@ int gpss_get_alpha(gpss_handle h, double* alpha);
 /* yhat = K*alpha as logLikelihood leaves it (GP_Utils.cpp:1147-1148), n doubles. */
 int gpss_get_yhat(gpss_handle h, double* yhat);
 
+/* distributed evaluation ---------------------------------------------------------------------------- */
+/* One process per GPU.  After gpss_dist_init every rank holds a handle over the SAME data and gpss_set_theta /
+ * gpss_nlml / gpss_nlml_grad / gpss_predict* become COLLECTIVE calls: all ranks must make them in the same order with
+ * the same theta, and all receive the same results.  Layout: 512-wide block columns of the
+ * Cholesky factor are owned round-robin, the owner factors its panel and broadcasts it (ncclBroadcast over NVLink),
+ * every rank updates only its own block columns; L^-T is computed in balanced row slices without communication and
+ * gathered once; B^-1 and the gradient reductions are split by rows and summed with one small ncclAllReduce.
+ * The reference has no counterpart (single process, single thread). */
+int gpss_nccl_unique_id(void* id128);                           /* rank 0 creates it, the caller distributes the 128 bytes */
+int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
+/* The balanced row partitions used above (kind 0: rows of L^-T, kind 1: rows of B^-1): bounds[0..world], multiples of 128. */
+int gpss_dist_partition(int n_pad, int world, int kind, int* bounds);
+
 /* prediction --------------------------------------------------------------------------------------- */
 /* GP_utils::Calc_Out / posteriorMeanVar (GP_Utils.cpp:159-178, 1016-1041): predictive mean and variance
  * of m standardised test points EXACTLY as the reference returns them, i.e. including its post-processing of the
