@@ -8,14 +8,18 @@ not fit in the 126 MB L2, so no L2 flush is needed between iterations.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--n 50000] [--impl reference]
 
-N > 1 (launched by torchrun, one rank per GPU): the evaluation is not yet partitioned across GPUs in this
-round, so every rank runs an independent replica on its own theta probes ("replicas only", DESIGN.md
-section 6); value = evaluations of all ranks / max-over-ranks time, scaling "weak".
+N > 1 (launched by torchrun, one rank per GPU): ONE evaluation is partitioned over all GPUs (DESIGN.md
+section 7: block-column-cyclic Cholesky with an NCCL panel broadcast, row-sliced inverse, all-reduced
+gradient partials); value = evaluations / max-over-ranks device time, scaling "strong".  --mode replicas
+runs one independent evaluation stream per GPU instead (weak scaling, no collective).
+The line also carries the prediction leg (metric iii): mean + variance of --pred-m block-model centroids
+per GPU against the same n-point model, test points split over the GPUs.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_HEADLINE = 50000
+GEMM_TRAFFIC_NOTE = None              # dram bytes per launch of the dominant kernel from profiles/ (ncu --set full), when captured
 FP64_PEAK_FALLBACK_TFLOPS = 37.13   # profiles/r01_fp64_peak_microbench.txt (DMMA.8x8x4 register loop on this pool's B200)
 
 
@@ -141,7 +146,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=N_HEADLINE)
     ap.add_argument("--impl", default="gpss")
+    ap.add_argument("--mode", default="distributed", choices=["distributed", "replicas"],
+                    help="N > 1: one evaluation partitioned over all GPUs (default), or one independent evaluation stream per GPU")
     ap.add_argument("--cpu-n", type=int, default=1500, help="sample size of the CPU baseline / reference-arm evaluation")
+    ap.add_argument("--pred-m", type=int, default=32768, help="test points PER GPU of the prediction leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -163,6 +171,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    distributed = world > 1 and args.mode == "distributed"
+    # distributed: every rank holds the SAME data and the same theta sequence (one evaluation spread over all GPUs);
+    # replicas: every rank has its own data set and theta sequence.
+    stream_id = 0 if (distributed or world == 1) else rank
 
     def barrier():
         if world > 1:
@@ -170,11 +182,15 @@ def main():
         torch.cuda.synchronize()
 
     n = args.n
-    X, y = datagen.drillholes(n, seed=rank)
-    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    X, y = datagen.drillholes(n, seed=stream_id)
+    Xs, ys, std_params = datagen.standardise_symmetric(X, y)
     Xf = np.asfortranarray(Xs)
     model = G.GpssModel(Xf, ys, device=local_rank)
     n_pad = model.padded_n()
+    if distributed:
+        ids = [G.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        model.dist_init(rank, world, ids[0])
 
     def checked_eval():
         """One Grad_Values; a NaN (Cholesky failure path) would skip trtri/lauum and fake the timing, so it is fatal."""
@@ -185,7 +201,7 @@ def main():
 
     # ---- warm-up (>= 3): also allocates U / Q and pages the kernels in ----
     for k in range(args.warmup):
-        model.set_theta(theta_probe(rank * 7919 + k))
+        model.set_theta(theta_probe(stream_id * 7919 + k))
         checked_eval()
 
     # ---- timed region 1: device-resident (`value`) ----
@@ -196,7 +212,7 @@ def main():
     dev_ms = []
     t0 = time.perf_counter()
     for k in range(args.steps):
-        model.set_theta(theta_probe(rank * 7919 + 100 + k))
+        model.set_theta(theta_probe(stream_id * 7919 + 100 + k))
         L, g = checked_eval()
         dev_ms.append(model.last_call_ms())      # CUDA events on the stream the kernels are launched on
     barrier()
@@ -209,7 +225,7 @@ def main():
     t1 = time.perf_counter()
     for k in range(args.steps):
         model.set_data(Xf, ys)                    # host -> device copy of this step's inputs
-        model.set_theta(theta_probe(rank * 7919 + 200 + k))
+        model.set_theta(theta_probe(stream_id * 7919 + 200 + k))
         L, g = checked_eval()                     # device -> host read of value + g[10]
     barrier()
     wall_e2e = time.perf_counter() - t1
@@ -218,12 +234,13 @@ def main():
 
     # ---- roofline of the dominant kernel (DMMA GEMM-NT) from a profiled evaluation ----
     model.set_profiling(True)
-    model.set_theta(theta_probe(rank * 7919 + 300))
+    model.set_theta(theta_probe(stream_id * 7919 + 300))
     checked_eval()
     ph = model.phase_ms()
     model.set_profiling(False)
-    gemm_ms = float(ph[1] + ph[3] + ph[4])        # potrf + trtri + lauum phases: >99% of it inside gemm_nt_kernel
-    alg_flops = float(n_pad) ** 3                 # n^3/3 each
+    gemm_ms = float(ph[1] + ph[3] + ph[4])        # potrf + trtri + lauum phases: >99% of it inside gemm_nt_ws_kernel
+    share = world if distributed else 1
+    alg_flops = float(n_pad) ** 3 / share         # n^3/3 each; per GPU when the evaluation is partitioned
     try:
         peak = G.measure_fp64_peak(local_rank)
         peak_src = "DMMA.8x8x4 register-loop micro-peak measured live by gpss_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)"
@@ -232,38 +249,84 @@ def main():
         peak_src = "profiles/r01_fp64_peak_microbench.txt"
     achieved = alg_flops / (gemm_ms * 1e-3) * 1e-12
 
+    # ---- prediction leg (BASELINE metric iii): mean + variance of block-model centroids, test points split over the GPUs,
+    #      L / alpha replicated; host buffers in, host buffers out (the public call), device time from the handle's events ----
+    pred = None
+    if args.pred_m > 0:
+        m_total = args.pred_m * world
+        side = int(round(m_total ** (1.0 / 3.0))) + 1
+        grid = datagen.block_model(side, side, side, X.min(axis=0), X.max(axis=0))[:m_total]
+        Xt = np.asfortranarray((grid - std_params[1:, 0]) / std_params[1:, 1])
+        sums = np.array([math.fsum(Xt[:, j]) for j in range(3)])
+        lo, hi = rank * args.pred_m, (rank + 1) * args.pred_m
+        shard = np.asfortranarray(Xt[lo:hi])
+        model.predict_shard(m_total, sums, shard[:8192])            # warm-up: builds W = L^-1, allocates the batch buffers
+        barrier()
+        tp0 = time.perf_counter()
+        mu_s, var_s = model.predict_shard(m_total, sums, shard)
+        t_pred_dev = model.last_call_ms() * 1e-3
+        barrier()
+        t_pred_wall = time.perf_counter() - tp0
+        if not (np.all(np.isfinite(mu_s)) and np.all(np.isfinite(var_s))):
+            raise SystemExit("bench.py: non-finite prediction")
+        pred = [t_pred_dev, t_pred_wall]
+
     # ---- max over ranks ----
     if world > 1:
-        t = torch.tensor([t_dev, wall, wall_e2e], device="cuda", dtype=torch.float64)
+        vals = [t_dev, wall, wall_e2e, gemm_ms] + (pred or [0.0, 0.0])
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, wall, wall_e2e = (float(v) for v in t.cpu())
+        t_dev, wall, wall_e2e, gemm_ms_max, p0, p1 = (float(v) for v in t.cpu())
+        if pred:
+            pred = [p0, p1]
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
 
     if rank == 0:
-        total_evals = args.steps * world
+        total_evals = args.steps * (1 if distributed else world)
         value = total_evals / t_dev
         e2e_value = total_evals / wall_e2e
+        if world == 1:
+            par = "single GPU"
+        elif distributed:
+            par = ("one evaluation over %d GPUs: 512-wide block columns of the Cholesky factor owned round-robin, NCCL panel broadcast, "
+                   "row-sliced triangular inverse / B^-1, all-reduced gradient partials" % world)
+        else:
+            par = "replicas x%d (independent evaluations)" % world
         line = {
             "metric": "ExpAns LML+grad evals/s at n=%dk" % (n // 1000), "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d, theta differs every step"
                                    % n, "n": n, "n_pad": n_pad, "l2_policy": "inputs larger than L2 (K, L, B^-1 = %.1f GB each)"
-                                   % (n_pad * n_pad * 8 / 1e9), "parallelism": "replicas x%d" % world if world > 1 else "single GPU"},
+                                   % (n_pad * n_pad * 8 / 1e9), "parallelism": par},
             "wall_ms_per_step": wall / args.steps * 1e3,
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(n * 4 * 8 + 80),
-                    "d2h_bytes_per_step": 88},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(n * 4 * 8 + 80) * (world if world > 1 else 1),
+                    "d2h_bytes_per_step": 88 * (world if world > 1 else 1)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
+                         "traffic": GEMM_TRAFFIC_NOTE,
+                         "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
                          "peak_source": peak_src,
-                         "note": "achieved = n_pad^3 algorithmic flops (potrf+trtri+lauum) / device time of those phases"},
-            "phases_ms": {"kbuild": ph[0], "potrf": ph[1], "solve_objective": ph[2], "trtri": ph[3], "lauum": ph[4], "grad_pass": ph[5]},
+                         "note": "achieved = n_pad^3%s algorithmic flops (potrf+trtri+lauum) / device time of those phases on rank 0"
+                                 % (" / %d GPUs" % world if distributed else "")},
+            "phases_ms": {"kbuild": ph[0], "potrf": ph[1], "solve_objective": ph[2], "trtri": ph[3], "lauum": ph[4], "grad_pass": ph[5],
+                          "gather_U": ph[8]},
             "cholesky_tflops": (float(n_pad) ** 3 / 3) / (ph[1] * 1e-3) * 1e-12,
         }
+        if pred:
+            m_total = args.pred_m * world
+            flop_pt = float(n_pad) ** 2       # one triangular solve per point, n^2/2 FMA
+            line["predict"] = {"metric": "test predictions/s (mean + variance) vs the n=%d model" % n, "value": m_total / pred[0],
+                               "unit": "preds/s", "m_total": m_total, "m_per_gpu": args.pred_m, "device_ms": pred[0] * 1e3,
+                               "e2e": {"value": m_total / pred[1], "unit": "preds/s", "h2d_bytes": 24 * m_total, "d2h_bytes": 16 * m_total},
+                               "roofline": {"bound": "tensor", "achieved": m_total / world * flop_pt / pred[0] * 1e-12, "peak": peak,
+                                            "unit": "TFLOP/s", "frac": m_total / world * flop_pt / pred[0] * 1e-12 / peak,
+                                            "note": "n_pad^2 flop per test point (triangular k-range of W = L^-1), per GPU"},
+                               "sharding": "test points split over %d GPUs, L / alpha replicated" % world}
         if not args.no_cpu_baseline:
             cores = os.cpu_count()
             secs, kind = cpu_reference_times(args.cpu_n, 1, 3)

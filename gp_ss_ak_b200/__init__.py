@@ -60,6 +60,7 @@ def load_library():
         "gpss_nccl_unique_id": (I, [ctypes.c_void_p]),
         "gpss_dist_init": (I, [H, I, I, ctypes.c_void_p]),
         "gpss_dist_partition": (I, [I, I, I, ctypes.POINTER(I)]),
+        "gpss_dist_potrf_schedule": (I, [I, I, I, ctypes.POINTER(I), I, ctypes.POINTER(I)]),
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
         "gpss_var_postprocess": (I, [L, D, P]),
@@ -231,6 +232,16 @@ def dist_partition(n_pad, world, kind):
     b = (ctypes.c_int * (world + 1))()
     _check(load_library().gpss_dist_partition(n_pad, world, kind, b))
     return list(b)
+
+
+def dist_potrf_schedule(nblk, world, rank):
+    """[(kind, col, first_panel, panel_count, root, stream), ...] executed by `rank` (host logic only)."""
+    cnt = ctypes.c_int(0)
+    lib = load_library()
+    _check(lib.gpss_dist_potrf_schedule(nblk, world, rank, None, 0, ctypes.byref(cnt)))
+    buf = (ctypes.c_int * (6 * cnt.value))()
+    _check(lib.gpss_dist_potrf_schedule(nblk, world, rank, buf, cnt.value, ctypes.byref(cnt)))
+    return [tuple(buf[6 * i:6 * i + 6]) for i in range(cnt.value)]
 
 
 def measure_fp64_peak(device=0):

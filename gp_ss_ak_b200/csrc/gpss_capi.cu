@@ -106,6 +106,7 @@ struct gpss_ctx {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
+  double* Tsplit = nullptr; size_t Tsplit_cap = 0;             // split-k partial products of the row-sliced inverse
   int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
   int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
   // host state
@@ -143,7 +144,8 @@ static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
   GemmArgs ga = g;
   ga.mt = g.M / T::BM;
   ga.nt = g.N / T::BN;
-  gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
+  const int parts = ga.ksplit > 1 ? ga.ksplit : 1;
+  gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt * parts), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
   c->launches++;
   CU(cudaGetLastError());
   return GPSS_OK;
@@ -263,6 +265,38 @@ static void balanced_rows(int n_pad, int world, int kind, std::vector<int>& boun
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The distributed Cholesky as a per-rank list of operations (pure host logic; gpss_dist_potrf_schedule exposes it so the
+// CPU tests can replay all ranks and check that every block column sees every earlier panel exactly once, in an order
+// the broadcasts make possible).  Block column j (owner j % P) receives, all on ONE low-priority side stream (they
+// update the same tiles, so they serialise anyway):
+//     chunk A(j):   panels 0 .. j-P        one long-k GEMM, issued as soon as the owner has factored its previous column
+//     single(j,t):  panel t, j-P < t < j-1 (k = NBO), issued when panel t arrives
+// and on the main stream U2(j) = panel j-1, the panel factorisation and the broadcast.  A rank therefore always has
+// about P panel periods of bulk work queued behind the critical path instead of one.
+// ---------------------------------------------------------------------------------------------------
+enum { DIST_WAIT_SIDE = 0, DIST_UPDATE_MAIN = 1, DIST_FACTOR = 2, DIST_BCAST = 3, DIST_UPDATE_SIDE = 4 };
+struct DistOp { int kind, col, pbeg, pcnt, root, stream; };   // update ops apply panels pbeg .. pbeg+pcnt-1 to block column col
+static void dist_potrf_schedule(int nblk_o, int P, int me, std::vector<DistOp>& ops)
+{
+  ops.clear();
+  for (int t = 0; t < nblk_o; t++) {
+    const bool mine = (t % P) == me;
+    if (mine) {
+      if (t >= 2) ops.push_back({DIST_WAIT_SIDE, t, 0, 0, 0, 0});
+      if (t >= 1) ops.push_back({DIST_UPDATE_MAIN, t, P == 1 ? 0 : t - 1, P == 1 ? t : 1, 0, 0});   // alone: plain left-looking
+      ops.push_back({DIST_FACTOR, t, 0, 0, 0, 0});
+    }
+    ops.push_back({DIST_BCAST, t, 0, 0, t % P, 0});
+    int j = t + ((me - t) % P + P) % P;        // my next block column after t
+    if (j == t) j = t + P;
+    if (j >= nblk_o || t >= j - 1) continue;   // panel j-1 is U2(j)
+    const int stream = (j / P) & 1;
+    if (mine) ops.push_back({DIST_UPDATE_SIDE, j, 0, t + 1, 0, stream});     // chunk A
+    else ops.push_back({DIST_UPDATE_SIDE, j, t, 1, 0, stream});              // one panel
+  }
+}
+
 // One outer panel: factor the NBO-wide block column starting at K0 (all rows below), 128 columns at a time.
 static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
 {
@@ -325,44 +359,73 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
     return gemm_ws_on(c, g, stream);
   };
+  if (P > 1) {
+    std::vector<DistOp> ops;
+    dist_potrf_schedule(nblk_o, P, me, ops);
+    for (const DistOp& op : ops) {
+      const int T0 = op.col * NBO;
+      const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+      switch (op.kind) {
+        case DIST_WAIT_SIDE:                                               // every side-stream update of my column
+          CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * op.col + 1], 0));
+          break;
+        case DIST_UPDATE_MAIN:                                             // U2: the panel just received, on the critical path
+          RET(update(T0, nbT, op.pbeg * NBO, op.pcnt * NBO, c->st));
+          break;
+        case DIST_FACTOR:
+          RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+          break;
+        case DIST_BCAST: {
+          // the owner's finished block column (+ its diagonal inverses and log-dets) goes to every rank: after the loop L,
+          // Winv and logdet_parts are replicated.  One NCCL broadcast per panel (<= 205 MB at n = 50k), on the main stream.
+          const bool mine = op.root == me;
+          const long rows = n_pad - T0;
+          const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
+          double* Wt = Winv + (size_t)(T0 / NB) * NB * NB;
+          if (mine) {
+            pack_kernel<<<592, 256, 0, c->st>>>(c->stage, A + (long)T0 * ld + T0, ld, rows, nbT);
+            CU(cudaMemcpyAsync(c->stage + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            c->launches++;
+          }
+          NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, op.root, c->comm, c->st));
+          if (!mine) {
+            unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
+            CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            c->launches++;
+          }
+          CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));            // panel op.col is complete on this rank
+          break;
+        }
+        case DIST_UPDATE_SIDE: {                                           // look-ahead: panels pbeg .. pbeg+pcnt-1 -> my column
+          cudaStream_t side = op.stream ? c->st2 : c->st3;
+          CU(cudaStreamWaitEvent(side, c->ev_pool[2 * (op.pbeg + op.pcnt - 1)], 0));
+          int klen = op.pcnt * NBO;
+          if (op.pbeg * NBO + klen > n_pad) klen = n_pad - op.pbeg * NBO;
+          RET(update(T0, nbT, op.pbeg * NBO, klen, side));
+          CU(cudaEventRecord(c->ev_pool[2 * op.col + 1], side));
+          break;
+        }
+      }
+    }
+  } else
   for (int t = 0; t < nblk_o; t++) {
     const int T0 = t * NBO;
     const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-    const bool mine = (t % P) == me;
     if (!la) {
       if (t >= 1) RET(update(T0, nbT, 0, T0, c->st));
       RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
       continue;
     }
     cudaEvent_t evP = c->ev_pool[2 * t], evU = c->ev_pool[2 * t + 1];
-    if (mine) {
-      if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));             // U1(t) was issued on a side stream below
-      if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));         // U2(t)
-      RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
-    }
-    if (P > 1) {
-      // the owner's finished block column (+ its diagonal inverses and log-dets) goes to every rank: after the loop L,
-      // Winv and logdet_parts are replicated.  One NCCL broadcast per panel (<= 205 MB at n = 50k), on the main stream.
-      const long rows = n_pad - T0;
-      const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
-      double* Wt = Winv + (size_t)(T0 / NB) * NB * NB;
-      if (mine) {
-        pack_kernel<<<592, 256, 0, c->st>>>(c->stage, A + (long)T0 * ld + T0, ld, rows, nbT);
-        CU(cudaMemcpyAsync(c->stage + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        c->launches++;
-      }
-      NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, t % P, c->comm, c->st));
-      if (!mine) {
-        unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
-        CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        c->launches++;
-      }
-    }
-    CU(cudaEventRecord(evP, c->st));                                   // panel t is complete on this rank
-    // issue U1(t+1) = panels 0..t-1 applied to block column t+1 if it is mine; it must only wait for panel t-1
-    if (t + 1 < nblk_o && t >= 1 && ((t + 1) % P) == me) {
+    if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
+    if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
+    RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+    CU(cudaEventRecord(evP, c->st));
+    // issue U1(t+1) = panels 0..t-1 applied to block column t+1; needs panel t-1 (complete: main stream order) --
+    // here, right after panel t was ENQUEUED, the side stream must only wait for panel t-1.
+    if (t + 1 < nblk_o && t >= 1) {
       const int T1 = T0 + NBO;
       const int nb1 = (n_pad - T1 < NBO) ? (n_pad - T1) : NBO;
       cudaStream_t side = (t & 1) ? c->st2 : c->st3;
@@ -400,6 +463,23 @@ static void destroy_streams(gpss_ctx* c)
   if (c->st) cudaStreamDestroy(c->st);
   c->ev_main = c->ev_side = nullptr;
   c->st = c->st2 = c->st3 = nullptr;
+}
+
+// Number of k-parts for a GEMM of `tiles` output tiles on 2 x 148 CTA slots: the smallest S whose CTA count fills
+// whole waves best, subject to parts of >= 2048 in k and to the capacity of the partial-product buffer.
+static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_doubles)
+{
+  const int slots = 296;
+  if (tiles <= 0 || tiles >= 4 * slots) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= 8; S++) {
+    if (S > 1 && (klen / S < 2048 || (size_t)part_doubles * S > cap_doubles)) break;
+    const int ctas = tiles * S;
+    const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = S; }
+  }
+  return best;
 }
 
 // U = L^-T (upper), block-column left-looking; only NT products (see gpss_gemm.cuh header):
@@ -462,7 +542,21 @@ static int trtri_upper(gpss_ctx* c)
     // (3) T[ra:rb] = U[ra:rb, 0:J0] * L[Jblk, 0:J0]^T      (k starts at each tile's own row: U is upper triangular)
     GemmArgs g = gemm_args(U + ra, ld, L + J0, ld, c->Tpanel + ra, ld, rb - ra, nbj, J0);
     g.kbeg_row = 1; g.krow_off = ra;
-    RET(gemm_ws_on(c, g, c->st2));
+    // A row slice has few tiles per step (rank 0 of 8 at n = 50k: 17 x 8 = 136 for 296 CTA slots) and the steps are
+    // sequential, so a distributed rank cuts the long k-range of every tile into S parts (one CTA each), sized to
+    // fill whole waves; the parts are summed in a fixed order by split_sum_kernel.
+    int S = 1;
+    if (c->world > 1) S = pick_ksplit((rb - ra) / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0 - ra, (long)(rb - ra) * nbj, c->Tsplit_cap);
+    if (S > 1) {
+      const int rows = rb - ra;
+      g.C = c->Tsplit; g.ldc = rows; g.ksplit = S; g.csplit = (long)rows * nbj;
+      RET(gemm_ws_on(c, g, c->st2));
+      split_sum_kernel<<<296, 256, 0, c->st2>>>(c->Tpanel + ra, ld, c->Tsplit, rows, nbj, S);
+      c->launches++;
+      CU(cudaGetLastError());
+    } else {
+      RET(gemm_ws_on(c, g, c->st2));
+    }
     // (4) U[ra:rb, Jblk] = -T * W_JJ^T
     GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
     g2.negate_out = 1; g2.kend_col = 1;
@@ -559,7 +653,7 @@ static int ensure_factor(gpss_ctx* c)
   {
     PhaseTimer t(c, 0);
     transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs, ld, c->n, n_pad, c->dP);
-    kbuild_lower_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0);
+    kbuild_lower_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank, NBO / NB);
     c->launches += 2;
     CU(cudaGetLastError());
   }
@@ -622,6 +716,11 @@ static int ensure_U(gpss_ctx* c)
   RET(ensure_lazy(&c->Um, nn));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
   RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
+  if (c->world > 1 && !c->Tsplit) {
+    const size_t cap = (size_t)24576 * NBO;                    // S * rows <= 24k rows of a 512-wide block column
+    CU(cudaMalloc(&c->Tsplit, cap * sizeof(double)));
+    c->Tsplit_cap = cap;
+  }
   {
     PhaseTimer t(c, 3);
     RET(trtri_upper(c));
@@ -661,6 +760,7 @@ int gpss_destroy(gpss_handle c)
   if (c->dP) cudaFree(c->dP);
   if (c->dflag) cudaFree(c->dflag);
   if (c->stage) cudaFree(c->stage);
+  if (c->Tsplit) cudaFree(c->Tsplit);
   if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -862,6 +962,20 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
   c->qrow0 = b[rank]; c->qrow1 = b[rank + 1];
   c->have_factor = c->have_alpha = c->have_U = false;
   c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_dist_potrf_schedule(int nblk, int world, int rank, int* ops6, int cap, int* count)
+{
+  if (!count || nblk < 1 || world < 1 || rank < 0 || rank >= world || (cap > 0 && !ops6)) return fail_arg("gpss_dist_potrf_schedule: bad argument");
+  std::vector<DistOp> ops;
+  dist_potrf_schedule(nblk, world, rank, ops);
+  *count = (int)ops.size();
+  for (int i = 0; i < (int)ops.size() && i < cap; i++) {
+    const DistOp& o = ops[i];
+    const int v[6] = {o.kind, o.col, o.pbeg, o.pcnt, o.root, o.stream};
+    memcpy(ops6 + 6 * i, v, sizeof v);
+  }
   return GPSS_OK;
 }
 
@@ -1249,7 +1363,17 @@ int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A
   CU(cudaEventCreate(&e1));
   int rc;
   CU(cudaEventRecord(e0, 0));
-  if (tile == 0) rc = gemm_ws_on(&tmp, g, tmp.st); else rc = gemm_legacy_on(&tmp, g, tmp.st);
+  double* dparts = nullptr;
+  if (tile == 0) rc = gemm_ws_on(&tmp, g, tmp.st);
+  else if (tile == 1) rc = gemm_legacy_on(&tmp, g, tmp.st);
+  else {
+    // tile = S in 2..8: the split-k form used by the distributed triangular inverse (S partial products + fixed-order sum)
+    if (tile > 8 || subtract_from_C) return fail_arg("gpss_test_gemm_nt: split-k hook takes 2 <= tile <= 8 and no accumulate");
+    CU(cudaMalloc(&dparts, sizeof(double) * (size_t)M * N * tile));
+    g.C = dparts; g.ldc = M; g.ksplit = tile; g.csplit = (long)M * N;
+    rc = gemm_ws_on(&tmp, g, tmp.st);
+    split_sum_kernel<<<296, 256, 0, tmp.st>>>(dC, M, dparts, M, N, tile);
+  }
   CU(cudaEventRecord(e1, 0));
   if (rc < 0) return rc;
   CU(cudaEventSynchronize(e1));
@@ -1257,7 +1381,7 @@ int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A
   CU(cudaEventElapsedTime(&ms, e0, e1));
   if (ms_out) *ms_out = ms;
   CU(cudaMemcpy(C, dC, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToHost));
-  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dparts);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GPSS_OK;
 }

@@ -36,6 +36,8 @@ struct GemmArgs {
   int kend_row;                  // k ends   at the tile's last row+1  (A lower-triangular in (row,k))
   int kend_col;                  // k ends   at the tile's last col+1  (B lower-triangular in (col,k))
   int rev_order;                 // schedule tiles with the longest k-range first
+  int ksplit;                    // > 1: every tile's k-range is cut into ksplit equal parts, one CTA each (grid = mt*nt*ksplit);
+  long csplit;                   //      part s stores its partial product at C + s*csplit (summed by the caller, fixed order)
   int mt, nt;                    // tile counts M/BM, N/BN (filled by the launcher)
 };
 
@@ -252,10 +254,12 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * BK * (LDAS + LDBS));
   uint64_t* empty_bar = full_bar + STAGES;
 
-  int tm, tn;
+  int tm, tn, split = 0;
   {
+    int bid = blockIdx.x;
+    if (g.ksplit > 1) { const int tiles = g.mt * g.nt; split = bid / tiles; bid -= split * tiles; }
     const int per_group = GEMM_RASTER_W * g.mt;
-    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
+    const int grp = bid / per_group, rem = bid - grp * per_group;
     const int w = min(GEMM_RASTER_W, g.nt - grp * GEMM_RASTER_W);
     tm = rem / w;
     tn = grp * GEMM_RASTER_W + (rem - tm * w);
@@ -269,7 +273,13 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   if (g.kend_row) kend = min(kend, g.krow_off + row0 + BM);
   if (g.kend_col) kend = min(kend, col0 + BN);
   kbeg = (kbeg / BK) * BK;
-  const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+  int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+  if (g.ksplit > 1) {   // this CTA's share of the tile's k-steps (possibly none: it then stores the initial accumulator)
+    const int chunk = (nk + g.ksplit - 1) / g.ksplit;
+    const int first = min(nk, split * chunk);
+    nk = min(nk - first, chunk);
+    kbeg += first * BK;
+  }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   const int lr = lane >> 2, lc = lane & 3;
 
   double acc[MI][NI][2];
-  double* Cg = g.C + (long)(col0 + wn0 + 2 * lc) * g.ldc + (row0 + wm0 + lr);
+  double* Cg = g.C + (long)split * g.csplit + (long)(col0 + wn0 + 2 * lc) * g.ldc + (row0 + wm0 + lr);
   if (g.init_mode == GEMM_INIT_NEGC) {
 #pragma unroll
     for (int i = 0; i < MI; i++)

@@ -68,10 +68,14 @@ __device__ __forceinline__ double kern_val(double d2, const DevParams& P)
 }
 
 __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ Bm, long ld, const double* __restrict__ zs, long ldz,
-                                                           int n, const DevParams* __restrict__ Pp, int raw_K)
+                                                           int n, const DevParams* __restrict__ Pp, int raw_K, int own_world, int own_rank,
+                                                           int own_width)
 {
+  // own_world > 1: only the tile columns of the block columns (own_width tiles wide) this rank owns in the distributed
+  // Cholesky are built -- every other block column arrives already factored with the owner's broadcast.
   const int tm = blockIdx.x, tn = blockIdx.y;
   if (tn > tm) return;
+  if (own_world > 1 && (tn / own_width) % own_world != own_rank) return;
   __shared__ double cz[4][NB];
   __shared__ DevParams P;
   const int tid = threadIdx.x;
@@ -670,6 +674,18 @@ __global__ void __launch_bounds__(256) transpose_kernel(double* __restrict__ out
   for (int r = ty; r < 32; r += 8) t[r][tx] = zero ? 0.0 : in[(long)(bj + r) * ldi + bi + tx];   // in(bi+tx, bj+r)
   __syncthreads();
   for (int r = ty; r < 32; r += 8) out[(long)(bi + r) * ldo + bj + tx] = t[tx][r];               // out(bj+tx, bi+r) = in(bi+r, bj+tx)
+}
+
+// dst(i, j) = sum_s parts[s][i + j*rows]  (s ascending: a fixed order, so the result is reproducible run to run)
+__global__ void __launch_bounds__(256) split_sum_kernel(double* __restrict__ dst, long ld, const double* __restrict__ parts, long rows,
+                                                        long cols, int S)
+{
+  const long total = rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    double v = parts[idx];
+    for (int s = 1; s < S; s++) v += parts[(long)s * total + idx];
+    dst[(idx / rows) * ld + (idx % rows)] = v;
+  }
 }
 
 // dst (rows x cols, contiguous) <- src (leading dimension ld), and back: staging of strided sub-matrices for NCCL

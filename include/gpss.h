@@ -76,6 +76,11 @@ int gpss_nccl_unique_id(void* id128);                           /* rank 0 create
 int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
 /* The balanced row partitions used above (kind 0: rows of L^-T, kind 1: rows of B^-1): bounds[0..world], multiples of 128. */
 int gpss_dist_partition(int n_pad, int world, int kind, int* bounds);
+/* The operation list one rank executes for a factor of `nblk` 512-wide block columns (pure host logic, no device needed):
+ * 6 ints per operation {kind, column, first panel, panel count, broadcast root, side stream}; kind 0 = main stream waits
+ * for the column's look-ahead updates, 1 = update on the main stream, 2 = factor the column, 3 = broadcast it from root,
+ * 4 = look-ahead update on a side stream.  Writes min(*count, cap) operations. */
+int gpss_dist_potrf_schedule(int nblk, int world, int rank, int* ops6, int cap, int* count);
 
 /* prediction --------------------------------------------------------------------------------------- */
 /* GP_utils::Calc_Out / posteriorMeanVar (GP_Utils.cpp:159-178, 1016-1041): predictive mean and variance
@@ -122,7 +127,9 @@ int gpss_padded_n(gpss_handle h, int* n_pad);
 
 /* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
 /* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised
- * bulk-copy/mbarrier kernel every product of the path uses, 1 = the legacy cp.async kernel (A/B baseline). */
+ * bulk-copy/mbarrier kernel every product of the path uses, 1 = the legacy cp.async kernel (A/B baseline),
+ * 2..8 = the same kernel in its split-k form (that many partial products summed in a fixed order), which the
+ * distributed triangular inverse uses to fill the machine from a narrow row slice. */
 int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C,
                       int subtract_from_C, double* ms_out);
 /* In-place blocked Cholesky of a host n x n SPD matrix (lower), through the full potrf driver. */

@@ -1,0 +1,121 @@
+"""CPU tests of the multi-GPU host logic (no device): the distributed Cholesky's per-rank operation lists replayed for all
+ranks, the balanced row partitions, and -- as a real world_size-2 `gloo` job -- the shard / gather / post-process flow
+of sharded prediction and the numerics of the block-column algorithm itself (numpy stands in for the DMMA kernels)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WAIT_SIDE, UPDATE_MAIN, FACTOR, BCAST, UPDATE_SIDE = range(5)
+
+
+def _replay(gpss, nblk, world):
+    """Execute the op lists of all ranks in lock step on the broadcasts; returns per-rank, per-column applied panels."""
+    ops = [gpss.dist_potrf_schedule(nblk, world, r) for r in range(world)]
+    pos = [0] * world
+    have = [set() for _ in range(world)]                  # panels complete on the rank
+    applied = [dict() for _ in range(world)]              # column -> list of panels applied (own columns only)
+    side_pending = [dict() for _ in range(world)]         # column -> panels applied on a side stream, not yet waited for
+    factored = [set() for _ in range(world)]
+    bcasts = 0
+    while any(pos[r] < len(ops[r]) for r in range(world)):
+        progressed = False
+        # run every rank up to its next broadcast
+        for r in range(world):
+            while pos[r] < len(ops[r]) and ops[r][pos[r]][0] != BCAST:
+                kind, col, pbeg, pcnt, root, stream = ops[r][pos[r]]
+                assert col % world == r, "rank %d touches column %d it does not own" % (r, col)
+                if kind == WAIT_SIDE:
+                    side_pending[r].pop(col, None)
+                elif kind in (UPDATE_MAIN, UPDATE_SIDE):
+                    panels = list(range(pbeg, pbeg + pcnt))
+                    assert all(p in have[r] for p in panels), "rank %d applies a panel it does not have yet: %r" % (r, panels)
+                    assert all(p < col for p in panels)
+                    applied[r].setdefault(col, []).extend(panels)
+                    if kind == UPDATE_SIDE:
+                        side_pending[r].setdefault(col, []).extend(panels)
+                        assert stream in (0, 1)
+                elif kind == FACTOR:
+                    assert col not in side_pending[r], "column %d factored before its side-stream updates were waited for" % col
+                    assert sorted(applied[r].get(col, [])) == list(range(col)), (r, col, applied[r].get(col))
+                    factored[r].add(col)
+                pos[r] += 1
+                progressed = True
+        # all ranks must now be at the SAME broadcast (NCCL collectives are matched by issue order)
+        heads = [ops[r][pos[r]] if pos[r] < len(ops[r]) else None for r in range(world)]
+        if all(h is None for h in heads):
+            break
+        assert all(h is not None and h[0] == BCAST for h in heads)
+        assert len({(h[1], h[4]) for h in heads}) == 1, "ranks disagree on the broadcast: %r" % (heads,)
+        col, root = heads[0][1], heads[0][4]
+        assert root == col % world and col in factored[root], "column %d broadcast before its owner factored it" % col
+        for r in range(world):
+            have[r].add(col)
+            pos[r] += 1
+        bcasts += 1
+        progressed = True
+        assert progressed
+    assert bcasts == nblk
+    for r in range(world):
+        assert have[r] == set(range(nblk))
+    return ops, applied
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("nblk", [1, 2, 5, 9, 40, 98])
+def test_distributed_cholesky_schedule_is_complete_and_ordered(gpss, nblk, world):
+    ops, applied = _replay(gpss, nblk, world)
+    for r in range(world):
+        for col, panels in applied[r].items():
+            assert len(panels) == len(set(panels)) == col            # every earlier panel exactly once
+
+
+def test_schedule_keeps_bulk_work_off_the_critical_path(gpss):
+    """At world 8 the main stream of a rank applies exactly ONE panel (k = 512) per own column; everything else is queued on
+    the side streams at least one broadcast earlier, and the long-k chunk as early as the rank's previous own column."""
+    nblk, world = 98, 8
+    for r in range(world):
+        ops = gpss.dist_potrf_schedule(nblk, world, r)
+        main_panels = sum(o[3] for o in ops if o[0] == UPDATE_MAIN)
+        own = [j for j in range(nblk) if j % world == r]
+        assert main_panels == len([j for j in own if j >= 1])
+        for i, o in enumerate(ops):
+            if o[0] == UPDATE_SIDE and o[3] > 1:                     # chunk A(j): issued right after broadcast j - world
+                assert ops[i - 1][0] == BCAST and ops[i - 1][1] == o[1] - world and o[2] == 0 and o[3] == o[1] - world + 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_balanced_row_partitions(gpss, world):
+    n_pad = 50048
+    for kind in (0, 1):
+        b = gpss.dist_partition(n_pad, world, kind)
+        assert b[0] == 0 and b[-1] == n_pad and all(x % 128 == 0 for x in b) and all(b[i] <= b[i + 1] for i in range(world))
+        x = np.array(b, dtype=float)
+        n = float(n_pad)
+        # work integrals of the two partitions (gpss_capi.cu balanced_rows): equal shares within the 128-row rounding
+        w = (n - x[:-1]) ** 3 - (n - x[1:]) ** 3 if kind == 0 else (n * x[1:] ** 2 / 2 - x[1:] ** 3 / 3) - (n * x[:-1] ** 2 / 2 - x[:-1] ** 3 / 3)
+        assert w.max() / w.mean() < 1.05
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_world2_gloo_block_column_cholesky_and_sharded_prediction(gpss):
+    """torchrun-style world_size-2 job on CPU (gloo): see tests/dist_worker.py."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py")], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
+    assert "WORKER OK" in outs[0]

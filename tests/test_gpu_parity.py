@@ -52,6 +52,18 @@ def test_gemm_nt_kernel_exact(gpss):
         assert np.array_equal(C, C0 - A @ B.T)
 
 
+def test_gemm_split_k_exact(gpss):
+    """The split-k form of the DMMA kernel (distributed triangular inverse): S partial products + fixed-order sum.
+    Small integers are exact in FP64, so any k-range bookkeeping error shows as an exact mismatch; K = 176 with S = 3, 8
+    leaves ragged and EMPTY parts (11 k-steps over 8 parts)."""
+    rng = np.random.default_rng(1)
+    for K, S in ((96, 2), (176, 3), (176, 8), (1024, 5)):
+        A = rng.integers(-8, 9, (256, K)).astype(float)
+        B = rng.integers(-8, 9, (192, K)).astype(float)
+        C, _ = gpss.test_gemm_nt(A, B, tile=S)
+        assert np.array_equal(C, A @ B.T), (K, S)
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 700, 1537])
 def test_potrf_driver(gpss, n):
     import scipy.linalg as sla
