@@ -1004,7 +1004,7 @@ static int ensure_W(gpss_ctx* c)
 }
 
 // mean and RAW variance (kD - k*' A k*, no post-processing) of one shard
-static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
+static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], long count, const double* Xs, long ldx, double* mu, double* var)
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
@@ -1041,7 +1041,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
     const int m_pad = ((mb + NB - 1) / NB) * NB;
     CU(cudaMemsetAsync(c->xt, 0, sizeof(double) * 3 * cap, c->st));
     for (int j = 0; j < 3; j++)
-      CU(cudaMemcpyAsync(c->xt + (long)j * cap, Xs + (long)j * count + off, sizeof(double) * mb, cudaMemcpyHostToDevice, c->st));
+      CU(cudaMemcpyAsync(c->xt + (long)j * cap, Xs + (long)j * ldx + off, sizeof(double) * mb, cudaMemcpyHostToDevice, c->st));
     transform_kernel<<<(m_pad + 255) / 256, 256, 0, c->st>>>(c->xt, cap, c->zt, cap, mb, m_pad, c->dP + 1);
     {
       PhaseTimer t(c, 6);
@@ -1071,7 +1071,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
 
 int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
 {
-  RET(predict_core(c, m_total, sums_total, count, Xs, mu, var));
+  RET(predict_core(c, m_total, sums_total, count, Xs, count, mu, var));
   return GPSS_OK;
 }
 
@@ -1098,7 +1098,31 @@ int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* va
   if (m < 1) return fail_arg("gpss_predict: m must be >= 1");
   double sums[3];
   seq_colsums(Xs, m, sums);
-  RET(predict_core(c, m, sums, m, Xs, mu, var));
+  if (c->world == 1) {
+    RET(predict_core(c, m, sums, m, Xs, m, mu, var));
+  } else {
+    // Distributed handle (collective call, same Xs on every rank): the test points are split over the ranks -- L and alpha
+    // are replicated -- every rank predicts rows [m r / P, m (r+1) / P) with the GLOBAL Mahalanobis centre, and the slices
+    // are exchanged with one ncclBroadcast per rank and output vector, so every rank returns the full vectors.
+    const long P = c->world;
+    const long lo = m * c->rank / P, hi = m * (c->rank + 1) / P;
+    RET(predict_core(c, m, sums, hi - lo, Xs + lo, m, mu + lo, var ? var + lo : nullptr));
+    const int nvec = var ? 2 : 1;
+    RET(ensure_stage(c, (size_t)nvec * m));
+    if (hi > lo) {
+      CU(cudaMemcpyAsync(c->stage + lo, mu + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, c->st));
+      if (var) CU(cudaMemcpyAsync(c->stage + m + lo, var + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, c->st));
+    }
+    for (long k = 0; k < P; k++) {
+      const long a = m * k / P, b = m * (k + 1) / P;
+      if (b <= a) continue;
+      for (int v = 0; v < nvec; v++)
+        NC(g_nccl.Broadcast(c->stage + v * m + a, c->stage + v * m + a, (size_t)(b - a), ncclDouble, (int)k, c->comm, c->st));
+    }
+    CU(cudaMemcpyAsync(mu, c->stage, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
+    if (var) CU(cudaMemcpyAsync(var, c->stage + m, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+  }
   if (var) return gpss_var_postprocess(m, c->theta[9], var);
   return GPSS_OK;
 }

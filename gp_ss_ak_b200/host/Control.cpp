@@ -1,5 +1,6 @@
 // See Control.h.  File:line citations are into /root/reference.
 #include "Control.h"
+#include "DistHost.h"
 
 #include <cmath>
 #include <fstream>
@@ -153,7 +154,7 @@ void Control::prepareData(mat& X, mat& y, int& Data_mode, bool& yscale, string M
     Statistics = join_horiz(Statistics, MaxData);
     Statistics = join_horiz(Statistics, MeanData);
     Statistics = join_horiz(Statistics, StData);
-    Statistics.save(ModelN + "_Statistics.txt", csv_ascii);
+    Statistics.save(gpss_host::out_path(ModelN + "_Statistics.txt"), csv_ascii);
   }
 }
 

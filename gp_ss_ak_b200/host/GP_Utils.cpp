@@ -1,5 +1,6 @@
 // See GP_Utils.h.  File:line citations are into /root/reference.
 #include "GP_Utils.h"
+#include "DistHost.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -55,8 +56,7 @@ void GP_utils::_init()
   data_stale = true;
   dirty = true;
   Chol_fail = false;
-  const char* dev = std::getenv("GPSS_DEVICE");
-  device = dev ? std::atoi(dev) : 0;
+  device = gpss_host::device();      // GPSS_DEVICE (or LOCAL_RANK in a multi-process launch), default 0
   L.zeros(1, 1);
 }
 
@@ -165,6 +165,22 @@ void GP_utils::sync_device() const
   }
   if (!handle) {
     if (gpss_create(device, n, 3, Xinp.memptr(), yTarg.memptr(), &handle) != GPSS_OK) device_failure("gpss_create");
+    if (gpss_host::world() > 1) {
+      // one process per GPU (DistHost.h): every rank holds the same data; from here on the objective / gradient /
+      // prediction calls are collective and return identical results everywhere
+      static int communicators = 0;
+      unsigned char id[128];
+      const std::string idf = gpss_host::id_file(communicators++);
+      if (gpss_host::rank() == 0) {
+        if (gpss_nccl_unique_id(id) != GPSS_OK) device_failure("gpss_nccl_unique_id");
+        if (!gpss_host::publish_id(idf, id)) { cout << "GP_utils: cannot write the rendezvous file " << idf << "\n"; exit(1); }
+      } else if (!gpss_host::fetch_id(idf, id)) {
+        cout << "GP_utils: rank 0 did not publish " << idf << "\n";
+        exit(1);
+      }
+      if (gpss_dist_init(handle, gpss_host::rank(), gpss_host::world(), id) != GPSS_OK) device_failure("gpss_dist_init");
+      if (gpss_host::rank() == 0) std::remove(idf.c_str());
+    }
     handle_n = n;
     data_stale = false;
     dirty = true;

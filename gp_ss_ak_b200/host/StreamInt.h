@@ -10,6 +10,8 @@
 #include <iostream>
 #include <string>
 
+#include "DistHost.h"
+
 class StreamIntfce {
  public:
   virtual ~StreamIntfce() {}
@@ -35,7 +37,7 @@ class StreamIntfce {
   // comment line first, then the object (StreamInt.h:102-111)
   void WFile(const std::string fileName, const std::string comment = "") const
   {
-    std::ofstream out(fileName.c_str());
+    std::ofstream out(gpss_host::out_path(fileName).c_str());
     if (!out) {
       std::cout << "The file " << fileName << " is open.\n";
       std::exit(1);

@@ -4,6 +4,7 @@
 //   gp_ss_ak [-v N] [-pm M] test  test.txt model train.txt [predictions.txt]
 // Everything numerical happens in GP_utils (device-resident); this file is argument handling and file I/O.
 #include "gp_ss_ak.h"
+#include "DistHost.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -22,6 +23,7 @@ using std::string;
 
 int main(int argc, char* argv[])
 {
+  gpss_host::silence_other_ranks();      // multi-GPU launch: rank 0 alone prints and writes files (DistHost.h)
   GP_Cntrl cmd(argc, argv);
   cmd.setFlgs(true);
   cmd.setprepM(1);          // 0: mean/std, 1: symmetric, 2: "0..1"
@@ -259,7 +261,7 @@ void GP_Cntrl::test()
   if (base.find("train")) plotName += "_train";
   if (base.find("test")) plotName += "_test";
 
-  std::ofstream outputs(PredictOut.c_str());
+  std::ofstream outputs(gpss_host::out_path(PredictOut).c_str());
   outputs << "# SampleNo, Y,  Yh, StdYh, Inputs" << "\n";
   for (uword i = 0; i < regr.n_rows; i++) {
     for (uword j = 0; j < regr.n_cols; j++) outputs << regr(i, j) << "\t";
@@ -271,7 +273,7 @@ void GP_Cntrl::test()
   const double hi = std::max(regr.col(1).max(), mat(regr.col(2) + regr.col(3)).max());
   const double lo = std::min(regr.col(1).min(), mat(regr.col(2) - regr.col(3)).min());
   const string script = plotName + "_gnu.plt";
-  std::ofstream plt(script.c_str());
+  std::ofstream plt(gpss_host::out_path(script).c_str());
   plt << "#gnuplot -persist output.plt\n set termoption enhanced\n set term wxt background rgb \"white\"\n set term pdf transparent enhanced \n ";
   plt << "set output '" + plotName + "_predict.pdf" + "'  \n";
   plt << "set style fill transparent solid 0.70 noborder\n set grid nopolar\n set key inside left top vertical Right noreverse enhanced "

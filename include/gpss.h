@@ -86,7 +86,9 @@ int gpss_dist_potrf_schedule(int nblk, int world, int rank, int* ops6, int cap, 
 /* GP_utils::Calc_Out / posteriorMeanVar (GP_Utils.cpp:159-178, 1016-1041): predictive mean and variance
  * of m standardised test points EXACTLY as the reference returns them, i.e. including its post-processing of the
  * variance vector (gpss_var_postprocess below); var may be NULL (posteriorMean, :1005-1015).
- * The Mahalanobis centre uses the training set and ALL m test points as MahaDist does (Kernel.cpp:1391). */
+ * The Mahalanobis centre uses the training set and ALL m test points as MahaDist does (Kernel.cpp:1391).
+ * On a distributed handle this is a COLLECTIVE call (same Xs on every rank): the test points are split over the ranks,
+ * L and alpha being replicated, and the slices are exchanged over NCCL so that every rank returns the full vectors. */
 int gpss_predict(gpss_handle h, long m, const double* Xs_colmajor, double* mu, double* var);
 /* One shard [first, first+count) of a test set of m_total points whose column sums are sums_total[3]: lets ranks
  * split the test points (L and alpha replicated) yet use the global centre.  var receives the RAW variance

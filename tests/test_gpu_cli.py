@@ -89,3 +89,35 @@ def test_cli_rejects_configurations_outside_the_hot_path(tmp_path):
     out = subprocess.run([CLI, "train", "-k", "RBF", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
                          stdin=subprocess.DEVNULL, cwd=tmp_path)
     assert out.returncode == 1 and "not part of the B200 hot-path build" in (out.stdout + out.stderr)
+
+
+def test_cli_two_gpu_launch_matches_single_gpu(tmp_path):
+    """Config 3 of BASELINE.json in miniature: the same LBFGS fit driven by the host CLI as one process per GPU
+    (scripts/run_dist_cli.sh, DistHost.h).  Every probe is a collective distributed evaluation, so the printed trajectory
+    and the written files must equal the single-GPU run's (rank 0 alone prints / writes).  Needs 2 devices: the driver's
+    one-GPU run skips it; `gpurun --gpus 2 -- python -m pytest tests -m gpu -k two_gpu` runs it."""
+    import gp_ss_ak_b200 as G
+    if G.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    from gp_ss_ak_b200 import datagen
+    X, y = datagen.drillholes(1500, 4)
+    datagen.write_data_file(str(tmp_path / "train.txt"), X, y)
+    Xt, yt = datagen.drillholes(300, 6)
+    datagen.write_data_file(str(tmp_path / "test.txt"), Xt, yt)
+    outs = {}
+    for tag, launcher in (("one", [CLI]), ("two", [os.path.join(ROOT, "scripts", "run_dist_cli.sh"), "2"])):
+        model = str(tmp_path / ("model_" + tag))
+        tr = subprocess.run(launcher + ["-v", "3", "-pm", "1", "train", "-k", "ExpAns", "-kn", "1", "-o", "LBFGS", "-#", "4",
+                                        str(tmp_path / "train.txt"), model], capture_output=True, text=True, stdin=subprocess.DEVNULL,
+                            cwd=tmp_path, timeout=900)
+        assert tr.returncode == 0, tr.stdout + tr.stderr
+        te = subprocess.run(launcher + ["-v", "3", "-pm", "1", "test", str(tmp_path / "test.txt"), model, str(tmp_path / "train.txt")],
+                            capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=900)
+        assert te.returncode == 0, te.stdout + te.stderr
+        outs[tag] = (tr.stdout, te.stdout, open(model).read(), _table(open(model + "_predict.txt").read()))
+    it1, it2 = _floats_after(outs["one"][0], "-logL:"), _floats_after(outs["two"][0], "-logL:")
+    assert len(it1) == len(it2) == 4
+    assert np.allclose(it1, it2, rtol=1e-9)                       # same trajectory (distributed sums differ in the last bits)
+    assert outs["one"][2].splitlines()[1:] == outs["two"][2].splitlines()[1:]     # 6-significant-digit model file: identical
+    assert np.allclose(outs["one"][3], outs["two"][3], rtol=1e-5, atol=1e-8)
+    assert outs["two"][0].count("Iteration: 1 -logL:") == 1       # only rank 0 printed
