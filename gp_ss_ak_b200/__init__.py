@@ -59,6 +59,7 @@ def load_library():
         "gpss_get_yhat": (I, [H, P]),
         "gpss_nccl_unique_id": (I, [ctypes.c_void_p]),
         "gpss_dist_init": (I, [H, I, I, ctypes.c_void_p]),
+        "gpss_create_partitioned": (I, [I, I, I, ctypes.c_void_p, I, I, P, P, ctypes.POINTER(H)]),
         "gpss_dist_partition": (I, [I, I, I, ctypes.POINTER(I)]),
         "gpss_dist_potrf_schedule": (I, [I, I, I, ctypes.POINTER(I), I, ctypes.POINTER(I)]),
         "gpss_predict": (I, [H, L, P, P, P]),
@@ -109,7 +110,9 @@ def _colmajor(X):
 class GpssModel:
     """Thin handle wrapper: one-to-one with the C ABI (see include/gpss.h for the reference citations)."""
 
-    def __init__(self, X, y, device=0):
+    def __init__(self, X, y, device=0, partitioned=None):
+        """partitioned=(rank, world, unique_id): collective constructor of a handle whose factor is stored as block
+        columns spread over the ranks (gpss_create_partitioned)."""
         lib = load_library()
         X = _colmajor(X)
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
@@ -117,7 +120,13 @@ class GpssModel:
             raise ValueError("X must be (n, d) and y (n,)")
         self.n, self.d = X.shape
         self._h = ctypes.c_void_p()
-        _check(lib.gpss_create(device, self.n, self.d, _dp(X), _dp(y), ctypes.byref(self._h)))
+        if partitioned is None:
+            _check(lib.gpss_create(device, self.n, self.d, _dp(X), _dp(y), ctypes.byref(self._h)))
+        else:
+            rank, world, uid = partitioned
+            buf = ctypes.create_string_buffer(bytes(uid), 128)
+            _check(lib.gpss_create_partitioned(device, rank, world, ctypes.cast(buf, ctypes.c_void_p), self.n, self.d, _dp(X), _dp(y),
+                                               ctypes.byref(self._h)))
         self._lib = lib
 
     def close(self):

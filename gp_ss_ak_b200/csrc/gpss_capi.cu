@@ -107,6 +107,8 @@ struct gpss_ctx {
   ncclComm_t comm = nullptr;
   double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
   double* Tsplit = nullptr; size_t Tsplit_cap = 0;             // split-k partial products of the row-sliced inverse
+  bool partitioned = false;                                    // Lm holds only my block columns, packed (n too large to replicate)
+  int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
   int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
   int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
   // host state
@@ -440,6 +442,125 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   return GPSS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PARTITIONED storage (n_pad^2 too large to replicate, e.g. n = 200 000: 320 GB): every rank keeps only the block columns
+// it owns (j % P == rank), packed side by side (40 GB per rank at n = 200 000, P = 8).  RIGHT-looking factorisation: the
+// owner factors block column t and broadcasts it; the broadcast buffer itself is the GEMM operand with which every rank
+// updates its own remaining block columns (one k = 512 DMMA launch per panel over all of them, lower-triangle tiles only
+// through the cyclic column map of gemm_nt_ws_kernel).  Look-ahead of one panel: the owner of t+1 updates that single
+// column on the high-priority stream, factors and broadcasts it while the bulk update with panel t is still running.
+// ---------------------------------------------------------------------------------------------------
+static int potrf_partitioned(gpss_ctx* c)
+{
+  const int P = c->world, me = c->rank, n_pad = c->n_pad;
+  const long ld = n_pad;
+  double* A = c->Lm;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  const size_t per = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
+  RET(ensure_stage(c, 3 * per));                                         // panels t, t-1, t-2 stay live (see the look-ahead below)
+  // update of my local block columns [q0, q0 + cnt) with panel t, which lies in its broadcast buffer (rows T0.., ld = rows)
+  auto update = [&](int t, int q0, int cnt, cudaStream_t stream) -> int {
+    if (cnt <= 0) return GPSS_OK;
+    const double* pan = c->stage + (size_t)(t % 3) * per;
+    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+    const long rows = n_pad - T0;
+    const int Rb = (q0 * P + me) * NBO;                                  // first global row (= first global column) touched
+    long ncols = (long)cnt * NBO;
+    if ((long)q0 * NBO + ncols > c->lcols) ncols = c->lcols - (long)q0 * NBO;   // ragged last block column
+    GemmArgs g = gemm_args(pan + (Rb - T0), rows, pan, rows, A + (long)q0 * NBO * ld + Rb, ld, n_pad - Rb, (int)ncols, nbT);
+    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = Rb;
+    g.cyc_P = P; g.cyc_me = me; g.cyc_w = NBO; g.cyc_lcol0 = q0 * NBO; g.cyc_boff = T0;
+    return gemm_ws_on(c, g, stream);
+  };
+  // Look-ahead: the bulk update with panel s (side stream) covers my block columns j >= s + 3 only; column j receives
+  // panels j-2 and j-1 on the MAIN stream when panel j-1 arrives.  The critical path (two k = 512 updates of one column,
+  // the panel factorisation, the broadcast) therefore waits for the bulk update that finished a whole panel period
+  // earlier (s = j - 3), never for the one in flight.
+  for (int t = 0; t < nblk_o; t++) {
+    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+    const bool mine = (t % P) == me;
+    double* buf = c->stage + (size_t)(t % 3) * per;
+    const long rows = n_pad - T0;
+    const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
+    double* Wt = c->Winv + (size_t)(T0 / NB) * NB * NB;
+    // bulk update t-3 read this buffer and was the last side-stream launch to write block column t
+    if (t >= 3) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (t - 3) + 1], 0));
+    if (mine) {
+      const int q = t / P;
+      if (t >= 2) RET(update(t - 2, q, 1, c->st));
+      if (t >= 1) RET(update(t - 1, q, 1, c->st));
+      double* Acol = A + (long)q * NBO * ld;                              // my packed copy of global block column t
+      RET(potrf_panel(c, Acol - (long)T0 * ld, ld, n_pad, T0, nbT, c->Winv, c->logdet_parts, c->dflag));   // indexes by global column
+      pack_kernel<<<592, 256, 0, c->st>>>(buf, Acol + T0, ld, rows, nbT);
+      CU(cudaMemcpyAsync(buf + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+      CU(cudaMemcpyAsync(buf + n_panel + n_w, c->logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+      c->launches++;
+    }
+    NC(g_nccl.Broadcast(buf, buf, n_panel + n_w + n_l, ncclDouble, t % P, c->comm, c->st));
+    if (!mine) {
+      CU(cudaMemcpyAsync(Wt, buf + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+      CU(cudaMemcpyAsync(c->logdet_parts + T0 / NB, buf + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    }
+    CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
+    int q0 = 0;                                                          // my first block column j >= t + 3
+    while (q0 < c->nq && q0 * P + me < t + 3) q0++;
+    CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
+    RET(update(t, q0, c->nq - q0, c->st2));
+    CU(cudaEventRecord(c->ev_pool[2 * t + 1], c->st2));
+  }
+  CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (nblk_o - 1) + 1], 0));
+  NC(g_nccl.AllReduce(c->dflag, c->dflag, 1, ncclInt, ncclMax, c->comm, c->st));
+  return GPSS_OK;
+}
+
+// alpha = L^-T L^-1 rhs with the partitioned factor.  Forward: the owner of block column t runs its four 128-steps and
+// broadcasts the updated tail of the right-hand side and the finished piece of z.  Backward: every rank keeps the
+// right-hand side current at the columns it owns and updates them with each new x_k; the owner of tile k-1 produces
+// x_{k-1}, broadcast 128 doubles at a time.  rhs in c->rvec (destroyed), result in c->alpha (replicated).
+static int potrs_vec_partitioned(gpss_ctx* c)
+{
+  const int P = c->world, me = c->rank, n_pad = c->n_pad, nblk = c->nblk;
+  const long ld = n_pad;
+  const int w = NBO / NB;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  if (me == 0) { trsv_fwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv, c->rvec, c->zvec); c->launches++; }
+  for (int t = 0; t < nblk_o; t++) {
+    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+    if ((t % P) == me) {
+      const double* Lg = c->Lm + (long)(t / P) * NBO * ld - (long)T0 * ld;     // indexed by global column inside my block column
+      for (int k = T0 / NB; k < (T0 + nbT) / NB && k + 1 < nblk; k++) {
+        trsv_fwd_step_kernel<<<nblk - 1 - k, TRSV_THREADS, 0, c->st>>>(Lg, ld, c->Winv, c->rvec, c->zvec, k * NB);
+        c->launches++;
+      }
+    }
+    const int zend = (T0 + nbT + NB <= n_pad) ? T0 + nbT + NB : n_pad;          // z of this block column and of the next tile
+    NC(g_nccl.Broadcast(c->zvec + T0, c->zvec + T0, (size_t)(zend - T0), ncclDouble, t % P, c->comm, c->st));
+    if (T0 + nbT < n_pad)
+      NC(g_nccl.Broadcast(c->rvec + T0 + nbT, c->rvec + T0 + nbT, (size_t)(n_pad - T0 - nbT), ncclDouble, t % P, c->comm, c->st));
+  }
+  CU(cudaGetLastError());
+  const int own_last = ((nblk - 1) / w) % P;
+  if (me == own_last) {
+    trsv_bwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv + (long)(nblk - 1) * NB * NB, c->zvec, c->alpha, (nblk - 1) * NB);
+    c->launches++;
+  }
+  NC(g_nccl.Broadcast(c->alpha + (long)(nblk - 1) * NB, c->alpha + (long)(nblk - 1) * NB, NB, ncclDouble, own_last, c->comm, c->st));
+  const int ltiles = (int)(c->lcols / NB);
+  for (int k = nblk - 1; k >= 1; k--) {
+    trsv_bwd_step_part_kernel<<<ltiles, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->zvec, c->alpha, k * NB, P, me, w);
+    c->launches++;
+    const int owner = ((k - 1) / w) % P;
+    NC(g_nccl.Broadcast(c->alpha + (long)(k - 1) * NB, c->alpha + (long)(k - 1) * NB, NB, ncclDouble, owner, c->comm, c->st));
+  }
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
 static int create_streams(gpss_ctx* c)
 {
   int lo = 0, hi = 0;
@@ -653,13 +774,18 @@ static int ensure_factor(gpss_ctx* c)
   {
     PhaseTimer t(c, 0);
     transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs, ld, c->n, n_pad, c->dP);
-    kbuild_lower_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank, NBO / NB);
+    if (c->partitioned)
+      kbuild_lower_kernel<<<dim3(c->nblk, (unsigned)(c->lcols / NB)), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank,
+                                                                                      -(NBO / NB));
+    else
+      kbuild_lower_kernel<<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank, NBO / NB);
     c->launches += 2;
     CU(cudaGetLastError());
   }
   {
     PhaseTimer t(c, 1);
-    RET(potrf_blocked(c, c->Lm, ld, n_pad, c->Winv, c->logdet_parts, c->dflag));
+    if (c->partitioned) RET(potrf_partitioned(c));
+    else RET(potrf_blocked(c, c->Lm, ld, n_pad, c->Winv, c->logdet_parts, c->dflag));
   }
   c->have_factor = true;
   c->have_alpha = false;
@@ -679,7 +805,8 @@ static int ensure_objective(gpss_ctx* c)
     // rhs = y / sn2: the IRLS fixed point alpha = B^-1 (y/sn2) = (K + sn2 I)^-1 y (GP_Utils.cpp:214-223)
     scale_copy_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->rvec, c->y, 1 / c->theta[9], c->n, n_pad);
     c->launches++;
-    RET(potrs_vec(c));
+    if (c->partitioned) RET(potrs_vec_partitioned(c));
+    else RET(potrs_vec(c));
     kmatvec_kernel<<<(c->n + 63) / 64, 256, 0, c->st>>>(c->zs, n_pad, c->alpha, c->fvec, c->n, c->dP);
     lml_terms_kernel<<<1, 256, 0, c->st>>>(c->y, c->alpha, c->fvec, c->n, c->dP, c->logdet_parts, c->nblk, c->red);
     c->launches += 2;
@@ -788,7 +915,8 @@ int gpss_set_data(gpss_handle c, const double* X, const double* y)
   return GPSS_OK;
 }
 
-int gpss_create(int device, int n, int d, const double* X, const double* y, gpss_handle* out)
+static int create_impl(int device, int n, int d, const double* X, const double* y, int part_world, int part_rank, const void* id128,
+                       gpss_handle* out)
 {
   if (!out || !X || !y) return fail_arg("gpss_create: null argument");
   if (d != 3) return fail_arg("gpss_create: only the 3-D ExpAns path is implemented (d must be 3)");
@@ -807,6 +935,21 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   c->urow1 = c->qrow1 = c->n_pad;
   memset(c->phase_ms, 0, sizeof c->phase_ms);
   const size_t np = c->n_pad;
+  size_t lm_cols = np;
+  if (part_world > 1) {
+    // partitioned storage: only my block columns j = q P + rank, packed; the last global block column may be narrower
+    const int nblk_o = (c->n_pad + NBO - 1) / NBO;
+    c->partitioned = true;
+    c->world = part_world;
+    c->rank = part_rank;
+    c->nq = 0;
+    c->lcols = 0;
+    for (int j = part_rank; j < nblk_o; j += part_world) {
+      c->nq++;
+      c->lcols += (c->n_pad - j * NBO < NBO) ? (c->n_pad - j * NBO) : NBO;
+    }
+    lm_cols = c->lcols > 0 ? (size_t)c->lcols : 1;
+  }
   auto fail = [&](int code) { gpss_destroy(c); return code; };
 #define CUF(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(fail_cuda(e__, #x, __LINE__)); } while (0)
   { int r__ = create_streams(c); if (r__ != GPSS_OK) return fail(r__); }
@@ -817,7 +960,7 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   CUF(cudaMalloc(&c->xs, sizeof(double) * 3 * np));
   CUF(cudaMalloc(&c->y, sizeof(double) * np));
   CUF(cudaMalloc(&c->zs, sizeof(double) * 4 * np));
-  CUF(cudaMalloc(&c->Lm, sizeof(double) * np * np));
+  CUF(cudaMalloc(&c->Lm, sizeof(double) * np * lm_cols));
   CUF(cudaMalloc(&c->Winv, sizeof(double) * (size_t)c->nblk * NB * NB));
   CUF(cudaMalloc(&c->logdet_parts, sizeof(double) * c->nblk));
   CUF(cudaMalloc(&c->rvec, sizeof(double) * np));
@@ -833,8 +976,28 @@ int gpss_create(int device, int n, int d, const double* X, const double* y, gpss
   for (int i = 0; i < GPSS_NPAR; i++) c->theta[i] = 0;
   int r = gpss_set_data(c, X, y);
   if (r != GPSS_OK) return fail(r);
+  if (part_world > 1) {
+    r = nccl_load();
+    if (r != GPSS_OK) return fail(r);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclResult_t nr = g_nccl.CommInitRank(&c->comm, part_world, id, part_rank);
+    if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __LINE__));
+  }
   *out = c;
   return GPSS_OK;
+}
+
+int gpss_create(int device, int n, int d, const double* X, const double* y, gpss_handle* out)
+{
+  return create_impl(device, n, d, X, y, 1, 0, nullptr, out);
+}
+
+int gpss_create_partitioned(int device, int rank, int world, const void* id128, int n, int d, const double* X, const double* y,
+                            gpss_handle* out)
+{
+  if (world < 2 || rank < 0 || rank >= world || !id128) return fail_arg("gpss_create_partitioned: needs world >= 2, 0 <= rank < world and the NCCL id");
+  return create_impl(device, n, d, X, y, world, rank, id128, out);
 }
 
 int gpss_set_theta(gpss_handle c, const double theta[GPSS_NPAR])
@@ -870,6 +1033,7 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
   CallTimer ct(c);
+  if (c->partitioned) { g_last_error = "gpss_nlml_grad: the gradient needs B^-1, which partitioned storage does not hold yet (objective, alpha and the predictive mean are available)"; return GPSS_ERR_STATE; }
   RET(ensure_objective(c));
   *nlml = c->nlml;
   if (c->chol_fail) {
@@ -946,7 +1110,7 @@ int gpss_nccl_unique_id(void* id128)
 int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
 {
   if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail_arg("gpss_dist_init: bad argument");
-  if (c->comm) return fail_arg("gpss_dist_init: already initialised");
+  if (c->comm || c->partitioned) return fail_arg("gpss_dist_init: already initialised");
   CU(cudaSetDevice(c->device));
   if (world == 1) return GPSS_OK;
   RET(nccl_load());
@@ -1008,6 +1172,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
+  if (c->partitioned && var) { g_last_error = "gpss_predict: the predictive variance needs L^-1, which partitioned storage does not hold yet (pass var = NULL for the mean)"; return GPSS_ERR_STATE; }
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
   CallTimer ct(c);

@@ -38,6 +38,9 @@ struct GemmArgs {
   int rev_order;                 // schedule tiles with the longest k-range first
   int ksplit;                    // > 1: every tile's k-range is cut into ksplit equal parts, one CTA each (grid = mt*nt*ksplit);
   long csplit;                   //      part s stores its partial product at C + s*csplit (summed by the caller, fixed order)
+  int cyc_P, cyc_me, cyc_w;      // cyc_P > 1: C holds only the block columns (cyc_w wide) that rank cyc_me of cyc_P owns, packed;
+  int cyc_lcol0, cyc_boff;       //   local column cyc_lcol0 + col is GLOBAL column gc = ((l / w) P + me) w + l % w, which lower_only
+                                 //   tests against the row and which selects the B rows: B(gc - cyc_boff, k)
   int mt, nt;                    // tile counts M/BM, N/BN (filled by the launcher)
 };
 
@@ -266,7 +269,13 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   }
   if (g.rev_order) { tm = g.mt - 1 - tm; }
   const int row0 = tm * BM, col0 = tn * BN;
-  if (g.lower_only && (g.gcol0 + col0) > (g.grow0 + row0 + BM - 1)) return;
+  int bcol0 = col0, gcol = g.gcol0 + col0;
+  if (g.cyc_P > 1) {
+    const int l = g.cyc_lcol0 + col0;
+    gcol = ((l / g.cyc_w) * g.cyc_P + g.cyc_me) * g.cyc_w + l % g.cyc_w;
+    bcol0 = gcol - g.cyc_boff;
+  }
+  if (g.lower_only && gcol > (g.grow0 + row0 + BM - 1)) return;
 
   int kbeg = 0, kend = g.K;
   if (g.kbeg_row) kbeg = g.krow_off + row0;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
     // ---------------- producer warp: lanes 0..15 copy the A rows, lanes 16..31 the B rows of each stage ----------------
     const int kk = lane & 15;
     const bool isA = lane < 16;
-    const double* src = isA ? (g.A + row0 + (long)(kbeg + kk) * g.lda) : (g.B + col0 + (long)(kbeg + kk) * g.ldb);
+    const double* src = isA ? (g.A + row0 + (long)(kbeg + kk) * g.lda) : (g.B + bcol0 + (long)(kbeg + kk) * g.ldb);
     const long src_step = (long)BK * (isA ? g.lda : g.ldb);
     double* dst0 = isA ? (As + kk * LDAS) : (Bs + kk * LDBS);
     const int dst_step = BK * (isA ? LDAS : LDBS);

@@ -73,9 +73,16 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
 {
   // own_world > 1: only the tile columns of the block columns (own_width tiles wide) this rank owns in the distributed
   // Cholesky are built -- every other block column arrives already factored with the owner's broadcast.
-  const int tm = blockIdx.x, tn = blockIdx.y;
+  // own_width < 0 (partitioned storage): Bm holds ONLY this rank's block columns, packed; blockIdx.y is the local tile column.
+  const int tm = blockIdx.x;
+  int tn = blockIdx.y;
+  const int tn_store = tn;
+  if (own_width < 0) {
+    const int w = -own_width;
+    tn = ((tn / w) * own_world + own_rank) * w + tn % w;
+    if (tn >= (int)gridDim.x) return;
+  } else if (own_world > 1 && (tn / own_width) % own_world != own_rank) return;
   if (tn > tm) return;
-  if (own_world > 1 && (tn / own_width) % own_world != own_rank) return;
   __shared__ double cz[4][NB];
   __shared__ DevParams P;
   const int tid = threadIdx.x;
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
       }
       o[e] = v;
     }
-    *reinterpret_cast<double2*>(Bm + (long)j * ld + i0) = out;
+    *reinterpret_cast<double2*>(Bm + (long)(tn_store * NB + jj) * ld + i0) = out;
   }
 }
 
@@ -454,6 +461,49 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
     rn[warp * 16 + lane] = v;
   }
   if ((int)blockIdx.x != k0 / NB - 1) return;
+  __syncthreads();
+  block_tri_matvec<true>(Winv + (long)(k0 / NB - 1) * NB * NB, rn, s, scratch);
+  if (t < NB) x[k0 - NB + t] = s[t];
+}
+
+// Partitioned storage (L held as packed block columns, `w` 128-tiles per block column, owner = block column % P): the backward
+// step k over THIS rank's column tiles.  blockIdx.x is a local tile; its global tile must lie left of block k.  r is valid on a
+// rank only at the columns it owns (each rank keeps its own columns current); the owner of tile k-1 produces x_{k-1}, which
+// the host then broadcasts.
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_part_kernel(const double* __restrict__ Lloc, long ld, const double* __restrict__ Winv,
+                                                                           double* __restrict__ r, double* __restrict__ x, int k0, int P,
+                                                                           int me, int w)
+{
+  const int lt = blockIdx.x;
+  const int gt = ((lt / w) * P + me) * w + lt % w;            // global 128-column tile
+  if (gt >= k0 / NB) return;
+  __shared__ double xk[NB], rn[NB], s[NB], scratch[2 * NB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < NB) xk[t] = x[k0 + t];
+  __syncthreads();
+  double acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const double* Lp = Lloc + (long)(lt * NB + warp * 16 + c) * ld + k0 + lane;
+    acc[c] = fma(Lp[0], xk[lane], fma(Lp[32], xk[lane + 32], fma(Lp[64], xk[lane + 64], Lp[96] * xk[lane + 96])));
+  }
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    double v = acc[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    acc[c] = v;
+  }
+  if (lane < 16) {
+    double mine = acc[0];
+#pragma unroll
+    for (int c = 1; c < 16; c++) if (lane == c) mine = acc[c];
+    const int j = gt * NB + warp * 16 + lane;
+    const double v = r[j] - mine;
+    r[j] = v;
+    rn[warp * 16 + lane] = v;
+  }
+  if (gt != k0 / NB - 1) return;
   __syncthreads();
   block_tri_matvec<true>(Winv + (long)(k0 / NB - 1) * NB * NB, rn, s, scratch);
   if (t < NB) x[k0 - NB + t] = s[t];
