@@ -272,7 +272,10 @@ def main():
         pred = [t_pred_dev, t_pred_wall]
 
     # ---- max over ranks ----
+    phases_all = None
     if world > 1:
+        phases_all = [None] * world
+        dist.all_gather_object(phases_all, [round(float(v), 2) for v in (ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[8])])
         vals = [t_dev, wall, wall_e2e, gemm_ms] + (pred or [0.0, 0.0])
         t = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,6 +320,9 @@ def main():
                           "gather_U": ph[8]},
             "cholesky_tflops": (float(n_pad) ** 3 / 3) / (ph[1] * 1e-3) * 1e-12,
         }
+        if phases_all:
+            line["phases_ms_per_rank"] = {"order": ["kbuild", "potrf", "solve_objective", "trtri", "lauum", "grad_pass", "gather_U"],
+                                          "ranks": phases_all}
         if pred:
             m_total = args.pred_m * world
             flop_pt = float(n_pad) ** 2       # one triangular solve per point, n^2/2 FMA

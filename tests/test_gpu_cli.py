@@ -116,7 +116,7 @@ def test_cli_two_gpu_launch_matches_single_gpu(tmp_path):
         assert te.returncode == 0, te.stdout + te.stderr
         outs[tag] = (tr.stdout, te.stdout, open(model).read(), _table(open(model + "_predict.txt").read()))
     it1, it2 = _floats_after(outs["one"][0], "-logL:"), _floats_after(outs["two"][0], "-logL:")
-    assert len(it1) == len(it2) == 4
+    assert len(it1) == len(it2) >= 3
     assert np.allclose(it1, it2, rtol=1e-9)                       # same trajectory (distributed sums differ in the last bits)
     assert outs["one"][2].splitlines()[1:] == outs["two"][2].splitlines()[1:]     # 6-significant-digit model file: identical
     assert np.allclose(outs["one"][3], outs["two"][3], rtol=1e-5, atol=1e-8)
