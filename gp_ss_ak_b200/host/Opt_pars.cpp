@@ -69,16 +69,147 @@ void Opt_Algs::Optimise()
   }
 }
 
-// BFGS and SCG ride the same callbacks but are outside the scope table of this build.
+// ---------------------------------------------------------------------------------------------------
+// BFGS (:451-538) -- the reference's DEFAULT optimiser (gp_ss_ak.cpp:91).  Restated operation by operation; what differs
+// from the textbook method is kept and marked [quirk].
+// ---------------------------------------------------------------------------------------------------
 void Opt_Algs::BFGSOptimize()
 {
-  cout << "The BFGS optimiser is not part of the B200 hot-path build; use -o LBFGS.\n";
-  exit(1);
+  const int D = getNumPars();
+  lb.ones(1, D);
+  lb = lb * 1e-4;
+  ub.ones(1, D);
+  ub = 6 * ub;
+  mat Hes(D, D);
+  Hes.eye(D, D);
+
+  mat X0(1, D), g(1, D);
+  get_GP_Pars(X0);
+  set_GP_Pars(X0);
+  mat X = X0;
+  double fx = Grad_Values(g);
+  const int Maxit = getMaxIters();
+  int iter = 0;
+  mat gnew = g, Xnew = X;
+  Hes = eye<mat>(D, D) / accu(g * X.t());               // [quirk] initial inverse Hessian = I / (g0 . x0) (:481-482)
+  double final_steplength = 1;
+  while (true) {
+    iter++;
+    const mat gold = gnew;
+    const mat Xold = Xnew;
+    // [quirk] the direction is always built from g, the INITIAL gradient: g is never refreshed inside the loop (:491)
+    mat search_direction = -g * Hes;
+    Efficient_line_search(fx, X0, gold, search_direction, final_steplength);
+    pull_step_inside(X0, search_direction, final_steplength, Xnew, 1.2);
+    set_GP_Pars(Xnew);
+    const double fnew = Grad_Values(gnew);
+    if (fnew < fx) {
+      X0 = Xnew;
+      fx = fnew;
+    }
+    const mat yk = gnew - gold;                          // gradient of the last TRIED point against the previous tried point
+    const mat sk = Xnew - Xold;
+    if (iter == 1) {
+      Hes = eye<mat>(D, D) * accu(sk * yk.t()) / accu(yk * yk.t());
+    } else {
+      const double rho = 1.0 / accu(yk * sk.t());
+      Hes = (eye<mat>(D, D) - rho * sk.t() * yk) * Hes * (eye<mat>(D, D) - rho * yk.t() * sk) + rho * sk.t() * sk;
+    }
+    if (iter >= Maxit) break;
+    if (getVerbose() > 0) cout << "Iteration: " << iter << " -logL: " << fx << endl;
+  }
+  set_GP_Pars(X0);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Moller's scaled conjugate gradient as the reference writes it (:979-1124).
+// [deviation] the reference never initialises its scale `lambda` (:1004) and reads it at :1036: undefined behaviour.  The
+// compiled reference prints "Scale: 6.9e-310" (a stale pointer seen as a denormal), which is 0 in every operation it
+// enters; lambda starts at 0.0 here, which reproduces the compiled reference's probe trace (tests/test_host_cpu.py).
+// ---------------------------------------------------------------------------------------------------
 void Opt_Algs::scgOptimise()
 {
-  cout << "The SCG optimiser is not part of the B200 hot-path build; use -o LBFGS.\n";
-  exit(1);
+  if (getVerbose() > 2) cout << "Scaled Conjugate Gradient Optimisation." << endl;
+  const int D = getNumPars();
+  lb.ones(1, D);
+  lb = lb * 1e-4;
+  ub.ones(1, D);
+  ub = 6 * ub;
+
+  mat w(1, D), rk(1, D), pk(1, D);
+  double sigmak;
+  const double sigma = 1e-4;
+  double lambdaBar = 0.0, fw = 0.0, muk = 0.0, alphak = 0.0, betak, Deltak;
+  double lambda = 0.0;
+  bool success = true;
+
+  get_GP_Pars(w);
+  mat Xnew = w;
+  fw = Grad_Values(rk);
+  double fnew = fw;
+  mat gnew = rk, rk_old = rk, g = gnew, gold = gnew, sk = gnew;
+  const double fw_old = fw;                              // [quirk] never updated: the stop test compares with the START (:1105)
+  rk = -1 * rk;
+  pk = rk;
+  double deltak = 0.0;
+  int iter = 0;
+  if (getVerbose() > 0) cout << "Iteration: " << iter << " -logL: " << fw << " Scale: " << lambda << endl;
+  while (true) {
+    iter++;
+    if (success) {                                       // step 2: second-order information by a finite difference
+      const double div = std::sqrt(accu(pk * pk.t()));
+      sigmak = sigma / div;
+      Xnew = w + pk * sigmak;
+      set_GP_Pars(Xnew);
+      fnew = Grad_Values(gnew);
+      (void)fnew;
+      sk = (gnew - gold) / sigma + lambda * pk;          // [quirk] divides by sigma, not sigmak; gold is the last PROBE's gradient
+      deltak = accu(pk * sk.t());
+      gold = gnew;
+    }
+    const double norm2p = accu(pk * pk.t());             // step 3
+    deltak += (lambda - lambdaBar) * norm2p;
+    sk += (lambda - lambdaBar) * pk;
+    if (deltak <= 0.0) {                                 // step 4: make the Hessian estimate positive definite
+      lambdaBar = 2.0 * (lambda - deltak / norm2p);
+      deltak -= lambda * norm2p;
+      lambda = lambdaBar;
+    }
+    muk = accu(pk * rk.t());                             // step 5
+    alphak = muk / deltak;
+    pull_step_inside(w, pk, alphak, Xnew, 1.2);          // step 6 (:1062-1075)
+    set_GP_Pars(Xnew);
+    const double falpha = ObjVal();
+    Deltak = 2.0 * deltak * (fw - falpha) / std::pow(muk, 2.0);
+    if (Deltak >= 0.0) {                                 // step 7
+      w = Xnew;
+      fw = falpha;
+      Grad_Values(g);
+      rk = -g;
+      lambdaBar = 0;
+      success = true;
+      if (iter % D == 0) {
+        pk = rk;
+      } else {
+        betak = (accu(rk * rk.t()) - accu(rk * rk_old.t())) / muk;
+        pk = rk + betak * pk;
+      }
+      if (Deltak >= 0.75) lambda *= 0.25;
+    } else {
+      set_GP_Pars(w);
+      lambdaBar = lambda;
+      success = false;
+    }
+    rk_old = rk;
+    if (std::fabs(fw - fw_old) < getTolObjVal() && (((iter % 3) == 0) & (iter > 10))) return;
+    if (Deltak < 0.25) lambda += (deltak * (1 - Deltak) / accu(pk * pk.t()));       // step 8
+    bool all_zero = true;                                // step 9
+    for (uword i = 0; i < rk.n_elem; i++) if (rk[i] != 0) all_zero = false;
+    if (all_zero) break;
+    if (iter >= (int)getMaxIters()) break;
+    if (getVerbose() > 0) cout << "Iteration: " << iter << " -logL: " << fw << " Scale: " << lambda << endl;
+  }
+  set_GP_Pars(w);
 }
 
 void Opt_Algs::ChkBnd(mat& A, const mat lo, const mat hi)

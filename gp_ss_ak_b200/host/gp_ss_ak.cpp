@@ -1,6 +1,6 @@
 // gp_ss_ak -- command line of the B200 exact-GP path.  Same commands, flags, prompts, files and printed lines as the
 // reference's gp_ss_ak.cpp (/root/reference; file:line citations below):
-//   gp_ss_ak [-v N] [-pm M] train [-k ExpAns] [-kn 1] [-o LBFGS] [-# iters] train.txt [model]
+//   gp_ss_ak [-v N] [-pm M] train [-k ExpAns] [-kn 1] [-o BFGS|LBFGS|SCG] [-# iters] train.txt [model]
 //   gp_ss_ak [-v N] [-pm M] test  test.txt model train.txt [predictions.txt]
 // Everything numerical happens in GP_utils (device-resident); this file is argument handling and file I/O.
 #include "gp_ss_ak.h"
@@ -314,7 +314,7 @@ void GP_Cntrl::Help()
     cout << "-mf ,--meanfunction\n \t GP mean function name (Default: zero [mean_zero])" << endl;
     cout << "-lf, --likefunction\n \t likelihood function name (default:  [Gauss]" << endl;
     cout << "-k, --kernel\n \t Kernel name (Exponential Anisotropic [ExpAns]; RBF / Exp / White are not part of this build)" << endl;
-    cout << "-o, --optimiser\n \t Optimization algorithm ([LBFGS]; the default BFGS and SCG are not part of this build)" << endl;
+    cout << "-o, --optimiser\n \t Optimization algorithm (Broyden-Fletcher-Goldfarb-Shanno [BFGS] (default), limited-memory BFGS [LBFGS], scaled conjugate gradient [SCG])" << endl;
     cout << "-kn, --Knoise\n \t Bias kernel (default: true [1], other options false [0])" << endl;
     cout << "trainFileName\n \t File containg trainig data (comma delimitted or tab delimitted file)." << endl;
     cout << "modelName\n \t File to store the model." << endl;

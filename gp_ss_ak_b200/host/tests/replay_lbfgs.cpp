@@ -2,7 +2,7 @@
 // probe trace of the unmodified reference (tests/golden/ref_n300.npz, written out by tests/test_host_cpu.py).  Every
 // ObjVal / Grad_Values call must arrive in the recorded order, of the recorded kind, at the recorded theta; it is then
 // answered with the recorded f (and g).  Any deviation of the optimiser's decision logic shows up as a mismatch.
-//   replay_lbfgs trace.txt iters tol
+//   replay_lbfgs trace.txt iters tol [LBFGS|BFGS|SCG]
 // trace line:  kind(0=ObjVal,1=Grad_Values) theta[10] f g[10]
 #include "../Opt_pars.h"
 
@@ -54,7 +54,7 @@ class ReplayModel : public Opt_Algs {
 
 int main(int argc, char** argv)
 {
-  if (argc < 4) { printf("usage: replay_lbfgs trace.txt iters tol\n"); return 2; }
+  if (argc < 4) { printf("usage: replay_lbfgs trace.txt iters tol [LBFGS|BFGS|SCG]\n"); return 2; }
   ReplayModel m;
   std::ifstream in(argv[1]);
   while (true) {
@@ -67,7 +67,7 @@ int main(int argc, char** argv)
   }
   m.tol = atof(argv[3]);
   for (int i = 0; i < 10; i++) m.cur[i] = m.trace[0].th[i];
-  m.setOptimiser(Opt_Algs::LBFGS);
+  m.setOptimiserStr(argc > 4 ? argv[4] : "LBFGS");      // LBFGS | BFGS | SCG
   m.setMaxIters(atoi(argv[2]));
   m.Optimise();
   printf("REPLAY OK probes %zu of %zu worst_theta_diff %.3e final", m.next, m.trace.size(), m.worst);

@@ -8,6 +8,7 @@
 //
 //   ref_driver <train.txt> <test.txt> <thetas.txt> <lbfgs_iters> <workdir> > dump.txt
 //   ref_driver --time <train.txt> <workdir> <warmup> <steps>     one line per timed set_GP_Pars + Grad_Values (bench.py)
+//   ref_driver --trace <SCG|BFGS|LBFGS> <train.txt> <iters> <workdir>      probe trace of one optimiser run
 #include "gp_ss_ak.h"
 #include <cstdio>
 #include <new>
@@ -82,9 +83,51 @@ static int time_mode(int argc, char** argv)
   return 0;
 }
 
+// ref_driver --trace <SCG|BFGS|LBFGS> train.txt iters workdir: the probe trace of one optimiser run of the unmodified
+// reference (Opt_pars.cpp:451-538 BFGS, 979-1124 SCG, 179-332 LBFGS), for the host drivers' replay tests.
+static int trace_mode(int argc, char** argv)
+{
+  if (argc < 6) { fprintf(stderr, "usage: ref_driver --trace OPT train.txt iters workdir\n"); return 2; }
+  const string opt = argv[2], trainFile = argv[3];
+  const int iters = atoi(argv[4]);
+  const string model = string(argv[5]) + "/ref_trace_model";
+  char* fake[] = {argv[0], 0};
+  int Data_mode = 0;
+  bool yscale = true;
+  Control ctl(1, fake);
+  ctl.setMode("train");
+  ctl.setprepM(1);
+  int* sz = ctl.readDataSize(trainFile);
+  mat X(sz[0], sz[1]), y(sz[0], 1);
+  ctl.readDataFile(X, y, sz, trainFile);
+  ctl.prepareData(X, y, Data_mode, yscale, model);
+  HybKerns Kerns(X);
+  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
+  Kerns.addNewKernel(new Kern_Bias(X));
+  void* raw = calloc(1, sizeof(TraceGP));                     // zero-filled storage: see the LBFGS block in main()
+  TraceGP& gp = *new (raw) TraceGP(&Kerns, X, y);
+  gp.setOptimiser(opt == "SCG" ? GP_utils::SCG : opt == "BFGS" ? GP_utils::BFGS : GP_utils::LBFGS);
+  gp.setMaxIters(iters);
+  gp.setVerbose(1);                                           // the per-iteration lines (SCG prints its scale there)
+  const unsigned np = gp.getNumPars();
+  mat th0(1, np);
+  gp.get_GP_Pars(th0);
+  dump("theta_start", th0);
+  gp.on = true;
+  gp.Optimise();
+  gp.on = false;
+  mat th(1, np);
+  gp.get_GP_Pars(th);
+  dump("theta_fit", th);
+  dump("nlml_fit", gp.logLikelihood());
+  dump("n_probes", (double)gp.count);
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   if (argc > 1 && string(argv[1]) == "--time") return time_mode(argc, argv);
+  if (argc > 1 && string(argv[1]) == "--trace") return trace_mode(argc, argv);
   if (argc < 6) { fprintf(stderr, "usage: ref_driver train.txt test.txt thetas.txt lbfgs_iters workdir\n"); return 2; }
   const string trainFile = argv[1], testFile = argv[2], thetaFile = argv[3];
   const int iters = atoi(argv[4]);

@@ -103,3 +103,24 @@ def test_reader_quirks(host_built, tmp_path):
     assert np.array_equal(rec["params"][1:], [[4.5, 4.5]] * 3)
     # integers are written as integers in the model file (Kernel.cpp:31-35)
     assert "1 1 1 1 1 1 1 1 \n" in (tmp_path / "host_model").read_text()
+
+
+@pytest.mark.parametrize("opt", ["BFGS", "SCG"])
+def test_bfgs_and_scg_replay_reference_traces(host_built, tmp_path, opt):
+    """The reference's other two optimisers (BFGS is its CLI default, gp_ss_ak.cpp:91), restated in host/Opt_pars.cpp, must
+    request exactly the probes the UNMODIFIED reference requested (tests/golden/ref_opt_traces.npz, made by
+    make_ref_opt_traces.py): same order, same kind, same theta, and end at the same parameters."""
+    z = np.load(os.path.join(GOLD, "ref_opt_traces.npz"))
+    kind, theta, fv, gv = z[opt + "_kind"], z[opt + "_theta"], z[opt + "_f"], z[opt + "_g"]
+    assert len(fv) >= 12
+    trace = tmp_path / "trace.txt"
+    with open(trace, "w") as f:
+        for k in range(len(fv)):
+            g = np.nan_to_num(gv[k], nan=0.0)
+            f.write("%d " % int(kind[k]) + " ".join("%.17g" % v for v in theta[k]) + " %.17g " % fv[k] + " ".join("%.17g" % v for v in g) + "\n")
+    out = subprocess.run([os.path.join(host_built, "tests", "replay_lbfgs"), str(trace), str(int(z[opt + "_iters"])), "1e-10", opt],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "REPLAY OK probes %d of %d" % (len(fv), len(fv)) in out.stdout
+    final = np.array(out.stdout.split("final")[1].split(), dtype=float)
+    assert np.abs(final - z[opt + "_theta_fit"].reshape(-1)).max() <= 1e-10
