@@ -57,6 +57,14 @@ def drillholes(n, seed=0):
     return np.ascontiguousarray(X), np.ascontiguousarray(y)
 
 
+def with_rock_column(P, seed=0):
+    """Appends a 4th input column: a rock-type code 1..4 (lithology bands that dip across the domain, a deterministic function
+    of position), the input of the reference's 4-column ExpAns branch (InversewidthR, Kernel.cpp:872-878)."""
+    t = 0.004 * P[:, 0] + 0.003 * P[:, 1] + 0.006 * P[:, 2] + 0.37 * (seed % 7)
+    code = 1.0 + np.floor(np.mod(t, 4.0))
+    return np.ascontiguousarray(np.concatenate([P, code[:, None]], axis=1))
+
+
 def block_model(nx, ny, nz, lo, hi):
     """Block-model centroids on a regular nx x ny x nz grid over the bounding box [lo, hi]."""
     ax = [lo[d] + (np.arange(k) + 0.5) * (hi[d] - lo[d]) / k for d, k in enumerate((nx, ny, nz))]

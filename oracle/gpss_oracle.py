@@ -139,6 +139,18 @@ def sig_inv(theta):
     return S
 
 
+def sig_inv_full(theta, d):
+    """The d x d sigInv of MahaDist: for the 4-column (rock-type) branch Rot(3,3) = 1 and lambda(3,3) = InversewidthR
+    (Kernel.cpp:1411-1424), so the matrix is block diagonal: [sig_inv(theta), theta[7]]."""
+    S3 = sig_inv(theta)
+    if d == 3:
+        return S3
+    S = np.zeros((4, 4))
+    S[:3, :3] = S3
+    S[3, 3] = theta[7]
+    return S
+
+
 def seq_colsum(X):
     """Column sums accumulated strictly in row order (defined order shared with the product host code)."""
     s = np.zeros(X.shape[1])
@@ -166,13 +178,17 @@ def centre(X1, X2, sums1=None, sums2=None):
 def maha_dist_blas(X1, X2, theta):
     """MahaDist exactly as written: centred copies, X*sigInv via dgemm, expansion-form D2 via dgemm, clamp."""
     c = centre(X1, X2)
-    S = sig_inv(theta)
+    S = sig_inv_full(theta, X1.shape[1])
     Z1 = (X1 - c) @ S
     Z2 = (X2 - c) @ S
     a1 = (Z1 * Z1)
-    a1 = (a1[:, 0] + a1[:, 1]) + a1[:, 2]
     a2 = (Z2 * Z2)
-    a2 = (a2[:, 0] + a2[:, 1]) + a2[:, 2]
+    s1 = (a1[:, 0] + a1[:, 1]) + a1[:, 2]
+    s2 = (a2[:, 0] + a2[:, 1]) + a2[:, 2]
+    if X1.shape[1] == 4:
+        s1 = s1 + a1[:, 3]
+        s2 = s2 + a2[:, 3]
+    a1, a2 = s1, s2
     D2 = (a1[:, None] + a2[None, :]) - 2.0 * (Z1 @ Z2.T)
     D2[D2 < 0] = 0.0
     return D2
@@ -205,15 +221,20 @@ def transform_defined(X, c, S):
     d0 = X[:, 0] - c[0]
     d1 = X[:, 1] - c[1]
     d2 = X[:, 2] - c[2]
-    Z = np.empty((X.shape[0], 3))
+    Z = np.empty((X.shape[0], X.shape[1]))
     for j in range(3):
         Z[:, j] = _fma_emul(d2, S[2, j], _fma_emul(d1, S[1, j], d0 * S[0, j]))
+    if X.shape[1] == 4:                      # 4-column branch: z_3 = (x_3 - c_3) * InversewidthR (block-diagonal sigInv)
+        Z[:, 3] = (X[:, 3] - c[3]) * S[3, 3]
     return Z
 
 
 def sqnorm_defined(Z):
     """a_i = fl(fl(z0^2 + z1^2) + z2^2) (sum(X%X,1), Kernel.cpp:1431)."""
-    return (Z[:, 0] * Z[:, 0] + Z[:, 1] * Z[:, 1]) + Z[:, 2] * Z[:, 2]
+    a = (Z[:, 0] * Z[:, 0] + Z[:, 1] * Z[:, 1]) + Z[:, 2] * Z[:, 2]
+    if Z.shape[1] == 4:
+        a = a + Z[:, 3] * Z[:, 3]
+    return a
 
 
 def maha_dist_defined(X1, X2, theta, c=None):
@@ -221,13 +242,15 @@ def maha_dist_defined(X1, X2, theta, c=None):
        c_ij = fma(z_i2, z_j2, fma(z_i1, z_j1, z_i0*z_j0));  D2 = max(0, fl(fl(a_i + a_j) - 2 c_ij))."""
     if c is None:
         c = centre(X1, X2)
-    S = sig_inv(theta)
+    S = sig_inv_full(theta, X1.shape[1])
     Z1 = transform_defined(X1, c, S)
     Z2 = transform_defined(X2, c, S)
     a1 = sqnorm_defined(Z1)
     a2 = sqnorm_defined(Z2)
     cij = _fma_emul(Z1[:, 2][:, None], Z2[:, 2][None, :],
                     _fma_emul(Z1[:, 1][:, None], Z2[:, 1][None, :], Z1[:, 0][:, None] * Z2[:, 0][None, :]))
+    if X1.shape[1] == 4:
+        cij = _fma_emul(Z1[:, 3][:, None], Z2[:, 3][None, :], cij)
     D2 = (a1[:, None] + a2[None, :]) - 2.0 * cij
     D2[D2 < 0] = 0.0
     return D2
@@ -634,14 +657,27 @@ def expans_gradients_literal(X, theta, QW, dist="defined"):
     np.fill_diagonal(dk, 0.0)
     Rm = Qs * dk
     g = np.zeros(8)
+    d = X.shape[1]
     XX = X * X
     for p in range(6):
-        M = S * Sp[p]                                   # Hadamard product S % S_p (Kernel.cpp:1192)
+        M = np.zeros((d, d))
+        M[:3, :3] = S * Sp[p]                           # Hadamard product S % S_p (Kernel.cpp:1192); 4th row/column of S_p are zero
         rowq = (2.0 * XX @ M).sum(axis=1)
         Di2 = rowq[:, None] + rowq[None, :] - 4.0 * ((X @ M) @ X.T)
         g[p] = float((Rm * Di2).sum())
     g[6] = 2.0 * float((KD2 * QW).sum()) * theta[6]     # Kernel.cpp:1239-1242
-    g[7] = 0.0                                          # Kernel.cpp:1256-1257
+    if d == 4:
+        # S(3,3) = 1 and InversewidthRock(3,3) = 1 (Kernel.cpp:1169-1173), so S % InversewidthRock = e4 e4':
+        # Di2 = 2 x_i4^2 + 2 x_j4^2 - 4 x_i4 x_j4.  [quirk] RColon was reassigned to KD2 = exp(-s) for the Sigma gradient
+        # just above (Kernel.cpp:1240) and is NOT restored: g[7] = -2 sum(exp(-s) % Di2) / n -- QW does not enter at all
+        # (Kernel.cpp:1246-1255; confirmed by the compiled reference, tests/golden/ref_rock_n300.npz).
+        M = np.zeros((4, 4))
+        M[3, 3] = 1.0
+        rowq = (2.0 * XX @ M).sum(axis=1)
+        Di2 = rowq[:, None] + rowq[None, :] - 4.0 * ((X @ M) @ X.T)
+        g[7] = -2.0 * float((KD2 * Di2).sum()) / n
+    else:
+        g[7] = 0.0                                      # Kernel.cpp:1256-1257
     return g
 
 
@@ -662,15 +698,19 @@ def expans_gradients_fused(X, theta, QW, DD2):
     np.fill_diagonal(w, 0.0)
     omega_r = w.sum(axis=1)
     omega_c = w.sum(axis=0)
-    T = X.T @ w @ X
+    X3 = X[:, :3]
+    T = X3.T @ w @ X3
     g = np.zeros(8)
-    XX = X * X
+    XX = X3 * X3
     for p in range(6):
         M = S * Sp[p]
         rho = M.sum(axis=0)        # (XX @ M).sum(axis=1) = XX @ (M 1)
         q = XX @ M.sum(axis=1)
         g[p] = 2.0 * float(q @ omega_r) + 2.0 * float(q @ omega_c) - 4.0 * float((M * T).sum())
     g[6] = 2.0 * theta[6] * float((QW * np.exp(-SD2)).sum())
+    if X.shape[1] == 4:            # g[7] = -4/n sum_ij exp(-s_ij) (x_i4 - x_j4)^2   (no QW: see expans_gradients_literal)
+        dx = X[:, 3][:, None] - X[:, 3][None, :]
+        g[7] = -4.0 * float((np.exp(-SD2) * dx * dx).sum()) / X.shape[0]
     return g
 
 

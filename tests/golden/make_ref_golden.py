@@ -48,11 +48,14 @@ def parse_dump(text):
     return rec
 
 
-def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_iters=0):
+def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_iters=0, rock=False):
     X, y = datagen.drillholes(n, seed)
     Xt, _ = datagen.drillholes(n_test, seed + 50)
     Xt = np.concatenate([Xt, X[:n_coincident]])
     yt = np.concatenate([datagen.grade_at(Xt[:n_test], seed), y[:n_coincident]])
+    if rock:        # the 4-column (rock-type) branch of the ExpAns kernel (Kernel.cpp:872-878, 1169-1173, 1246-1255)
+        X = datagen.with_rock_column(X, seed)
+        Xt = datagen.with_rock_column(Xt, seed)
     with tempfile.TemporaryDirectory() as d:
         datagen.write_data_file(os.path.join(d, "train.txt"), X, y)
         datagen.write_data_file(os.path.join(d, "test.txt"), Xt, yt)
@@ -102,3 +105,4 @@ if __name__ == "__main__":
     th2 = np.clip(THETA0 * rng.uniform(0.8, 1.25, 10), 1e-4, 6.0)
     make("ref_n300.npz", 300, 0, [THETA0, th1, th2], lbfgs_iters=30, cli_iters=6)
     make("ref_n1000.npz", 1000, 1, [THETA0, th1], lbfgs_iters=4)
+    make("ref_rock_n300.npz", 300, 2, [THETA0, th1, th2], lbfgs_iters=6, cli_iters=3, rock=True)
