@@ -65,8 +65,8 @@ def load_library():
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
         "gpss_var_postprocess": (I, [L, D, P]),
-        "gpss_compute_K": (I, [I, P, I, P, I, P, P, P]),
-        "gpss_expans_gradients": (I, [I, P, I, P, P, P]),
+        "gpss_compute_K": (I, [I, P, I, I, P, I, P, P, P]),
+        "gpss_expans_gradients": (I, [I, P, I, I, P, P, P]),
         "gpss_set_profiling": (I, [H, I]),
         "gpss_get_phase_ms": (I, [H, P]),
         "gpss_get_last_call_ms": (I, [H, P]),
@@ -266,7 +266,7 @@ def compute_K(theta, X1, X2, want_K=True, want_D2=True, device=0):
     th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
     K = np.zeros((X1.shape[0], X2.shape[0]), order="F") if want_K else None
     D2 = np.zeros((X1.shape[0], X2.shape[0]), order="F") if want_D2 else None
-    _check(lib.gpss_compute_K(device, _dp(th), X1.shape[0], _dp(X1), X2.shape[0], _dp(X2), _dp(K), _dp(D2)))
+    _check(lib.gpss_compute_K(device, _dp(th), X1.shape[1], X1.shape[0], _dp(X1), X2.shape[0], _dp(X2), _dp(K), _dp(D2)))
     return K, D2
 
 
@@ -276,7 +276,7 @@ def expans_gradients(theta, X, QW, device=0):
     QW = _colmajor(QW)
     th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
     g = np.zeros(8)
-    _check(load_library().gpss_expans_gradients(device, _dp(th), X.shape[0], _dp(X), _dp(QW), _dp(g)))
+    _check(load_library().gpss_expans_gradients(device, _dp(th), X.shape[1], X.shape[0], _dp(X), _dp(QW), _dp(g)))
     return g
 
 

@@ -82,6 +82,7 @@ enum QState { Q_NONE = 0, Q_IS_BINV = 1, Q_IS_W = 2 };
 struct gpss_ctx {
   int device = 0;
   int n = 0, n_pad = 0, nblk = 0;
+  int d = 3;                                                   // input columns: 3, or 4 with the rock-type column
   cudaStream_t st = nullptr;                                  // main stream (highest priority): critical-path kernels
   cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
   cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
@@ -89,7 +90,7 @@ struct gpss_ctx {
   cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
   std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
   // data
-  double *xs = nullptr, *y = nullptr, *zs = nullptr;           // 3 x n_pad, n_pad, 4 x n_pad
+  double *xs = nullptr, *y = nullptr, *zs = nullptr;           // NX x n_pad, n_pad, NZ x n_pad
   double *Lm = nullptr, *Um = nullptr, *Qm = nullptr;          // n_pad^2 each (Um, Qm lazily)
   double *Winv = nullptr;                                      // nblk x 128 x 128
   double *logdet_parts = nullptr;                              // nblk
@@ -113,7 +114,7 @@ struct gpss_ctx {
   int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
   // host state
   double theta[GPSS_NPAR];
-  double sums_train[3];
+  double sums_train[4];
   bool have_factor = false, have_alpha = false, have_U = false;
   int qstate = Q_NONE;
   int chol_fail = 0;
@@ -207,10 +208,13 @@ struct PhaseTimer {
 // ---------------------------------------------------------------------------------------------------
 // parameters -> device
 // ---------------------------------------------------------------------------------------------------
-static void fill_params(const double theta[GPSS_NPAR], const double centre[3], DevParams& P)
+static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3)
 {
+  memset(&P, 0, sizeof P);
   sig_inv(theta, P.S);
-  for (int j = 0; j < 3; j++) P.c[j] = centre[j];
+  for (int j = 0; j < dim; j++) P.c[j] = centre[j];
+  P.dim = dim;
+  P.lr = theta[7];                                     // InversewidthR: sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
   P.var2 = theta[6] * theta[6];
   P.bias = theta[8];
   P.sn2 = theta[9];
@@ -753,10 +757,10 @@ __global__ void scale_copy_kernel(double* __restrict__ dst, const double* __rest
 // ---------------------------------------------------------------------------------------------------
 // objective pieces
 // ---------------------------------------------------------------------------------------------------
-static int upload_params(gpss_ctx* c, int slot, const double centre[3])
+static int upload_params(gpss_ctx* c, int slot, const double* centre)
 {
   DevParams P;
-  fill_params(c->theta, centre, P);
+  fill_params(c->theta, centre, P, c->d);
   CU(cudaMemcpyAsync(c->dP + slot, &P, sizeof P, cudaMemcpyHostToDevice, c->st));
   CU(cudaStreamSynchronize(c->st));   // P is a stack object
   return GPSS_OK;
@@ -767,8 +771,8 @@ static int ensure_factor(gpss_ctx* c)
   if (c->have_factor) return GPSS_OK;
   const int n_pad = c->n_pad;
   const long ld = n_pad;
-  double centre[3];
-  maha_centre(c->n, c->sums_train, c->n, c->sums_train, centre);
+  double centre[4];
+  maha_centre(c->n, c->sums_train, c->n, c->sums_train, centre, c->d);
   RET(upload_params(c, 0, centre));
   CU(cudaMemsetAsync(c->dflag, 0, sizeof(int), c->st));
   {
@@ -903,9 +907,9 @@ int gpss_set_data(gpss_handle c, const double* X, const double* y)
   if (!c || !X || !y) return fail_arg("gpss_set_data: null argument");
   CU(cudaSetDevice(c->device));
   const int n = c->n, n_pad = c->n_pad;
-  seq_colsums(X, n, c->sums_train);
-  CU(cudaMemsetAsync(c->xs, 0, sizeof(double) * 3 * n_pad, c->st));
-  for (int j = 0; j < 3; j++)
+  seq_colsums(X, n, c->sums_train, c->d);
+  CU(cudaMemsetAsync(c->xs, 0, sizeof(double) * NX * n_pad, c->st));
+  for (int j = 0; j < c->d; j++)
     CU(cudaMemcpyAsync(c->xs + (long)j * n_pad, X + (long)j * n, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
   CU(cudaMemsetAsync(c->y, 0, sizeof(double) * n_pad, c->st));
   CU(cudaMemcpyAsync(c->y, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
@@ -919,7 +923,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
                        gpss_handle* out)
 {
   if (!out || !X || !y) return fail_arg("gpss_create: null argument");
-  if (d != 3) return fail_arg("gpss_create: only the 3-D ExpAns path is implemented (d must be 3)");
+  if (d != 3 && d != 4) return fail_arg("gpss_create: d must be 3, or 4 with a rock-type column (Kernel.cpp:872-878)");
   if (n < 2) return fail_arg("gpss_create: n must be >= 2");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -929,6 +933,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
   gpss_ctx* c = new gpss_ctx();
   c->device = device;
   c->n = n;
+  c->d = d;
   c->n_pad = ((n + NB - 1) / NB) * NB;
   c->nblk = c->n_pad / NB;
   c->urow0 = c->qrow0 = 0;
@@ -957,9 +962,9 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
   CUF(cudaEventCreate(&c->ev[1]));
   CUF(cudaEventCreate(&c->ev_call[0]));
   CUF(cudaEventCreate(&c->ev_call[1]));
-  CUF(cudaMalloc(&c->xs, sizeof(double) * 3 * np));
+  CUF(cudaMalloc(&c->xs, sizeof(double) * NX * np));
   CUF(cudaMalloc(&c->y, sizeof(double) * np));
-  CUF(cudaMalloc(&c->zs, sizeof(double) * 4 * np));
+  CUF(cudaMalloc(&c->zs, sizeof(double) * NZ * np));
   CUF(cudaMalloc(&c->Lm, sizeof(double) * np * lm_cols));
   CUF(cudaMalloc(&c->Winv, sizeof(double) * (size_t)c->nblk * NB * NB));
   CUF(cudaMalloc(&c->logdet_parts, sizeof(double) * c->nblk));
@@ -1071,7 +1076,7 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   double red[NGRAD];
   CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
-  combine_gradient(c->theta, red, c->s3, g);
+  combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
   return GPSS_OK;
 }
 
@@ -1168,7 +1173,7 @@ static int ensure_W(gpss_ctx* c)
 }
 
 // mean and RAW variance (kD - k*' A k*, no post-processing) of one shard
-static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], long count, const double* Xs, long ldx, double* mu, double* var)
+static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, long count, const double* Xs, long ldx, double* mu, double* var)
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
@@ -1182,9 +1187,9 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
   const int n_pad = c->n_pad;
   const int cap = PRED_BATCH;
   if (!c->pred_cap) {
-    RET(ensure_lazy(&c->xt, (size_t)3 * cap));
-    RET(ensure_lazy(&c->zt, (size_t)4 * cap));
-    RET(ensure_lazy(&c->zsp, (size_t)4 * n_pad));
+    RET(ensure_lazy(&c->xt, (size_t)NX * cap));
+    RET(ensure_lazy(&c->zt, (size_t)NZ * cap));
+    RET(ensure_lazy(&c->zsp, (size_t)NZ * n_pad));
     RET(ensure_lazy(&c->mu_part, (size_t)c->nblk * cap));
     RET(ensure_lazy(&c->dmu, cap));
     RET(ensure_lazy(&c->dvar, cap));
@@ -1195,8 +1200,8 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
     RET(ensure_lazy(&c->Vm, (size_t)cap * n_pad));
   }
   // centre over the training set and ALL test points (Kernel.cpp:1391-1392)
-  double centre[3];
-  maha_centre(c->n, c->sums_train, m_total, sums_total, centre);
+  double centre[4];
+  maha_centre(c->n, c->sums_train, m_total, sums_total, centre, c->d);
   RET(upload_params(c, 1, centre));
   transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
   c->launches++;
@@ -1204,8 +1209,8 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
   for (long off = 0; off < count; off += cap) {
     const int mb = (int)((count - off < cap) ? (count - off) : cap);
     const int m_pad = ((mb + NB - 1) / NB) * NB;
-    CU(cudaMemsetAsync(c->xt, 0, sizeof(double) * 3 * cap, c->st));
-    for (int j = 0; j < 3; j++)
+    CU(cudaMemsetAsync(c->xt, 0, sizeof(double) * NX * cap, c->st));
+    for (int j = 0; j < c->d; j++)
       CU(cudaMemcpyAsync(c->xt + (long)j * cap, Xs + (long)j * ldx + off, sizeof(double) * mb, cudaMemcpyHostToDevice, c->st));
     transform_kernel<<<(m_pad + 255) / 256, 256, 0, c->st>>>(c->xt, cap, c->zt, cap, mb, m_pad, c->dP + 1);
     {
@@ -1234,7 +1239,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double sums_total[3], l
   return GPSS_OK;
 }
 
-int gpss_predict_shard(gpss_handle c, long m_total, const double sums_total[3], long count, const double* Xs, double* mu, double* var)
+int gpss_predict_shard(gpss_handle c, long m_total, const double* sums_total, long count, const double* Xs, double* mu, double* var)
 {
   RET(predict_core(c, m_total, sums_total, count, Xs, count, mu, var));
   return GPSS_OK;
@@ -1261,8 +1266,8 @@ int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* va
 {
   if (!c || !Xs || !mu) return fail_arg("gpss_predict: null argument");
   if (m < 1) return fail_arg("gpss_predict: m must be >= 1");
-  double sums[3];
-  seq_colsums(Xs, m, sums);
+  double sums[4];
+  seq_colsums(Xs, m, sums, c->d);
   if (c->world == 1) {
     RET(predict_core(c, m, sums, m, Xs, m, mu, var));
   } else {
@@ -1301,38 +1306,40 @@ __global__ void __launch_bounds__(256) full_K_kernel(double* __restrict__ Km, do
   const int i = blockIdx.x * 64 + (threadIdx.x & 63);
   const int jb = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
   if (i >= n1) return;
-  const double a0 = z1[i], a1 = z1[ld1 + i], a2 = z1[2 * ld1 + i], aa = z1[3 * ld1 + i];
+  const double a0 = z1[i], a1 = z1[ld1 + i], a2 = z1[2 * ld1 + i], aa = z1[3 * ld1 + i], a3 = z1[4 * ld1 + i];
   for (int j = jb; j < jb + 16 && j < n2; j++) {
-    const double d2 = pair_d2(a0, a1, a2, aa, z2[j], z2[ld2 + j], z2[2 * ld2 + j], z2[3 * ld2 + j]);
+    const double d2 = pair_d2(a0, a1, a2, aa, z2[j], z2[ld2 + j], z2[2 * ld2 + j], z2[3 * ld2 + j], a3, z2[4 * ld2 + j]);
     if (Km) Km[(long)j * ld + i] = kern_val(d2, P);
     if (D2m) D2m[(long)j * ld + i] = d2;
   }
 }
 
-int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const double* X1, int n2, const double* X2, double* K, double* D2)
+int gpss_compute_K(int device, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2, const double* X2, double* K, double* D2)
 {
-  if (!theta || !X1 || !X2 || n1 < 1 || n2 < 1) return fail_arg("gpss_compute_K: bad argument");
+  if (!theta || !X1 || !X2 || n1 < 1 || n2 < 1 || (d != 3 && d != 4)) return fail_arg("gpss_compute_K: bad argument");
   CU(cudaSetDevice(device));
-  double s1[3], s2[3], centre[3];
-  seq_colsums(X1, n1, s1);
-  seq_colsums(X2, n2, s2);
-  maha_centre(n1, s1, n2, s2, centre);
+  double s1[4], s2[4], centre[4];
+  seq_colsums(X1, n1, s1, d);
+  seq_colsums(X2, n2, s2, d);
+  maha_centre(n1, s1, n2, s2, centre, d);
   DevParams P;
-  fill_params(theta, centre, P);
+  fill_params(theta, centre, P, d);
   double *dx1 = nullptr, *dx2 = nullptr, *dz1 = nullptr, *dz2 = nullptr, *dK = nullptr, *dD = nullptr;
   DevParams* dP = nullptr;
   int rc = GPSS_OK;
   auto cleanup = [&]() { cudaFree(dx1); cudaFree(dx2); cudaFree(dz1); cudaFree(dz2); cudaFree(dK); cudaFree(dD); cudaFree(dP); };
 #define CUK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
-  CUK(cudaMalloc(&dx1, sizeof(double) * 3 * n1));
-  CUK(cudaMalloc(&dx2, sizeof(double) * 3 * n2));
-  CUK(cudaMalloc(&dz1, sizeof(double) * 4 * n1));
-  CUK(cudaMalloc(&dz2, sizeof(double) * 4 * n2));
+  CUK(cudaMalloc(&dx1, sizeof(double) * NX * n1));
+  CUK(cudaMalloc(&dx2, sizeof(double) * NX * n2));
+  CUK(cudaMalloc(&dz1, sizeof(double) * NZ * n1));
+  CUK(cudaMalloc(&dz2, sizeof(double) * NZ * n2));
+  CUK(cudaMemset(dx1, 0, sizeof(double) * NX * n1));
+  CUK(cudaMemset(dx2, 0, sizeof(double) * NX * n2));
   CUK(cudaMalloc(&dP, sizeof(DevParams)));
   if (K) CUK(cudaMalloc(&dK, sizeof(double) * (size_t)n1 * n2));
   if (D2) CUK(cudaMalloc(&dD, sizeof(double) * (size_t)n1 * n2));
-  CUK(cudaMemcpy(dx1, X1, sizeof(double) * 3 * n1, cudaMemcpyHostToDevice));
-  CUK(cudaMemcpy(dx2, X2, sizeof(double) * 3 * n2, cudaMemcpyHostToDevice));
+  CUK(cudaMemcpy(dx1, X1, sizeof(double) * d * n1, cudaMemcpyHostToDevice));
+  CUK(cudaMemcpy(dx2, X2, sizeof(double) * d * n2, cudaMemcpyHostToDevice));
   CUK(cudaMemcpy(dP, &P, sizeof P, cudaMemcpyHostToDevice));
   transform_kernel<<<(n1 + 255) / 256, 256>>>(dx1, n1, dz1, n1, n1, n1, dP);
   transform_kernel<<<(n2 + 255) / 256, 256>>>(dx2, n2, dz2, n2, n2, n2, dP);
@@ -1350,7 +1357,7 @@ int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const doub
 // interface that do not go through the device-resident GradLL.  One pass over ALL (i, j) pairs (QW need not be
 // symmetric) accumulating  T = X' w X (3x3),  V1_k = sum w x_ik^2,  V2_k = sum w x_jk^2,  G6 = sum QW e^{-s}  with
 // w_ij = Sigma^2 QW_ij e^{-s_ij} (-0.5 / s_ij), zero on the diagonal and where s_ij == 0 (Kernel.cpp:1176-1185).
-constexpr int NGFULL = 16;
+constexpr int NGFULL = 17;
 __global__ void __launch_bounds__(256) grad_full_kernel(const double* __restrict__ QW, long ldq, const double* __restrict__ z, long ldz,
                                                         const double* __restrict__ x, long ldx, int n, const DevParams* __restrict__ Pp,
                                                         double* __restrict__ partial)
@@ -1362,13 +1369,16 @@ __global__ void __launch_bounds__(256) grad_full_kernel(const double* __restrict
 #pragma unroll
   for (int q = 0; q < NGFULL; q++) v[q] = 0.0;
   if (i < n) {
-    const double zi0 = z[i], zi1 = z[ldz + i], zi2 = z[2 * ldz + i], ai = z[3 * ldz + i];
+    const double zi0 = z[i], zi1 = z[ldz + i], zi2 = z[2 * ldz + i], ai = z[3 * ldz + i], zi3 = z[4 * ldz + i];
     const double xi[3] = {x[i], x[ldx + i], x[2 * ldx + i]};
+    const double xr = x[3 * ldx + i];
     for (int j = jb; j < jb + 16 && j < n; j++) {
-      const double d2 = pair_d2(zi0, zi1, zi2, ai, z[j], z[ldz + j], z[2 * ldz + j], z[3 * ldz + j]);
+      const double d2 = pair_d2(zi0, zi1, zi2, ai, z[j], z[ldz + j], z[2 * ldz + j], z[3 * ldz + j], zi3, z[4 * ldz + j]);
       const double s = sqrt(d2), es = exp(-s);
       const double q = QW[(long)j * ldq + i];
       v[15] += q * es;
+      const double dr = xr - x[3 * ldx + j];
+      v[16] = fma(es, dr * dr, v[16]);            // 4-column branch: sum_ij exp(-s) (x_i3 - x_j3)^2 (Kernel.cpp:1246-1255, no QW)
       if (i != j && s != 0.0) {
         const double w = (P.var2 * q) * (es * (-0.5 / s));
         const double xj[3] = {x[j], x[ldx + j], x[2 * ldx + j]};
@@ -1385,15 +1395,15 @@ __global__ void __launch_bounds__(256) grad_full_kernel(const double* __restrict
   block_reduce_store<NGFULL>(v, partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * NGFULL);
 }
 
-int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, const double* X, const double* QW, double g8[8])
+int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int d, int n, const double* X, const double* QW, double g8[8])
 {
-  if (!theta || !X || !QW || !g8 || n < 1) return fail_arg("gpss_expans_gradients: bad argument");
+  if (!theta || !X || !QW || !g8 || n < 1 || (d != 3 && d != 4)) return fail_arg("gpss_expans_gradients: bad argument");
   CU(cudaSetDevice(device));
-  double s1[3], centre[3];
-  seq_colsums(X, n, s1);
-  maha_centre(n, s1, n, s1, centre);
+  double s1[4], centre[4];
+  seq_colsums(X, n, s1, d);
+  maha_centre(n, s1, n, s1, centre, d);
   DevParams P;
-  fill_params(theta, centre, P);
+  fill_params(theta, centre, P, d);
   const dim3 grid((n + 63) / 64, (n + 63) / 64);
   const long nblocks = (long)grid.x * grid.y;
   double *dx = nullptr, *dz = nullptr, *dQ = nullptr, *dpart = nullptr, *dred = nullptr;
@@ -1401,13 +1411,14 @@ int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, cons
   int rc = GPSS_OK;
   auto cleanup = [&]() { cudaFree(dx); cudaFree(dz); cudaFree(dQ); cudaFree(dpart); cudaFree(dred); cudaFree(dP); };
 #define CUG(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
-  CUG(cudaMalloc(&dx, sizeof(double) * 3 * n));
-  CUG(cudaMalloc(&dz, sizeof(double) * 4 * n));
+  CUG(cudaMalloc(&dx, sizeof(double) * NX * n));
+  CUG(cudaMalloc(&dz, sizeof(double) * NZ * n));
+  CUG(cudaMemset(dx, 0, sizeof(double) * NX * n));
   CUG(cudaMalloc(&dQ, sizeof(double) * (size_t)n * n));
   CUG(cudaMalloc(&dpart, sizeof(double) * nblocks * NGFULL));
   CUG(cudaMalloc(&dred, sizeof(double) * NGFULL));
   CUG(cudaMalloc(&dP, sizeof(DevParams)));
-  CUG(cudaMemcpy(dx, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  CUG(cudaMemcpy(dx, X, sizeof(double) * d * n, cudaMemcpyHostToDevice));
   CUG(cudaMemcpy(dQ, QW, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
   CUG(cudaMemcpy(dP, &P, sizeof P, cudaMemcpyHostToDevice));
   transform_kernel<<<(n + 255) / 256, 256>>>(dx, n, dz, n, n, n, dP);
@@ -1430,7 +1441,7 @@ int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, cons
     g8[p] = 2.0 * qv - 4.0 * mt;               // sum_ij w_ij (2 q_p(x_i) + 2 q_p(x_j) - 4 x_i' M_p x_j), Kernel.cpp:1192-1233
   }
   g8[6] = 2.0 * red[15] * theta[6];            // Kernel.cpp:1239-1242
-  g8[7] = 0.0;                                 // Kernel.cpp:1256-1257 (3-D)
+  g8[7] = (d == 4) ? (-2.0 * (2.0 * red[16])) / (double)n : 0.0;   // Kernel.cpp:1246-1257 (see combine_gradient)
   return GPSS_OK;
 }
 

@@ -2,8 +2,8 @@
 // which lives in gpss_gemm.cuh).  File:line citations are into /root/reference.
 //
 // Data layout in HBM (all FP64, column-major like arma::mat):
-//   xs[3][n_pad]   standardised, UNcentred coordinates (the reference's Xinp), SoA
-//   zs[4][n_pad]   z = (x - c) * sigInv (3 rows) and a = |z|^2 (4th row), SoA
+//   xs[4][n_pad]   standardised, UNcentred coordinates (the reference's Xinp), SoA; row 3 = rock-type column (zeros when d = 3)
+//   zs[5][n_pad]   z = (x - c) * sigInv (rows 0-2), a = |z|^2 (row 3), z_3 = (x_3 - c_3) * InversewidthR (row 4; 0 when d = 3), SoA
 //   Lm[n_pad^2]    B = I + (Sw Sw') o K  -> overwritten by its Cholesky factor L (lower)
 //   Um[n_pad^2]    U = L^-T (upper)
 //   Qm[n_pad^2]    Q = B^-1 (lower triangle)  (also W = L^-1 for prediction)
@@ -17,9 +17,15 @@ namespace gpss {
 
 constexpr int NB = 128;          // diagonal / tile block
 
+constexpr int NZ = 5;            // rows of a transformed-coordinate array
+constexpr int NX = 4;            // rows of a coordinate array
+
 struct DevParams {
   double S[9];        // sigInv = Rot*diag(l)*Rot' (Kernel.cpp:1425), S[k*3+j]
-  double c[3];        // MahaDist centre (Kernel.cpp:1391-1392)
+  double c[4];        // MahaDist centre (Kernel.cpp:1391-1392)
+  double lr;          // InversewidthR_ExpAns = sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
+  int dim;            // 3, or 4 with the rock-type column
+  int pad_;
   double var2;        // Sigma_ExpAns^2 (Kernel.cpp:861)
   double bias;        // Sigma_Bias (Kernel.cpp:366)
   double sn2;         // hyperlf(0) (GP_Utils.cpp:406)
@@ -32,10 +38,12 @@ struct DevParams {
 // ---------------------------------------------------------------------------------------------------
 // defined-order Mahalanobis pieces (SURVEY.md section 7 hard part 1; mirrors oracle maha_dist_defined)
 // ---------------------------------------------------------------------------------------------------
+// The 4th coordinate (z_3, zero in the 3-column case) enters last, so with d = 3 every value below is bit-identical to
+// the 3-term form: fma(0, 0, c) = c and a + 0 = a.
 __device__ __forceinline__ double pair_d2(double zi0, double zi1, double zi2, double ai,
-                                          double zj0, double zj1, double zj2, double aj)
+                                          double zj0, double zj1, double zj2, double aj, double zi3, double zj3)
 {
-  const double cij = fma(zi2, zj2, fma(zi1, zj1, __dmul_rn(zi0, zj0)));
+  const double cij = fma(zi3, zj3, fma(zi2, zj2, fma(zi1, zj1, __dmul_rn(zi0, zj0))));
   const double d2 = __dadd_rn(__dadd_rn(ai, aj), __dmul_rn(-2.0, cij));
   return d2 < 0.0 ? 0.0 : d2;     // find(D2<0) -> 0 (Kernel.cpp:1433-1434)
 }
@@ -46,7 +54,7 @@ __global__ void transform_kernel(const double* __restrict__ xs, long ldx, double
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
-  if (i >= n) { zs[i] = 0; zs[ldz + i] = 0; zs[2 * ldz + i] = 0; zs[3 * ldz + i] = 0; return; }
+  if (i >= n) { zs[i] = 0; zs[ldz + i] = 0; zs[2 * ldz + i] = 0; zs[3 * ldz + i] = 0; zs[4 * ldz + i] = 0; return; }
   const double d0 = __dsub_rn(xs[i], P->c[0]);
   const double d1 = __dsub_rn(xs[ldx + i], P->c[1]);
   const double d2 = __dsub_rn(xs[2 * ldx + i], P->c[2]);
@@ -54,7 +62,9 @@ __global__ void transform_kernel(const double* __restrict__ xs, long ldx, double
 #pragma unroll
   for (int j = 0; j < 3; j++) z[j] = fma(d2, P->S[6 + j], fma(d1, P->S[3 + j], __dmul_rn(d0, P->S[j])));
   zs[i] = z[0]; zs[ldz + i] = z[1]; zs[2 * ldz + i] = z[2];
-  zs[3 * ldz + i] = __dadd_rn(__dadd_rn(__dmul_rn(z[0], z[0]), __dmul_rn(z[1], z[1])), __dmul_rn(z[2], z[2]));
+  const double z3 = (P->dim == 4) ? __dmul_rn(__dsub_rn(xs[3 * ldx + i], P->c[3]), P->lr) : 0.0;
+  zs[4 * ldz + i] = z3;
+  zs[3 * ldz + i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(z[0], z[0]), __dmul_rn(z[1], z[1])), __dmul_rn(z[2], z[2])), __dmul_rn(z3, z3));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -83,19 +93,19 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
     if (tn >= (int)gridDim.x) return;
   } else if (own_world > 1 && (tn / own_width) % own_world != own_rank) return;
   if (tn > tm) return;
-  __shared__ double cz[4][NB];
+  __shared__ double cz[NZ][NB];
   __shared__ DevParams P;
   const int tid = threadIdx.x;
   if (tid == 0) P = *Pp;
   const int r0 = tm * NB, c0 = tn * NB;
-  for (int idx = tid; idx < 4 * NB; idx += 256) cz[idx / NB][idx % NB] = zs[(long)(idx / NB) * ldz + c0 + idx % NB];
+  for (int idx = tid; idx < NZ * NB; idx += 256) cz[idx / NB][idx % NB] = zs[(long)(idx / NB) * ldz + c0 + idx % NB];
   const int tx = tid & 63, ty = tid >> 6;
   const int i0 = r0 + 2 * tx;
-  double zi[2][4];
+  double zi[2][NZ];
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int q = 0; q < 4; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+    for (int q = 0; q < NZ; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
   __syncthreads();
 #pragma unroll 4
   for (int jj = ty; jj < NB; jj += 4) {
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
       const int i = i0 + e;
       double v;
       if (i < n && j < n) {
-        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj]);
+        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
         v = kern_val(d2, P);
         if (!raw_K) {
           v = __dmul_rn(P.sww, v);
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_part_kernel(const 
 __global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
                                                       double* __restrict__ f, int n, const DevParams* __restrict__ Pp)
 {
-  __shared__ double cz[5][256];
+  __shared__ double cz[6][256];
   __shared__ double part[4][64];
   __shared__ DevParams P;
   const int tid = threadIdx.x, rr = tid & 63, pp = tid >> 6;
@@ -524,19 +534,19 @@ __global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__
   const int i = blockIdx.x * 64 + rr;
   const bool vi = i < n;
   const int ic = vi ? i : 0;
-  const double z0 = zs[ic], z1 = zs[ldz + ic], z2 = zs[2 * ldz + ic], ai = zs[3 * ldz + ic];
+  const double z0 = zs[ic], z1 = zs[ldz + ic], z2 = zs[2 * ldz + ic], ai = zs[3 * ldz + ic], z3 = zs[4 * ldz + ic];
   double acc = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     __syncthreads();
     const int j = j0 + tid;
     if (j < n) {
       cz[0][tid] = zs[j]; cz[1][tid] = zs[ldz + j]; cz[2][tid] = zs[2 * ldz + j]; cz[3][tid] = zs[3 * ldz + j];
-      cz[4][tid] = alpha[j];
-    } else { cz[0][tid] = cz[1][tid] = cz[2][tid] = cz[3][tid] = 0; cz[4][tid] = 0; }
+      cz[4][tid] = alpha[j]; cz[5][tid] = zs[4 * ldz + j];
+    } else { cz[0][tid] = cz[1][tid] = cz[2][tid] = cz[3][tid] = 0; cz[4][tid] = 0; cz[5][tid] = 0; }
     __syncthreads();
 #pragma unroll 4
     for (int q = pp; q < 256; q += 4) {
-      const double d2 = pair_d2(z0, z1, z2, ai, cz[0][q], cz[1][q], cz[2][q], cz[3][q]);
+      const double d2 = pair_d2(z0, z1, z2, ai, cz[0][q], cz[1][q], cz[2][q], cz[3][q], z3, cz[5][q]);
       acc = fma(kern_val(d2, P), cz[4][q], acc);
     }
   }
@@ -594,9 +604,10 @@ __global__ void __launch_bounds__(256) lml_terms_kernel(const double* __restrict
 //       w_ij  = var2*QW_ij*exp(-s_ij)*(-0.5/s_ij)   (0 on the diagonal and where s_ij == 0)
 //       T_kl  = sum_ij w_ij x_ik x_jl ; V_k = sum_ij w_ij x_ik^2 ; G6 = sum_ij QW_ij exp(-s_ij)
 //       TR    = sum_i QW_ii ; QK = sum_ij Q_ij K_ij
-//     partial[block][16] = {T00,T01,T02,T11,T12,T22, V0,V1,V2, G6, TR, QK}; combined on the host into g[0..9].
+//       RK    = sum_{i>j} e^{-s_ij} (x_i3 - x_j3)^2   (4-column branch only: g[7], Kernel.cpp:1246-1255 -- no QW, see combine_gradient)
+//     partial[block][13] = {T00,T01,T02,T11,T12,T22, V0,V1,V2, G6, TR, QK, RK}; combined on the host into g[0..9].
 // ---------------------------------------------------------------------------------------------------
-constexpr int NGRAD = 12;
+constexpr int NGRAD = 13;
 
 __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict__ Qm, long ld, const double* __restrict__ zs, long ldz,
                                                         const double* __restrict__ xs, long ldx, const double* __restrict__ alpha,
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
   const int tm = tm0 + blockIdx.x, tn = blockIdx.y;
   double* out = partial + ((long)tn * gridDim.x + blockIdx.x) * NGRAD;
   if (tn > tm) { if (threadIdx.x < NGRAD) out[threadIdx.x] = 0.0; return; }
-  __shared__ double cz[4][NB], cx[3][NB], ca[NB];
+  __shared__ double cz[NZ][NB], cx[NX][NB], ca[NB];
   __shared__ DevParams P;
   const int tid = threadIdx.x;
   if (tid == 0) P = *Pp;
@@ -614,25 +625,25 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
   for (int idx = tid; idx < NB; idx += 256) {
     const int j = c0 + idx;
 #pragma unroll
-    for (int q = 0; q < 4; q++) cz[q][idx] = zs[(long)q * ldz + j];
+    for (int q = 0; q < NZ; q++) cz[q][idx] = zs[(long)q * ldz + j];
 #pragma unroll
-    for (int q = 0; q < 3; q++) cx[q][idx] = xs[(long)q * ldx + j];
+    for (int q = 0; q < NX; q++) cx[q][idx] = xs[(long)q * ldx + j];
     ca[idx] = alpha[j];
   }
   const int tx = tid & 63, ty = tid >> 6;
   const int i0 = r0 + 2 * tx;
-  double zi[2][4], xi[2][3], al[2];
+  double zi[2][NZ], xi[2][NX], al[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+    for (int q = 0; q < NZ; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
 #pragma unroll
-    for (int q = 0; q < 3; q++) xi[e][q] = xs[(long)q * ldx + i0 + e];
+    for (int q = 0; q < NX; q++) xi[e][q] = xs[(long)q * ldx + i0 + e];
     al[e] = alpha[i0 + e];
   }
   __syncthreads();
   double om[2] = {0, 0}, u[2][3] = {{0, 0, 0}, {0, 0, 0}}, pq[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  double g6 = 0, tr = 0, qk = 0;
+  double g6 = 0, tr = 0, qk = 0, rk = 0;
   for (int jj = ty; jj < NB; jj += 4) {
     const int j = c0 + jj;
     const double2 qv = *reinterpret_cast<const double2*>(Qm + (long)j * ld + i0);
@@ -641,7 +652,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
     for (int e = 0; e < 2; e++) {
       const int i = i0 + e;
       if (i < n && j < n && i >= j) {
-        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj]);
+        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
         const double s = sqrt(d2);
         const double es = exp(-s);
         const double QWij = qe[e] * P.inv_sn2 - al[e] * ca[jj];
@@ -653,6 +664,8 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
         } else {
           g6 += 2.0 * (QWij * es);
           qk += 2.0 * (qe[e] * Kij);
+          const double dr = xi[e][3] - cx[3][jj];
+          rk = fma(es, dr * dr, rk);
           if (s != 0.0) {
             const double w = (P.var2 * QWij) * (es * (-0.5 / s));
             om[e] += w;
@@ -682,7 +695,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
 #pragma unroll
     for (int q = 0; q < 3; q++) v[6 + q] += xi[e][q] * xi[e][q] * om[e] + pq[e][q];
   }
-  v[9] = g6; v[10] = tr; v[11] = qk;
+  v[9] = g6; v[10] = tr; v[11] = qk; v[12] = rk;
   block_reduce_store<NGRAD>(v, out);
 }
 
@@ -775,7 +788,7 @@ __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ B
                                                           int m, int n, const DevParams* __restrict__ Pp,
                                                           double* __restrict__ mu_part, long ldmu, int write_B)
 {
-  __shared__ double cz[4][NB], ca[NB];
+  __shared__ double cz[NZ][NB], ca[NB];
   __shared__ double mred[4][NB];
   __shared__ DevParams P;
   const int tid = threadIdx.x;
@@ -784,16 +797,16 @@ __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ B
   for (int idx = tid; idx < NB; idx += 256) {
     const int i = i0t + idx;
 #pragma unroll
-    for (int q = 0; q < 4; q++) cz[q][idx] = zs[(long)q * ldz + i];
+    for (int q = 0; q < NZ; q++) cz[q][idx] = zs[(long)q * ldz + i];
     ca[idx] = (i < n) ? alpha[i] : 0.0;
   }
   const int tx = tid & 63, ty = tid >> 6;
   const int j0 = j0t + 2 * tx;
-  double zj[2][4];
+  double zj[2][NZ];
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int q = 0; q < 4; q++) zj[e][q] = zt[(long)q * ldzt + j0 + e];
+    for (int q = 0; q < NZ; q++) zj[e][q] = zt[(long)q * ldzt + j0 + e];
   __syncthreads();
   double mu[2] = {0, 0};
   for (int ii = ty; ii < NB; ii += 4) {
@@ -805,7 +818,7 @@ __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ B
       double v = 0.0;
       if (i < n && (j0 + e) < m) {
         // K(X_train, X_test)(i,j): first argument is the training point (GP_Utils.cpp:946-947)
-        const double d2 = pair_d2(cz[0][ii], cz[1][ii], cz[2][ii], cz[3][ii], zj[e][0], zj[e][1], zj[e][2], zj[e][3]);
+        const double d2 = pair_d2(cz[0][ii], cz[1][ii], cz[2][ii], cz[3][ii], zj[e][0], zj[e][1], zj[e][2], zj[e][3], cz[4][ii], zj[e][4]);
         const double k = kern_val(d2, P);
         mu[e] = fma(ca[ii], k, mu[e]);
         v = __dmul_rn(k, P.sw);

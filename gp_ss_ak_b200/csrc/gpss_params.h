@@ -41,17 +41,17 @@ inline void sig_inv(const double theta[10], double S[9])
 }
 
 // MahaDist centre (Kernel.cpp:1391-1392) from column sums accumulated in row order
-inline void maha_centre(long n, const double sums1[3], long m, const double sums2[3], double c[3])
+inline void maha_centre(long n, const double* sums1, long m, const double* sums2, double* c, int d = 3)
 {
-  for (int j = 0; j < 3; j++) {
+  for (int j = 0; j < d; j++) {
     const double mX1 = ((double)n / (double)(n + m)) * sums1[j] / (double)n;
     c[j] = ((double)m / (double)(n + m)) * sums2[j] / (double)m + mX1;
   }
 }
 
-inline void seq_colsums(const double* X_colmajor, long n, double sums[3])
+inline void seq_colsums(const double* X_colmajor, long n, double* sums, int d = 3)
 {
-  for (int j = 0; j < 3; j++) {
+  for (int j = 0; j < d; j++) {
     double acc = 0.0;
     const double* col = X_colmajor + (long)j * n;
     for (long i = 0; i < n; i++) acc += col[i];
@@ -114,8 +114,8 @@ inline void grad_M_matrices(const double theta[10], double M[6][9])
 }
 
 // Combine the device reductions into the reference's g[0..9].
-//   red = {T00,T01,T02,T11,T12,T22, V0,V1,V2, G6, TR, QK},  s3 = sum((y-f)^2/sn2 - 1)
-inline void combine_gradient(const double theta[10], const double red[12], double s3, double g[10])
+//   red = {T00,T01,T02,T11,T12,T22, V0,V1,V2, G6, TR, QK, RK},  s3 = sum((y-f)^2/sn2 - 1)
+inline void combine_gradient(const double theta[10], const double red[13], double s3, double g[10], int dim = 3, long n = 1)
 {
   double M[6][9];
   grad_M_matrices(theta, M);
@@ -130,7 +130,10 @@ inline void combine_gradient(const double theta[10], const double red[12], doubl
     g[p] = 4.0 * qv - 4.0 * mt;                 // Kernel.cpp:1192-1233 in reduced form
   }
   g[6] = 2.0 * red[9] * theta[6];               // Kernel.cpp:1239-1242
-  g[7] = 0.0;                                   // Kernel.cpp:1256-1257 (3-D)
+  // 3 columns: 0 (Kernel.cpp:1256-1257).  4 columns (Kernel.cpp:1246-1255): dhp = -2 RColon' * Di2(:) / n with
+  // Di2_ij = 2 (x_i3 - x_j3)^2 and [quirk] RColon still holding exp(-s) from the Sigma gradient (:1240) -- QW does not
+  // enter; RK is the sum over i > j, so the ordered-pair sum is 2 RK.
+  g[7] = (dim == 4) ? (-2.0 * (2.0 * (2.0 * red[12]))) / (double)n : 0.0;
   g[8] = red[10];                               // Kern_Bias::getGradients = trace(QW) (Kernel.cpp:370-377)
   g[9] = -1.0 * (0.5 * red[11]) * (2.0 / theta[9]) - s3;   // GP_Utils.cpp:1226 with dW = 0.5*rowsum(Q%K) (:1206)
 }

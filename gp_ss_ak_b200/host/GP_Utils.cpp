@@ -138,7 +138,7 @@ void GP_utils::check_supported() const
   else if (!hyb || KerenlW->getKerName() != "Hyb" || hyb->getNumKerns() != 2 || hyb->getKern(0)->getKerName() != "ExpAns" ||
            hyb->getKern(1)->getKerName() != "Bias")
     why = "the kernel must be Hyb{ExpAns, Bias} (train with -k ExpAns -kn 1)";
-  else if (Xinp.n_cols != 3) why = "inputs must have 3 columns";
+  else if (Xinp.n_cols != 3 && Xinp.n_cols != 4) why = "inputs must have 3 columns, or 4 with the rock-type column";
   else if (yTarg.n_cols != 1 || getOutDim() != 1) why = "exactly one output column is supported";
   else if (likelihoodType_ != likeL_Gaussian || getNumlikfpar() != 1) why = "only the Gaussian likelihood is supported";
   else if (MeanType_ != mean_zero || getNumMFpar() != 0) why = "only the zero mean function is supported";
@@ -164,7 +164,7 @@ void GP_utils::sync_device() const
     handle = 0;
   }
   if (!handle) {
-    if (gpss_create(device, n, 3, Xinp.memptr(), yTarg.memptr(), &handle) != GPSS_OK) device_failure("gpss_create");
+    if (gpss_create(device, n, (int)Xinp.n_cols, Xinp.memptr(), yTarg.memptr(), &handle) != GPSS_OK) device_failure("gpss_create");
     if (gpss_host::world() > 1) {
       // one process per GPU (DistHost.h): every rank holds the same data; from here on the objective / gradient /
       // prediction calls are collective and return identical results everywhere
@@ -258,7 +258,7 @@ double GP_utils::GradLL(mat& g) const
 // ---------------------------------------------------------------------------------------------------
 void GP_utils::posteriorMeanVar(mat& mu, mat& varSigma, const mat& X) const
 {
-  if (X.n_cols != 3) { cout << "GP_utils: test inputs must have 3 columns\n"; exit(1); }
+  if (X.n_cols != Xinp.n_cols) { cout << "GP_utils: test inputs must have as many columns as the training inputs\n"; exit(1); }
   sync_device();
   mu.set_size(X.n_rows, 1);
   varSigma.set_size(X.n_rows, 1);
@@ -273,7 +273,7 @@ void GP_utils::posteriorMeanVar(mat& mu, mat& varSigma, const mat& X) const
 
 void GP_utils::posteriorMean(mat& mu, const mat& X) const
 {
-  if (X.n_cols != 3) { cout << "GP_utils: test inputs must have 3 columns\n"; exit(1); }
+  if (X.n_cols != Xinp.n_cols) { cout << "GP_utils: test inputs must have as many columns as the training inputs\n"; exit(1); }
   sync_device();
   mu.set_size(X.n_rows, 1);
   const int rc = gpss_predict(handle, (long)X.n_rows, X.memptr(), mu.memptr(), 0);

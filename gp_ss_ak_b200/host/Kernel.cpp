@@ -253,7 +253,7 @@ double Kern_ExpAnisotropic::getParam(unsigned int paramNo) const
 namespace {
 void require_3d(const mat& X, const char* who)
 {
-  if (X.n_cols != 3) fatal(string(who) + ": only 3-column inputs are implemented by the B200 path (the 4-column rock-type branch is not)");
+  if (X.n_cols != 3 && X.n_cols != 4) fatal(string(who) + ": inputs must have 3 columns, or 4 with the rock-type column (Kernel.cpp:864-878)");
 }
 // theta in the C ABI's order with the ExpAns block filled in and no bias / unit noise
 void theta_of(const double par[8], double theta[GPSS_NPAR])
@@ -272,7 +272,8 @@ void Kern_ExpAnisotropic::computeK(const mat& X1, const mat& X2, mat& K, mat& D2
   theta_of(par, theta);
   K.set_size(X1.n_rows, X2.n_rows);
   D2.set_size(X1.n_rows, X2.n_rows);
-  check(gpss_compute_K(0, theta, (int)X1.n_rows, X1.memptr(), (int)X2.n_rows, X2.memptr(), K.memptr(), D2.memptr()), "gpss_compute_K");
+  if (X1.n_cols != X2.n_cols) fatal("Kern_ExpAnisotropic::computeK: X1 and X2 must have the same number of columns");
+  check(gpss_compute_K(0, theta, (int)X1.n_cols, (int)X1.n_rows, X1.memptr(), (int)X2.n_rows, X2.memptr(), K.memptr(), D2.memptr()), "gpss_compute_K");
 }
 
 void Kern_ExpAnisotropic::getGradients(mat& g, const mat& X, const mat& X2, const mat&, const mat& QW) const
@@ -282,7 +283,7 @@ void Kern_ExpAnisotropic::getGradients(mat& g, const mat& X, const mat& X2, cons
     fatal("Kern_ExpAnisotropic::getGradients: the B200 path implements the X2 == X (training) case only");
   double theta[GPSS_NPAR], g8[8];
   theta_of(par, theta);
-  check(gpss_expans_gradients(0, theta, (int)X.n_rows, X.memptr(), QW.memptr(), g8), "gpss_expans_gradients");
+  check(gpss_expans_gradients(0, theta, (int)X.n_cols, (int)X.n_rows, X.memptr(), QW.memptr(), g8), "gpss_expans_gradients");
   for (int i = 0; i < 8; i++) g[i] = g8[i];
 }
 

@@ -43,7 +43,9 @@ const char* gpss_last_error(void);
 
 /* model state ------------------------------------------------------------------------------------ */
 /* Replaces GP_utils::GP_utils + initialize_vars (GP_Utils.cpp:9-86): takes the standardised training
- * inputs X (n x d, d == 3) and targets y (n) and makes them device resident. */
+ * inputs X (n x d) and targets y (n) and makes them device resident.  d == 3, or d == 4 for the reference's rock-type
+ * branch of the ExpAns kernel: the 4th column is scaled by theta[7] = InversewidthR and g[7] is no longer zero
+ * (Kernel.cpp:872-878, 1411-1424, 1246-1255). */
 int gpss_create(int device, int n, int d, const double* X_colmajor, const double* y, gpss_handle* out);
 int gpss_destroy(gpss_handle h);
 /* Re-upload training data of the same shape (test() assigns Xinp / yTarg, gp_ss_ak.cpp:389-395). */
@@ -101,7 +103,7 @@ int gpss_predict(gpss_handle h, long m, const double* Xs_colmajor, double* mu, d
  * split the test points (L and alpha replicated) yet use the global centre.  var receives the RAW variance
  * kD - k*' (K + sn2 I)^-1 k* (GP_Utils.cpp:997-998) with no post-processing: the reference's next step is index
  * arithmetic over the whole vector, so the caller gathers the shards and calls gpss_var_postprocess once. */
-int gpss_predict_shard(gpss_handle h, long m_total, const double sums_total[3], long count,
+int gpss_predict_shard(gpss_handle h, long m_total, const double* sums_total /* [d] */, long count,
                        const double* Xs_shard_colmajor, double* mu, double* var);
 /* GP_Utils.cpp:1001-1003 + 1033-1040, literally: `uvec ind = varSigma < 0; varSigma.elem(ind) = 0` uses the 0/1
  * comparison flags AS INDICES (element 0 is zeroed if any entry is >= 0, element 1 if any entry is < 0, negative
@@ -109,13 +111,13 @@ int gpss_predict_shard(gpss_handle h, long m_total, const double sums_total[3], 
 int gpss_var_postprocess(long m, double sn2, double* var_inout);
 
 /* Kernels::computeK compatibility (host matrices; Kernel.cpp:140-154, 856-882, 362-367) ---------- */
-/* K and D2 are n1 x n2 column-major host buffers (either may be NULL). */
-int gpss_compute_K(int device, const double theta[GPSS_NPAR], int n1, const double* X1, int n2, const double* X2,
+/* K and D2 are n1 x n2 column-major host buffers (either may be NULL); X1, X2 have d (3 or 4) columns. */
+int gpss_compute_K(int device, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2, const double* X2,
                    double* K, double* D2);
 
 /* Kern_ExpAnisotropic::getGradients compatibility (Kernel.cpp:886-1263): the 8 kernel-parameter entries of the
- * reference's gradient for a HOST n x n matrix QW (column-major, need not be symmetric) and X1 == X2 == X (n x 3). */
-int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int n, const double* X_colmajor,
+ * reference's gradient for a HOST n x n matrix QW (column-major, need not be symmetric) and X1 == X2 == X (n x d). */
+int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int d, int n, const double* X_colmajor,
                           const double* QW_colmajor, double g8[8]);
 
 /* instrumentation ---------------------------------------------------------------------------------- */

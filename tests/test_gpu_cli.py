@@ -121,3 +121,37 @@ def test_cli_two_gpu_launch_matches_single_gpu(tmp_path):
     assert outs["one"][2].splitlines()[1:] == outs["two"][2].splitlines()[1:]     # 6-significant-digit model file: identical
     assert np.allclose(outs["one"][3], outs["two"][3], rtol=1e-5, atol=1e-8)
     assert outs["two"][0].count("Iteration: 1 -logL:") == 1       # only rank 0 printed
+
+
+def test_cli_four_column_rock_type_branch_matches_reference_binary(tmp_path):
+    """`gp_ss_ak train/test` on a 4-column data file (x y z rock grade): the reference's rock-type branch of the ExpAns kernel.
+    Compared with what the UNMODIFIED reference binary printed and wrote for the same files (tests/golden/ref_rock_n300.npz)."""
+    z = np.load(os.path.join(GOLD, "ref_rock_n300.npz"))
+    (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
+    (tmp_path / "test.txt").write_text(str(z["test_file_text"]))
+    iters = int(z["cli_iters"])
+    tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train", "-k", "ExpAns", "-kn", "1", "-o", "LBFGS", "-#", str(iters),
+                         str(tmp_path / "train.txt"), str(tmp_path / "cli_model")], capture_output=True, text=True,
+                        stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=600)
+    assert tr.returncode == 0, tr.stdout + tr.stderr
+    ref_out = str(z["cli_train_stdout"])
+    init_mine, init_ref = _floats_after(tr.stdout, "Log likelihood:")[0], _floats_after(ref_out, "Log likelihood:")[0]
+    assert np.isclose(init_mine, init_ref, rtol=2e-5)
+    it_mine, it_ref = _floats_after(tr.stdout, "-logL:"), _floats_after(ref_out, "-logL:")
+    assert len(it_mine) == len(it_ref) and np.isclose(it_mine[0], it_ref[0], rtol=1e-4)      # the first iteration is not yet noise-driven
+    assert (tmp_path / "cli_model_Statistics.txt").read_text() == str(z["cli_stats_text"])   # 5 rows: y, x, y, z, rock
+    mine_model = (tmp_path / "cli_model").read_text().splitlines()
+    ref_model = str(z["cli_model_text"]).splitlines()
+    assert [l.split("=")[0] for l in mine_model if "=" in l] == [l.split("=")[0] for l in ref_model if "=" in l]
+    assert "inputDim=4" in mine_model
+    (tmp_path / "ref_model").write_text(str(z["cli_model_text"]))
+    (tmp_path / "ref_model_Statistics.txt").write_text(str(z["cli_stats_text"]))
+    te = subprocess.run([CLI, "-v", "3", "-pm", "1", "test", str(tmp_path / "test.txt"), str(tmp_path / "ref_model"),
+                         str(tmp_path / "train.txt")], capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=600)
+    assert te.returncode == 0, te.stdout + te.stderr
+    mine_pred = _table((tmp_path / "ref_model_predict.txt").read_text())
+    ref_pred = _table(str(z["cli_predict_text"]))
+    assert mine_pred.shape == ref_pred.shape and mine_pred.shape[1] == 4 + 4
+    assert np.array_equal(mine_pred[:, 0], ref_pred[:, 0])
+    assert np.allclose(mine_pred[:, 2], ref_pred[:, 2], rtol=2e-5, atol=1e-6)
+    assert np.allclose(mine_pred[:, 3], ref_pred[:, 3], rtol=2e-5, atol=1e-6)

@@ -177,7 +177,32 @@ def test_parity_with_oracle(gpss, n, seed):
     _check_against_oracle(gpss, Xs, ys, O.THETA0.copy(), Xt)
 
 
-@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz"])
+@pytest.mark.parametrize("n,seed", [(129, 2), (700, 5), (2100, 1)])
+def test_parity_with_oracle_rock_type_column(gpss, n, seed):
+    """The reference's 4-column branch: the 4th input is a rock-type code scaled by
+    InversewidthR = theta[7] (Kernel.cpp:872-878, 1411-1424) and g[7] = -2 sum(exp(-s) % Di2_R) / n (Kernel.cpp:1246-1255).
+    Same tolerances as the 3-column path; the kernel matrix and the host-matrix compatibility entry points are checked too."""
+    X, y = datagen.drillholes(n, seed)
+    X4 = datagen.with_rock_column(X, seed)
+    Xs, ys, params = datagen.standardise_symmetric(X4, y)
+    assert Xs.shape[1] == 4 and np.isclose(Xs[:, 3].min(), -1) and np.isclose(Xs[:, 3].max(), 1)      # column 4: its own centre / half-range
+    Xt_raw, _ = datagen.drillholes(120, seed + 100)
+    Xt = (np.concatenate([datagen.with_rock_column(Xt_raw, seed), X4[:20]]) - params[1:, 0]) / params[1:, 1]
+    th = O.THETA0.copy()
+    th[7] = 0.8
+    _check_against_oracle(gpss, Xs, ys, th, Xt)
+    Lo, go, gp = O.nlml_and_grad(Xs, ys, th, literal=False)
+    assert go[7] != 0.0
+    K, D2 = gpss.compute_K(th, Xs[:300], Xs[:300])
+    Ko, D2o = O.compute_K(Xs[:300], Xs[:300], th)
+    assert np.array_equal(D2, D2o)                                   # defined operation order: bit-exact, 4th term included
+    assert np.abs(K - Ko).max() <= 4 * np.finfo(float).eps
+    if n <= 700:
+        g8 = gpss.expans_gradients(th, Xs, gp.QW)
+        assert np.abs(g8 - go[:8]).max() <= 1e-9 * np.abs(go[:8]).max()
+
+
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_rock_n300.npz"])
 def test_against_compiled_reference(gpss, name):
     """The CUDA path against numbers computed by the UNMODIFIED reference classes (tests/golden/make_ref_golden.py).
     Tolerances = the reference's own BLAS-dependent reproducibility floor (oracle/gpss_oracle.py header)."""
