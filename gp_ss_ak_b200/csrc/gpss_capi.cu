@@ -368,6 +368,8 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   if (P > 1) {
     std::vector<DistOp> ops;
     dist_potrf_schedule(nblk_o, P, me, ops);
+    int kchunk = 1 << 30;
+    if (const char* e = getenv("GPSS_DIST_KCHUNK")) { const int v = atoi(e); if (v >= NBO) kchunk = (v / NBO) * NBO; }
     for (const DistOp& op : ops) {
       const int T0 = op.col * NBO;
       const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
@@ -409,7 +411,11 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
           CU(cudaStreamWaitEvent(side, c->ev_pool[2 * (op.pbeg + op.pcnt - 1)], 0));
           int klen = op.pcnt * NBO;
           if (op.pbeg * NBO + klen > n_pad) klen = n_pad - op.pbeg * NBO;
-          RET(update(T0, nbT, op.pbeg * NBO, klen, side));
+          // Optional cut of the long-k chunk into launches of <= kchunk (GPSS_DIST_KCHUNK).  Measured at 8 GPUs, n = 50k:
+          // potrf 219 / 219 / 223 / 226 ms for kchunk = inf / 8192 / 4096 / 2048 (profiles/r01_dist_kchunk_sweep_8gpu.log),
+          // i.e. the critical path is NOT waiting for CTA slots held by long-lived bulk CTAs; default: one launch.
+          for (int k0 = 0; k0 < klen; k0 += kchunk)
+            RET(update(T0, nbT, op.pbeg * NBO + k0, (klen - k0 < kchunk) ? (klen - k0) : kchunk, side));
           CU(cudaEventRecord(c->ev_pool[2 * op.col + 1], side));
           break;
         }
