@@ -370,18 +370,32 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     dist_potrf_schedule(nblk_o, P, me, ops);
     int kchunk = 1 << 30;
     if (const char* e = getenv("GPSS_DIST_KCHUNK")) { const int v = atoi(e); if (v >= NBO) kchunk = (v / NBO) * NBO; }
+    // GPSS_DIST_TRACE: timing events around every main-stream step, summed per kind after the factorisation (diagnostic)
+    const bool trace = getenv("GPSS_DIST_TRACE") != nullptr;
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    auto mark = [&](int what) {
+      if (!trace) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, c->st);
+      marks.push_back({what, e});
+    };
+    mark(-1);
     for (const DistOp& op : ops) {
       const int T0 = op.col * NBO;
       const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
       switch (op.kind) {
         case DIST_WAIT_SIDE:                                               // every side-stream update of my column
           CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * op.col + 1], 0));
+          mark(0);
           break;
         case DIST_UPDATE_MAIN:                                             // U2: the panel just received, on the critical path
           RET(update(T0, nbT, op.pbeg * NBO, op.pcnt * NBO, c->st));
+          mark(1);
           break;
         case DIST_FACTOR:
           RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+          mark(2);
           break;
         case DIST_BCAST: {
           // the owner's finished block column (+ its diagonal inverses and log-dets) goes to every rank: after the loop L,
@@ -396,7 +410,9 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
             CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             c->launches++;
           }
+          if (mine) mark(3);
           NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, op.root, c->comm, c->st));
+          mark(mine ? 4 : 5);
           if (!mine) {
             unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
             CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
@@ -404,6 +420,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
             c->launches++;
           }
           CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));            // panel op.col is complete on this rank
+          if (!mine) mark(6);
           break;
         }
         case DIST_UPDATE_SIDE: {                                           // look-ahead: panels pbeg .. pbeg+pcnt-1 -> my column
@@ -420,6 +437,23 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
           break;
         }
       }
+    }
+    if (trace) {
+      CU(cudaStreamSynchronize(c->st));
+      static const char* names[7] = {"wait for look-ahead updates", "U2 (panel j-1 -> my column)", "panel factorisation", "pack", "broadcast (as root)",
+                                     "broadcast (as receiver, incl. waiting for the owner)", "unpack"};
+      double sum[7] = {0, 0, 0, 0, 0, 0, 0};
+      int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (size_t i = 1; i < marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+        sum[marks[i].first] += ms;
+        cnt[marks[i].first]++;
+      }
+      for (auto& m : marks) cudaEventDestroy(m.second);
+      fprintf(stderr, "[gpss dist trace] rank %d of %d, n_pad %d:", me, P, n_pad);
+      for (int k = 0; k < 7; k++) fprintf(stderr, " %s: %.1f ms / %d;", names[k], sum[k], cnt[k]);
+      fprintf(stderr, "\n");
     }
   } else
   for (int t = 0; t < nblk_o; t++) {

@@ -39,6 +39,22 @@ import scipy.linalg as sla
 # ----------------------------------------------------------------------------------
 THETA0 = np.array([math.pi / 3.1, 1.5, math.pi / 3.1, 1.5, math.pi / 3.1, 1.3, 0.9, 0.6, 0.2, 0.016])
 NPAR = 10
+# The isotropic members of the kernel family.  A parameter vector is always
+# [kernel parameters..., Sigma_Bias, sn2]; its LENGTH names the main kernel of the Hyb{main, Bias} covariance:
+#   10  ExpAns  (8 kernel parameters, Kernel.cpp:763-838)
+#    4  Exp     (Hayper_Euc_Exp, Sigma_Exp; Kernel.cpp:575-589)
+#    5  RBF     (Hayper_Euc_RBF, inverseWidth_RBF, Sigma_RBF; Kernel.cpp:414-431)
+THETA0_EXP = np.array([0.5, 0.9, 0.2, 0.016])
+THETA0_RBF = np.array([0.5, 0.9, 0.5, 0.2, 0.016])
+
+
+def kernel_of(theta):
+    return {10: "ExpAns", 4: "Exp", 5: "RBF"}[len(theta)]
+
+
+def sigma_of(theta):
+    """The kernel's amplitude parameter: Sigma_ExpAns / Sigma_Exp / Sigma_RBF (third from the end in every layout)."""
+    return theta[6] if len(theta) == 10 else theta[-3]
 
 
 # ----------------------------------------------------------------------------------
@@ -256,16 +272,64 @@ def maha_dist_defined(X1, X2, theta, c=None):
     return D2
 
 
+def eucl_dist_blas(X1, X2, hyp):
+    """EuclDist as written (Kernel.cpp:1343-1368, mlA :1437-1441): centred copies, AX = X * exp(-2 log(hyp)),
+    D2 = sum(AX1 % X1, 1) 1' + 1 sum(AX2 % X2, 1)' - 2 X1 AX2', negatives -> 0.  Net: |x - x'|^2 / hyp^2."""
+    c = centre(X1, X2)
+    Z1 = X1 - c
+    Z2 = X2 - c
+    f = math.exp(-2.0 * math.log(hyp))
+    A1 = Z1 * f
+    A2 = Z2 * f
+    a1 = (A1 * Z1)
+    a2 = (A2 * Z2)
+    s1, s2 = a1[:, 0], a2[:, 0]
+    for j in range(1, X1.shape[1]):
+        s1 = s1 + a1[:, j]
+        s2 = s2 + a2[:, j]
+    D2 = (s1[:, None] + s2[None, :]) - 2.0 * (Z1 @ A2.T)
+    D2[D2 < 0] = 0.0
+    return D2
+
+
+def eucl_dist_defined(X1, X2, hyp, c=None):
+    """The defined-order form the CUDA kernels use for the isotropic kernels: the same pair-distance code as ExpAns with
+    sigInv = (1/hyp) I, i.e. z = (x - c) * (1/hyp) and D2 = max(0, fl(fl(a_i + a_j) - 2 c_ij)) (maha_dist_defined)."""
+    if c is None:
+        c = centre(X1, X2)
+    d = X1.shape[1]
+    S = np.zeros((d, d))
+    np.fill_diagonal(S, 1.0 / hyp)
+    Z1 = transform_defined(X1, c, S)
+    Z2 = transform_defined(X2, c, S)
+    a1 = sqnorm_defined(Z1)
+    a2 = sqnorm_defined(Z2)
+    cij = _fma_emul(Z1[:, 2][:, None], Z2[:, 2][None, :],
+                    _fma_emul(Z1[:, 1][:, None], Z2[:, 1][None, :], Z1[:, 0][:, None] * Z2[:, 0][None, :]))
+    if d == 4:
+        cij = _fma_emul(Z1[:, 3][:, None], Z2[:, 3][None, :], cij)
+    D2 = (a1[:, None] + a2[None, :]) - 2.0 * cij
+    D2[D2 < 0] = 0.0
+    return D2
+
+
 def compute_K(X1, X2, theta, dist="defined", c=None):
-    """HybKerns::computeK = ExpAns + Bias (Kernel.cpp:140-154, 856-882, 362-367):
-       K = Sigma^2 * exp(-sqrt(D2)) + Sigma_Bias  (bias added to EVERY element)."""
-    if dist == "blas":
-        D2 = maha_dist_blas(X1, X2, theta)
+    """HybKerns::computeK = main kernel + Bias (Kernel.cpp:140-154, 362-367), bias added to EVERY element:
+       ExpAns  K = Sigma^2 * exp(-sqrt(D2)) + Sigma_Bias, D2 = MahaDist            (Kernel.cpp:856-882)
+       Exp     K = Sigma^2 * exp(-sqrt(D2)) + Sigma_Bias, D2 = EuclDist(hyp)       (Kernel.cpp:636-642)
+       RBF     K = exp(-0.5 * inverseWidth * D2) * Sigma^2 + Sigma_Bias            (Kernel.cpp:482-488)"""
+    kern = kernel_of(theta)
+    if kern == "ExpAns":
+        D2 = maha_dist_blas(X1, X2, theta) if dist == "blas" else maha_dist_defined(X1, X2, theta, c)
     else:
-        D2 = maha_dist_defined(X1, X2, theta, c)
-    var2 = theta[6] * theta[6]
-    K = var2 * np.exp(-1 * np.sqrt(D2))
-    K += theta[8]
+        D2 = eucl_dist_blas(X1, X2, theta[0]) if dist == "blas" else eucl_dist_defined(X1, X2, theta[0], c)
+    sig = sigma_of(theta)
+    var2 = sig * sig
+    if kern == "RBF":
+        K = np.exp(-0.5 * theta[1] * D2) * var2
+    else:
+        K = var2 * np.exp(-1 * np.sqrt(D2))
+    K += theta[-2]
     return K, D2
 
 
@@ -306,7 +370,7 @@ class OracleGP:
 
     @property
     def sn2(self):
-        return self.theta[9]
+        return self.theta[-1]
 
     # -- kernel (GP_Utils.cpp:1100-1113) --
     def update_kernel(self):
@@ -501,7 +565,7 @@ class OracleGP:
     def grad_ll(self):
         L = self.log_likelihood()
         if self.chol_fail:
-            return math.nan, np.full(NPAR, math.nan)
+            return math.nan, np.full(len(self.theta), math.nan)
         n = self.n
         Sw = self.Sw
         R = self.Lchol
@@ -518,9 +582,16 @@ class OracleGP:
         QW = Q * (self.d2lp[:, None] * np.ones((1, n))) - np.outer(self.Alpha, self.Alpha) \
             + np.outer(self.dlp, dahat) * 2.0
         self.QW = QW
-        g = np.zeros(NPAR)
-        g[0:8] = expans_gradients_literal(self.X, self.theta, QW, self.dist)
-        g[8] = bias_gradient_literal(QW)
+        npar = len(self.theta)
+        g = np.zeros(npar)
+        kern = kernel_of(self.theta)
+        if kern == "ExpAns":
+            g[0:8] = expans_gradients_literal(self.X, self.theta, QW, self.dist)
+        elif kern == "Exp":
+            g[0:2] = exp_gradients_literal(self.theta, QW, self.D2)      # HybKerns hands the members the SUMMED D2 (Kernel.cpp:156-169)
+        else:
+            g[0:3] = rbf_gradients_literal(self.theta, QW, self.D2)
+        g[npar - 2] = bias_gradient_literal(QW)
         # likelihood hyper-parameter (GP_Utils.cpp:1222-1235, 846-871)
         sn2 = self.sn2
         ymmu = self.y - self.yhat
@@ -533,7 +604,7 @@ class OracleGP:
         B = self._solve_chol(R, B * Sw) * Sw
         B = -1 * B + B0
         g_tmp0 += -1.0 * (dfhat @ B)
-        g[9] = g_tmp0
+        g[npar - 1] = g_tmp0
         self.dW = dW
         return L, g
 
@@ -543,7 +614,7 @@ class OracleGP:
         kX, _ = compute_K(self.X, Xs, self.theta, self.dist)      # n x m, centre uses BOTH sets (Kernel.cpp:1391)
         self.update_alpha()
         mu = kX.T @ self.Alpha
-        kD = np.full(Xs.shape[0], self.theta[6] * self.theta[6] + self.theta[8])   # diag_Compute (Kernel.cpp:782,331)
+        kD = np.full(Xs.shape[0], sigma_of(self.theta) ** 2 + self.theta[-2])      # diag_Compute (Kernel.cpp:782, 331, 449, 594)
         self.log_likelihood()                                         # GP_Utils.cpp:980
         Wh = np.sqrt(self.d2lp)
         LKs = kX * Wh[:, None]
@@ -679,6 +750,42 @@ def expans_gradients_literal(X, theta, QW, dist="defined"):
     else:
         g[7] = 0.0                                      # Kernel.cpp:1256-1257
     return g
+
+
+def exp_gradients_literal(theta, QW, D2):
+    """Kern_Exponential::getGradients (Kernel.cpp:646-695) on the D2 it is handed:
+       dk = exp(-s) % (-0.5 / s) with the DIAGONAL zeroed only -- an off-diagonal s == 0 (duplicate points) gives
+       -inf * 0 = NaN, as in the reference;  g[0] = sum(var2 QW % dk % D2);  g[1] = Sigma * sum(exp(-s) % (QW % exp(-s)))
+       [quirk: exp(-s) enters squared]."""
+    sig = theta[1]
+    var2 = sig * sig
+    SD2 = np.sqrt(D2)
+    KD2 = np.exp(-1 * SD2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dk = np.exp(-1 * SD2) * (-0.5 / SD2)
+    np.fill_diagonal(dk, 0.0)
+    Rm = (var2 * QW) * dk
+    with np.errstate(invalid="ignore"):
+        g0 = float((Rm * D2).sum())
+    Q = QW * KD2
+    g1 = float((KD2 * Q).sum()) * sig
+    return np.array([g0, g1])
+
+
+def rbf_gradients_literal(theta, QW, D2):
+    """Kern_RBF::getGradients (Kernel.cpp:491-541): with KD2 = exp(-0.5 w D2), Qs = Sigma^2 QW,
+       g[0] = (-2 sum(Qs % (KD2 * (-w/2)) % D2)) / 2;  g[1] = sum(-0.5 (Qs % KD2) % D2) / 2;
+       g[2] = ((sum(QW % KD2) Sigma + sum((QW % KD2)') Sigma) * Sigma) / 2."""
+    w, sig = theta[1], theta[2]
+    var2 = sig * sig
+    Qs = var2 * QW
+    KD2 = np.exp(-0.5 * w * D2)
+    dk = np.exp(-w / 2 * D2) * (-w / 2)
+    g1 = -2.0 * float(((Qs * dk) * D2).sum())
+    g2 = float((-0.5 * (Qs * KD2) * D2).sum())
+    Q = QW * KD2
+    g3 = (float((Q * sig).sum()) + float((Q.T * sig).sum())) * sig
+    return np.array([g1 / 2, g2 / 2, g3 / 2])
 
 
 def bias_gradient_literal(QW):

@@ -45,6 +45,19 @@ class TraceGP : public GP_utils {
   mutable int count;
 };
 
+// The main covariance of the Hyb kernel: GPSS_REF_KERNEL = ExpAns (default) | Exp | RBF (gp_ss_ak.cpp:146-170); GPSS_REF_BIAS=0
+// drops the Bias member (-kn 0, gp_ss_ak.cpp:179-184).
+static void add_kernels(HybKerns& K, const mat& X)
+{
+  const char* e = getenv("GPSS_REF_KERNEL");
+  const string name = e ? e : "ExpAns";
+  if (name == "Exp") K.addNewKernel(new Kern_Exponential(X));
+  else if (name == "RBF") K.addNewKernel(new Kern_RBF(X));
+  else K.addNewKernel(new Kern_ExpAnisotropic(X));
+  const char* b = getenv("GPSS_REF_BIAS");
+  if (!b || atoi(b) != 0) K.addNewKernel(new Kern_Bias(X));
+}
+
 #include <chrono>
 // bench.py --impl reference: W untimed + K timed LML+gradient evaluations (set_GP_Pars(theta_k); Grad_Values(g)) by the
 // unmodified reference, a different theta every step so nothing is cached (GP_Utils.cpp:130-133)
@@ -65,8 +78,7 @@ static int time_mode(int argc, char** argv)
   ctl.readDataFile(X, y, sz, trainFile);
   ctl.prepareData(X, y, Data_mode, yscale, model);
   HybKerns Kerns(X);
-  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
-  Kerns.addNewKernel(new Kern_Bias(X));
+  add_kernels(Kerns, X);
   GP_utils gp(&Kerns, X, y, GP_utils::inf_laplace, GP_utils::likeL_Gaussian, GP_utils::mean_zero, 8, 1, 0, 0);
   const unsigned np = gp.getNumPars();
   mat th0(1, np), g(1, np);
@@ -102,8 +114,7 @@ static int trace_mode(int argc, char** argv)
   ctl.readDataFile(X, y, sz, trainFile);
   ctl.prepareData(X, y, Data_mode, yscale, model);
   HybKerns Kerns(X);
-  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
-  Kerns.addNewKernel(new Kern_Bias(X));
+  add_kernels(Kerns, X);
   void* raw = calloc(1, sizeof(TraceGP));                     // zero-filled storage: see the LBFGS block in main()
   TraceGP& gp = *new (raw) TraceGP(&Kerns, X, y);
   gp.setOptimiser(opt == "SCG" ? GP_utils::SCG : opt == "BFGS" ? GP_utils::BFGS : GP_utils::LBFGS);
@@ -152,8 +163,7 @@ int main(int argc, char** argv)
 
   // ---- kernels and model (gp_ss_ak.cpp:146-190, 230) ----
   HybKerns Kerns(X);
-  Kerns.addNewKernel(new Kern_ExpAnisotropic(X));
-  Kerns.addNewKernel(new Kern_Bias(X));
+  add_kernels(Kerns, X);
   TraceGP gp(&Kerns, X, y);
   const unsigned np = gp.getNumPars();
 
@@ -208,8 +218,7 @@ int main(int argc, char** argv)
   // ---- LBFGS fit with the probe trace (gp_ss_ak.cpp:288-296; Opt_pars.cpp:179-332) ----
   if (iters > 0) {
     HybKerns Kerns2(X);
-    Kerns2.addNewKernel(new Kern_ExpAnisotropic(X));
-    Kerns2.addNewKernel(new Kern_Bias(X));
+    add_kernels(Kerns2, X);
     // Opt_Algs never initialises fail_pre_bfgs (Opt_pars.h:218, read at Opt_pars.cpp:577): construct the object in
     // zero-filled storage so the flag starts false, which is what a fresh heap page gives the CLI's `new GP_utils`
     void* raw = calloc(1, sizeof(TraceGP));

@@ -33,9 +33,10 @@ def parse_dump(text):
         if tok[0] == "probe":
             kind = tok[2]
             vals = tok[3:]
-            th = np.array(vals[:10], dtype=float)
-            f = float(vals[11])
-            g = np.array(vals[13:23], dtype=float) if kind == "G" else np.full(10, np.nan)
+            npar = vals.index("f")                      # 10 for Hyb{ExpAns, Bias}; 4 / 5 for Hyb{Exp | RBF, Bias}
+            th = np.array(vals[:npar], dtype=float)
+            f = float(vals[npar + 1])
+            g = np.array(vals[npar + 3:2 * npar + 3], dtype=float) if kind == "G" else np.full(npar, np.nan)
             probes.append((0.0 if kind == "O" else 1.0, th, f, g))
         else:
             r, c = int(tok[1]), int(tok[2])
@@ -48,7 +49,7 @@ def parse_dump(text):
     return rec
 
 
-def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_iters=0, rock=False):
+def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_iters=0, rock=False, kernel="ExpAns"):
     X, y = datagen.drillholes(n, seed)
     Xt, _ = datagen.drillholes(n_test, seed + 50)
     Xt = np.concatenate([Xt, X[:n_coincident]])
@@ -62,7 +63,7 @@ def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_ite
         with open(os.path.join(d, "thetas.txt"), "w") as f:
             for th in thetas:
                 f.write(" ".join("%.17g" % v for v in th) + "\n")
-        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")          # one BLAS thread: bit-reproducible fixtures
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", GPSS_REF_KERNEL=kernel)   # one BLAS thread: bit-reproducible fixtures
         out = subprocess.run([DRIVER, os.path.join(d, "train.txt"), os.path.join(d, "test.txt"), os.path.join(d, "thetas.txt"),
                               str(lbfgs_iters), d], capture_output=True, text=True, check=True, env=env)
         rec = parse_dump(out.stdout)
@@ -77,7 +78,7 @@ def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_ite
         # deterministic starting state as oracle/ref_driver.cpp and the product's host code.
         env = dict(env, MALLOC_PERTURB_="255")
         if cli_iters > 0:
-            tr = subprocess.run([cli, "-v", "3", "-pm", "1", "train", "-k", "ExpAns", "-kn", "1", "-o", "LBFGS", "-#", str(cli_iters),
+            tr = subprocess.run([cli, "-v", "3", "-pm", "1", "train", "-k", kernel, "-kn", "1", "-o", "LBFGS", "-#", str(cli_iters),
                                  os.path.join(d, "train.txt"), os.path.join(d, "cli_model")], capture_output=True, text=True,
                                 stdin=subprocess.DEVNULL, env=env, cwd=d)
             te = subprocess.run([cli, "-v", "3", "-pm", "1", "test", os.path.join(d, "test.txt"), os.path.join(d, "cli_model"),
@@ -93,6 +94,7 @@ def make(name, n, seed, thetas, lbfgs_iters, n_test=40, n_coincident=10, cli_ite
     rec["yt_raw"] = yt
     rec["Xt_raw"] = Xt
     rec["lbfgs_iters"] = lbfgs_iters
+    rec["kernel"] = np.array(kernel)
     np.savez_compressed(os.path.join(HERE, name), **rec)
     print(name, "nlml", [rec["nlml_%d" % k] for k in range(int(rec["n_theta"]))], "probes", len(rec.get("probe_f", [])))
 
@@ -106,3 +108,16 @@ if __name__ == "__main__":
     make("ref_n300.npz", 300, 0, [THETA0, th1, th2], lbfgs_iters=30, cli_iters=6)
     make("ref_n1000.npz", 1000, 1, [THETA0, th1], lbfgs_iters=4)
     make("ref_rock_n300.npz", 300, 2, [THETA0, th1, th2], lbfgs_iters=6, cli_iters=3, rock=True)
+    make_iso()
+
+
+THETA0_EXP = np.array([0.5, 0.9, 0.2, 0.016])            # Hayper_Euc_Exp, Sigma_Exp (Kernel.cpp:585-589), Sigma_Bias, sn2
+THETA0_RBF = np.array([0.5, 0.9, 0.5, 0.2, 0.016])       # Hayper_Euc_RBF, inverseWidth_RBF, Sigma_RBF (Kernel.cpp:425-431), Sigma_Bias, sn2
+
+
+def make_iso():
+    """The isotropic members of the kernel family: Hyb{Exp, Bias} and Hyb{RBF, Bias}."""
+    rng = np.random.default_rng(7)
+    for kernel, th0 in (("Exp", THETA0_EXP), ("RBF", THETA0_RBF)):
+        ths = [th0] + [np.clip(th0 * rng.uniform(0.8, 1.25, th0.shape[0]), 1e-4, 6.0) for _ in range(2)]
+        make("ref_%s_n300.npz" % kernel.lower(), 300, 3, ths, lbfgs_iters=5, cli_iters=3, kernel=kernel)
