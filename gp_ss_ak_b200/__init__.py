@@ -18,6 +18,7 @@ NPAR = 10
 
 GPSS_OK = 0
 GPSS_NOT_POSDEF = 1
+KERNEL_KINDS = {"ExpAns": 0, "Exp": 1, "RBF": 2}
 
 _lib = None
 
@@ -53,6 +54,7 @@ def load_library():
         "gpss_set_data": (I, [H, P, P]),
         "gpss_set_theta": (I, [H, P]),
         "gpss_get_theta": (I, [H, P]),
+        "gpss_set_kernel": (I, [H, I]),
         "gpss_nlml": (I, [H, P]),
         "gpss_nlml_grad": (I, [H, P, P]),
         "gpss_get_alpha": (I, [H, P]),
@@ -65,7 +67,7 @@ def load_library():
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
         "gpss_var_postprocess": (I, [L, D, P]),
-        "gpss_compute_K": (I, [I, P, I, I, P, I, P, P, P]),
+        "gpss_compute_K": (I, [I, I, P, I, I, P, I, P, P, P]),
         "gpss_expans_gradients": (I, [I, P, I, I, P, P, P]),
         "gpss_set_profiling": (I, [H, I]),
         "gpss_get_phase_ms": (I, [H, P]),
@@ -151,10 +153,20 @@ class GpssModel:
         assert X.shape == (self.n, self.d) and y.shape == (self.n,)
         _check(self._lib.gpss_set_data(self._h, _dp(X), _dp(y)))
 
+    def set_kernel(self, name):
+        """Main kernel of Hyb{main, Bias}: "ExpAns" (default, 10 parameters), "Exp" (4) or "RBF" (5)."""
+        self._kind = KERNEL_KINDS[name]
+        _check(self._lib.gpss_set_kernel(self._h, self._kind))
+
+    def npar(self):
+        return (10, 4, 5)[getattr(self, "_kind", 0)]
+
     def set_theta(self, theta):
         th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1))
-        assert th.shape == (NPAR,)
-        _check(self._lib.gpss_set_theta(self._h, _dp(th)))
+        assert th.shape == (self.npar(),)
+        full = np.zeros(NPAR)
+        full[:th.shape[0]] = th
+        _check(self._lib.gpss_set_theta(self._h, _dp(full)))
 
     def nlml(self):
         out = ctypes.c_double(0.0)
@@ -165,7 +177,7 @@ class GpssModel:
         out = ctypes.c_double(0.0)
         g = np.zeros(NPAR)
         _check(self._lib.gpss_nlml_grad(self._h, ctypes.byref(out), _dp(g)), allow_not_posdef=True)
-        return out.value, g
+        return out.value, g[:self.npar()]
 
     def alpha(self):
         a = np.zeros(self.n)
@@ -260,13 +272,17 @@ def measure_fp64_peak(device=0):
 
 
 def compute_K(theta, X1, X2, want_K=True, want_D2=True, device=0):
+    """K and D2 of Hyb{main, Bias}; the main kernel follows from len(theta): 10 ExpAns, 4 Exp, 5 RBF."""
     lib = load_library()
     X1 = _colmajor(X1)
     X2 = _colmajor(X2)
-    th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+    th0 = np.asarray(theta, dtype=np.float64).reshape(-1)
+    kind = {10: 0, 4: 1, 5: 2}[th0.shape[0]]
+    th = np.zeros(NPAR)
+    th[:th0.shape[0]] = th0
     K = np.zeros((X1.shape[0], X2.shape[0]), order="F") if want_K else None
     D2 = np.zeros((X1.shape[0], X2.shape[0]), order="F") if want_D2 else None
-    _check(lib.gpss_compute_K(device, _dp(th), X1.shape[1], X1.shape[0], _dp(X1), X2.shape[0], _dp(X2), _dp(K), _dp(D2)))
+    _check(lib.gpss_compute_K(device, kind, _dp(th), X1.shape[1], X1.shape[0], _dp(X1), X2.shape[0], _dp(X2), _dp(K), _dp(D2)))
     return K, D2
 
 

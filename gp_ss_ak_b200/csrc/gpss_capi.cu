@@ -83,6 +83,7 @@ struct gpss_ctx {
   int device = 0;
   int n = 0, n_pad = 0, nblk = 0;
   int d = 3;                                                   // input columns: 3, or 4 with the rock-type column
+  int kind = 0;                                                // main kernel: GPSS_KERNEL_EXPANS | _EXP | _RBF
   cudaStream_t st = nullptr;                                  // main stream (highest priority): critical-path kernels
   cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
   cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
@@ -208,20 +209,30 @@ struct PhaseTimer {
 // ---------------------------------------------------------------------------------------------------
 // parameters -> device
 // ---------------------------------------------------------------------------------------------------
-static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3)
+static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0)
 {
   memset(&P, 0, sizeof P);
-  sig_inv(theta, P.S);
   for (int j = 0; j < dim; j++) P.c[j] = centre[j];
   P.dim = dim;
-  P.lr = theta[7];                                     // InversewidthR: sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
-  P.var2 = theta[6] * theta[6];
-  P.bias = theta[8];
-  P.sn2 = theta[9];
-  P.inv_sn2 = 1 / theta[9];
+  P.kind = kind;
+  if (kind == 0) {
+    sig_inv(theta, P.S);
+    P.lr = theta[7];                                   // InversewidthR: sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
+  } else {
+    // EuclDist (Kernel.cpp:1343-1368): D2 = |x - x'|^2 / hyp^2 -> the same pair-distance code with sigInv = (1/hyp) I
+    const double ih = 1.0 / theta[0];
+    P.S[0] = P.S[4] = P.S[8] = ih;
+    P.lr = ih;
+    if (kind == 2) P.rbf_c = -0.5 * theta[1];
+  }
+  const double sig = theta_sigma(kind, theta), sn2 = theta_sn2(kind, theta);
+  P.var2 = sig * sig;
+  P.bias = theta_bias(kind, theta);
+  P.sn2 = sn2;
+  P.inv_sn2 = 1 / sn2;
   P.sw = std::sqrt(P.inv_sn2);
   P.sww = P.sw * P.sw;
-  P.lp_const = std::log(2.0 * M_PI * theta[9]) / 2;
+  P.lp_const = std::log(2.0 * M_PI * sn2) / 2;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -800,7 +811,7 @@ __global__ void scale_copy_kernel(double* __restrict__ dst, const double* __rest
 static int upload_params(gpss_ctx* c, int slot, const double* centre)
 {
   DevParams P;
-  fill_params(c->theta, centre, P, c->d);
+  fill_params(c->theta, centre, P, c->d, c->kind);
   CU(cudaMemcpyAsync(c->dP + slot, &P, sizeof P, cudaMemcpyHostToDevice, c->st));
   CU(cudaStreamSynchronize(c->st));   // P is a stack object
   return GPSS_OK;
@@ -847,7 +858,7 @@ static int ensure_objective(gpss_ctx* c)
   {
     PhaseTimer t(c, 2);
     // rhs = y / sn2: the IRLS fixed point alpha = B^-1 (y/sn2) = (K + sn2 I)^-1 y (GP_Utils.cpp:214-223)
-    scale_copy_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->rvec, c->y, 1 / c->theta[9], c->n, n_pad);
+    scale_copy_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->rvec, c->y, 1 / theta_sn2(c->kind, c->theta), c->n, n_pad);
     c->launches++;
     if (c->partitioned) RET(potrs_vec_partitioned(c));
     else RET(potrs_vec(c));
@@ -1054,6 +1065,16 @@ int gpss_set_theta(gpss_handle c, const double theta[GPSS_NPAR])
   return GPSS_OK;
 }
 
+// Main kernel of the Hyb{main, Bias} covariance (HybKerns, Kernel.cpp:140-169): the reference's -k choice.
+int gpss_set_kernel(gpss_handle c, int kind)
+{
+  if (!c || kind < 0 || kind > 2) return fail_arg("gpss_set_kernel: kind must be GPSS_KERNEL_EXPANS, _EXP or _RBF");
+  c->kind = kind;
+  c->have_factor = c->have_alpha = c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
 int gpss_get_theta(gpss_handle c, double theta[GPSS_NPAR])
 {
   if (!c || !theta) return fail_arg("gpss_get_theta: null argument");
@@ -1116,7 +1137,8 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   double red[NGRAD];
   CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
-  combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
+  if (c->kind == 0) combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
+  else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, red, c->s3, g); }
   return GPSS_OK;
 }
 
@@ -1245,7 +1267,8 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
   RET(upload_params(c, 1, centre));
   transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
   c->launches++;
-  const double kD = c->theta[6] * c->theta[6] + c->theta[8];   // diag_Compute (Kernel.cpp:782, 331, 127-136)
+  const double sig_k = theta_sigma(c->kind, c->theta);
+  const double kD = sig_k * sig_k + theta_bias(c->kind, c->theta);   // diag_Compute (Kernel.cpp:782, 449, 594, 331, 127-136)
   for (long off = 0; off < count; off += cap) {
     const int mb = (int)((count - off < cap) ? (count - off) : cap);
     const int m_pad = ((mb + NB - 1) / NB) * NB;
@@ -1333,7 +1356,7 @@ int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* va
     if (var) CU(cudaMemcpyAsync(var, c->stage + m, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
   }
-  if (var) return gpss_var_postprocess(m, c->theta[9], var);
+  if (var) return gpss_var_postprocess(m, theta_sn2(c->kind, c->theta), var);
   return GPSS_OK;
 }
 
@@ -1354,16 +1377,16 @@ __global__ void __launch_bounds__(256) full_K_kernel(double* __restrict__ Km, do
   }
 }
 
-int gpss_compute_K(int device, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2, const double* X2, double* K, double* D2)
+int gpss_compute_K(int device, int kind, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2, const double* X2, double* K, double* D2)
 {
-  if (!theta || !X1 || !X2 || n1 < 1 || n2 < 1 || (d != 3 && d != 4)) return fail_arg("gpss_compute_K: bad argument");
+  if (!theta || !X1 || !X2 || n1 < 1 || n2 < 1 || (d != 3 && d != 4) || kind < 0 || kind > 2) return fail_arg("gpss_compute_K: bad argument");
   CU(cudaSetDevice(device));
   double s1[4], s2[4], centre[4];
   seq_colsums(X1, n1, s1, d);
   seq_colsums(X2, n2, s2, d);
   maha_centre(n1, s1, n2, s2, centre, d);
   DevParams P;
-  fill_params(theta, centre, P, d);
+  fill_params(theta, centre, P, d, kind);
   double *dx1 = nullptr, *dx2 = nullptr, *dz1 = nullptr, *dz2 = nullptr, *dK = nullptr, *dD = nullptr;
   DevParams* dP = nullptr;
   int rc = GPSS_OK;

@@ -25,7 +25,9 @@ struct DevParams {
   double c[4];        // MahaDist centre (Kernel.cpp:1391-1392)
   double lr;          // InversewidthR_ExpAns = sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
   int dim;            // 3, or 4 with the rock-type column
-  int pad_;
+  int kind;           // main kernel of Hyb{main, Bias}: 0 ExpAns, 1 Exp, 2 RBF (GPSS_KERNEL_*); the isotropic kernels use
+                      // S = (1/hyp) I, lr = 1/hyp, i.e. EuclDist (Kernel.cpp:1343-1368) through the same pair-distance code
+  double rbf_c;       // -0.5 * inverseWidth_RBF (Kernel.cpp:486)
   double var2;        // Sigma_ExpAns^2 (Kernel.cpp:861)
   double bias;        // Sigma_Bias (Kernel.cpp:366)
   double sn2;         // hyperlf(0) (GP_Utils.cpp:406)
@@ -74,7 +76,8 @@ __global__ void transform_kernel(const double* __restrict__ xs, long ldx, double
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double kern_val(double d2, const DevParams& P)
 {
-  return __dadd_rn(__dmul_rn(P.var2, exp(-sqrt(d2))), P.bias);
+  if (P.kind == 2) return __dadd_rn(__dmul_rn(exp(__dmul_rn(P.rbf_c, d2)), P.var2), P.bias);   // RBF (Kernel.cpp:486)
+  return __dadd_rn(__dmul_rn(P.var2, exp(-sqrt(d2))), P.bias);                                  // ExpAns, Exp (Kernel.cpp:881, 640)
 }
 
 __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ Bm, long ld, const double* __restrict__ zs, long ldz,
@@ -653,9 +656,31 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
       const int i = i0 + e;
       if (i < n && j < n && i >= j) {
         const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
+        const double QWij = qe[e] * P.inv_sn2 - al[e] * ca[jj];
+        if (P.kind != 0) {
+          // isotropic kernels: two pair sums each (slots G6 and RK), see combine_gradient_iso
+          //   Exp (Kernel.cpp:646-695):  A = sum QW e^{-2s} (all pairs),  B = sum_{i != j} QW (e^{-s} (-0.5/s)) D2  (NaN for duplicates, as there)
+          //   RBF (Kernel.cpp:491-541):  A = sum QW KD2 D2,               B = sum QW KD2,  KD2 = exp(-0.5 w D2)
+          const double mult = (i == j) ? 1.0 : 2.0;
+          double kd, a, b;
+          if (P.kind == 1) {
+            const double s = sqrt(d2);
+            kd = exp(-s);
+            a = QWij * (kd * kd);
+            b = (i == j) ? 0.0 : QWij * ((kd * (-0.5 / s)) * d2);
+          } else {
+            kd = exp(__dmul_rn(P.rbf_c, d2));
+            a = (QWij * kd) * d2;
+            b = QWij * kd;
+          }
+          g6 += mult * a;
+          rk += mult * b;
+          if (i == j) tr += QWij;
+          qk += mult * (qe[e] * kern_val(d2, P));
+          continue;
+        }
         const double s = sqrt(d2);
         const double es = exp(-s);
-        const double QWij = qe[e] * P.inv_sn2 - al[e] * ca[jj];
         const double Kij = __dadd_rn(__dmul_rn(P.var2, es), P.bias);
         if (i == j) {
           g6 += QWij * es;

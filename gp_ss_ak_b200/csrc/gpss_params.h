@@ -138,4 +138,33 @@ inline void combine_gradient(const double theta[10], const double red[13], doubl
   g[9] = -1.0 * (0.5 * red[11]) * (2.0 / theta[9]) - s3;   // GP_Utils.cpp:1226 with dW = 0.5*rowsum(Q%K) (:1206)
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The isotropic members of the kernel family: Hyb{Exp, Bias} and Hyb{RBF, Bias}.  theta layouts in the C ABI's 10-array:
+//   kind 0 ExpAns  {AngleX, iWx, AngleY, iWy, AngleZ, iWz, Sigma, iWR, Sigma_Bias, sn2}          10 parameters
+//   kind 1 Exp     {Hayper_Euc_Exp, Sigma_Exp, Sigma_Bias, sn2}                                  4
+//   kind 2 RBF     {Hayper_Euc_RBF, inverseWidth_RBF, Sigma_RBF, Sigma_Bias, sn2}                5
+// ---------------------------------------------------------------------------------------------------
+inline int kernel_npar(int kind) { return kind == 0 ? 10 : kind == 1 ? 4 : 5; }
+inline double theta_sigma(int kind, const double* theta) { return kind == 0 ? theta[6] : theta[kernel_npar(kind) - 3]; }
+inline double theta_bias(int kind, const double* theta) { return theta[kernel_npar(kind) - 2]; }
+inline double theta_sn2(int kind, const double* theta) { return theta[kernel_npar(kind) - 1]; }
+
+// red as combine_gradient (slots 9 = A, 10 = tr QW, 11 = sum Q o K, 12 = B of grad_pass_kernel's isotropic branch)
+inline void combine_gradient_iso(int kind, const double* theta, const double red[13], double s3, double* g)
+{
+  const double sig = theta_sigma(kind, theta), var2 = sig * sig;
+  const int np = kernel_npar(kind);
+  if (kind == 1) {
+    g[0] = var2 * red[12];                      // sum((var2 QW) % dk % D2), Kernel.cpp:668-681
+    g[1] = red[9] * sig;                        // sum(KD2 % (QW % KD2)) * Sigma_Exp, Kernel.cpp:683-691
+  } else {
+    const double w = theta[1];
+    g[0] = (-2.0 * ((var2 * (-w / 2)) * red[9])) / 2;      // Kernel.cpp:517-525, 537
+    g[1] = ((-0.5 * var2) * red[9]) / 2;                   // Kernel.cpp:527-528, 538
+    g[2] = (((red[12] * sig) + (red[12] * sig)) * sig) / 2;   // Kernel.cpp:530-536, 539
+  }
+  g[np - 2] = red[10];                                         // Kern_Bias: trace(QW)
+  g[np - 1] = -1.0 * (0.5 * red[11]) * (2.0 / theta[np - 1]) - s3;
+}
+
 }  // namespace gpss

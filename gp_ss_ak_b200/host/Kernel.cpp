@@ -273,7 +273,7 @@ void Kern_ExpAnisotropic::computeK(const mat& X1, const mat& X2, mat& K, mat& D2
   K.set_size(X1.n_rows, X2.n_rows);
   D2.set_size(X1.n_rows, X2.n_rows);
   if (X1.n_cols != X2.n_cols) fatal("Kern_ExpAnisotropic::computeK: X1 and X2 must have the same number of columns");
-  check(gpss_compute_K(0, theta, (int)X1.n_cols, (int)X1.n_rows, X1.memptr(), (int)X2.n_rows, X2.memptr(), K.memptr(), D2.memptr()), "gpss_compute_K");
+  check(gpss_compute_K(0, GPSS_KERNEL_EXPANS, theta, (int)X1.n_cols, (int)X1.n_rows, X1.memptr(), (int)X2.n_rows, X2.memptr(), K.memptr(), D2.memptr()), "gpss_compute_K");
 }
 
 void Kern_ExpAnisotropic::getGradients(mat& g, const mat& X, const mat& X2, const mat&, const mat& QW) const

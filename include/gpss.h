@@ -53,6 +53,16 @@ int gpss_set_data(gpss_handle h, const double* X_colmajor, const double* y);
 /* GP_utils::set_GP_Pars (GP_Utils.cpp:130-157): stores theta and invalidates the caches; no GPU work. */
 int gpss_set_theta(gpss_handle h, const double theta[GPSS_NPAR]);
 int gpss_get_theta(gpss_handle h, double theta[GPSS_NPAR]);
+/* The main kernel of the Hyb{main, Bias} covariance -- the reference's `-k` choice (gp_ss_ak.cpp:146-170; HybKerns,
+ * Kernel.cpp:140-169).  theta and g keep their 10-slot arrays; the slots in use are
+ *   GPSS_KERNEL_EXPANS  {AngleX, iWx, AngleY, iWy, AngleZ, iWz, Sigma, iWR, Sigma_Bias, sn2}      (default; Kernel.cpp:856-1263)
+ *   GPSS_KERNEL_EXP     {Hayper_Euc_Exp, Sigma_Exp, Sigma_Bias, sn2}                              (Kernel.cpp:636-695)
+ *   GPSS_KERNEL_RBF     {Hayper_Euc_RBF, inverseWidth_RBF, Sigma_RBF, Sigma_Bias, sn2}            (Kernel.cpp:482-541)
+ * (a covariance without the Bias member is the same call with Sigma_Bias = 0; its gradient slot is then ignored). */
+#define GPSS_KERNEL_EXPANS 0
+#define GPSS_KERNEL_EXP 1
+#define GPSS_KERNEL_RBF 2
+int gpss_set_kernel(gpss_handle h, int kind);
 
 /* objective ---------------------------------------------------------------------------------------- */
 /* Opt_Algs::ObjVal -> GP_utils::logLikelihood (Opt_pars.h:248-251, GP_Utils.cpp:1138-1162):
@@ -112,8 +122,8 @@ int gpss_var_postprocess(long m, double sn2, double* var_inout);
 
 /* Kernels::computeK compatibility (host matrices; Kernel.cpp:140-154, 856-882, 362-367) ---------- */
 /* K and D2 are n1 x n2 column-major host buffers (either may be NULL); X1, X2 have d (3 or 4) columns. */
-int gpss_compute_K(int device, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2, const double* X2,
-                   double* K, double* D2);
+int gpss_compute_K(int device, int kind, const double theta[GPSS_NPAR], int d, int n1, const double* X1, int n2,
+                   const double* X2, double* K, double* D2);
 
 /* Kern_ExpAnisotropic::getGradients compatibility (Kernel.cpp:886-1263): the 8 kernel-parameter entries of the
  * reference's gradient for a HOST n x n matrix QW (column-major, need not be symmetric) and X1 == X2 == X (n x d). */

@@ -202,25 +202,58 @@ def test_parity_with_oracle_rock_type_column(gpss, n, seed):
         assert np.abs(g8 - go[:8]).max() <= 1e-9 * np.abs(go[:8]).max()
 
 
-@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_rock_n300.npz"])
+@pytest.mark.parametrize("kernel,seed", [("Exp", 8), ("RBF", 9)])
+def test_isotropic_kernels_parity_with_oracle(gpss, kernel, seed):
+    """Hyb{Exp, Bias} and Hyb{RBF, Bias} (EuclDist; Kernel.cpp:636-695, 482-541, 1343-1368)
+    through the same device path (sigInv = (1/hyp) I), against the oracle at the path's usual tolerances."""
+    X, y = datagen.drillholes(900, seed)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt_raw, _ = datagen.drillholes(100, seed + 100)
+    Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
+    th0 = O.THETA0_EXP if kernel == "Exp" else O.THETA0_RBF
+    for th in (th0, th0 * np.array([1.13, 0.9, 1.2, 1.1, 0.95][:len(th0)])):
+        Lo, go, gp = O.nlml_and_grad(Xs, ys, th, literal=True)
+        m = gpss.GpssModel(Xs, ys)
+        m.set_kernel(kernel)
+        m.set_theta(th)
+        L = m.nlml()
+        L2, g = m.nlml_grad()
+        assert L == L2 and g.shape == th.shape
+        assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+        assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+        assert np.linalg.norm(m.alpha() - gp.Alpha) <= TOL_ALPHA * np.linalg.norm(gp.Alpha)
+        mu_o, var_o = gp.predict(Xt)
+        mu, var = m.predict(Xt)
+        assert np.abs(mu - mu_o).max() <= TOL_MU and np.abs(var - var_o).max() <= TOL_VAR
+        m.close()
+        K, D2 = gpss.compute_K(th, Xs[:256], Xs[:256])
+        Ko, D2o = O.compute_K(Xs[:256], Xs[:256], th)
+        assert np.array_equal(D2, D2o) and np.abs(K - Ko).max() <= 4 * np.finfo(float).eps
+
+
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz"])
 def test_against_compiled_reference(gpss, name):
     """The CUDA path against numbers computed by the UNMODIFIED reference classes (tests/golden/make_ref_golden.py).
-    Tolerances = the reference's own BLAS-dependent reproducibility floor (oracle/gpss_oracle.py header)."""
+    Tolerances = the reference's own BLAS-dependent reproducibility floor (oracle/gpss_oracle.py header); for the Exp kernel
+    that floor is 10x higher (its K_diag is off by up to 7e-8 at the perturbed thetas, see tests/test_oracle.py)."""
     z = np.load(os.path.join(GOLD, name))
     m = gpss.GpssModel(z["Xs"], z["ys"].reshape(-1))
+    kernel = str(z["kernel"]) if "kernel" in z.files else "ExpAns"
+    m.set_kernel(kernel)
+    loose = 10.0 if kernel == "Exp" else 1.0
     for k in range(int(z["n_theta"])):
         th = z["theta_%d" % k].reshape(-1)
         m.set_theta(th)
         L, g = m.nlml_grad()
         Lr, gr = float(z["nlml_%d" % k]), z["g_%d" % k].reshape(-1)
-        assert abs(L - Lr) <= 2e-7 * abs(Lr)
-        assert np.abs(g - gr).max() <= 5e-7 * np.abs(gr).max()
+        assert abs(L - Lr) <= loose * 2e-7 * abs(Lr)
+        assert np.abs(g - gr).max() <= loose * 5e-7 * np.abs(gr).max()
         ar = z["alpha_%d" % k].reshape(-1)
-        assert np.linalg.norm(m.alpha() - ar) <= 5e-7 * np.linalg.norm(ar)
+        assert np.linalg.norm(m.alpha() - ar) <= loose * 5e-7 * np.linalg.norm(ar)
         mu, var = m.predict(z["Xt"])
-        assert np.abs(mu - z["mu_%d" % k].reshape(-1)).max() <= 5e-7
+        assert np.abs(mu - z["mu_%d" % k].reshape(-1)).max() <= loose * 5e-7
         assert np.abs(var - z["var_%d" % k].reshape(-1)).max() <= 1e-7
-        assert var[0] == th[9]                       # GP_Utils.cpp:1001-1003: element 0 zeroed, then + sn2
+        assert var[0] == th[-1]                      # GP_Utils.cpp:1001-1003: element 0 zeroed, then + sn2
     m.close()
 
 
