@@ -53,6 +53,7 @@ void GP_utils::_init()
   MeanType_ = mean_zero;
   handle = 0;
   handle_n = -1;
+  kind_dev = -1;
   data_stale = true;
   dirty = true;
   Chol_fail = false;
@@ -135,9 +136,9 @@ void GP_utils::check_supported() const
   const char* why = 0;
   const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
   if (!KerenlW) why = "no kernel";
-  else if (!hyb || KerenlW->getKerName() != "Hyb" || hyb->getNumKerns() != 2 || hyb->getKern(0)->getKerName() != "ExpAns" ||
-           hyb->getKern(1)->getKerName() != "Bias")
-    why = "the kernel must be Hyb{ExpAns, Bias} (train with -k ExpAns -kn 1)";
+  else if (!hyb || KerenlW->getKerName() != "Hyb" || hyb->getNumKerns() < 1 || hyb->getNumKerns() > 2 || kernel_kind() < 0 ||
+           (hyb->getNumKerns() == 2 && hyb->getKern(1)->getKerName() != "Bias"))
+    why = "the kernel must be Hyb{ExpAns | Exp | RBF [, Bias]} (train with -k ExpAns|Exp|RBF and -kn 0|1)";
   else if (Xinp.n_cols != 3 && Xinp.n_cols != 4) why = "inputs must have 3 columns, or 4 with the rock-type column";
   else if (yTarg.n_cols != 1 || getOutDim() != 1) why = "exactly one output column is supported";
   else if (likelihoodType_ != likeL_Gaussian || getNumlikfpar() != 1) why = "only the Gaussian likelihood is supported";
@@ -149,10 +150,24 @@ void GP_utils::check_supported() const
   }
 }
 
+// GPSS_KERNEL_* of the Hyb kernel's first member, -1 if it is none of the three
+int GP_utils::kernel_kind() const
+{
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+  if (!hyb || hyb->getNumKerns() < 1) return -1;
+  const string name = hyb->getKern(0)->getKerName();
+  return name == "ExpAns" ? GPSS_KERNEL_EXPANS : name == "Exp" ? GPSS_KERNEL_EXP : name == "RBF" ? GPSS_KERNEL_RBF : -1;
+}
+
+// The C ABI's slot layout (include/gpss.h, gpss_set_kernel): main-kernel parameters, Sigma_Bias (0 without a Bias member), sn2.
 void GP_utils::theta_now(double theta[GPSS_NPAR]) const
 {
-  for (unsigned int i = 0; i < 9; i++) theta[i] = KerenlW->getParam(i);
-  theta[9] = hyperlf(0);
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+  const unsigned int nk = hyb->getKern(0)->getNPars();
+  for (int i = 0; i < GPSS_NPAR; i++) theta[i] = 0.0;
+  for (unsigned int i = 0; i < nk; i++) theta[i] = KerenlW->getParam(i);
+  theta[nk] = (hyb->getNumKerns() == 2) ? KerenlW->getParam(nk) : 0.0;
+  theta[nk + 1] = hyperlf(0);
 }
 
 void GP_utils::sync_device() const
@@ -182,11 +197,17 @@ void GP_utils::sync_device() const
       if (gpss_host::rank() == 0) std::remove(idf.c_str());
     }
     handle_n = n;
+    kind_dev = GPSS_KERNEL_EXPANS;       // a new handle starts with the default kernel
     data_stale = false;
     dirty = true;
   } else if (data_stale) {
     if (gpss_set_data(handle, Xinp.memptr(), yTarg.memptr()) != GPSS_OK) device_failure("gpss_set_data");
     data_stale = false;
+    dirty = true;
+  }
+  if (kernel_kind() != kind_dev) {
+    if (gpss_set_kernel(handle, kernel_kind()) != GPSS_OK) device_failure("gpss_set_kernel");
+    kind_dev = kernel_kind();
     dirty = true;
   }
   double theta[GPSS_NPAR];
@@ -243,10 +264,12 @@ double GP_utils::GradLL(mat& g) const
   L.zeros(1, 1);
   L[0] = nlml;
   // same packing as GP_Utils.cpp:1243-1260: kernel entries, likelihood entry, mean entries
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+  const unsigned int nk = hyb->getKern(0)->getNPars();
   g_param.set_size(1, KerenlW->getNPars());
-  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g_param(i) = gv[i];
+  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g_param(i) = gv[i];      // main kernel entries, then Sigma_Bias if present
   g_hyperlf.zeros(1, 1);
-  g_hyperlf(0) = gv[9];
+  g_hyperlf(0) = gv[nk + 1];                                                      // the slot after Sigma_Bias (include/gpss.h)
   unsigned int c = 0;
   for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g(0, c++) = g_param(0, i);
   for (unsigned int i = 0; i < getNumlikfpar(); i++) g(0, c++) = g_hyperlf(0, i);

@@ -99,6 +99,8 @@ class GP_utils : public Modeling, public Main_Opt_Algs, public StreamIntfce {
   int device;
   mutable gpss_handle handle;
   mutable int handle_n;
+  mutable int kind_dev;                            // kernel kind last sent to the device (gpss_set_kernel)
+  int kernel_kind() const;                         // GPSS_KERNEL_* of the Hyb kernel's first member, -1 if unsupported
   mutable bool data_stale;                         // Xinp / yTarg changed since the last upload
   mutable bool dirty;                              // parameters changed since the last gpss_set_theta
   mutable double theta_dev[GPSS_NPAR];

@@ -288,6 +288,84 @@ void Kern_ExpAnisotropic::getGradients(mat& g, const mat& X, const mat& X2, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Kern_Exponential, Kern_RBF: host-matrix computeK through the device (gpss_compute_K with the kernel kind, bias 0, unit noise).
+// The members' getGradients with a HOST QW are not needed by GP_utils (GradLL runs device-resident, gpss_nlml_grad) and are
+// not provided for these two kernels.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+void iso_compute(int kind, const double* par, int npar, const mat& X1, const mat& X2, mat& K, mat& D2, const char* who)
+{
+  require_3d(X1, who);
+  require_3d(X2, who);
+  if (X1.n_cols != X2.n_cols) fatal(string(who) + ": X1 and X2 must have the same number of columns");
+  double theta[GPSS_NPAR];
+  for (int i = 0; i < GPSS_NPAR; i++) theta[i] = 0.0;
+  for (int i = 0; i < npar; i++) theta[i] = par[i];
+  theta[npar] = 0.0;          // Sigma_Bias
+  theta[npar + 1] = 1.0;      // sn2 (unused by computeK)
+  K.set_size(X1.n_rows, X2.n_rows);
+  D2.set_size(X1.n_rows, X2.n_rows);
+  check(gpss_compute_K(0, kind, theta, (int)X1.n_cols, (int)X1.n_rows, X1.memptr(), (int)X2.n_rows, X2.memptr(), K.memptr(), D2.memptr()),
+        "gpss_compute_K");
+}
+}  // namespace
+
+void Kern_Exponential::_init()
+{
+  nParams = 2;
+  setKerName("Exp");
+  setParamName("Hayper_Euc_Exp", 0);
+  setParamName("Sigma_Exp", 1);
+  setInitPars();
+}
+void Kern_Exponential::setParam(double val, unsigned int paramNo)
+{
+  if (paramNo >= 2) fatal("Requested parameter doesn't exist.");
+  par[paramNo] = val;
+}
+double Kern_Exponential::getParam(unsigned int paramNo) const
+{
+  if (paramNo >= 2) fatal("Requested parameter doesn't exist.");
+  return par[paramNo];
+}
+void Kern_Exponential::computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const
+{
+  iso_compute(GPSS_KERNEL_EXP, par, 2, X1, X2, K, D2, "Kern_Exponential::computeK");
+}
+void Kern_Exponential::getGradients(mat&, const mat&, const mat&, const mat&, const mat&) const
+{
+  fatal("Kern_Exponential::getGradients with host matrices is not provided: GP_utils::GradLL computes the gradient on the device");
+}
+
+void Kern_RBF::_init()
+{
+  nParams = 3;
+  setKerName("RBF");
+  setParamName("Hayper_Euc_RBF", 0);
+  setParamName("inverseWidth_RBF", 1);
+  setParamName("Sigma_RBF", 2);
+  setInitPars();
+}
+void Kern_RBF::setParam(double val, unsigned int paramNo)
+{
+  if (paramNo >= 3) fatal("Requested parameter doesn't exist.");
+  par[paramNo] = val;
+}
+double Kern_RBF::getParam(unsigned int paramNo) const
+{
+  if (paramNo >= 3) fatal("Requested parameter doesn't exist.");
+  return par[paramNo];
+}
+void Kern_RBF::computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const
+{
+  iso_compute(GPSS_KERNEL_RBF, par, 3, X1, X2, K, D2, "Kern_RBF::computeK");
+}
+void Kern_RBF::getGradients(mat&, const mat&, const mat&, const mat&, const mat&) const
+{
+  fatal("Kern_RBF::getGradients with host matrices is not provided: GP_utils::GradLL computes the gradient on the device");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // model-file helpers (Kernel.cpp:1281-1307)
 // ---------------------------------------------------------------------------------------------------
 void WriteKernelPas(const Kernels& kern, std::ostream& out) { kern.StrmOut(out); }
@@ -301,7 +379,9 @@ Kernels* ReadKerFromFile(std::istream& in)
   if (name == "Bias") k = new Kern_Bias();
   else if (name == "ExpAns") k = new Kern_ExpAnisotropic();
   else if (name == "Hyb") k = new HybKerns();
-  else if (name == "white" || name == "RBF" || name == "Exp") fatal("The " + name + " kernel is not part of the B200 hot-path build.");
+  else if (name == "Exp") k = new Kern_Exponential();
+  else if (name == "RBF") k = new Kern_RBF();
+  else if (name == "white") fatal("The " + name + " kernel is not part of the B200 hot-path build.");
   else fatal("Unknown kernel type ");
   k->FromFile_GP_Params(in);
   return k;

@@ -177,6 +177,51 @@ class Kern_ExpAnisotropic : public Kernels {
   double par[8];
 };
 
+// Isotropic members of the family.  Distance: EuclDist, D2 = |x - x'|^2 / Hayper_Euc^2
+// (reference Kernel.cpp:1343-1368, 1437-1441).  On the device they run through the ExpAns pair-distance code with
+// sigInv = (1/Hayper_Euc) I (gpss_set_kernel, include/gpss.h).
+// K_ij = Sigma_Exp^2 exp(-sqrt(D2_ij))   (reference Kernel.cpp:544-695)
+class Kern_Exponential : public Kernels {
+ public:
+  Kern_Exponential() : Kernels() { _init(); }
+  explicit Kern_Exponential(unsigned int inDim) : Kernels(inDim) { _init(); setInputDim(inDim); }
+  explicit Kern_Exponential(const mat& X) : Kernels(X) { _init(); setInputDim(X.n_cols); }
+  Kern_Exponential* clone() const { return new Kern_Exponential(*this); }
+
+  void setInitPars() { par[0] = 0.5; par[1] = 0.9; }              // Hayper_Euc_Exp, Sigma_Exp (Kernel.cpp:585-589)
+  double Diag_Kernel(const mat&, unsigned int) const { return par[1] * par[1]; }
+  void diag_Compute(mat& d, const mat&) const { d.fill(par[1] * par[1]); }
+  void setParam(double val, unsigned int paramNo);
+  double getParam(unsigned int paramNo) const;
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const;
+
+ private:
+  void _init();
+  double par[2];
+};
+
+// K_ij = exp(-0.5 inverseWidth_RBF D2_ij) Sigma_RBF^2   (reference Kernel.cpp:380-541)
+class Kern_RBF : public Kernels {
+ public:
+  Kern_RBF() : Kernels() { _init(); }
+  explicit Kern_RBF(unsigned int inDim) : Kernels(inDim) { _init(); setInputDim(inDim); }
+  explicit Kern_RBF(const mat& X) : Kernels(X) { _init(); setInputDim(X.n_cols); }
+  Kern_RBF* clone() const { return new Kern_RBF(*this); }
+
+  void setInitPars() { par[0] = 0.5; par[1] = 0.9; par[2] = 0.5; }   // Hayper_Euc_RBF, inverseWidth_RBF, Sigma_RBF (Kernel.cpp:425-431)
+  double Diag_Kernel(const mat&, unsigned int) const { return par[2] * par[2]; }
+  void diag_Compute(mat& d, const mat&) const { d.fill(par[2] * par[2]); }
+  void setParam(double val, unsigned int paramNo);
+  double getParam(unsigned int paramNo) const;
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat& X, const mat& X2, const mat& D2, const mat& QW) const;
+
+ private:
+  void _init();
+  double par[3];
+};
+
 void WriteKernelPas(const Kernels& kern, std::ostream& out);
 Kernels* ReadKerFromFile(std::istream& in);
 

@@ -126,8 +126,10 @@ void GP_Cntrl::train()
     Kernels* k = 0;
     if (KernT[i] == "ExpAns") k = new Kern_ExpAnisotropic(X);
     else if (KernT[i] == "Bias") k = new Kern_Bias(X);
-    else if (KernT[i] == "RBF" || KernT[i] == "Exp" || KernT[i] == "White")
-      ErrorTermination("The " + KernT[i] + " covariance function is not part of the B200 hot-path build (use -k ExpAns).");
+    else if (KernT[i] == "RBF") k = new Kern_RBF(X);
+    else if (KernT[i] == "Exp") k = new Kern_Exponential(X);
+    else if (KernT[i] == "White")
+      ErrorTermination("The " + KernT[i] + " covariance function is not part of the B200 hot-path build (use -k ExpAns, Exp or RBF).");
     else ErrorTermination("Unknown covariance function: " + KernT[i]);
     Kerns.addNewKernel(k);
     delete k;
@@ -313,7 +315,7 @@ void GP_Cntrl::Help()
     cout << "Arguments:" << endl;
     cout << "-mf ,--meanfunction\n \t GP mean function name (Default: zero [mean_zero])" << endl;
     cout << "-lf, --likefunction\n \t likelihood function name (default:  [Gauss]" << endl;
-    cout << "-k, --kernel\n \t Kernel name (Exponential Anisotropic [ExpAns]; RBF / Exp / White are not part of this build)" << endl;
+    cout << "-k, --kernel\n \t Kernel name (Exponential Anisotropic [ExpAns], Exponential [Exp], Radial Basis Function [RBF])" << endl;
     cout << "-o, --optimiser\n \t Optimization algorithm (Broyden-Fletcher-Goldfarb-Shanno [BFGS] (default), limited-memory BFGS [LBFGS], scaled conjugate gradient [SCG])" << endl;
     cout << "-kn, --Knoise\n \t Bias kernel (default: true [1], other options false [0])" << endl;
     cout << "trainFileName\n \t File containg trainig data (comma delimitted or tab delimitted file)." << endl;

@@ -86,7 +86,7 @@ def test_cli_train_and_test_match_reference_binary(tmp_path):
 def test_cli_rejects_configurations_outside_the_hot_path(tmp_path):
     z = np.load(os.path.join(GOLD, "ref_n300.npz"))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
-    out = subprocess.run([CLI, "train", "-k", "RBF", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
+    out = subprocess.run([CLI, "train", "-k", "White", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
                          stdin=subprocess.DEVNULL, cwd=tmp_path)
     assert out.returncode == 1 and "not part of the B200 hot-path build" in (out.stdout + out.stderr)
 
@@ -123,14 +123,16 @@ def test_cli_two_gpu_launch_matches_single_gpu(tmp_path):
     assert outs["two"][0].count("Iteration: 1 -logL:") == 1       # only rank 0 printed
 
 
-def test_cli_four_column_rock_type_branch_matches_reference_binary(tmp_path):
-    """`gp_ss_ak train/test` on a 4-column data file (x y z rock grade): the reference's rock-type branch of the ExpAns kernel.
-    Compared with what the UNMODIFIED reference binary printed and wrote for the same files (tests/golden/ref_rock_n300.npz)."""
-    z = np.load(os.path.join(GOLD, "ref_rock_n300.npz"))
+@pytest.mark.parametrize("fixture,kernel,ncol", [("ref_rock_n300.npz", "ExpAns", 4), ("ref_exp_n300.npz", "Exp", 3), ("ref_rbf_n300.npz", "RBF", 3)])
+def test_cli_widened_configurations_match_reference_binary(tmp_path, fixture, kernel, ncol):
+    """`gp_ss_ak train/test` for the SURVEY.md section 8(f) rows: a 4-column data file (x y z rock grade: the rock-type branch of the
+    ExpAns kernel) and the isotropic kernels `-k Exp`, `-k RBF`.  Compared with what the UNMODIFIED reference binary printed and
+    wrote for the same files (tests/golden/ref_rock_n300.npz, ref_exp_n300.npz, ref_rbf_n300.npz)."""
+    z = np.load(os.path.join(GOLD, fixture))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
     (tmp_path / "test.txt").write_text(str(z["test_file_text"]))
     iters = int(z["cli_iters"])
-    tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train", "-k", "ExpAns", "-kn", "1", "-o", "LBFGS", "-#", str(iters),
+    tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train", "-k", kernel, "-kn", "1", "-o", "LBFGS", "-#", str(iters),
                          str(tmp_path / "train.txt"), str(tmp_path / "cli_model")], capture_output=True, text=True,
                         stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=600)
     assert tr.returncode == 0, tr.stdout + tr.stderr
@@ -143,7 +145,7 @@ def test_cli_four_column_rock_type_branch_matches_reference_binary(tmp_path):
     mine_model = (tmp_path / "cli_model").read_text().splitlines()
     ref_model = str(z["cli_model_text"]).splitlines()
     assert [l.split("=")[0] for l in mine_model if "=" in l] == [l.split("=")[0] for l in ref_model if "=" in l]
-    assert "inputDim=4" in mine_model
+    assert "inputDim=%d" % ncol in mine_model and "KernelName=%s" % kernel in mine_model
     (tmp_path / "ref_model").write_text(str(z["cli_model_text"]))
     (tmp_path / "ref_model_Statistics.txt").write_text(str(z["cli_stats_text"]))
     te = subprocess.run([CLI, "-v", "3", "-pm", "1", "test", str(tmp_path / "test.txt"), str(tmp_path / "ref_model"),
@@ -151,7 +153,7 @@ def test_cli_four_column_rock_type_branch_matches_reference_binary(tmp_path):
     assert te.returncode == 0, te.stdout + te.stderr
     mine_pred = _table((tmp_path / "ref_model_predict.txt").read_text())
     ref_pred = _table(str(z["cli_predict_text"]))
-    assert mine_pred.shape == ref_pred.shape and mine_pred.shape[1] == 4 + 4
+    assert mine_pred.shape == ref_pred.shape and mine_pred.shape[1] == 4 + ncol
     assert np.array_equal(mine_pred[:, 0], ref_pred[:, 0])
     assert np.allclose(mine_pred[:, 2], ref_pred[:, 2], rtol=2e-5, atol=1e-6)
     assert np.allclose(mine_pred[:, 3], ref_pred[:, 3], rtol=2e-5, atol=1e-6)
