@@ -32,7 +32,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_HEADLINE = 50000
-GEMM_TRAFFIC_NOTE = None              # dram bytes per launch of the dominant kernel from profiles/ (ncu --set full), when captured
+# DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed ncu --set full capture
+# (profiles/r01_gemm_ws_ncu_full_summary.txt): the B^-1 = U U^T launch at n_pad = 20096 (76.7 ms, 96.7 % DMMA-pipe activity);
+# its algorithmic operand bytes are 2 x 1.6 GB read + 1.6 GB written.
+GEMM_TRAFFIC_BYTES = 24.010501e9 + 1.599763e9
+GEMM_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 20096 (one launch, 76.7 ms); ~5x its "
+                     "algorithmic 4.8 GB because operand slabs are re-fetched per wave through L2 (hit rate 83 %), yet only 4 % of the HBM peak: "
+                     "the kernel runs at 96.7 % DMMA-pipe activity (profiles/r01_gemm_ws_ncu_full_summary.txt)")
 FP64_PEAK_FALLBACK_TFLOPS = 37.13   # profiles/r01_fp64_peak_microbench.txt (DMMA.8x8x4 register loop on this pool's B200)
 
 
@@ -311,7 +317,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": GEMM_TRAFFIC_NOTE,
+                         "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE,
                          "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
                          "peak_source": peak_src,
                          "note": "achieved = n_pad^3%s algorithmic flops (potrf+trtri+lauum) / device time of those phases on rank 0"
