@@ -3,6 +3,7 @@
 #include "DistHost.h"
 
 #include <cmath>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -26,35 +27,122 @@ void Control::ErrorTermination(const string error)
 void Control::NormalTermination() { exit(0); }
 
 namespace {
-// next field of a line: everything up to the next tab or comma; the cursor moves past the separator (Control.cpp:52-59)
-string next_field(const string& line, size_t& pos)
+// Streaming reader (at 10 M test points the text I/O is what is left once prediction is
+// fast).  The file is read in one piece and scanned in place -- no per-field std::string -- with the reference's rules
+// (Control.cpp:27-141): lines starting with '#' are comments; fields are separated by a tab or a comma; EMPTY fields are
+// skipped; a field's value is atof() of its text; every non-comment line is a row (an empty line too, Control.cpp:100-103);
+// a final segment without a newline is a line if it is non-empty (std::getline).
+struct FileText {
+  std::string buf;
+  bool ok;
+  explicit FileText(const string& name) : ok(false)
+  {
+    std::ifstream in(name.c_str(), std::ios::binary);
+    if (!in.is_open()) return;
+    in.seekg(0, std::ios::end);
+    const std::streamoff len = in.tellg();
+    in.seekg(0, std::ios::beg);
+    buf.resize((size_t)len);
+    if (len > 0) in.read(&buf[0], len);
+    ok = true;
+  }
+};
+
+// atof of the field [b, e): the text is copied to a small NUL-terminated buffer so that strtod can neither run into the next
+// field (it skips leading white space, and a tab IS white space) nor past the end of the file
+inline double field_value(const char* b, const char* e)
 {
-  string token;
-  while (pos < line.size() && line[pos] != '\t' && line[pos] != ',') token += line[pos++];
-  pos++;
-  return token;
+  // Fast path (Clinger): [sign] digits [. digits] [e|E [sign] digits] and nothing else, with a decimal significand below 2^53
+  // and a power of ten within 10^+-22, is m * 10^k or m / 10^k with BOTH factors exact doubles, hence one correctly rounded
+  // operation -- the same double atof returns.  Anything else (white space, trailing text, 17-digit values, inf/nan, hex)
+  // takes atof itself below.
+  {
+    static const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* p = b;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) neg = (*p++ == '-');
+    unsigned long long m = 0;
+    int digits = 0, frac = 0;
+    bool ok = true;
+    while (p < e && *p >= '0' && *p <= '9') { if (digits < 19) { m = m * 10 + (unsigned)(*p - '0'); digits++; } else ok = false; p++; }
+    const bool int_part = p > b + ((b < e && (*b == '-' || *b == '+')) ? 1 : 0);
+    bool frac_part = false;
+    if (p < e && *p == '.') {
+      p++;
+      while (p < e && *p >= '0' && *p <= '9') { if (digits < 19) { m = m * 10 + (unsigned)(*p - '0'); digits++; frac++; } else ok = false; p++; frac_part = true; }
+    }
+    int ex = 0;
+    if (ok && (int_part || frac_part) && p < e && (*p == 'e' || *p == 'E')) {
+      const char* q = p + 1;
+      bool eneg = false;
+      if (q < e && (*q == '-' || *q == '+')) eneg = (*q++ == '-');
+      if (q < e && *q >= '0' && *q <= '9') {
+        int v = 0;
+        while (q < e && *q >= '0' && *q <= '9' && v < 10000) v = v * 10 + (*q++ - '0');
+        ex = eneg ? -v : v;
+        p = q;
+      }
+    }
+    if (ok && (int_part || frac_part) && p == e && m < (1ULL << 53)) {
+      const int k = ex - frac;
+      if (k >= -22 && k <= 22) {
+        const double v = k >= 0 ? (double)m * p10[k] : (double)m / p10[-k];
+        return neg ? -v : v;
+      }
+    }
+  }
+  char tmp[64];
+  size_t len = (size_t)(e - b);
+  if (len < sizeof tmp) {
+    std::memcpy(tmp, b, len);
+    tmp[len] = 0;
+    return std::atof(tmp);
+  }
+  return std::atof(string(b, e).c_str());
 }
-bool is_comment(const string& line) { return !line.empty() && line[0] == '#'; }
+
+// calls row(line_begin, line_end) for every non-comment line
+template <class F>
+void for_each_row(const std::string& text, F row)
+{
+  const char* p = text.data();
+  const char* const end = p + text.size();
+  while (p < end) {
+    const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    if (!(le > p && *p == '#')) row(p, le);
+    p = nl ? nl + 1 : end;
+  }
+}
+
+// calls field(b, e) for every NON-EMPTY field of the line
+template <class F>
+inline void for_each_field(const char* p, const char* le, F field)
+{
+  while (p < le) {
+    const char* q = p;
+    while (q < le && *q != '\t' && *q != ',') q++;
+    if (q > p) field(p, q);
+    p = q + 1;
+  }
+}
 }  // namespace
 
-// Rows = every non-comment line (an empty line counts, Control.cpp:100-103); D = (largest number of non-empty
-// fields on a line) - 1, the last field being the target (Control.cpp:118-130).
+// Rows = every non-comment line; D = (largest number of non-empty fields on a line) - 1, the last field being the target
+// (Control.cpp:118-130).
 int* Control::readDataSize(const string fileName)
 {
   int* data_size = new int[2];
-  std::ifstream in(fileName.c_str());
-  if (!in.is_open()) ErrorTermination("File is " + fileName + " not readable");
-  string line;
+  FileText file(fileName);
+  if (!file.ok) ErrorTermination("File is " + fileName + " not readable");
   int rows = 0, maxD = 0;
-  while (std::getline(in, line)) {
-    if (is_comment(line)) continue;
+  for_each_row(file.buf, [&](const char* b, const char* e) {
     rows++;
-    size_t pos = 0;
     int fields = 0;
-    while (pos < line.size())
-      if (next_field(line, pos).size() > 0) fields++;
+    for_each_field(b, e, [&](const char*, const char*) { fields++; });
     if (fields - 1 > maxD) maxD = fields - 1;
-  }
+  });
   data_size[0] = rows;
   data_size[1] = maxD;
   if (verbose > 0) {
@@ -67,27 +155,23 @@ int* Control::readDataSize(const string fileName)
 // The first D non-empty fields of a line go to X, every later one overwrites y (Control.cpp:61-77); atof semantics.
 void Control::readDataFile(mat& X, mat& y, int* data_size, const string fileName)
 {
-  std::ifstream in(fileName.c_str());
-  if (!in.is_open()) ErrorTermination("File is " + fileName + " not readable");
+  FileText file(fileName);
+  if (!file.ok) ErrorTermination("File is " + fileName + " not readable");
   const int rows = data_size[0], D = data_size[1];
-  string line;
+  double* Xp = X.memptr();
+  double* yp = y.memptr();
+  const size_t ldx = X.n_rows;
   int row = 0;
-  while (std::getline(in, line)) {
-    if (is_comment(line)) continue;
-    size_t pos = 0;
+  for_each_row(file.buf, [&](const char* b, const char* e) {
     int col = 0;
-    while (pos < line.size()) {
-      const string field = next_field(line, pos);
-      if (field.empty()) continue;
-      if (col < D) {
-        if (row < 0 || row >= rows) ErrorTermination("Erro while reading" + fileName);
-        X(row, col++) = std::atof(field.c_str());
-      } else {
-        y[row] = std::atof(field.c_str());
-      }
-    }
+    for_each_field(b, e, [&](const char* fb, const char* fe) {
+      if (row < 0 || row >= rows) ErrorTermination("Erro while reading" + fileName);
+      const double v = field_value(fb, fe);
+      if (col < D) Xp[(size_t)(col++) * ldx + row] = v;
+      else yp[row] = v;
+    });
     row++;
-  }
+  });
 }
 
 // per-column min / max / mean / sample standard deviation, plus the global extremes of X and y (Control.h:46-73)

@@ -7,6 +7,7 @@
 #include "DistHost.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -263,13 +264,22 @@ void GP_Cntrl::test()
   if (base.find("train")) plotName += "_train";
   if (base.find("test")) plotName += "_test";
 
-  std::ofstream outputs(gpss_host::out_path(PredictOut).c_str());
-  outputs << "# SampleNo, Y,  Yh, StdYh, Inputs" << "\n";
-  for (uword i = 0; i < regr.n_rows; i++) {
-    for (uword j = 0; j < regr.n_cols; j++) outputs << regr(i, j) << "\t";
-    outputs << "\n";
+  // Buffered writer: "%g" is exactly what `ostream << double` prints with the default format (6 significant digits), which is
+  // what the reference's loop does value by value (gp_ss_ak.cpp:470-481); 1 MiB blocks instead of one stream insertion per number.
+  {
+    FILE* outputs = std::fopen(gpss_host::out_path(PredictOut).c_str(), "w");
+    if (!outputs) ErrorTermination("File is " + PredictOut + " not writable");
+    std::fputs("# SampleNo, Y,  Yh, StdYh, Inputs\n", outputs);
+    std::vector<char> block(1 << 20);
+    size_t used = 0;
+    for (uword i = 0; i < regr.n_rows; i++) {
+      if (used + 32 * (regr.n_cols + 1) > block.size()) { std::fwrite(block.data(), 1, used, outputs); used = 0; }
+      for (uword j = 0; j < regr.n_cols; j++) used += (size_t)std::snprintf(block.data() + used, 32, "%g\t", regr(i, j));
+      block[used++] = '\n';
+    }
+    std::fwrite(block.data(), 1, used, outputs);
+    std::fclose(outputs);
   }
-  outputs.close();
 
   // gnuplot script (gp_ss_ak.cpp:482-505); gnuplot itself is run only when GPSS_RUN_GNUPLOT is set
   const double hi = std::max(regr.col(1).max(), mat(regr.col(2) + regr.col(3)).max());

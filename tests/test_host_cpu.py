@@ -105,6 +105,32 @@ def test_reader_quirks(host_built, tmp_path):
     assert "1 1 1 1 1 1 1 1 \n" in (tmp_path / "host_model").read_text()
 
 
+def test_streaming_reader_number_parsing_equals_atof(host_built, tmp_path):
+    """The streaming reader's in-place number parser (Clinger fast path + atof fallback, host/Control.cpp) must return exactly
+    what atof returns for every field: short decimals, exponents, signs, 17-digit values, leading blanks, trailing text, text
+    without digits, a last line without newline, CRLF line ends, empty fields (skipped, Control.cpp:52-77)."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.atof.restype = ctypes.c_double
+    rng = np.random.default_rng(3)
+    fields = ["1", "-2.5", "+.75", "3.", "1e-3", "2.5E+3", "-7e22", "1e23", "123456789012345678", "0.1", "9007199254740993", "1e-22", "1e-23",
+              "  7", "12abc", "abc", "-", ".", "1e", "1e+", "0x10", "inf", "nan", "4.9e-324", "1.7976931348623157e308", "00012.500", "-0.0"]
+    fields += ["%.17g" % v for v in rng.standard_normal(40) * 10.0 ** rng.integers(-8, 9, 40)]
+    fields += ["%.6g" % v for v in rng.standard_normal(40) * 10.0 ** rng.integers(-3, 4, 40)]
+    fields += ["%d" % v for v in rng.integers(-10 ** 9, 10 ** 9, 20)]
+    rows = [fields[i:i + 4] for i in range(0, len(fields) - 3, 4)]
+    text = "# numbers\n" + "\n".join("\t".join(r[:2]) + ",," + ",".join(r[2:]) for r in rows[:-1]) + "\r\n" + "\t".join(rows[-1])   # no final newline
+    (tmp_path / "n.txt").write_text(text)
+    (tmp_path / "theta.txt").write_text(" ".join(["1"] * 10))
+    out = subprocess.run([os.path.join(host_built, "tests", "host_io_check"), str(tmp_path / "n.txt"), str(tmp_path / "n.txt"),
+                          str(tmp_path / "theta.txt"), str(tmp_path)], capture_output=True, text=True)
+    rec = _parse(out.stdout.split("Xs ")[0])                   # X_raw / y_raw are dumped before the standardisation (inf / nan there)
+    got = np.concatenate([rec["X_raw"], rec["y_raw"].reshape(-1, 1)], axis=1)
+    want = np.array([[libc.atof(f.encode()) for f in r] for r in rows])
+    assert got.shape == want.shape == (len(rows), 4)
+    assert np.array_equal(got, want, equal_nan=True), (got - want)
+
+
 @pytest.mark.parametrize("opt", ["BFGS", "SCG"])
 def test_bfgs_and_scg_replay_reference_traces(host_built, tmp_path, opt):
     """The reference's other two optimisers (BFGS is its CLI default, gp_ss_ak.cpp:91), restated in host/Opt_pars.cpp, must
