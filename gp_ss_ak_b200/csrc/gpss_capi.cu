@@ -44,6 +44,7 @@ struct NcclApi {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   bool ok = false;
 };
@@ -60,6 +61,7 @@ static int nccl_load()
   NCCL_SYM(CommDestroy, "ncclCommDestroy")
   NCCL_SYM(Broadcast, "ncclBroadcast")
   NCCL_SYM(AllReduce, "ncclAllReduce")
+  NCCL_SYM(AllGather, "ncclAllGather")
   NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
   g_nccl.ok = true;
@@ -109,6 +111,7 @@ struct gpss_ctx {
   ncclComm_t comm = nullptr;
   double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
   double* Tsplit = nullptr; size_t Tsplit_cap = 0;             // split-k partial products of the row-sliced inverse
+  double* pgather = nullptr;                                   // partitioned inverse: my piece of an L row strip + the all-gathered pieces
   bool partitioned = false;                                    // Lm holds only my block columns, packed (n too large to replicate)
   int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
   int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
@@ -620,6 +623,158 @@ static int potrs_vec_partitioned(gpss_ctx* c)
   return GPSS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PARTITIONED storage, gradient: B^-1 = U U^T with U = L^-T held as block ROWS owned cyclically (rank r keeps rows
+// I = q P + r, packed: local row block q), 40 GB per rank at n = 200 000 like L itself.
+//   inverse (left-looking over block columns J of U, as trtri_upper):
+//       every rank contributes its blocks of the ROW strip L[J, 0:J] (ncclAllGather, then laid out in global column order);
+//       the owner of J inverts the diagonal block and broadcasts W_JJ = inv(L_JJ);
+//       T = U_loc[rows < J, 0:J0] L[J, 0:J0]^T  (k from each row's own start: cyclic row map of the GEMM kernel, split-k for
+//       short slices),  U_loc[rows < J, J] = -T W_JJ^T.
+//   B^-1 and the gradient, one block column J at a time: the owner broadcasts the row strip U[J, J0:], every rank forms
+//       Q[I >= J, J] = U_loc[I, J0:] U[J, J0:]^T for its rows and feeds the 512-wide strip straight into the fused gradient
+//       reductions -- B^-1 is never stored.
+// Everything on the main stream; results (13 sums) all-reduced at the end.
+// ---------------------------------------------------------------------------------------------------
+static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj);
+static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_doubles);
+static int ensure_lazy(double** p, size_t count);
+
+static int part_buffers(gpss_ctx* c)
+{
+  const size_t ldu = (size_t)(c->nq > 0 ? c->nq : 1) * NBO;
+  RET(ensure_lazy(&c->Um, ldu * c->n_pad));
+  RET(ensure_lazy(&c->Tpanel, ldu * NBO));                       // T, later the Q strip
+  RET(ensure_lazy(&c->Wjj, (size_t)2 * NBO * NBO));              // W_JJ and the owner's U_JJ scratch
+  const int nblk_o = (c->n_pad + NBO - 1) / NBO;
+  const size_t cmax = (size_t)(nblk_o + c->world - 1) / c->world;
+  RET(ensure_lazy(&c->pgather, (size_t)(c->world + 1) * cmax * NBO * NBO));   // [my piece | P gathered pieces]
+  if (!c->Tsplit) {
+    const size_t cap = (size_t)24576 * NBO;
+    CU(cudaMalloc(&c->Tsplit, cap * sizeof(double)));
+    c->Tsplit_cap = cap;
+  }
+  const long nblocks = (long)(ldu / NB) * c->nblk;               // every (local row tile, global column tile)
+  if (c->partial_blocks < nblocks || !c->partial) {
+    if (c->partial) cudaFree(c->partial);
+    c->partial = nullptr;
+    CU(cudaMalloc(&c->partial, sizeof(double) * (nblocks > 0 ? nblocks : 1) * NGRAD));
+    c->partial_blocks = nblocks;
+  }
+  return GPSS_OK;
+}
+
+static int trtri_partitioned(gpss_ctx* c)
+{
+  const int P = c->world, me = c->rank, n_pad = c->n_pad;
+  const long ld = n_pad;
+  const long ldu = (long)(c->nq > 0 ? c->nq : 1) * NBO;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  const int cmax = (nblk_o + P - 1) / P;
+  const size_t blk = (size_t)NBO * NBO;
+  double* piece = c->pgather;                                     // my blocks of the row strip
+  double* gathered = c->pgather + (size_t)cmax * blk;             // P segments of cmax blocks
+  double* Lrow = c->stage;                                        // the strip in global column order (the panel buffers are free now)
+  double* Wjj = c->Wjj;
+  double* Ujj = c->Wjj + blk;
+  CU(cudaMemsetAsync(c->Um, 0, sizeof(double) * (size_t)ldu * n_pad, c->st));
+  for (int J = 0; J < nblk_o; J++) {
+    const int J0 = J * NBO, nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
+    const int owner = J % P;
+    if (owner == me) {
+      // U_JJ from my packed copy of block column J (global addressing through shifted base pointers), W_JJ = U_JJ^T
+      const double* Lg = c->Lm + (long)(J / P) * NBO * ld - (long)J0 * ld;
+      double* Ug = Ujj - ((long)J0 * NBO + J0);
+      CU(cudaMemsetAsync(Ujj, 0, sizeof(double) * blk, c->st));
+      RET(trtri_diag_block(c, Ug, NBO, Lg, ld, J0, nbj));
+      transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, Ujj, NBO, 1);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
+    NC(g_nccl.Broadcast(Wjj, Wjj, blk, ncclDouble, owner, c->comm, c->st));
+    int cnt = 0;                                                  // my row blocks above J = my column blocks left of J
+    while (cnt < c->nq && cnt * P + me < J) cnt++;
+    if (J > 0) {
+      const int jc = (J + P - 1) / P;                             // blocks per segment needed for this J (<= cmax)
+      if (cnt > 0) {
+        pack_rowstrip_kernel<<<592, 256, 0, c->st>>>(piece, c->Lm, ld, J0, nbj, NBO, cnt);
+        c->launches++;
+      }
+      NC(g_nccl.AllGather(piece, gathered, (size_t)jc * blk, ncclDouble, c->comm, c->st));
+      order_rowstrip_kernel<<<592, 256, 0, c->st>>>(Lrow, gathered, nbj, NBO, J, P, (long)jc * (long)blk);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
+    if (cnt > 0 && J > 0) {
+      const int rows = cnt * NBO;
+      // T = U_loc[0:rows, 0:J0] * Lrow^T, k from each row's own global start
+      GemmArgs g = gemm_args(c->Um, ldu, Lrow, nbj, c->Tpanel, ldu, rows, nbj, J0);
+      g.kbeg_row = 1; g.rcyc_P = P; g.rcyc_me = me; g.rcyc_w = NBO; g.rcyc_l0 = 0; g.rcyc_koff = 0;
+      const int S = pick_ksplit(rows / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0, (long)rows * nbj, c->Tsplit_cap);
+      if (S > 1) {
+        g.C = c->Tsplit; g.ldc = rows; g.ksplit = S; g.csplit = (long)rows * nbj;
+        RET(gemm(c, g));
+        split_sum_kernel<<<296, 256, 0, c->st>>>(c->Tpanel, ldu, c->Tsplit, rows, nbj, S);
+        c->launches++;
+        CU(cudaGetLastError());
+      } else {
+        RET(gemm(c, g));
+      }
+      GemmArgs g2 = gemm_args(c->Tpanel, ldu, Wjj, NBO, c->Um + (long)J0 * ldu, ldu, rows, nbj, nbj);
+      g2.negate_out = 1; g2.kend_col = 1;
+      RET(gemm(c, g2));
+    }
+    if (owner == me) {                                            // my diagonal block
+      copy2d_kernel<<<64, 256, 0, c->st>>>(c->Um + (long)J0 * ldu + (long)(J / P) * NBO, ldu, Ujj, NBO, nbj, nbj);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  return GPSS_OK;
+}
+
+static int gradient_partitioned(gpss_ctx* c)
+{
+  const int P = c->world, me = c->rank, n_pad = c->n_pad;
+  const long ldu = (long)(c->nq > 0 ? c->nq : 1) * NBO;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  const int ltiles = (int)(ldu / NB);                             // my local row tiles (128 high)
+  const int w = NBO / NB;
+  double* strip = c->stage;                                       // U[J, J0:] as nbj x (n_pad - J0), contiguous
+  double* Qs = c->Tpanel;                                         // Q[my rows >= J, J], ld = ldu
+  const long nblocks = (long)ltiles * c->nblk;
+  CU(cudaMemsetAsync(c->partial, 0, sizeof(double) * nblocks * NGRAD, c->st));
+  for (int J = 0; J < nblk_o; J++) {
+    const int J0 = J * NBO, nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
+    const int owner = J % P;
+    const long cols = n_pad - J0;
+    if (owner == me) {
+      pack_kernel<<<592, 256, 0, c->st>>>(strip, c->Um + (long)J0 * ldu + (long)(J / P) * NBO, ldu, nbj, cols);
+      c->launches++;
+    }
+    NC(g_nccl.Broadcast(strip, strip, (size_t)nbj * cols, ncclDouble, owner, c->comm, c->st));
+    int q0 = 0;                                                   // my first row block I >= J
+    while (q0 < c->nq && q0 * P + me < J) q0++;
+    const int rows = (c->nq - q0) * NBO - ((q0 < c->nq && (c->nq - 1) * P + me == nblk_o - 1) ? (NBO - (n_pad - (nblk_o - 1) * NBO)) : 0);
+    if (rows <= 0) continue;
+    // Q strip = U_loc[q0 rows.., J0:] * strip^T, k from each row's own start (relative to J0)
+    GemmArgs g = gemm_args(c->Um + (long)J0 * ldu + (long)q0 * NBO, ldu, strip, nbj, Qs, ldu, rows, nbj, (int)cols);
+    g.kbeg_row = 1; g.rcyc_P = P; g.rcyc_me = me; g.rcyc_w = NBO; g.rcyc_l0 = q0 * NBO; g.rcyc_koff = J0;
+    RET(gemm(c, g));
+    // fused gradient reductions over the strip: local row tiles q0*w .., global column tiles J*w ..
+    const int ntm = rows / NB, ntn = nbj / NB;
+    grad_pass_kernel<<<dim3(ntm, ntn), 256, 0, c->st>>>(Qs, ldu, c->zs, n_pad, c->xs, n_pad, c->alpha, c->n, c->dP,
+                                                       c->partial + (long)(J * w) * ltiles * NGRAD, q0 * w, J * w, P, me, w);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
+  sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);
+  c->launches++;
+  CU(cudaGetLastError());
+  NC(g_nccl.AllReduce(c->red + 8, c->red + 8, NGRAD, ncclDouble, ncclSum, c->comm, c->st));
+  return GPSS_OK;
+}
+
 static int create_streams(gpss_ctx* c)
 {
   int lo = 0, hi = 0;
@@ -667,6 +822,33 @@ static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_double
 //     U[0:J,J] = -(U[0:J,0:J] L[J,0:J]^T) U[J,J]     one long-k GEMM + one k = NBO GEMM           (side stream)
 // The diagonal blocks depend only on L, so the main stream produces them (latency-bound small launches) ahead of
 // the side stream, which runs the bulk GEMMs back to back.
+// The diagonal block U[J0:J0+nbj, J0:J0+nbj] = inv(L[J0.., J0..])^T in 128-steps from the stored 128 x 128 inverses (main stream).
+// U and L are addressed by GLOBAL row / column (callers with packed storage pass suitably shifted base pointers).
+static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj)
+{
+  for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
+    const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
+    put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, c->st>>>(U + (long)i0 * ldu + i0, ldu, Wi);
+    c->launches++;
+    CU(cudaGetLastError());
+    const int mr = i0 - J0;
+    if (mr > 0) {
+      double* Uc = U + (long)i0 * ldu + J0;                 // U[J0:i0, i0:i0+128]
+      GemmArgs g = gemm_args(U + (long)J0 * ldu + J0, ldu, L + (long)J0 * ldl + i0, ldl, Uc, ldu, mr, NB, mr);
+      g.kbeg_row = 1;
+      RET(gemm(c, g));
+      // Uc <- -Uc Wi^T in place: columns 64..127 first (all 128 inputs), then 0..63 (inputs 0..63 only)
+      GemmArgs g1 = gemm_args(Uc, ldu, Wi + 64, NB, Uc + 64 * ldu, ldu, mr, 64, NB);
+      g1.negate_out = 1;
+      RET(gemm(c, g1));
+      GemmArgs g2 = gemm_args(Uc, ldu, Wi, NB, Uc, ldu, mr, 64, 64);
+      g2.negate_out = 1;
+      RET(gemm(c, g2));
+    }
+  }
+  return GPSS_OK;
+}
+
 static int trtri_upper(gpss_ctx* c)
 {
   const long ld = c->n_pad;
@@ -690,26 +872,7 @@ static int trtri_upper(gpss_ctx* c)
     const int nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
     double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
     // (1) the diagonal NBO-block of U in 128-steps
-    for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
-      const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
-      put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, c->st>>>(U + (long)i0 * ld + i0, ld, Wi);
-      c->launches++;
-      CU(cudaGetLastError());
-      const int mr = i0 - J0;
-      if (mr > 0) {
-        double* Uc = U + (long)i0 * ld + J0;                 // U[J0:i0, i0:i0+128]
-        GemmArgs g = gemm_args(U + (long)J0 * ld + J0, ld, L + (long)J0 * ld + i0, ld, Uc, ld, mr, NB, mr);
-        g.kbeg_row = 1;
-        RET(gemm(c, g));
-        // Uc <- -Uc Wi^T in place: columns 64..127 first (all 128 inputs), then 0..63 (inputs 0..63 only)
-        GemmArgs g1 = gemm_args(Uc, ld, Wi + 64, NB, Uc + 64 * ld, ld, mr, 64, NB);
-        g1.negate_out = 1;
-        RET(gemm(c, g1));
-        GemmArgs g2 = gemm_args(Uc, ld, Wi, NB, Uc, ld, mr, 64, 64);
-        g2.negate_out = 1;
-        RET(gemm(c, g2));
-      }
-    }
+    RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj));
     if (t == 0) continue;
     // (2) W_JJ = U_JJ^T into this block's scratch
     transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
@@ -1040,6 +1203,7 @@ int gpss_destroy(gpss_handle c)
   if (c->graph[1]) cudaGraphExecDestroy(c->graph[1]);
   if (c->stage) cudaFree(c->stage);
   if (c->Tsplit) cudaFree(c->Tsplit);
+  if (c->pgather) cudaFree(c->pgather);
   if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -1196,12 +1360,29 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
   CallTimer ct(c);
-  if (c->partitioned) { g_last_error = "gpss_nlml_grad: the gradient needs B^-1, which partitioned storage does not hold yet (objective, alpha and the predictive mean are available)"; return GPSS_ERR_STATE; }
   RET(ensure_objective(c));
   *nlml = c->nlml;
   if (c->chol_fail) {
     for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
     return GPSS_NOT_POSDEF;
+  }
+  if (c->partitioned) {
+    RET(part_buffers(c));
+    if (!c->have_U) {
+      PhaseTimer t(c, 3);
+      RET(trtri_partitioned(c));
+      c->have_U = true;
+    }
+    {
+      PhaseTimer t(c, 4);
+      RET(gradient_partitioned(c));
+    }
+    double redp[NGRAD];
+    CU(cudaMemcpyAsync(redp, c->red + 8, sizeof redp, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (c->kind == 0) combine_gradient(c->theta, redp, c->s3, g, c->d, c->n);
+    else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, redp, c->s3, g); }
+    return GPSS_OK;
   }
   RET(ensure_gradient_buffers(c));
   bool replayed = false;
@@ -1264,8 +1445,8 @@ static int enqueue_gradient(gpss_ctx* c)
   {
     PhaseTimer t(c, 5);
     if (ntm > 0) {
-      grad_pass_kernel<<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
-                                                             c->dP, c->partial, tm0);
+      grad_pass_kernel<<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm + (long)tm0 * NB, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
+                                                             c->dP, c->partial, tm0, 0, 0, 0, 1);
       c->launches++;
     }
     sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);

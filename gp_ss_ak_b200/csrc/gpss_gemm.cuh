@@ -41,6 +41,8 @@ struct GemmArgs {
   int cyc_P, cyc_me, cyc_w;      // cyc_P > 1: C holds only the block columns (cyc_w wide) that rank cyc_me of cyc_P owns, packed;
   int cyc_lcol0, cyc_boff;       //   local column cyc_lcol0 + col is GLOBAL column gc = ((l / w) P + me) w + l % w, which lower_only
                                  //   tests against the row and which selects the B rows: B(gc - cyc_boff, k)
+  int rcyc_P, rcyc_me, rcyc_w;   // rcyc_P > 1: the ROWS of A / C are block rows (rcyc_w high) owned cyclically and packed; local row
+  int rcyc_l0, rcyc_koff;        //   rcyc_l0 + row is GLOBAL row gr = ((l / w) P + me) w + l % w, and kbeg_row starts k at gr - rcyc_koff
   int mt, nt;                    // tile counts M/BM, N/BN (filled by the launcher)
 };
 
@@ -278,7 +280,14 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
   if (g.lower_only && gcol > (g.grow0 + row0 + BM - 1)) return;
 
   int kbeg = 0, kend = g.K;
-  if (g.kbeg_row) kbeg = g.krow_off + row0;
+  if (g.kbeg_row) {
+    if (g.rcyc_P > 1) {
+      const int l = g.rcyc_l0 + row0;
+      kbeg = max(0, ((l / g.rcyc_w) * g.rcyc_P + g.rcyc_me) * g.rcyc_w + l % g.rcyc_w - g.rcyc_koff);
+    } else {
+      kbeg = g.krow_off + row0;
+    }
+  }
   if (g.kend_row) kend = min(kend, g.krow_off + row0 + BM);
   if (g.kend_col) kend = min(kend, col0 + BN);
   kbeg = (kbeg / BK) * BK;

@@ -614,11 +614,17 @@ constexpr int NGRAD = 13;
 
 __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict__ Qm, long ld, const double* __restrict__ zs, long ldz,
                                                         const double* __restrict__ xs, long ldx, const double* __restrict__ alpha,
-                                                        int n, const DevParams* __restrict__ Pp, double* __restrict__ partial, int tm0)
+                                                        int n, const DevParams* __restrict__ Pp, double* __restrict__ partial, int tm0,
+                                                        int tn0, int rmap_P, int rmap_me, int rmap_w)
 {
-  // tile rows tm0 .. tm0 + gridDim.x - 1 (a rank's slice of B^-1 when the evaluation is distributed), all tile columns
-  const int tm = tm0 + blockIdx.x, tn = blockIdx.y;
-  double* out = partial + ((long)tn * gridDim.x + blockIdx.x) * NGRAD;
+  // Qm points at the FIRST tile handed to this launch: tile (blockIdx.x, blockIdx.y) of the buffer is global tile (tm, tn) with
+  //   tm = tm0 + blockIdx.x                      rows of a contiguous slice (single GPU, replicated layout), or, rmap_P > 1,
+  //   tm = ((l / w) P + me) w + l % w, l = tm0 + blockIdx.x     packed block rows owned cyclically (partitioned storage)
+  //   tn = tn0 + blockIdx.y
+  int tm = tm0 + blockIdx.x;
+  if (rmap_P > 1) tm = ((tm / rmap_w) * rmap_P + rmap_me) * rmap_w + tm % rmap_w;
+  const int tn = tn0 + blockIdx.y;
+  double* out = partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * NGRAD;
   if (tn > tm) { if (threadIdx.x < NGRAD) out[threadIdx.x] = 0.0; return; }
   __shared__ double cz[NZ][NB], cx[NX][NB], ca[NB];
   __shared__ DevParams P;
@@ -649,7 +655,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
   double g6 = 0, tr = 0, qk = 0, rk = 0;
   for (int jj = ty; jj < NB; jj += 4) {
     const int j = c0 + jj;
-    const double2 qv = *reinterpret_cast<const double2*>(Qm + (long)j * ld + i0);
+    const double2 qv = *reinterpret_cast<const double2*>(Qm + (long)(blockIdx.y * NB + jj) * ld + (blockIdx.x * NB + 2 * tx));
     const double qe[2] = {qv.x, qv.y};
 #pragma unroll
     for (int e = 0; e < 2; e++) {
@@ -774,6 +780,36 @@ __global__ void __launch_bounds__(256) split_sum_kernel(double* __restrict__ dst
     for (int s = 1; s < S; s++) v += parts[(long)s * total + idx];
     dst[(idx / rows) * ld + (idx % rows)] = v;
   }
+}
+
+// Partitioned storage: rows [r0, r0 + h) of this rank's first `cnt` packed block columns (w wide each) -> dst as cnt contiguous
+// h x w blocks (the rank's piece of a ROW strip of L), and the inverse permutation that lays the all-gathered pieces
+// (P segments of cmax blocks, owner-major) out in global column order: strip(:, k w + c) = seg[k % P][k / P](:, c).
+__global__ void pack_rowstrip_kernel(double* __restrict__ dst, const double* __restrict__ Lloc, long ld, int r0, int h, int w, int cnt)
+{
+  const long total = (long)cnt * w * h;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % h);
+    const long col = idx / h;                       // local column 0 .. cnt*w-1
+    dst[idx] = Lloc[col * ld + r0 + r];
+  }
+}
+__global__ void order_rowstrip_kernel(double* __restrict__ strip, const double* __restrict__ gathered, int h, int w, int nblocks, int P,
+                                      long seg_stride)
+{
+  const long blk = (long)h * w, total = (long)nblocks * blk;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / blk);
+    const long within = idx % blk;
+    strip[idx] = gathered[(long)(k % P) * seg_stride + (long)(k / P) * blk + within];
+  }
+}
+// dst(i, j) = src(i, j) for an rows x cols block, both with their own leading dimension
+__global__ void copy2d_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src, long lds, long rows, long cols)
+{
+  const long total = rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    dst[(idx / rows) * ldd + (idx % rows)] = src[(idx / rows) * lds + (idx % rows)];
 }
 
 // dst (rows x cols, contiguous) <- src (leading dimension ld), and back: staging of strided sub-matrices for NCCL

@@ -88,9 +88,11 @@ int gpss_nccl_unique_id(void* id128);                           /* rank 0 create
 int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
 /* PARTITIONED storage for n too large to replicate (n = 200 000: n^2 doubles = 320 GB; 8 x B200 hold 40 GB of block columns
  * each): collective constructor, every rank passes the same data.  The handle supports gpss_set_theta, gpss_nlml,
- * gpss_get_alpha, gpss_get_yhat and gpss_predict with var == NULL (mean); the gradient and the predictive variance need
- * B^-1 / L^-1 and return GPSS_ERR_STATE.  Right-looking block-column-cyclic Cholesky: the owner's NCCL panel broadcast buffer is
- * itself the DMMA operand of every rank's trailing update; the triangular solves pass the right-hand side around. */
+ * gpss_nlml_grad, gpss_get_alpha, gpss_get_yhat and gpss_predict with var == NULL (mean); the predictive variance needs L^-1
+ * replicated and returns GPSS_ERR_STATE.  Right-looking block-column-cyclic Cholesky: the owner's NCCL panel broadcast buffer is
+ * itself the DMMA operand of every rank's trailing update; the triangular solves pass the right-hand side around; for the gradient
+ * U = L^-T is held as block rows owned cyclically and B^-1 is produced one 512-wide strip at a time and consumed by the fused
+ * gradient reductions without ever being stored. */
 int gpss_create_partitioned(int device, int rank, int world, const void* id128, int n, int d, const double* X_colmajor,
                             const double* y, gpss_handle* out);
 /* The balanced row partitions used above (kind 0: rows of L^-T, kind 1: rows of B^-1): bounds[0..world], multiples of 128. */

@@ -35,7 +35,7 @@ for n in sizes:
     if rank == 0 and n <= 20000:
         ms = G.GpssModel(Xs, ys, device=local)
         ms.set_theta(base)
-        ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0])
+        ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1])
         ms.close()
     times = []
     for rep in range(3 if n <= 60000 else 2):
@@ -77,10 +77,33 @@ for n in sizes:
         print("PART_RESULT " + json.dumps({"n": n, "n_pad": n_pad, "world": world, "nlml": L0, "nlml_ms": float(np.min(times)),
                                            "potrf_ms": max(p[1] for p in allph), "solve_ms": max(p[2] for p in allph),
                                            "cholesky_tflops": chol_tf, "residual": resid, "identical": bool(same)}), flush=True)
+    # the gradient: U = L^-T as cyclic block rows, B^-1 consumed strip by strip (gpss_nlml_grad on a partitioned handle)
+    if os.environ.get("GPSS_PART_GRAD", "1") != "0":
+        m.set_profiling(True)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Lg, g = m.nlml_grad()                      # the objective at `base` is cached: this times the inverse + gradient only
+        torch.cuda.synchronize(); dist.barrier()
+        dtg = time.perf_counter() - t0
+        phg = m.phase_ms()
+        m.set_profiling(False)
+        tg = torch.tensor(g, device="cuda")
+        tgl = [torch.zeros_like(tg) for _ in range(world)]
+        dist.all_gather(tgl, tg)
+        same_g = all(torch.equal(tgl[0], v) for v in tgl)
+        if rank == 0:
+            print("   gradient: %.1f ms (inverse %.1f, B^-1 strips + reductions %.1f)  identical across ranks: %s" % (dtg * 1e3, phg[3], phg[4], same_g), flush=True)
+            print("   g = " + " ".join("%.6e" % v for v in g), flush=True)
+            ok &= same_g and bool(np.all(np.isfinite(g))) and Lg == L0
+            if ref is not None:
+                eg = np.abs(g - ref[4]).max() / np.abs(ref[4]).max()
+                print("   vs single GPU: g rel %.2e   (ref g = %s)" % (eg, " ".join("%.6e" % v for v in ref[4])), flush=True)
+                ok &= eg < 1e-9
+            print("PART_GRAD_RESULT " + json.dumps({"n": n, "world": world, "grad_ms": dtg * 1e3, "trtri_ms": float(phg[3]), "binv_grad_ms": float(phg[4])}), flush=True)
     try:
-        m.nlml_grad()
+        m.predict(Xs[:256], want_var=True)
         ok = False
-        print("   ERROR: the gradient call should have been refused", flush=True)
+        print("   ERROR: the variance call should have been refused", flush=True)
     except G.GpssError:
         pass
     m.close()
