@@ -38,7 +38,7 @@ for n in sizes:
         ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1])
         ms.close()
     times = []
-    for rep in range(3 if n <= 60000 else 2):
+    for rep in range(3 if n <= 60000 else 1):
         th = base * (1 + 0.01 * rep)
         m.set_theta(th)
         dist.barrier(); torch.cuda.synchronize()
