@@ -119,3 +119,57 @@ def test_world2_gloo_block_column_cholesky_and_sharded_prediction(gpss):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
     assert "WORKER OK" in outs[0]
+
+
+@pytest.mark.parametrize("P,nb", [(2, 5), (3, 7), (8, 11)])
+def test_partitioned_inverse_algorithm_and_index_maps(P, nb):
+    """numpy replay of trtri_partitioned / gradient_partitioned (gpss_capi.cu) with the SAME index maps the CUDA path uses:
+    block columns of L and block rows of U = L^-T owned cyclically and packed (local block q <-> global q P + r), the L row
+    strip assembled from an owner-major all-gather (segment stride jc blocks, block k at segment k % P, slot k / P -- the
+    formula of order_rowstrip_kernel), the prefix / suffix row counts, and B^-1 produced strip by strip.  Must reproduce
+    inv(L)^T and the lower triangle of inv(B)."""
+    W = 4
+    n = W * nb
+    rng = np.random.default_rng(P * 100 + nb)
+    M = rng.standard_normal((n, n))
+    B = M @ M.T + n * np.eye(n)
+    L = np.linalg.cholesky(B)
+    own = lambda j: j % P
+    Lloc = [np.concatenate([L[:, j * W:(j + 1) * W] for j in range(nb) if own(j) == r] or [np.zeros((n, 0))], axis=1) for r in range(P)]
+    nq = [Lloc[r].shape[1] // W for r in range(P)]
+    Uloc = [np.zeros((max(nq[r], 1) * W, n)) for r in range(P)]
+    for J in range(nb):
+        J0, o = J * W, own(J)
+        Wjj = np.linalg.inv(Lloc[o][J0:J0 + W, (J // P) * W:(J // P + 1) * W])
+        if J > 0:
+            jc = (J + P - 1) // P                                               # blocks per all-gather segment
+            gathered = np.full((P * jc, W, W), np.nan)
+            for r in range(P):
+                cnt = len([q for q in range(nq[r]) if q * P + r < J])
+                for b in range(cnt):                                            # pack_rowstrip_kernel: my first cnt block columns, rows J0..
+                    gathered[r * jc + b] = Lloc[r][J0:J0 + W, b * W:(b + 1) * W]
+            Lrow = np.concatenate([gathered[(k % P) * jc + k // P] for k in range(J)], axis=1)   # order_rowstrip_kernel
+            assert np.isfinite(Lrow).all() and np.array_equal(Lrow, L[J0:J0 + W, :J0])
+        for r in range(P):
+            cnt = len([q for q in range(nq[r]) if q * P + r < J])
+            if cnt and J > 0:
+                T = Uloc[r][:cnt * W, :J0] @ Lrow.T
+                Uloc[r][:cnt * W, J0:J0 + W] = -T @ Wjj.T
+            if r == o:
+                Uloc[r][(J // P) * W:(J // P + 1) * W, J0:J0 + W] = Wjj.T
+    Uref = np.linalg.inv(L).T
+    for r in range(P):
+        for q in range(nq[r]):
+            I = q * P + r
+            assert np.allclose(Uloc[r][q * W:(q + 1) * W], Uref[I * W:(I + 1) * W], atol=1e-12)
+    Q = np.zeros((n, n))
+    for J in range(nb):
+        J0, o = J * W, own(J)
+        strip = Uloc[o][(J // P) * W:(J // P + 1) * W, J0:]
+        for r in range(P):
+            q0 = len([q for q in range(nq[r]) if q * P + r < J])
+            if q0 < nq[r]:
+                Qs = Uloc[r][q0 * W:nq[r] * W, J0:] @ strip.T
+                for q in range(q0, nq[r]):
+                    Q[(q * P + r) * W:(q * P + r + 1) * W, J0:J0 + W] = Qs[(q - q0) * W:(q - q0 + 1) * W]
+    assert np.allclose(np.tril(Q), np.tril(np.linalg.inv(B)), atol=1e-12)
