@@ -90,6 +90,8 @@ struct gpss_ctx {
   cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
   cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
                                                               // the tail wave of one is filled by the head of the next
+  cudaStream_t st4 = nullptr;                                 // communication stream of the pipelined panel broadcast (highest priority)
+  std::vector<cudaEvent_t> ev_pipe;                           // per 128-column sub-panel: [2 i] factored on the owner, [2 i + 1] received
   cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
   std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
   // data
@@ -322,7 +324,9 @@ static void dist_potrf_schedule(int nblk_o, int P, int me, std::vector<DistOp>& 
 }
 
 // One outer panel: factor the NBO-wide block column starting at K0 (all rows below), 128 columns at a time.
-static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
+template <class StepDone>
+static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag,
+                       StepDone step_done)
 {
   for (int k = K0; k < K0 + nbk; k += NB) {
     double* Akk = A + (long)k * ld + k;
@@ -331,7 +335,7 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
     c->launches++;
     CU(cudaGetLastError());
     const int m = n_pad - k - NB;
-    if (m <= 0) continue;
+    if (m <= 0) { RET(step_done(k)); continue; }
     double* A21 = A + (long)k * ld + (k + NB);
     {  // panel solve, in place: A21 <- A21 * inv(L11)^T, with the 128x64 tile (it shares an SM with a resident
        // trailing-update CTA, which the 128x128 tile cannot).  Columns 64..127 first: they read all 128 input
@@ -341,6 +345,7 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
       GemmArgs g2 = gemm_args(A21, ld, Wk, NB, A21, ld, m, 64, 64);
       RET(gemm(c, g2));
     }
+    RET(step_done(k));            // columns k .. k+127 of the factor are final from here on
     const int ncols = K0 + nbk - (k + NB);
     if (ncols > 0) {  // update of the remaining columns of the outer panel
       double* A22 = A + (long)(k + NB) * ld + (k + NB);
@@ -350,6 +355,11 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
     }
   }
   return GPSS_OK;
+}
+
+static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
+{
+  return potrf_panel(c, A, ld, n_pad, K0, nbk, Winv, logdet_parts, dflag, [](int) { return (int)GPSS_OK; });
 }
 
 // LEFT-looking blocked Cholesky with look-ahead.  Block column T (width NBO) receives
@@ -399,9 +409,68 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
       marks.push_back({what, e});
     };
     mark(-1);
+    // GPSS_DIST_PIPE=1 (experimental): the panel travels in its four 128-column sub-panels, each broadcast -- on a separate
+    // communication stream -- as soon as the owner's step has finalised it, and the next owner applies U2 in four k = 128
+    // pieces as they arrive: U2 and 3/4 of the broadcast overlap the factorisation instead of following it.
+    const bool pipe = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
+    const int nsub_all = n_pad / NB;
+    if (pipe) {
+      if (!c->st4) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, hi));
+      }
+      while ((int)c->ev_pipe.size() < 2 * nsub_all + 2) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_pipe.push_back(e);
+      }
+      CU(cudaEventRecord(c->ev_main, c->st));                             // the K build precedes everything on the comm stream too
+      CU(cudaStreamWaitEvent(c->st4, c->ev_main, 0));
+    }
     for (const DistOp& op : ops) {
       const int T0 = op.col * NBO;
       const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
+      if (pipe && (op.kind == DIST_UPDATE_MAIN || op.kind == DIST_FACTOR || op.kind == DIST_BCAST)) {
+        if (op.kind == DIST_UPDATE_MAIN) {
+          // U2 in k = 128 pieces, each as soon as its sub-panel has been received (op.pcnt == 1 whenever P > 1)
+          const int Kp = op.pbeg * NBO;
+          const int nbK = (n_pad - Kp < NBO) ? (n_pad - Kp) : NBO;
+          for (int k0 = 0; k0 < nbK; k0 += NB) {
+            CU(cudaStreamWaitEvent(c->st, c->ev_pipe[2 * ((Kp + k0) / NB) + 1], 0));
+            RET(update(T0, nbT, Kp + k0, NB, c->st));
+          }
+        } else if (op.kind == DIST_FACTOR) {
+          RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag, [&](int k) -> int {
+            CU(cudaEventRecord(c->ev_pipe[2 * (k / NB)], c->st));           // sub-panel k is final on the owner
+            return GPSS_OK;
+          }));
+        } else {
+          const bool mine = op.root == me;
+          for (int k = T0; k < T0 + nbT; k += NB) {
+            const long rows = n_pad - k;
+            const size_t n_panel = (size_t)rows * NB, n_w = (size_t)NB * NB;
+            double* Wk = Winv + (size_t)(k / NB) * NB * NB;
+            if (mine) {
+              CU(cudaStreamWaitEvent(c->st4, c->ev_pipe[2 * (k / NB)], 0));
+              pack_kernel<<<592, 256, 0, c->st4>>>(c->stage, A + (long)k * ld + k, ld, rows, NB);
+              CU(cudaMemcpyAsync(c->stage + n_panel, Wk, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
+              CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + k / NB, sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
+              c->launches++;
+            }
+            NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + 1, ncclDouble, op.root, c->comm, c->st4));
+            if (!mine) {
+              unpack_kernel<<<592, 256, 0, c->st4>>>(A + (long)k * ld + k, ld, c->stage, rows, NB);
+              CU(cudaMemcpyAsync(Wk, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
+              CU(cudaMemcpyAsync(logdet_parts + k / NB, c->stage + n_panel + n_w, sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
+              c->launches++;
+            }
+            CU(cudaEventRecord(c->ev_pipe[2 * (k / NB) + 1], c->st4));      // sub-panel k is complete on this rank
+          }
+          CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st4));              // panel op.col is complete on this rank
+        }
+        continue;
+      }
       switch (op.kind) {
         case DIST_WAIT_SIDE:                                               // every side-stream update of my column
           CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * op.col + 1], 0));
@@ -456,6 +525,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
         }
       }
     }
+    if (pipe) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (nblk_o - 1)], 0));   // the last panel has arrived on the comm stream
     if (trace) {
       CU(cudaStreamSynchronize(c->st));
       static const char* names[7] = {"wait for look-ahead updates", "U2 (panel j-1 -> my column)", "panel factorisation", "pack", "broadcast (as root)",
@@ -793,6 +863,10 @@ static void destroy_streams(gpss_ctx* c)
   if (c->ev_side) cudaEventDestroy(c->ev_side);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   c->ev_pool.clear();
+  for (auto e : c->ev_pipe) cudaEventDestroy(e);
+  c->ev_pipe.clear();
+  if (c->st4) cudaStreamDestroy(c->st4);
+  c->st4 = nullptr;
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
   if (c->st) cudaStreamDestroy(c->st);
