@@ -1989,6 +1989,8 @@ int gpss_debug_fetch(gpss_handle c, int which, double* host_out, long count)
   CU(cudaSetDevice(c->device));
   const double* src = which == 0 ? c->Lm : which == 1 ? c->Um : which == 2 ? c->Qm : c->zs;
   if (!src) return fail_arg("gpss_debug_fetch: buffer not allocated");
+  if (c->partitioned && which != 3) return fail_arg("gpss_debug_fetch: a partitioned handle holds packed block columns / rows, not n_pad x n_pad buffers");
+  if (count < 0 || (size_t)count > (which == 3 ? (size_t)NZ * c->n_pad : (size_t)c->n_pad * c->n_pad)) return fail_arg("gpss_debug_fetch: count exceeds the buffer");
   CU(cudaStreamSynchronize(c->st));
   CU(cudaMemcpy(host_out, src, sizeof(double) * count, cudaMemcpyDeviceToHost));
   return GPSS_OK;
