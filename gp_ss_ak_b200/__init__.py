@@ -230,9 +230,10 @@ class GpssModel:
         return v.value
 
     def debug_fetch(self, which):
+        """0 = L factor, 1 = U = L^-T, 2 = B^-1 / L^-1 (n_pad x n_pad each); 3 = the transformed coordinates (n_pad x 5)."""
         npad = self.padded_n()
-        out = np.zeros((npad, npad), order="F")
-        _check(self._lib.gpss_debug_fetch(self._h, which, _dp(out), npad * npad))
+        out = np.zeros((npad, 5 if which == 3 else npad), order="F")
+        _check(self._lib.gpss_debug_fetch(self._h, which, _dp(out), out.size))
         return out
 
 
