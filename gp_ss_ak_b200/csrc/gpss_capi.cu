@@ -2,1045 +2,10 @@
 // lauum, gradient reductions and batched prediction, each a fixed sequence of launches of the kernels in
 // gpss_kernels.cuh / gpss_gemm.cuh on one stream.  No cuBLAS / cuSOLVER, no CPU fallback.
 // File:line citations are into /root/reference.
-#include "../../include/gpss.h"
-#include "gpss_gemm.cuh"
-#include "gpss_kernels.cuh"
-#include "gpss_params.h"
+#include "gpss_ctx.cuh"
+#include "gpss_potrf.cuh"
+#include "gpss_inverse.cuh"
 
-#include <dlfcn.h>
-#include <nccl.h>       // types and prototypes only: the library is dlopen'ed when a communicator is first needed
-
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <cmath>
-#include <string>
-#include <vector>
-#include <limits>
-
-using namespace gpss;
-
-static thread_local std::string g_last_error;
-
-static int fail_cuda(cudaError_t e, const char* what, int line)
-{
-  char buf[512];
-  snprintf(buf, sizeof buf, "CUDA error '%s' in %s (gpss_capi.cu:%d)", cudaGetErrorString(e), what, line);
-  g_last_error = buf;
-  return GPSS_ERR_CUDA;
-}
-#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail_cuda(e__, #x, __LINE__); } while (0)
-#define RET(x) do { int r__ = (x); if (r__ < 0) return r__; } while (0)
-
-static int fail_arg(const char* msg) { g_last_error = msg; return GPSS_ERR_ARG; }
-
-// ---------------------------------------------------------------------------------------------------
-// NCCL, resolved at run time (libnccl.so.2: the copy torch has already loaded, else the system one), so that the
-// single-GPU library has no hard dependency on it.
-// ---------------------------------------------------------------------------------------------------
-struct NcclApi {
-  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
-  decltype(&ncclCommInitRank) CommInitRank = nullptr;
-  decltype(&ncclCommDestroy) CommDestroy = nullptr;
-  decltype(&ncclBroadcast) Broadcast = nullptr;
-  decltype(&ncclAllReduce) AllReduce = nullptr;
-  decltype(&ncclAllGather) AllGather = nullptr;
-  decltype(&ncclGetErrorString) GetErrorString = nullptr;
-  bool ok = false;
-};
-static NcclApi g_nccl;
-static int nccl_load()
-{
-  if (g_nccl.ok) return GPSS_OK;
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) { g_last_error = std::string("cannot load libnccl.so.2: ") + dlerror(); return GPSS_ERR_NCCL; }
-#define NCCL_SYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) { g_last_error = "libnccl.so.2 lacks " name; return GPSS_ERR_NCCL; }
-  NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
-  NCCL_SYM(CommInitRank, "ncclCommInitRank")
-  NCCL_SYM(CommDestroy, "ncclCommDestroy")
-  NCCL_SYM(Broadcast, "ncclBroadcast")
-  NCCL_SYM(AllReduce, "ncclAllReduce")
-  NCCL_SYM(AllGather, "ncclAllGather")
-  NCCL_SYM(GetErrorString, "ncclGetErrorString")
-#undef NCCL_SYM
-  g_nccl.ok = true;
-  return GPSS_OK;
-}
-static int fail_nccl(ncclResult_t r, const char* what, int line)
-{
-  char buf[512];
-  snprintf(buf, sizeof buf, "NCCL error '%s' in %s (gpss_capi.cu:%d)", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what, line);
-  g_last_error = buf;
-  return GPSS_ERR_NCCL;
-}
-#define NC(x) do { ncclResult_t r__ = (x); if (r__ != ncclSuccess) return fail_nccl(r__, #x, __LINE__); } while (0)
-
-constexpr int NBO = 512;      // outer block (k-depth of the big trailing updates)
-constexpr int PRED_BATCH = 8192;
-
-enum QState { Q_NONE = 0, Q_IS_BINV = 1, Q_IS_W = 2 };
-
-struct gpss_ctx {
-  int device = 0;
-  int n = 0, n_pad = 0, nblk = 0;
-  int d = 3;                                                   // input columns: 3, or 4 with the rock-type column
-  int kind = 0;                                                // main kernel: GPSS_KERNEL_EXPANS | _EXP | _RBF
-  cudaStream_t st = nullptr;                                  // main stream (highest priority): critical-path kernels
-  cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
-  cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
-                                                              // the tail wave of one is filled by the head of the next
-  cudaStream_t st4 = nullptr;                                 // communication stream of the pipelined panel broadcast (highest priority)
-  std::vector<cudaEvent_t> ev_pipe;                           // per 128-column sub-panel: [2 i] factored on the owner, [2 i + 1] received
-  cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
-  std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
-  // data
-  double *xs = nullptr, *y = nullptr, *zs = nullptr;           // NX x n_pad, n_pad, NZ x n_pad
-  double *Lm = nullptr, *Um = nullptr, *Qm = nullptr;          // n_pad^2 each (Um, Qm lazily)
-  double *Winv = nullptr;                                      // nblk x 128 x 128
-  double *logdet_parts = nullptr;                              // nblk
-  double *rvec = nullptr, *zvec = nullptr, *alpha = nullptr, *fvec = nullptr;   // n_pad each
-  double *Tpanel = nullptr, *Wjj = nullptr;                    // n_pad x NBO, NBO x NBO (lazily)
-  double *partial = nullptr; long partial_blocks = 0;          // gradient partial sums
-  double *red = nullptr;                                       // 32 doubles of reduced scalars
-  DevParams* dP = nullptr;                                     // [0] training, [1] prediction
-  int* dflag = nullptr;
-  // prediction scratch (lazily)
-  double *xt = nullptr, *zt = nullptr, *zsp = nullptr, *Bm = nullptr, *Vm = nullptr, *mu_part = nullptr, *dmu = nullptr, *dvar = nullptr;
-  int pred_cap = 0;
-  // distributed evaluation (one process per GPU; rank/world = 0/1 when not initialised)
-  int rank = 0, world = 1;
-  ncclComm_t comm = nullptr;
-  double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
-  double* Tsplit = nullptr; size_t Tsplit_cap = 0;             // split-k partial products of the row-sliced inverse
-  double* pgather = nullptr;                                   // partitioned inverse: my piece of an L row strip + the all-gathered pieces
-  bool partitioned = false;                                    // Lm holds only my block columns, packed (n too large to replicate)
-  int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
-  int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
-  int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
-  // host state
-  double theta[GPSS_NPAR];
-  double sums_train[4];
-  bool have_factor = false, have_alpha = false, have_U = false;
-  int qstate = Q_NONE;
-  int chol_fail = 0;
-  double nlml = std::numeric_limits<double>::quiet_NaN();
-  double s3 = 0.0;
-  // CUDA graphs of the launch-bound small-n evaluation: [0] K build + Cholesky + solves + objective terms, [1] inverse + gradient pass
-  cudaGraphExec_t graph[2] = {nullptr, nullptr};
-  long graph_launches[2] = {0, 0};
-  bool graph_failed = false;
-  // instrumentation
-  bool profiling = false;
-  double phase_ms[16];
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  cudaEvent_t ev_call[2] = {nullptr, nullptr};   // bracket the device work of the last objective / predict call
-  double last_call_ms = 0.0;
-  long launches = 0;
-};
-
-// ---------------------------------------------------------------------------------------------------
-static int configure_kernels()
-{
-  CU(cudaFuncSetAttribute(gemm_nt_ws_kernel<GemmTileWideWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWideWS::SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTileWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWide::SMEM_BYTES));
-  CU(cudaFuncSetAttribute(potrf_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-  return GPSS_OK;
-}
-
-// Every O(n^3) product of the path goes through the warp-specialised 128x64 DMMA kernel (gemm_nt_ws_kernel).
-static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
-{
-  using T = GemmTileWideWS;
-  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
-  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
-  GemmArgs ga = g;
-  ga.mt = g.M / T::BM;
-  ga.nt = g.N / T::BN;
-  const int parts = ga.ksplit > 1 ? ga.ksplit : 1;
-  gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt * parts), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
-  c->launches++;
-  CU(cudaGetLastError());
-  return GPSS_OK;
-}
-
-// legacy cp.async kernel (kept as the A/B baseline of bench_micro/gemm_bench.cu and for the tile=1 test hook)
-static int gemm_legacy_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
-{
-  using T = GemmTileWide;
-  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
-  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
-  GemmArgs ga = g;
-  ga.mt = g.M / T::BM;
-  ga.nt = g.N / T::BN;
-  gemm_nt_kernel<T><<<(unsigned)(ga.mt * ga.nt), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
-  c->launches++;
-  CU(cudaGetLastError());
-  return GPSS_OK;
-}
-
-static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st); }
-static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K)
-{
-  GemmArgs g;
-  memset(&g, 0, sizeof g);
-  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
-  return g;
-}
-
-// CUDA-event bracket of a whole C-ABI call on the handle's stream (always on; read with gpss_get_last_call_ms)
-struct CallTimer {
-  gpss_ctx* c;
-  explicit CallTimer(gpss_ctx* c_) : c(c_) { cudaEventRecord(c->ev_call[0], c->st); }
-  ~CallTimer()
-  {
-    cudaEventRecord(c->ev_call[1], c->st);
-    cudaEventSynchronize(c->ev_call[1]);
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]);
-    c->last_call_ms = ms;
-  }
-};
-
-struct PhaseTimer {
-  gpss_ctx* c; int idx;
-  PhaseTimer(gpss_ctx* c_, int idx_) : c(c_), idx(idx_) { if (c->profiling) cudaEventRecord(c->ev[0], c->st); }
-  ~PhaseTimer()
-  {
-    if (c->profiling) {
-      cudaEventRecord(c->ev[1], c->st);
-      cudaEventSynchronize(c->ev[1]);
-      float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-      c->phase_ms[idx] += ms;
-    }
-  }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// parameters -> device
-// ---------------------------------------------------------------------------------------------------
-static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0)
-{
-  memset(&P, 0, sizeof P);
-  for (int j = 0; j < dim; j++) P.c[j] = centre[j];
-  P.dim = dim;
-  P.kind = kind;
-  if (kind == 0) {
-    sig_inv(theta, P.S);
-    P.lr = theta[7];                                   // InversewidthR: sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
-  } else {
-    // EuclDist (Kernel.cpp:1343-1368): D2 = |x - x'|^2 / hyp^2 -> the same pair-distance code with sigInv = (1/hyp) I
-    const double ih = 1.0 / theta[0];
-    P.S[0] = P.S[4] = P.S[8] = ih;
-    P.lr = ih;
-    if (kind == 2) P.rbf_c = -0.5 * theta[1];
-  }
-  const double sig = theta_sigma(kind, theta), sn2 = theta_sn2(kind, theta);
-  P.var2 = sig * sig;
-  P.bias = theta_bias(kind, theta);
-  P.sn2 = sn2;
-  P.inv_sn2 = 1 / sn2;
-  P.sw = std::sqrt(P.inv_sn2);
-  P.sww = P.sw * P.sw;
-  P.lp_const = std::log(2.0 * M_PI * sn2) / 2;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// blocked right-looking Cholesky, two-level (outer NBO = 512 for deep-k trailing updates, inner 128)
-// A: n_pad x n_pad lower, in place.  Replaces arma::chol -> dpotrf (GP_Utils.cpp:881,903).
-// ---------------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------------
-// distributed evaluation helpers (world > 1): staging buffer, balanced row partitions
-// ---------------------------------------------------------------------------------------------------
-static int ensure_stage(gpss_ctx* c, size_t count)
-{
-  if (c->stage_count >= count) return GPSS_OK;
-  if (c->stage) cudaFree(c->stage);
-  c->stage = nullptr;
-  c->stage_count = 0;
-  CU(cudaMalloc(&c->stage, count * sizeof(double)));
-  c->stage_count = count;
-  return GPSS_OK;
-}
-
-// Row boundaries (multiples of 128) that give every rank the same share of work:
-//   kind 0: rows of U = L^-T in the block-column inverse, cost(row i) ~ (n - i)^2 / 2   -> (n - r_k)^3 = n^3 (1 - k/P)
-//   kind 1: rows of B^-1 = U U^T (lower),                 cost(row i) ~ (i + 1)(n - i)  -> n x^2/2 - x^3/3 = (k/P) n^3/6
-static void balanced_rows(int n_pad, int world, int kind, std::vector<int>& bounds)
-{
-  bounds.assign(world + 1, 0);
-  bounds[world] = n_pad;
-  const double n = n_pad;
-  for (int k = 1; k < world; k++) {
-    const double f = (double)k / world;
-    double x;
-    if (kind == 0) {
-      x = n * (1.0 - std::cbrt(1.0 - f));
-    } else {
-      double lo = 0.0, hi = n;
-      const double target = f * n * n * n / 6.0;
-      for (int it = 0; it < 100; it++) {
-        const double mid = 0.5 * (lo + hi);
-        if (n * mid * mid / 2.0 - mid * mid * mid / 3.0 < target) lo = mid; else hi = mid;
-      }
-      x = 0.5 * (lo + hi);
-    }
-    int b = (int)std::lround(x / NB) * NB;
-    if (b < bounds[k - 1]) b = bounds[k - 1];
-    if (b > n_pad) b = n_pad;
-    bounds[k] = b;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// The distributed Cholesky as a per-rank list of operations (pure host logic; gpss_dist_potrf_schedule exposes it so the
-// CPU tests can replay all ranks and check that every block column sees every earlier panel exactly once, in an order
-// the broadcasts make possible).  Block column j (owner j % P) receives, all on ONE low-priority side stream (they
-// update the same tiles, so they serialise anyway):
-//     chunk A(j):   panels 0 .. j-P        one long-k GEMM, issued as soon as the owner has factored its previous column
-//     single(j,t):  panel t, j-P < t < j-1 (k = NBO), issued when panel t arrives
-// and on the main stream U2(j) = panel j-1, the panel factorisation and the broadcast.  A rank therefore always has
-// about P panel periods of bulk work queued behind the critical path instead of one.
-// ---------------------------------------------------------------------------------------------------
-enum { DIST_WAIT_SIDE = 0, DIST_UPDATE_MAIN = 1, DIST_FACTOR = 2, DIST_BCAST = 3, DIST_UPDATE_SIDE = 4 };
-struct DistOp { int kind, col, pbeg, pcnt, root, stream; };   // update ops apply panels pbeg .. pbeg+pcnt-1 to block column col
-static void dist_potrf_schedule(int nblk_o, int P, int me, std::vector<DistOp>& ops)
-{
-  ops.clear();
-  for (int t = 0; t < nblk_o; t++) {
-    const bool mine = (t % P) == me;
-    if (mine) {
-      if (t >= 2) ops.push_back({DIST_WAIT_SIDE, t, 0, 0, 0, 0});
-      if (t >= 1) ops.push_back({DIST_UPDATE_MAIN, t, P == 1 ? 0 : t - 1, P == 1 ? t : 1, 0, 0});   // alone: plain left-looking
-      ops.push_back({DIST_FACTOR, t, 0, 0, 0, 0});
-    }
-    ops.push_back({DIST_BCAST, t, 0, 0, t % P, 0});
-    int j = t + ((me - t) % P + P) % P;        // my next block column after t
-    if (j == t) j = t + P;
-    if (j >= nblk_o || t >= j - 1) continue;   // panel j-1 is U2(j)
-    const int stream = (j / P) & 1;
-    if (mine) ops.push_back({DIST_UPDATE_SIDE, j, 0, t + 1, 0, stream});     // chunk A
-    else ops.push_back({DIST_UPDATE_SIDE, j, t, 1, 0, stream});              // one panel
-  }
-}
-
-// One outer panel: factor the NBO-wide block column starting at K0 (all rows below), 128 columns at a time.
-template <class StepDone>
-static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag,
-                       StepDone step_done)
-{
-  for (int k = K0; k < K0 + nbk; k += NB) {
-    double* Akk = A + (long)k * ld + k;
-    double* Wk = Winv + (long)(k / NB) * NB * NB;
-    potrf_diag_inv_kernel<<<1, DIAG_THREADS, DIAG_SMEM, c->st>>>(Akk, ld, Wk, logdet_parts + k / NB, dflag);
-    c->launches++;
-    CU(cudaGetLastError());
-    const int m = n_pad - k - NB;
-    if (m <= 0) { RET(step_done(k)); continue; }
-    double* A21 = A + (long)k * ld + (k + NB);
-    {  // panel solve, in place: A21 <- A21 * inv(L11)^T, with the 128x64 tile (it shares an SM with a resident
-       // trailing-update CTA, which the 128x128 tile cannot).  Columns 64..127 first: they read all 128 input
-       // columns; columns 0..63 then need only inputs 0..63 because inv(L11) is lower triangular.
-      GemmArgs g1 = gemm_args(A21, ld, Wk + 64, NB, A21 + 64 * ld, ld, m, 64, NB);
-      RET(gemm(c, g1));
-      GemmArgs g2 = gemm_args(A21, ld, Wk, NB, A21, ld, m, 64, 64);
-      RET(gemm(c, g2));
-    }
-    RET(step_done(k));            // columns k .. k+127 of the factor are final from here on
-    const int ncols = K0 + nbk - (k + NB);
-    if (ncols > 0) {  // update of the remaining columns of the outer panel
-      double* A22 = A + (long)(k + NB) * ld + (k + NB);
-      GemmArgs g = gemm_args(A21, ld, A21, ld, A22, ld, m, ncols, NB);
-      g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = k + NB; g.gcol0 = k + NB;
-      RET(gemm(c, g));
-    }
-  }
-  return GPSS_OK;
-}
-
-static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
-{
-  return potrf_panel(c, A, ld, n_pad, K0, nbk, Winv, logdet_parts, dflag, [](int) { return (int)GPSS_OK; });
-}
-
-// LEFT-looking blocked Cholesky with look-ahead.  Block column T (width NBO) receives
-//     U1(T):  A[T:, T] -= L[T:, 0:T-1] L[T, 0:T-1]^T     (panels 0..T-2: one long-k DMMA GEMM, side stream)
-//     U2(T):  A[T:, T] -= L[T:, T-1]   L[T, T-1]^T       (panel T-1, k = NBO, main stream)
-// and is then factored by potrf_panel on the main stream.  U1(T+1) only needs panels <= T-1, so it runs on the
-// side stream WHILE the main stream does U2(T) and the latency-bound panel T: the DMMA pipe never waits for a
-// panel, every output tile is written once per update instead of once per outer step (the right-looking form
-// re-read and re-wrote the whole trailing matrix n/NBO times), and nearly all flops run in long-k GEMMs.
-static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Winv, double* logdet_parts, int* dflag)
-{
-  const int P = c->world, me = c->rank;
-  const bool la = c->st2 != nullptr && !getenv("GPSS_NO_LOOKAHEAD");
-  if (P > 1 && !la) return fail_arg("the distributed factorisation needs the look-ahead streams");
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  if (la && (int)c->ev_pool.size() < 2 * nblk_o + 2) {
-    const size_t want = 2 * nblk_o + 2;
-    while (c->ev_pool.size() < want) {
-      cudaEvent_t e;
-      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      c->ev_pool.push_back(e);
-    }
-  }
-  // staging layout of one broadcast: [panel rows T0.. x nbT | the panel's 128x128 diagonal inverses | their log-dets]
-  const size_t stage_need = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
-  if (P > 1) RET(ensure_stage(c, stage_need));
-  auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
-    // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
-    const double* Lp = A + (long)kbeg * ld + T0;
-    GemmArgs g = gemm_args(Lp, ld, Lp, ld, A + (long)T0 * ld + T0, ld, n_pad - T0, nbT, klen);
-    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
-    return gemm_ws_on(c, g, stream);
-  };
-  if (P > 1) {
-    std::vector<DistOp> ops;
-    dist_potrf_schedule(nblk_o, P, me, ops);
-    int kchunk = 1 << 30;
-    if (const char* e = getenv("GPSS_DIST_KCHUNK")) { const int v = atoi(e); if (v >= NBO) kchunk = (v / NBO) * NBO; }
-    // GPSS_DIST_TRACE: timing events around every main-stream step, summed per kind after the factorisation (diagnostic)
-    const bool trace = getenv("GPSS_DIST_TRACE") != nullptr;
-    std::vector<std::pair<int, cudaEvent_t>> marks;
-    auto mark = [&](int what) {
-      if (!trace) return;
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      cudaEventRecord(e, c->st);
-      marks.push_back({what, e});
-    };
-    mark(-1);
-    // GPSS_DIST_PIPE=1 (experimental): the panel travels in its four 128-column sub-panels, each broadcast -- on a separate
-    // communication stream -- as soon as the owner's step has finalised it, and the next owner applies U2 in four k = 128
-    // pieces as they arrive: U2 and 3/4 of the broadcast overlap the factorisation instead of following it.
-    const bool pipe = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
-    const int nsub_all = n_pad / NB;
-    if (pipe) {
-      if (!c->st4) {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, hi));
-      }
-      while ((int)c->ev_pipe.size() < 2 * nsub_all + 2) {
-        cudaEvent_t e;
-        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->ev_pipe.push_back(e);
-      }
-      CU(cudaEventRecord(c->ev_main, c->st));                             // the K build precedes everything on the comm stream too
-      CU(cudaStreamWaitEvent(c->st4, c->ev_main, 0));
-    }
-    for (const DistOp& op : ops) {
-      const int T0 = op.col * NBO;
-      const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-      if (pipe && (op.kind == DIST_UPDATE_MAIN || op.kind == DIST_FACTOR || op.kind == DIST_BCAST)) {
-        if (op.kind == DIST_UPDATE_MAIN) {
-          // U2 in k = 128 pieces, each as soon as its sub-panel has been received (op.pcnt == 1 whenever P > 1)
-          const int Kp = op.pbeg * NBO;
-          const int nbK = (n_pad - Kp < NBO) ? (n_pad - Kp) : NBO;
-          for (int k0 = 0; k0 < nbK; k0 += NB) {
-            CU(cudaStreamWaitEvent(c->st, c->ev_pipe[2 * ((Kp + k0) / NB) + 1], 0));
-            RET(update(T0, nbT, Kp + k0, NB, c->st));
-          }
-        } else if (op.kind == DIST_FACTOR) {
-          RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag, [&](int k) -> int {
-            CU(cudaEventRecord(c->ev_pipe[2 * (k / NB)], c->st));           // sub-panel k is final on the owner
-            return GPSS_OK;
-          }));
-        } else {
-          const bool mine = op.root == me;
-          for (int k = T0; k < T0 + nbT; k += NB) {
-            const long rows = n_pad - k;
-            const size_t n_panel = (size_t)rows * NB, n_w = (size_t)NB * NB;
-            double* Wk = Winv + (size_t)(k / NB) * NB * NB;
-            if (mine) {
-              CU(cudaStreamWaitEvent(c->st4, c->ev_pipe[2 * (k / NB)], 0));
-              pack_kernel<<<592, 256, 0, c->st4>>>(c->stage, A + (long)k * ld + k, ld, rows, NB);
-              CU(cudaMemcpyAsync(c->stage + n_panel, Wk, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
-              CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + k / NB, sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
-              c->launches++;
-            }
-            NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + 1, ncclDouble, op.root, c->comm, c->st4));
-            if (!mine) {
-              unpack_kernel<<<592, 256, 0, c->st4>>>(A + (long)k * ld + k, ld, c->stage, rows, NB);
-              CU(cudaMemcpyAsync(Wk, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
-              CU(cudaMemcpyAsync(logdet_parts + k / NB, c->stage + n_panel + n_w, sizeof(double), cudaMemcpyDeviceToDevice, c->st4));
-              c->launches++;
-            }
-            CU(cudaEventRecord(c->ev_pipe[2 * (k / NB) + 1], c->st4));      // sub-panel k is complete on this rank
-          }
-          CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st4));              // panel op.col is complete on this rank
-        }
-        continue;
-      }
-      switch (op.kind) {
-        case DIST_WAIT_SIDE:                                               // every side-stream update of my column
-          CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * op.col + 1], 0));
-          mark(0);
-          break;
-        case DIST_UPDATE_MAIN:                                             // U2: the panel just received, on the critical path
-          RET(update(T0, nbT, op.pbeg * NBO, op.pcnt * NBO, c->st));
-          mark(1);
-          break;
-        case DIST_FACTOR:
-          RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
-          mark(2);
-          break;
-        case DIST_BCAST: {
-          // the owner's finished block column (+ its diagonal inverses and log-dets) goes to every rank: after the loop L,
-          // Winv and logdet_parts are replicated.  One NCCL broadcast per panel (<= 205 MB at n = 50k), on the main stream.
-          const bool mine = op.root == me;
-          const long rows = n_pad - T0;
-          const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
-          double* Wt = Winv + (size_t)(T0 / NB) * NB * NB;
-          if (mine) {
-            pack_kernel<<<592, 256, 0, c->st>>>(c->stage, A + (long)T0 * ld + T0, ld, rows, nbT);
-            CU(cudaMemcpyAsync(c->stage + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-            CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-            c->launches++;
-          }
-          if (mine) mark(3);
-          NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, op.root, c->comm, c->st));
-          mark(mine ? 4 : 5);
-          if (!mine) {
-            unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
-            CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-            CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-            c->launches++;
-          }
-          CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));            // panel op.col is complete on this rank
-          if (!mine) mark(6);
-          break;
-        }
-        case DIST_UPDATE_SIDE: {                                           // look-ahead: panels pbeg .. pbeg+pcnt-1 -> my column
-          cudaStream_t side = op.stream ? c->st2 : c->st3;
-          CU(cudaStreamWaitEvent(side, c->ev_pool[2 * (op.pbeg + op.pcnt - 1)], 0));
-          int klen = op.pcnt * NBO;
-          if (op.pbeg * NBO + klen > n_pad) klen = n_pad - op.pbeg * NBO;
-          // Optional cut of the long-k chunk into launches of <= kchunk (GPSS_DIST_KCHUNK).  Measured at 8 GPUs, n = 50k:
-          // potrf 219 / 219 / 223 / 226 ms for kchunk = inf / 8192 / 4096 / 2048 (profiles/r01_dist_kchunk_sweep_8gpu.log),
-          // i.e. the critical path is NOT waiting for CTA slots held by long-lived bulk CTAs; default: one launch.
-          for (int k0 = 0; k0 < klen; k0 += kchunk)
-            RET(update(T0, nbT, op.pbeg * NBO + k0, (klen - k0 < kchunk) ? (klen - k0) : kchunk, side));
-          CU(cudaEventRecord(c->ev_pool[2 * op.col + 1], side));
-          break;
-        }
-      }
-    }
-    if (pipe) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (nblk_o - 1)], 0));   // the last panel has arrived on the comm stream
-    if (trace) {
-      CU(cudaStreamSynchronize(c->st));
-      static const char* names[7] = {"wait for look-ahead updates", "U2 (panel j-1 -> my column)", "panel factorisation", "pack", "broadcast (as root)",
-                                     "broadcast (as receiver, incl. waiting for the owner)", "unpack"};
-      double sum[7] = {0, 0, 0, 0, 0, 0, 0};
-      int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (size_t i = 1; i < marks.size(); i++) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
-        sum[marks[i].first] += ms;
-        cnt[marks[i].first]++;
-      }
-      for (auto& m : marks) cudaEventDestroy(m.second);
-      fprintf(stderr, "[gpss dist trace] rank %d of %d, n_pad %d:", me, P, n_pad);
-      for (int k = 0; k < 7; k++) fprintf(stderr, " %s: %.1f ms / %d;", names[k], sum[k], cnt[k]);
-      fprintf(stderr, "\n");
-    }
-  } else
-  for (int t = 0; t < nblk_o; t++) {
-    const int T0 = t * NBO;
-    const int nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-    if (!la) {
-      if (t >= 1) RET(update(T0, nbT, 0, T0, c->st));
-      RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
-      continue;
-    }
-    cudaEvent_t evP = c->ev_pool[2 * t], evU = c->ev_pool[2 * t + 1];
-    if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
-    if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
-    RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
-    CU(cudaEventRecord(evP, c->st));
-    // issue U1(t+1) = panels 0..t-1 applied to block column t+1; needs panel t-1 (complete: main stream order) --
-    // here, right after panel t was ENQUEUED, the side stream must only wait for panel t-1.
-    if (t + 1 < nblk_o && t >= 1) {
-      const int T1 = T0 + NBO;
-      const int nb1 = (n_pad - T1 < NBO) ? (n_pad - T1) : NBO;
-      cudaStream_t side = (t & 1) ? c->st2 : c->st3;
-      CU(cudaStreamWaitEvent(side, c->ev_pool[2 * (t - 1)], 0));
-      RET(update(T1, nb1, 0, T0, side));
-      CU(cudaEventRecord(c->ev_pool[2 * (t + 1) + 1], side));
-    }
-  }
-  if (P > 1) {   // a failed pivot anywhere must be seen everywhere
-    NC(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMax, c->comm, c->st));
-  }
-  return GPSS_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// PARTITIONED storage (n_pad^2 too large to replicate, e.g. n = 200 000: 320 GB): every rank keeps only the block columns
-// it owns (j % P == rank), packed side by side (40 GB per rank at n = 200 000, P = 8).  RIGHT-looking factorisation: the
-// owner factors block column t and broadcasts it; the broadcast buffer itself is the GEMM operand with which every rank
-// updates its own remaining block columns (one k = 512 DMMA launch per panel over all of them, lower-triangle tiles only
-// through the cyclic column map of gemm_nt_ws_kernel).  Look-ahead of one panel: the owner of t+1 updates that single
-// column on the high-priority stream, factors and broadcasts it while the bulk update with panel t is still running.
-// ---------------------------------------------------------------------------------------------------
-static int potrf_partitioned(gpss_ctx* c)
-{
-  const int P = c->world, me = c->rank, n_pad = c->n_pad;
-  const long ld = n_pad;
-  double* A = c->Lm;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev_pool.push_back(e);
-  }
-  const size_t per = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
-  RET(ensure_stage(c, 3 * per));                                         // panels t, t-1, t-2 stay live (see the look-ahead below)
-  // update of my local block columns [q0, q0 + cnt) with panel t, which lies in its broadcast buffer (rows T0.., ld = rows)
-  auto update = [&](int t, int q0, int cnt, cudaStream_t stream) -> int {
-    if (cnt <= 0) return GPSS_OK;
-    const double* pan = c->stage + (size_t)(t % 3) * per;
-    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-    const long rows = n_pad - T0;
-    const int Rb = (q0 * P + me) * NBO;                                  // first global row (= first global column) touched
-    long ncols = (long)cnt * NBO;
-    if ((long)q0 * NBO + ncols > c->lcols) ncols = c->lcols - (long)q0 * NBO;   // ragged last block column
-    GemmArgs g = gemm_args(pan + (Rb - T0), rows, pan, rows, A + (long)q0 * NBO * ld + Rb, ld, n_pad - Rb, (int)ncols, nbT);
-    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = Rb;
-    g.cyc_P = P; g.cyc_me = me; g.cyc_w = NBO; g.cyc_lcol0 = q0 * NBO; g.cyc_boff = T0;
-    return gemm_ws_on(c, g, stream);
-  };
-  // Look-ahead: the bulk update with panel s (side stream) covers my block columns j >= s + 3 only; column j receives
-  // panels j-2 and j-1 on the MAIN stream when panel j-1 arrives.  The critical path (two k = 512 updates of one column,
-  // the panel factorisation, the broadcast) therefore waits for the bulk update that finished a whole panel period
-  // earlier (s = j - 3), never for the one in flight.
-  for (int t = 0; t < nblk_o; t++) {
-    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-    const bool mine = (t % P) == me;
-    double* buf = c->stage + (size_t)(t % 3) * per;
-    const long rows = n_pad - T0;
-    const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
-    double* Wt = c->Winv + (size_t)(T0 / NB) * NB * NB;
-    // bulk update t-3 read this buffer and was the last side-stream launch to write block column t
-    if (t >= 3) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (t - 3) + 1], 0));
-    if (mine) {
-      const int q = t / P;
-      if (t >= 2) RET(update(t - 2, q, 1, c->st));
-      if (t >= 1) RET(update(t - 1, q, 1, c->st));
-      double* Acol = A + (long)q * NBO * ld;                              // my packed copy of global block column t
-      RET(potrf_panel(c, Acol - (long)T0 * ld, ld, n_pad, T0, nbT, c->Winv, c->logdet_parts, c->dflag));   // indexes by global column
-      pack_kernel<<<592, 256, 0, c->st>>>(buf, Acol + T0, ld, rows, nbT);
-      CU(cudaMemcpyAsync(buf + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-      CU(cudaMemcpyAsync(buf + n_panel + n_w, c->logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-      c->launches++;
-    }
-    NC(g_nccl.Broadcast(buf, buf, n_panel + n_w + n_l, ncclDouble, t % P, c->comm, c->st));
-    if (!mine) {
-      CU(cudaMemcpyAsync(Wt, buf + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-      CU(cudaMemcpyAsync(c->logdet_parts + T0 / NB, buf + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-    }
-    CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
-    int q0 = 0;                                                          // my first block column j >= t + 3
-    while (q0 < c->nq && q0 * P + me < t + 3) q0++;
-    CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
-    RET(update(t, q0, c->nq - q0, c->st2));
-    CU(cudaEventRecord(c->ev_pool[2 * t + 1], c->st2));
-  }
-  CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (nblk_o - 1) + 1], 0));
-  NC(g_nccl.AllReduce(c->dflag, c->dflag, 1, ncclInt, ncclMax, c->comm, c->st));
-  return GPSS_OK;
-}
-
-// alpha = L^-T L^-1 rhs with the partitioned factor.  Forward: the owner of block column t runs its four 128-steps and
-// broadcasts the updated tail of the right-hand side and the finished piece of z.  Backward: every rank keeps the
-// right-hand side current at the columns it owns and updates them with each new x_k; the owner of tile k-1 produces
-// x_{k-1}, broadcast 128 doubles at a time.  rhs in c->rvec (destroyed), result in c->alpha (replicated).
-static int potrs_vec_partitioned(gpss_ctx* c)
-{
-  const int P = c->world, me = c->rank, n_pad = c->n_pad, nblk = c->nblk;
-  const long ld = n_pad;
-  const int w = NBO / NB;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  if (me == 0) { trsv_fwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv, c->rvec, c->zvec); c->launches++; }
-  for (int t = 0; t < nblk_o; t++) {
-    const int T0 = t * NBO, nbT = (n_pad - T0 < NBO) ? (n_pad - T0) : NBO;
-    if ((t % P) == me) {
-      const double* Lg = c->Lm + (long)(t / P) * NBO * ld - (long)T0 * ld;     // indexed by global column inside my block column
-      for (int k = T0 / NB; k < (T0 + nbT) / NB && k + 1 < nblk; k++) {
-        trsv_fwd_step_kernel<<<nblk - 1 - k, TRSV_THREADS, 0, c->st>>>(Lg, ld, c->Winv, c->rvec, c->zvec, k * NB);
-        c->launches++;
-      }
-    }
-    const int zend = (T0 + nbT + NB <= n_pad) ? T0 + nbT + NB : n_pad;          // z of this block column and of the next tile
-    NC(g_nccl.Broadcast(c->zvec + T0, c->zvec + T0, (size_t)(zend - T0), ncclDouble, t % P, c->comm, c->st));
-    if (T0 + nbT < n_pad)
-      NC(g_nccl.Broadcast(c->rvec + T0 + nbT, c->rvec + T0 + nbT, (size_t)(n_pad - T0 - nbT), ncclDouble, t % P, c->comm, c->st));
-  }
-  CU(cudaGetLastError());
-  const int own_last = ((nblk - 1) / w) % P;
-  if (me == own_last) {
-    trsv_bwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv + (long)(nblk - 1) * NB * NB, c->zvec, c->alpha, (nblk - 1) * NB);
-    c->launches++;
-  }
-  NC(g_nccl.Broadcast(c->alpha + (long)(nblk - 1) * NB, c->alpha + (long)(nblk - 1) * NB, NB, ncclDouble, own_last, c->comm, c->st));
-  const int ltiles = (int)(c->lcols / NB);
-  for (int k = nblk - 1; k >= 1; k--) {
-    trsv_bwd_step_part_kernel<<<ltiles, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->zvec, c->alpha, k * NB, P, me, w);
-    c->launches++;
-    const int owner = ((k - 1) / w) % P;
-    NC(g_nccl.Broadcast(c->alpha + (long)(k - 1) * NB, c->alpha + (long)(k - 1) * NB, NB, ncclDouble, owner, c->comm, c->st));
-  }
-  CU(cudaGetLastError());
-  return GPSS_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// PARTITIONED storage, gradient: B^-1 = U U^T with U = L^-T held as block ROWS owned cyclically (rank r keeps rows
-// I = q P + r, packed: local row block q), 40 GB per rank at n = 200 000 like L itself.
-//   inverse (left-looking over block columns J of U, as trtri_upper):
-//       every rank contributes its blocks of the ROW strip L[J, 0:J] (ncclAllGather, then laid out in global column order);
-//       the owner of J inverts the diagonal block and broadcasts W_JJ = inv(L_JJ);
-//       T = U_loc[rows < J, 0:J0] L[J, 0:J0]^T  (k from each row's own start: cyclic row map of the GEMM kernel, split-k for
-//       short slices),  U_loc[rows < J, J] = -T W_JJ^T.
-//   B^-1 and the gradient, one block column J at a time: the owner broadcasts the row strip U[J, J0:], every rank forms
-//       Q[I >= J, J] = U_loc[I, J0:] U[J, J0:]^T for its rows and feeds the 512-wide strip straight into the fused gradient
-//       reductions -- B^-1 is never stored.
-// Everything on the main stream; results (13 sums) all-reduced at the end.
-// ---------------------------------------------------------------------------------------------------
-static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj);
-static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_doubles);
-static int ensure_lazy(double** p, size_t count);
-
-static int part_buffers(gpss_ctx* c)
-{
-  const size_t ldu = (size_t)(c->nq > 0 ? c->nq : 1) * NBO;
-  RET(ensure_lazy(&c->Um, ldu * c->n_pad));
-  RET(ensure_lazy(&c->Tpanel, ldu * NBO));                       // T, later the Q strip
-  RET(ensure_lazy(&c->Wjj, (size_t)2 * NBO * NBO));              // W_JJ and the owner's U_JJ scratch
-  const int nblk_o = (c->n_pad + NBO - 1) / NBO;
-  const size_t cmax = (size_t)(nblk_o + c->world - 1) / c->world;
-  RET(ensure_lazy(&c->pgather, (size_t)(c->world + 1) * cmax * NBO * NBO));   // [my piece | P gathered pieces]
-  if (!c->Tsplit) {
-    const size_t cap = (size_t)24576 * NBO;
-    CU(cudaMalloc(&c->Tsplit, cap * sizeof(double)));
-    c->Tsplit_cap = cap;
-  }
-  const long nblocks = (long)(ldu / NB) * c->nblk;               // every (local row tile, global column tile)
-  if (c->partial_blocks < nblocks || !c->partial) {
-    if (c->partial) cudaFree(c->partial);
-    c->partial = nullptr;
-    CU(cudaMalloc(&c->partial, sizeof(double) * (nblocks > 0 ? nblocks : 1) * NGRAD));
-    c->partial_blocks = nblocks;
-  }
-  return GPSS_OK;
-}
-
-static int trtri_partitioned(gpss_ctx* c)
-{
-  const int P = c->world, me = c->rank, n_pad = c->n_pad;
-  const long ld = n_pad;
-  const long ldu = (long)(c->nq > 0 ? c->nq : 1) * NBO;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  const int cmax = (nblk_o + P - 1) / P;
-  const size_t blk = (size_t)NBO * NBO;
-  double* piece = c->pgather;                                     // my blocks of the row strip
-  double* gathered = c->pgather + (size_t)cmax * blk;             // P segments of cmax blocks
-  double* Lrow = c->stage;                                        // the strip in global column order (the panel buffers are free now)
-  double* Wjj = c->Wjj;
-  double* Ujj = c->Wjj + blk;
-  CU(cudaMemsetAsync(c->Um, 0, sizeof(double) * (size_t)ldu * n_pad, c->st));
-  for (int J = 0; J < nblk_o; J++) {
-    const int J0 = J * NBO, nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
-    const int owner = J % P;
-    if (owner == me) {
-      // U_JJ from my packed copy of block column J (global addressing through shifted base pointers), W_JJ = U_JJ^T
-      const double* Lg = c->Lm + (long)(J / P) * NBO * ld - (long)J0 * ld;
-      double* Ug = Ujj - ((long)J0 * NBO + J0);
-      CU(cudaMemsetAsync(Ujj, 0, sizeof(double) * blk, c->st));
-      RET(trtri_diag_block(c, Ug, NBO, Lg, ld, J0, nbj));
-      transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, Ujj, NBO, 1);
-      c->launches++;
-      CU(cudaGetLastError());
-    }
-    NC(g_nccl.Broadcast(Wjj, Wjj, blk, ncclDouble, owner, c->comm, c->st));
-    int cnt = 0;                                                  // my row blocks above J = my column blocks left of J
-    while (cnt < c->nq && cnt * P + me < J) cnt++;
-    if (J > 0) {
-      const int jc = (J + P - 1) / P;                             // blocks per segment needed for this J (<= cmax)
-      if (cnt > 0) {
-        pack_rowstrip_kernel<<<592, 256, 0, c->st>>>(piece, c->Lm, ld, J0, nbj, NBO, cnt);
-        c->launches++;
-      }
-      NC(g_nccl.AllGather(piece, gathered, (size_t)jc * blk, ncclDouble, c->comm, c->st));
-      order_rowstrip_kernel<<<592, 256, 0, c->st>>>(Lrow, gathered, nbj, NBO, J, P, (long)jc * (long)blk);
-      c->launches++;
-      CU(cudaGetLastError());
-    }
-    if (cnt > 0 && J > 0) {
-      const int rows = cnt * NBO;
-      // T = U_loc[0:rows, 0:J0] * Lrow^T, k from each row's own global start
-      GemmArgs g = gemm_args(c->Um, ldu, Lrow, nbj, c->Tpanel, ldu, rows, nbj, J0);
-      g.kbeg_row = 1; g.rcyc_P = P; g.rcyc_me = me; g.rcyc_w = NBO; g.rcyc_l0 = 0; g.rcyc_koff = 0;
-      const int S = pick_ksplit(rows / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0, (long)rows * nbj, c->Tsplit_cap);
-      if (S > 1) {
-        g.C = c->Tsplit; g.ldc = rows; g.ksplit = S; g.csplit = (long)rows * nbj;
-        RET(gemm(c, g));
-        split_sum_kernel<<<296, 256, 0, c->st>>>(c->Tpanel, ldu, c->Tsplit, rows, nbj, S);
-        c->launches++;
-        CU(cudaGetLastError());
-      } else {
-        RET(gemm(c, g));
-      }
-      GemmArgs g2 = gemm_args(c->Tpanel, ldu, Wjj, NBO, c->Um + (long)J0 * ldu, ldu, rows, nbj, nbj);
-      g2.negate_out = 1; g2.kend_col = 1;
-      RET(gemm(c, g2));
-    }
-    if (owner == me) {                                            // my diagonal block
-      copy2d_kernel<<<64, 256, 0, c->st>>>(c->Um + (long)J0 * ldu + (long)(J / P) * NBO, ldu, Ujj, NBO, nbj, nbj);
-      c->launches++;
-      CU(cudaGetLastError());
-    }
-  }
-  return GPSS_OK;
-}
-
-static int gradient_partitioned(gpss_ctx* c)
-{
-  const int P = c->world, me = c->rank, n_pad = c->n_pad;
-  const long ldu = (long)(c->nq > 0 ? c->nq : 1) * NBO;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  const int ltiles = (int)(ldu / NB);                             // my local row tiles (128 high)
-  const int w = NBO / NB;
-  double* strip = c->stage;                                       // U[J, J0:] as nbj x (n_pad - J0), contiguous
-  double* Qs = c->Tpanel;                                         // Q[my rows >= J, J], ld = ldu
-  const long nblocks = (long)ltiles * c->nblk;
-  CU(cudaMemsetAsync(c->partial, 0, sizeof(double) * nblocks * NGRAD, c->st));
-  for (int J = 0; J < nblk_o; J++) {
-    const int J0 = J * NBO, nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
-    const int owner = J % P;
-    const long cols = n_pad - J0;
-    if (owner == me) {
-      pack_kernel<<<592, 256, 0, c->st>>>(strip, c->Um + (long)J0 * ldu + (long)(J / P) * NBO, ldu, nbj, cols);
-      c->launches++;
-    }
-    NC(g_nccl.Broadcast(strip, strip, (size_t)nbj * cols, ncclDouble, owner, c->comm, c->st));
-    int q0 = 0;                                                   // my first row block I >= J
-    while (q0 < c->nq && q0 * P + me < J) q0++;
-    const int rows = (c->nq - q0) * NBO - ((q0 < c->nq && (c->nq - 1) * P + me == nblk_o - 1) ? (NBO - (n_pad - (nblk_o - 1) * NBO)) : 0);
-    if (rows <= 0) continue;
-    // Q strip = U_loc[q0 rows.., J0:] * strip^T, k from each row's own start (relative to J0)
-    GemmArgs g = gemm_args(c->Um + (long)J0 * ldu + (long)q0 * NBO, ldu, strip, nbj, Qs, ldu, rows, nbj, (int)cols);
-    g.kbeg_row = 1; g.rcyc_P = P; g.rcyc_me = me; g.rcyc_w = NBO; g.rcyc_l0 = q0 * NBO; g.rcyc_koff = J0;
-    RET(gemm(c, g));
-    // fused gradient reductions over the strip: local row tiles q0*w .., global column tiles J*w ..
-    const int ntm = rows / NB, ntn = nbj / NB;
-    grad_pass_kernel<<<dim3(ntm, ntn), 256, 0, c->st>>>(Qs, ldu, c->zs, n_pad, c->xs, n_pad, c->alpha, c->n, c->dP,
-                                                       c->partial + (long)(J * w) * ltiles * NGRAD, q0 * w, J * w, P, me, w);
-    c->launches++;
-    CU(cudaGetLastError());
-  }
-  sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);
-  c->launches++;
-  CU(cudaGetLastError());
-  NC(g_nccl.AllReduce(c->red + 8, c->red + 8, NGRAD, ncclDouble, ncclSum, c->comm, c->st));
-  return GPSS_OK;
-}
-
-static int create_streams(gpss_ctx* c)
-{
-  int lo = 0, hi = 0;
-  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (largest number), hi = greatest
-  CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, hi));
-  CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, lo));
-  CU(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, lo));
-  CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
-  return GPSS_OK;
-}
-
-static void destroy_streams(gpss_ctx* c)
-{
-  if (c->ev_main) cudaEventDestroy(c->ev_main);
-  if (c->ev_side) cudaEventDestroy(c->ev_side);
-  for (auto e : c->ev_pool) cudaEventDestroy(e);
-  c->ev_pool.clear();
-  for (auto e : c->ev_pipe) cudaEventDestroy(e);
-  c->ev_pipe.clear();
-  if (c->st4) cudaStreamDestroy(c->st4);
-  c->st4 = nullptr;
-  if (c->st2) cudaStreamDestroy(c->st2);
-  if (c->st3) cudaStreamDestroy(c->st3);
-  if (c->st) cudaStreamDestroy(c->st);
-  c->ev_main = c->ev_side = nullptr;
-  c->st = c->st2 = c->st3 = nullptr;
-}
-
-// Number of k-parts for a GEMM of `tiles` output tiles on 2 x 148 CTA slots: the smallest S whose CTA count fills
-// whole waves best, subject to parts of >= 2048 in k and to the capacity of the partial-product buffer.
-static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_doubles)
-{
-  const int slots = 296;
-  if (tiles <= 0 || tiles >= 4 * slots) return 1;
-  int best = 1;
-  double best_eff = 0.0;
-  for (int S = 1; S <= 8; S++) {
-    if (S > 1 && (klen / S < 2048 || (size_t)part_doubles * S > cap_doubles)) break;
-    const int ctas = tiles * S;
-    const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
-    if (eff > best_eff + 0.03) { best_eff = eff; best = S; }
-  }
-  return best;
-}
-
-// U = L^-T (upper), block-column left-looking; only NT products (see gpss_gemm.cuh header):
-//     U[J,J]   = inv(L[J,J])^T                       built from the stored 128x128 inverses      (main stream)
-//     U[0:J,J] = -(U[0:J,0:J] L[J,0:J]^T) U[J,J]     one long-k GEMM + one k = NBO GEMM           (side stream)
-// The diagonal blocks depend only on L, so the main stream produces them (latency-bound small launches) ahead of
-// the side stream, which runs the bulk GEMMs back to back.
-// The diagonal block U[J0:J0+nbj, J0:J0+nbj] = inv(L[J0.., J0..])^T in 128-steps from the stored 128 x 128 inverses (main stream).
-// U and L are addressed by GLOBAL row / column (callers with packed storage pass suitably shifted base pointers).
-static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj)
-{
-  for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
-    const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
-    put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, c->st>>>(U + (long)i0 * ldu + i0, ldu, Wi);
-    c->launches++;
-    CU(cudaGetLastError());
-    const int mr = i0 - J0;
-    if (mr > 0) {
-      double* Uc = U + (long)i0 * ldu + J0;                 // U[J0:i0, i0:i0+128]
-      GemmArgs g = gemm_args(U + (long)J0 * ldu + J0, ldu, L + (long)J0 * ldl + i0, ldl, Uc, ldu, mr, NB, mr);
-      g.kbeg_row = 1;
-      RET(gemm(c, g));
-      // Uc <- -Uc Wi^T in place: columns 64..127 first (all 128 inputs), then 0..63 (inputs 0..63 only)
-      GemmArgs g1 = gemm_args(Uc, ldu, Wi + 64, NB, Uc + 64 * ldu, ldu, mr, 64, NB);
-      g1.negate_out = 1;
-      RET(gemm(c, g1));
-      GemmArgs g2 = gemm_args(Uc, ldu, Wi, NB, Uc, ldu, mr, 64, 64);
-      g2.negate_out = 1;
-      RET(gemm(c, g2));
-    }
-  }
-  return GPSS_OK;
-}
-
-static int trtri_upper(gpss_ctx* c)
-{
-  const long ld = c->n_pad;
-  const int n_pad = c->n_pad;
-  double *L = c->Lm, *U = c->Um;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev_pool.push_back(e);
-  }
-  // Distributed: every row of U depends only on L and on the SAME row of earlier block columns, so a rank computes
-  // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
-  // rank needs as right factors, are cheap and computed redundantly).
-  const int R0 = c->urow0, R1 = c->urow1;
-  // the side stream must not start before the factor is complete on the main stream
-  CU(cudaEventRecord(c->ev_main, c->st));
-  CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
-  for (int t = 0; t < nblk_o; t++) {
-    const int J0 = t * NBO;
-    const int nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
-    double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
-    // (1) the diagonal NBO-block of U in 128-steps
-    RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj));
-    if (t == 0) continue;
-    // (2) W_JJ = U_JJ^T into this block's scratch
-    transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
-    c->launches++;
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
-    CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
-    const int ra = R0, rb = (R1 < J0) ? R1 : J0;             // my rows above this block column
-    if (rb <= ra) continue;
-    // (3) T[ra:rb] = U[ra:rb, 0:J0] * L[Jblk, 0:J0]^T      (k starts at each tile's own row: U is upper triangular)
-    GemmArgs g = gemm_args(U + ra, ld, L + J0, ld, c->Tpanel + ra, ld, rb - ra, nbj, J0);
-    g.kbeg_row = 1; g.krow_off = ra;
-    // A row slice has few tiles per step (rank 0 of 8 at n = 50k: 17 x 8 = 136 for 296 CTA slots) and the steps are
-    // sequential, so a distributed rank cuts the long k-range of every tile into S parts (one CTA each), sized to
-    // fill whole waves; the parts are summed in a fixed order by split_sum_kernel.
-    int S = 1;
-    if (c->world > 1) S = pick_ksplit((rb - ra) / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0 - ra, (long)(rb - ra) * nbj, c->Tsplit_cap);
-    if (S > 1) {
-      const int rows = rb - ra;
-      g.C = c->Tsplit; g.ldc = rows; g.ksplit = S; g.csplit = (long)rows * nbj;
-      RET(gemm_ws_on(c, g, c->st2));
-      split_sum_kernel<<<296, 256, 0, c->st2>>>(c->Tpanel + ra, ld, c->Tsplit, rows, nbj, S);
-      c->launches++;
-      CU(cudaGetLastError());
-    } else {
-      RET(gemm_ws_on(c, g, c->st2));
-    }
-    // (4) U[ra:rb, Jblk] = -T * W_JJ^T
-    GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
-    g2.negate_out = 1; g2.kend_col = 1;
-    RET(gemm_ws_on(c, g2, c->st2));
-  }
-  CU(cudaEventRecord(c->ev_side, c->st2));
-  CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
-  return GPSS_OK;
-}
-
-// Distributed: every rank has computed its rows of U; B^-1 = U U^T and W = U^T need all of them.  Each rank's slice
-// (rows [b_k, b_k+1) x columns b_k..n, a strided region of the column-major buffer) is packed, broadcast and unpacked.
-static int allgather_U(gpss_ctx* c)
-{
-  if (c->world == 1) return GPSS_OK;
-  const long ld = c->n_pad;
-  std::vector<int> b;
-  balanced_rows(c->n_pad, c->world, 0, b);
-  size_t need = 0;
-  for (int k = 0; k < c->world; k++) need = std::max(need, (size_t)(b[k + 1] - b[k]) * (size_t)(c->n_pad - b[k]));
-  RET(ensure_stage(c, need));
-  for (int k = 0; k < c->world; k++) {
-    const long rows = b[k + 1] - b[k], cols = c->n_pad - b[k];
-    if (rows <= 0) continue;
-    double* slice = c->Um + (long)b[k] * ld + b[k];
-    if (k == c->rank) { pack_kernel<<<1184, 256, 0, c->st>>>(c->stage, slice, ld, rows, cols); c->launches++; }
-    NC(g_nccl.Broadcast(c->stage, c->stage, (size_t)rows * cols, ncclDouble, k, c->comm, c->st));
-    if (k != c->rank) { unpack_kernel<<<1184, 256, 0, c->st>>>(slice, ld, c->stage, rows, cols); c->launches++; }
-  }
-  CU(cudaGetLastError());
-  return GPSS_OK;
-}
-
-// Q (lower) = U U^T = B^-1; a rank computes the rows [qrow0, qrow1) of its balanced slice (all rows when alone)
-static int lauum_lower(gpss_ctx* c)
-{
-  const long ld = c->n_pad;
-  const int q0 = c->qrow0, q1 = c->qrow1;
-  if (q1 <= q0) return GPSS_OK;
-  GemmArgs g = gemm_args(c->Um + q0, ld, c->Um, ld, c->Qm + q0, ld, q1 - q0, q1, c->n_pad);
-  g.lower_only = 1; g.kbeg_row = 1; g.krow_off = q0; g.grow0 = q0; g.gcol0 = 0;
-  return gemm(c, g);
-}
-
-// x = L^-T L^-1 rhs through the stored diagonal inverses; rhs in c->rvec (destroyed), result in c->alpha
-static int potrs_vec(gpss_ctx* c)
-{
-  const long ld = c->n_pad;
-  const int nblk = c->nblk;
-  trsv_fwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv, c->rvec, c->zvec);
-  c->launches++;
-  for (int k = 0; k + 1 < nblk; k++) {
-    trsv_fwd_step_kernel<<<nblk - 1 - k, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->rvec, c->zvec, k * NB);
-    c->launches++;
-  }
-  CU(cudaGetLastError());
-  trsv_bwd_first_kernel<<<1, TRSV_THREADS, 0, c->st>>>(c->Winv + (long)(nblk - 1) * NB * NB, c->zvec, c->alpha, (nblk - 1) * NB);
-  c->launches++;
-  for (int k = nblk - 1; k >= 1; k--) {
-    trsv_bwd_step_kernel<<<k, TRSV_THREADS, 0, c->st>>>(c->Lm, ld, c->Winv, c->zvec, c->alpha, k * NB);
-    c->launches++;
-  }
-  CU(cudaGetLastError());
-  return GPSS_OK;
-}
-
-// dst = src / sn2 (the factor comes from the device parameters, so the launch carries no theta-dependent argument and can sit in a graph)
 __global__ void scale_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, const DevParams* __restrict__ P, int n, int n_pad)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1342,7 +307,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     lm_cols = c->lcols > 0 ? (size_t)c->lcols : 1;
   }
   auto fail = [&](int code) { gpss_destroy(c); return code; };
-#define CUF(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(fail_cuda(e__, #x, __LINE__)); } while (0)
+#define CUF(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(fail_cuda(e__, #x, __FILE__, __LINE__)); } while (0)
   { int r__ = create_streams(c); if (r__ != GPSS_OK) return fail(r__); }
   CUF(cudaEventCreate(&c->ev[0]));
   CUF(cudaEventCreate(&c->ev[1]));
@@ -1373,7 +338,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     ncclResult_t nr = g_nccl.CommInitRank(&c->comm, part_world, id, part_rank);
-    if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __LINE__));
+    if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __FILE__, __LINE__));
   }
   *out = c;
   return GPSS_OK;
@@ -1782,7 +747,7 @@ int gpss_compute_K(int device, int kind, const double theta[GPSS_NPAR], int d, i
   DevParams* dP = nullptr;
   int rc = GPSS_OK;
   auto cleanup = [&]() { cudaFree(dx1); cudaFree(dx2); cudaFree(dz1); cudaFree(dz2); cudaFree(dK); cudaFree(dD); cudaFree(dP); };
-#define CUK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
+#define CUK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
   CUK(cudaMalloc(&dx1, sizeof(double) * NX * n1));
   CUK(cudaMalloc(&dx2, sizeof(double) * NX * n2));
   CUK(cudaMalloc(&dz1, sizeof(double) * NZ * n1));
@@ -1864,7 +829,7 @@ int gpss_expans_gradients(int device, const double theta[GPSS_NPAR], int d, int 
   DevParams* dP = nullptr;
   int rc = GPSS_OK;
   auto cleanup = [&]() { cudaFree(dx); cudaFree(dz); cudaFree(dQ); cudaFree(dpart); cudaFree(dred); cudaFree(dP); };
-#define CUG(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __LINE__); cleanup(); return rc; } } while (0)
+#define CUG(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = fail_cuda(e__, #x, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
   CUG(cudaMalloc(&dx, sizeof(double) * NX * n));
   CUG(cudaMalloc(&dz, sizeof(double) * NZ * n));
   CUG(cudaMemset(dx, 0, sizeof(double) * NX * n));
@@ -2092,3 +1057,4 @@ int gpss_test_potrf(int device, int n, double* A, double* logdet_half, double* m
 }
 
 }  // extern "C"
+

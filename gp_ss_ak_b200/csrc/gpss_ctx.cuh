@@ -1,0 +1,246 @@
+// gpss_ctx.cuh -- part of the single translation unit gpss_capi.cu (not a standalone header): error plumbing, the run-time
+// NCCL binding, the handle (gpss_ctx), GEMM launch helpers, timers and the theta -> device-parameter mapping.
+#pragma once
+#include "../../include/gpss.h"
+#include "gpss_gemm.cuh"
+#include "gpss_kernels.cuh"
+#include "gpss_params.h"
+
+#include <dlfcn.h>
+#include <nccl.h>       // types and prototypes only: the library is dlopen'ed when a communicator is first needed
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <limits>
+
+using namespace gpss;
+
+static thread_local std::string g_last_error;
+
+static const char* base_name(const char* path) { const char* b = std::strrchr(path, '/'); return b ? b + 1 : path; }
+static int fail_cuda(cudaError_t e, const char* what, const char* file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error '%s' in %s (%s:%d)", cudaGetErrorString(e), what, base_name(file), line);
+  g_last_error = buf;
+  return GPSS_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail_cuda(e__, #x, __FILE__, __LINE__); } while (0)
+#define RET(x) do { int r__ = (x); if (r__ < 0) return r__; } while (0)
+
+static int fail_arg(const char* msg) { g_last_error = msg; return GPSS_ERR_ARG; }
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (libnccl.so.2: the copy torch has already loaded, else the system one), so that the
+// single-GPU library has no hard dependency on it.
+// ---------------------------------------------------------------------------------------------------
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+  if (g_nccl.ok) return GPSS_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_last_error = std::string("cannot load libnccl.so.2: ") + dlerror(); return GPSS_ERR_NCCL; }
+#define NCCL_SYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) { g_last_error = "libnccl.so.2 lacks " name; return GPSS_ERR_NCCL; }
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  NCCL_SYM(Broadcast, "ncclBroadcast")
+  NCCL_SYM(AllReduce, "ncclAllReduce")
+  NCCL_SYM(AllGather, "ncclAllGather")
+  NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+  g_nccl.ok = true;
+  return GPSS_OK;
+}
+static int fail_nccl(ncclResult_t r, const char* what, const char* file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "NCCL error '%s' in %s (%s:%d)", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what, base_name(file), line);
+  g_last_error = buf;
+  return GPSS_ERR_NCCL;
+}
+#define NC(x) do { ncclResult_t r__ = (x); if (r__ != ncclSuccess) return fail_nccl(r__, #x, __FILE__, __LINE__); } while (0)
+
+constexpr int NBO = 512;      // outer block (k-depth of the big trailing updates)
+constexpr int PRED_BATCH = 8192;
+
+enum QState { Q_NONE = 0, Q_IS_BINV = 1, Q_IS_W = 2 };
+
+struct gpss_ctx {
+  int device = 0;
+  int n = 0, n_pad = 0, nblk = 0;
+  int d = 3;                                                   // input columns: 3, or 4 with the rock-type column
+  int kind = 0;                                                // main kernel: GPSS_KERNEL_EXPANS | _EXP | _RBF
+  cudaStream_t st = nullptr;                                  // main stream (highest priority): critical-path kernels
+  cudaStream_t st2 = nullptr;                                 // look-ahead stream (lowest priority): bulk trailing updates
+  cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
+                                                              // the tail wave of one is filled by the head of the next
+  cudaStream_t st4 = nullptr;                                 // communication stream of the pipelined panel broadcast (highest priority)
+  std::vector<cudaEvent_t> ev_pipe;                           // per 128-column sub-panel: [2 i] factored on the owner, [2 i + 1] received
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
+  std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
+  // data
+  double *xs = nullptr, *y = nullptr, *zs = nullptr;           // NX x n_pad, n_pad, NZ x n_pad
+  double *Lm = nullptr, *Um = nullptr, *Qm = nullptr;          // n_pad^2 each (Um, Qm lazily)
+  double *Winv = nullptr;                                      // nblk x 128 x 128
+  double *logdet_parts = nullptr;                              // nblk
+  double *rvec = nullptr, *zvec = nullptr, *alpha = nullptr, *fvec = nullptr;   // n_pad each
+  double *Tpanel = nullptr, *Wjj = nullptr;                    // n_pad x NBO, NBO x NBO (lazily)
+  double *partial = nullptr; long partial_blocks = 0;          // gradient partial sums
+  double *red = nullptr;                                       // 32 doubles of reduced scalars
+  DevParams* dP = nullptr;                                     // [0] training, [1] prediction
+  int* dflag = nullptr;
+  // prediction scratch (lazily)
+  double *xt = nullptr, *zt = nullptr, *zsp = nullptr, *Bm = nullptr, *Vm = nullptr, *mu_part = nullptr, *dmu = nullptr, *dvar = nullptr;
+  int pred_cap = 0;
+  // distributed evaluation (one process per GPU; rank/world = 0/1 when not initialised)
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  double* stage = nullptr; size_t stage_count = 0;            // contiguous staging for strided sub-matrices
+  double* Tsplit = nullptr; size_t Tsplit_cap = 0;             // split-k partial products of the row-sliced inverse
+  double* pgather = nullptr;                                   // partitioned inverse: my piece of an L row strip + the all-gathered pieces
+  bool partitioned = false;                                    // Lm holds only my block columns, packed (n too large to replicate)
+  int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
+  int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
+  int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
+  // host state
+  double theta[GPSS_NPAR];
+  double sums_train[4];
+  bool have_factor = false, have_alpha = false, have_U = false;
+  int qstate = Q_NONE;
+  int chol_fail = 0;
+  double nlml = std::numeric_limits<double>::quiet_NaN();
+  double s3 = 0.0;
+  // CUDA graphs of the launch-bound small-n evaluation: [0] K build + Cholesky + solves + objective terms, [1] inverse + gradient pass
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  long graph_launches[2] = {0, 0};
+  bool graph_failed = false;
+  // instrumentation
+  bool profiling = false;
+  double phase_ms[16];
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};   // bracket the device work of the last objective / predict call
+  double last_call_ms = 0.0;
+  long launches = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------
+static int configure_kernels()
+{
+  CU(cudaFuncSetAttribute(gemm_nt_ws_kernel<GemmTileWideWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWideWS::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTileWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWide::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(potrf_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  return GPSS_OK;
+}
+
+// Every O(n^3) product of the path goes through the warp-specialised 128x64 DMMA kernel (gemm_nt_ws_kernel).
+static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
+{
+  using T = GemmTileWideWS;
+  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
+  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
+  GemmArgs ga = g;
+  ga.mt = g.M / T::BM;
+  ga.nt = g.N / T::BN;
+  const int parts = ga.ksplit > 1 ? ga.ksplit : 1;
+  gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt * parts), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+// legacy cp.async kernel (kept as the A/B baseline of bench_micro/gemm_bench.cu and for the tile=1 test hook)
+static int gemm_legacy_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
+{
+  using T = GemmTileWide;
+  if (g.M <= 0 || g.N <= 0) return GPSS_OK;
+  if (g.M % T::BM || g.N % T::BN || g.K % T::BK) return fail_arg("gemm: dimensions not tile multiples");
+  GemmArgs ga = g;
+  ga.mt = g.M / T::BM;
+  ga.nt = g.N / T::BN;
+  gemm_nt_kernel<T><<<(unsigned)(ga.mt * ga.nt), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st); }
+static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K)
+{
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+// CUDA-event bracket of a whole C-ABI call on the handle's stream (always on; read with gpss_get_last_call_ms)
+struct CallTimer {
+  gpss_ctx* c;
+  explicit CallTimer(gpss_ctx* c_) : c(c_) { cudaEventRecord(c->ev_call[0], c->st); }
+  ~CallTimer()
+  {
+    cudaEventRecord(c->ev_call[1], c->st);
+    cudaEventSynchronize(c->ev_call[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]);
+    c->last_call_ms = ms;
+  }
+};
+
+struct PhaseTimer {
+  gpss_ctx* c; int idx;
+  PhaseTimer(gpss_ctx* c_, int idx_) : c(c_), idx(idx_) { if (c->profiling) cudaEventRecord(c->ev[0], c->st); }
+  ~PhaseTimer()
+  {
+    if (c->profiling) {
+      cudaEventRecord(c->ev[1], c->st);
+      cudaEventSynchronize(c->ev[1]);
+      float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      c->phase_ms[idx] += ms;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// parameters -> device
+// ---------------------------------------------------------------------------------------------------
+static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0)
+{
+  memset(&P, 0, sizeof P);
+  for (int j = 0; j < dim; j++) P.c[j] = centre[j];
+  P.dim = dim;
+  P.kind = kind;
+  if (kind == 0) {
+    sig_inv(theta, P.S);
+    P.lr = theta[7];                                   // InversewidthR: sigInv(3,3) of the 4-column branch (Kernel.cpp:1411-1424)
+  } else {
+    // EuclDist (Kernel.cpp:1343-1368): D2 = |x - x'|^2 / hyp^2 -> the same pair-distance code with sigInv = (1/hyp) I
+    const double ih = 1.0 / theta[0];
+    P.S[0] = P.S[4] = P.S[8] = ih;
+    P.lr = ih;
+    if (kind == 2) P.rbf_c = -0.5 * theta[1];
+  }
+  const double sig = theta_sigma(kind, theta), sn2 = theta_sn2(kind, theta);
+  P.var2 = sig * sig;
+  P.bias = theta_bias(kind, theta);
+  P.sn2 = sn2;
+  P.inv_sn2 = 1 / sn2;
+  P.sw = std::sqrt(P.inv_sn2);
+  P.sww = P.sw * P.sw;
+  P.lp_const = std::log(2.0 * M_PI * sn2) / 2;
+}
+
