@@ -83,6 +83,46 @@ def test_cli_train_and_test_match_reference_binary(tmp_path):
     assert os.path.exists(tmp_path / expected), os.listdir(tmp_path)
 
 
+def test_cli_baseline_config0_n2000(tmp_path):
+    """BASELINE.json configs[0]: `./gp_ss_ak -v 3 -pm 1 train -k ExpAns -kn 1 -o LBFGS` on the synthetic 3-D ore-grade set,
+    n = 2 000, against what the unmodified reference binary printed and wrote for the same file (tests/golden/ref_n2000.npz,
+    made by tests/golden/make_ref_n2000.py; `-# 2` bounds the reference's CPU time).  The optimiser's decisions are pinned
+    probe by probe on the CPU (tests/test_host_cpu.py, same fixture); here: same start, a decreasing objective, identical
+    statistics file, same model-file structure, and -- with the REFERENCE's model -- the reference's predictions."""
+    assert os.path.exists(CLI), "host CLI not built (run __graft_entry__.build())"
+    z = np.load(os.path.join(GOLD, "ref_n2000.npz"))
+    (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
+    (tmp_path / "test.txt").write_text(str(z["test_file_text"]))
+    tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train", "-k", "ExpAns", "-kn", "1", "-o", "LBFGS", "-#", str(int(z["cli_iters"])),
+                         str(tmp_path / "train.txt"), str(tmp_path / "cli_model")], capture_output=True, text=True,
+                        stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=900)
+    assert tr.returncode == 0, tr.stdout + tr.stderr
+    ref_out = str(z["cli_train_stdout"])
+    ll_mine, ll_ref = _floats_after(tr.stdout, "Log likelihood:"), _floats_after(ref_out, "Log likelihood:")
+    assert len(ll_mine) == len(ll_ref) == 2
+    assert np.isclose(ll_mine[0], ll_ref[0], rtol=2e-5)                 # objective at the hard-coded starting point (6 digits printed)
+    assert ll_mine[1] < ll_mine[0] and ll_ref[1] < ll_ref[0]            # both fits descend; where they stop is noise-driven (see above)
+    assert "Data Set Size: 2000" in tr.stdout
+    assert (tmp_path / "cli_model_Statistics.txt").read_text() == str(z["cli_stats_text"])
+    mine_model = (tmp_path / "cli_model").read_text().splitlines()
+    ref_model = str(z["cli_model_text"]).splitlines()
+    assert len(mine_model) == len(ref_model)
+    assert [l.split("=")[0] for l in mine_model if "=" in l] == [l.split("=")[0] for l in ref_model if "=" in l]
+    (tmp_path / "ref_model").write_text(str(z["cli_model_text"]))
+    (tmp_path / "ref_model_Statistics.txt").write_text(str(z["cli_stats_text"]))
+    te = subprocess.run([CLI, "-v", "3", "-pm", "1", "test", str(tmp_path / "test.txt"), str(tmp_path / "ref_model"),
+                         str(tmp_path / "train.txt")], capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path, timeout=900)
+    assert te.returncode == 0, te.stdout + te.stderr
+    ref_te = str(z["cli_test_stdout"])
+    assert np.allclose(_floats_after(te.stdout, "Mean Square Error of testing:"), _floats_after(ref_te, "Mean Square Error of testing:"), rtol=1e-4)
+    mine_pred = _table((tmp_path / "ref_model_predict.txt").read_text())
+    ref_pred = _table(str(z["cli_predict_text"]))
+    assert mine_pred.shape == ref_pred.shape and mine_pred.shape[0] == 220
+    assert np.array_equal(mine_pred[:, 0], ref_pred[:, 0])              # sorted by observed y
+    assert np.allclose(mine_pred[:, 2], ref_pred[:, 2], rtol=5e-5, atol=2e-6)        # Yh (6 significant digits printed)
+    assert np.allclose(mine_pred[:, 3], ref_pred[:, 3], rtol=5e-5, atol=2e-6)        # StdYh
+
+
 def test_cli_rejects_configurations_outside_the_hot_path(tmp_path):
     z = np.load(os.path.join(GOLD, "ref_n300.npz"))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))

@@ -27,12 +27,13 @@ def _parse(text):
     return rec
 
 
-def test_lbfgs_replays_reference_trace(host_built, tmp_path):
+@pytest.mark.parametrize("fixture", ["ref_n300.npz", "ref_n2000.npz"])
+def test_lbfgs_replays_reference_trace(host_built, tmp_path, fixture):
     """Every ObjVal / Grad_Values probe of a 30-iteration fit by the UNMODIFIED reference (recorded in
-    tests/golden/ref_n300.npz) must be requested by the host driver in the same order, of the same kind, at the same
-    theta (1e-12 relative); it is answered with the recorded f and g.  Exercises cauchy_point, Primal_Conjugate_grad,
-    Efficient_line_search and the memory updates, quirks included."""
-    z = np.load(os.path.join(GOLD, "ref_n300.npz"))
+    tests/golden/ref_n300.npz; ref_n2000.npz = BASELINE.json configs[0], 4 iterations / 63 probes) must be requested by the
+    host driver in the same order, of the same kind, at the same theta (1e-12 relative); it is answered with the recorded
+    f and g.  Exercises cauchy_point, Primal_Conjugate_grad, Efficient_line_search and the memory updates, quirks included."""
+    z = np.load(os.path.join(GOLD, fixture))
     trace = tmp_path / "trace.txt"
     with open(trace, "w") as f:
         for k in range(len(z["probe_f"])):
@@ -62,8 +63,9 @@ def test_lbfgs_replay_detects_a_wrong_decision(host_built, tmp_path):
     assert out.returncode != 0 and "MISMATCH" in out.stdout
 
 
-def test_reader_standardisation_and_files_match_reference(host_built, tmp_path):
-    z = np.load(os.path.join(GOLD, "ref_n300.npz"))
+@pytest.mark.parametrize("fixture", ["ref_n300.npz", "ref_n2000.npz"])
+def test_reader_standardisation_and_files_match_reference(host_built, tmp_path, fixture):
+    z = np.load(os.path.join(GOLD, fixture))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
     (tmp_path / "test.txt").write_text(str(z["test_file_text"]))
     th = z["theta_fit"].reshape(-1)
@@ -85,7 +87,7 @@ def test_reader_standardisation_and_files_match_reference(host_built, tmp_path):
     # read-back: 6 significant digits survive (default ostream precision), structure intact
     rb = rec["theta_readback"].reshape(-1)
     assert np.abs(rb - th).max() <= 5e-6 * np.abs(th).max()
-    assert "readback numData 300 inputDim 3 outputDim 1 kernel Hyb nkern_params 9" in out.stdout
+    assert "readback numData %d inputDim 3 outputDim 1 kernel Hyb nkern_params 9" % z["X_raw"].shape[0] in out.stdout
 
 
 def test_reader_quirks(host_built, tmp_path):

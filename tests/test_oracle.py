@@ -119,9 +119,10 @@ def test_oracle_reproduces_golden(name, nth):
 REF_TOL_NLML, REF_TOL_G, REF_TOL_ALPHA, REF_TOL_MU, REF_TOL_VAR = 2e-7, 5e-7, 5e-7, 5e-7, 1e-7
 
 
-@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz"])
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_n2000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz"])
 def test_oracle_matches_compiled_reference(name):
-    """The restatement against numbers produced by the unmodified reference classes (tests/golden/make_ref_golden.py)."""
+    """The restatement against numbers produced by the unmodified reference classes (tests/golden/make_ref_golden.py;
+    ref_n2000.npz = BASELINE.json configs[0], tests/golden/make_ref_n2000.py)."""
     z = np.load(os.path.join(GOLD, name))
     Xs0, ys0, params, _ = O.standardise_train(z["X_raw"], z["y_raw"].reshape(-1))
     assert np.array_equal(Xs0, z["Xs"]) and np.array_equal(ys0, z["ys"].reshape(-1))        # Control.cpp:299-324 bit-exact
