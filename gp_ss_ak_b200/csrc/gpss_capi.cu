@@ -193,6 +193,7 @@ static int ensure_U(gpss_ctx* c)
   if (c->have_U) return GPSS_OK;
   const size_t nn = (size_t)c->n_pad * c->n_pad;
   RET(ensure_lazy(&c->Um, nn));
+  if (oz_active(c)) RET(oz_ensure_planes(c, &c->ozU, c->oz_tmU));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
   RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
   if (c->world > 1 && !c->Tsplit) {
@@ -243,6 +244,8 @@ int gpss_destroy(gpss_handle c)
   if (c->stage) cudaFree(c->stage);
   if (c->Tsplit) cudaFree(c->Tsplit);
   if (c->pgather) cudaFree(c->pgather);
+  if (c->ozL) cudaFree(c->ozL);
+  if (c->ozU) cudaFree(c->ozU);
   if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -339,6 +342,18 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     memcpy(&id, id128, sizeof id);
     ncclResult_t nr = g_nccl.CommInitRank(&c->comm, part_world, id, part_rank);
     if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __FILE__, __LINE__));
+  }
+  // opt-in int8 tensor-core path (gpss_ozaki.cuh): GPSS_OZAKI = number of 7-bit slices (6, 7 or 8); single-GPU handles only
+  if (const char* e = getenv("GPSS_OZAKI")) {
+    const int v = atoi(e);
+    if (v != 0 && part_world <= 1) {
+      if (v < 6 || v > 8) return fail(fail_arg("GPSS_OZAKI must be 6, 7 or 8 (7-bit slices per operand)"));
+      if (c->n_pad > 65536) return fail(fail_arg("GPSS_OZAKI: int32 accumulation is exact up to n = 65 536 only"));
+      c->oz_s = v;
+      r = oz_configure();
+      if (r == GPSS_OK) r = oz_ensure_planes(c, &c->ozL, c->oz_tmL);
+      if (r != GPSS_OK) return fail(r);
+    }
   }
   *out = c;
   return GPSS_OK;
@@ -452,6 +467,7 @@ static int ensure_gradient_buffers(gpss_ctx* c)
 {
   const size_t nn = (size_t)c->n_pad * c->n_pad;
   RET(ensure_lazy(&c->Um, nn));
+  if (oz_active(c)) RET(oz_ensure_planes(c, &c->ozU, c->oz_tmU));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
   RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
   if (c->world > 1 && !c->Tsplit) {
@@ -542,6 +558,7 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
+  c->oz_s = 0;                                           // the int8 path is single-GPU only (oz_active)
   std::vector<int> b;
   balanced_rows(c->n_pad, world, 0, b);
   c->urow0 = b[rank]; c->urow1 = b[rank + 1];

@@ -5,6 +5,7 @@
 #include "gpss_gemm.cuh"
 #include "gpss_kernels.cuh"
 #include "gpss_params.h"
+#include "gpss_ozaki.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>       // types and prototypes only: the library is dlopen'ed when a communicator is first needed
@@ -118,6 +119,11 @@ struct gpss_ctx {
   int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
   int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
   int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
+  // opt-in int8 tensor-core path (GPSS_OZAKI = 6 | 7 | 8, gpss_ozaki.cuh): signed base-128 digit planes of L and of U = L^-T,
+  // [oz_s][n_pad rows][n_pad bytes of k] each, and their TMA descriptors ([0] 128-row box = A operand, [1] 64-row box = B operand)
+  int oz_s = 0;
+  int8_t *ozL = nullptr, *ozU = nullptr;
+  CUtensorMap oz_tmL[2], oz_tmU[2];
   // host state
   double theta[GPSS_NPAR];
   double sums_train[4];
@@ -180,6 +186,65 @@ static int gemm_legacy_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
 }
 
 static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st); }
+
+// ---------------------------------------------------------------------------------------------------
+// opt-in int8 (Ozaki) path: active on single-GPU, replicated-storage handles with the look-ahead streams
+// ---------------------------------------------------------------------------------------------------
+static int oz_active(const gpss_ctx* c) { return (c->oz_s > 0 && c->world == 1 && !c->partitioned && c->st2) ? c->oz_s : 0; }
+
+static int oz_configure()
+{
+  CU(oz::configure<6>());
+  CU(oz::configure<7>());
+  CU(oz::configure<8>());
+  return GPSS_OK;
+}
+
+// digit planes of one n_pad x n_pad operand + its two TMA descriptors (allocation: never while a graph is being captured)
+static int oz_ensure_planes(gpss_ctx* c, int8_t** planes, CUtensorMap* tm)
+{
+  if (*planes) return GPSS_OK;
+  const size_t bytes = (size_t)c->oz_s * c->n_pad * c->n_pad;
+  CU(cudaMalloc(planes, bytes));
+  CU(cudaMemsetAsync(*planes, 0, bytes, c->st));
+  if (oz::make_plane_map(&tm[0], *planes, (long)c->oz_s * c->n_pad, c->n_pad, oz::BM) != 0 ||
+      oz::make_plane_map(&tm[1], *planes, (long)c->oz_s * c->n_pad, c->n_pad, oz::BN) != 0)
+    return fail_arg("GPSS_OZAKI: cuTensorMapEncodeTiled failed");
+  return GPSS_OK;
+}
+
+static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, oz::Args a, cudaStream_t st)
+{
+  if (a.m <= 0 || a.n <= 0) return GPSS_OK;
+  if (a.m % oz::BM || a.n % oz::BN || a.k0 % oz::BK || a.k1 % oz::BK) return fail_arg("oz_gemm: dimensions not tile multiples");
+  a.a_rows = a.b_rows = c->n_pad;
+  a.dP = c->dP;
+  switch (c->oz_s) {
+    case 6: oz::launch<6>(ta, tb, a, st); break;
+    case 7: oz::launch<7>(ta, tb, a, st); break;
+    case 8: oz::launch<8>(ta, tb, a, st); break;
+    default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
+// X addressed by global (row, k) -> planes[p][row][k] for the block [row0, row0 + rows) x [k0, k0 + kcnt)
+static int oz_slice_on(gpss_ctx* c, const double* X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask, int8_t* planes,
+                       cudaStream_t st)
+{
+  if (rows <= 0 || kcnt <= 0) return GPSS_OK;
+  switch (c->oz_s) {
+    case 6: oz::slice<6>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
+    case 7: oz::slice<7>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
+    case 8: oz::slice<8>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
+    default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
 static GemmArgs gemm_args(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K)
 {
   GemmArgs g;

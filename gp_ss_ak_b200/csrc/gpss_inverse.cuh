@@ -246,6 +246,9 @@ static int trtri_upper(gpss_ctx* c)
   // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
   // rank needs as right factors, are cheap and computed redundantly).
   const int R0 = c->urow0, R1 = c->urow1;
+  // opt-in int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
+  // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
+  const bool ozk = oz_active(c) && c->ozL && c->ozU;
   // the side stream must not start before the factor is complete on the main stream
   CU(cudaEventRecord(c->ev_main, c->st));
   CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
@@ -255,7 +258,14 @@ static int trtri_upper(gpss_ctx* c)
     double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
     // (1) the diagonal NBO-block of U in 128-steps
     RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj));
-    if (t == 0) continue;
+    if (t == 0) {
+      if (ozk) {                                             // digit planes of block column 0 (only its diagonal block)
+        CU(cudaEventRecord(c->ev_pool[0], c->st));
+        CU(cudaStreamWaitEvent(c->st2, c->ev_pool[0], 0));
+        RET(oz_slice_on(c, U, ld, 0, nbj, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
+      }
+      continue;
+    }
     // (2) W_JJ = U_JJ^T into this block's scratch
     transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
     c->launches++;
@@ -270,6 +280,19 @@ static int trtri_upper(gpss_ctx* c)
     // A row slice has few tiles per step (rank 0 of 8 at n = 50k: 17 x 8 = 136 for 296 CTA slots) and the steps are
     // sequential, so a distributed rank cuts the long k-range of every tile into S parts (one CTA each), sized to
     // fill whole waves; the parts are summed in a fixed order by split_sum_kernel.
+    if (ozk) {
+      oz::Args a;
+      memset(&a, 0, sizeof a);
+      a.C = c->Tpanel; a.ldc = ld; a.m = J0; a.n = nbj;
+      a.a_row0 = 0; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
+      a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
+      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, c->st2));
+      GemmArgs g2 = gemm_args(c->Tpanel, ld, Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
+      g2.negate_out = 1; g2.kend_col = 1;
+      RET(gemm_ws_on(c, g2, c->st2));
+      RET(oz_slice_on(c, U, ld, 0, J0 + nbj, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));   // planes of block column t
+      continue;
+    }
     int S = 1;
     if (c->world > 1) S = pick_ksplit((rb - ra) / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0 - ra, (long)(rb - ra) * nbj, c->Tsplit_cap);
     if (S > 1) {
@@ -321,6 +344,14 @@ static int lauum_lower(gpss_ctx* c)
   const long ld = c->n_pad;
   const int q0 = c->qrow0, q1 = c->qrow1;
   if (q1 <= q0) return GPSS_OK;
+  if (oz_active(c) && c->ozU) {                              // opt-in int8 path: both operands are the digit planes of U
+    oz::Args a;
+    memset(&a, 0, sizeof a);
+    a.C = c->Qm; a.ldc = ld; a.m = c->n_pad; a.n = c->n_pad;
+    a.a_row0 = 0; a.b_row0 = 0; a.k0 = 0; a.k1 = c->n_pad; a.kbeg_row = 1;
+    a.lower_only = 1; a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_UNIT;
+    return oz_gemm_on(c, c->oz_tmU[0], c->oz_tmU[1], a, c->st);
+  }
   GemmArgs g = gemm_args(c->Um + q0, ld, c->Um, ld, c->Qm + q0, ld, q1 - q0, q1, c->n_pad);
   g.lower_only = 1; g.kbeg_row = 1; g.krow_off = q0; g.grow0 = q0; g.gcol0 = 0;
   return gemm(c, g);

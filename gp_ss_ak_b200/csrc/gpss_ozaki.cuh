@@ -1,0 +1,339 @@
+// gpss_ozaki.cuh -- OPT-IN (GPSS_OZAKI=6|7|8, single-GPU handles; default off): the three long-k FP64 contractions of the
+// path (look-ahead update of the Cholesky, bulk product of the triangular inverse, B^-1 = U U^T) evaluated on the int8
+// tensor cores of sm_100a -- tcgen05.mma kind::i8, operands by TMA, int32 accumulators in TMEM -- with the Ozaki splitting,
+// instead of the 37 TFLOP/s DMMA pipe.  Measured on B200 (profiles/r01_ozaki_int8_gemm_microbench.txt, 16384^2 x 8192):
+// 83.7 FP64-equivalent TFLOP/s with S = 7 slices, 69.0 with S = 8, against 35.9 for gemm_nt_ws_kernel; error of S = 8
+// against a long-double reference 1.3e-15 (DMMA: 1.4e-14).  Numerics of the whole path: scripts/ozaki_numerics.py.
+//
+//   operand x -> t = x / 2^e (ONE a-priori exponent per operand kind, see oz_exponent), v = rint(t 2^(7S-1)),
+//   signed base-128 digits d_0 .. d_{S-1} in [-64, 64]:  t = sum_p d_p 2^-(7p+6)          (oz_slice_kernel, K-major int8 planes)
+//   A B^T = 2^(eA+eB-12) sum_g 2^(-7g) G_g,  G_g = sum_{i+j=g} A_i B_j^T  exact in int32 (|G_g| <= (g+1) k 2^12 < 2^31 for
+//   k <= 65 536 at S = 8); pairs with i + j >= S are dropped (below the rounding of v).
+//
+// oz_gemm_kernel<S>: one CTA per 128 x 64 tile of C, 192 threads.
+//   warp 4   : TMA producer -- per 64-byte k-chunk all S planes of the A tile (128 rows) and of the B tile (64 rows) as
+//              SWIZZLE_64B boxes, one mbarrier per stage (2 stages at S = 7 / 8);
+//   warp 5   : allocates TMEM (S x 64 columns), issues S (S + 1) / 2 x 2 MMAs (M 128, N 64, K 32) per chunk; group g
+//              accumulates in TMEM columns [64 g, 64 g + 64); tcgen05.commit releases the stage;
+//   warps 0-3: epilogue -- tcgen05.ld of the S group accumulators, Horner in FP64, C written / updated (TMEM lane = row
+//              of C, so a warp touches 32 consecutive doubles of a column).
+// Every plane of a chunk is loaded ONCE and feeds up to S products.
+#pragma once
+#include "gpss_gemm.cuh"          // mbarrier helpers
+#include "gpss_kernels.cuh"       // DevParams
+#include <cuda.h>
+#include <cstdint>
+
+namespace oz {
+
+constexpr int BM = 128, BN = 64, BK = 64;        // BK in bytes (= int8 elements) per stage and plane: one SWIZZLE_64B row
+constexpr int UMMA_K = 32;                       // kind::i8: 32 bytes of k per instruction
+constexpr int DIGIT_BITS = 7;
+constexpr int RASTER_W = 8;
+
+enum { SCALE_UNIT = 0, SCALE_CHOL = 1 };         // operand kinds: |x| <= 1 (U = L^-T: B >= I), |x| <= sqrt(max B_ii) (L)
+enum { MASK_NONE = 0, MASK_LOWER = 1, MASK_UPPER = 2 };
+
+template <int S>
+struct Cfg {
+  static constexpr int PAIRS = S * (S + 1) / 2;
+  static constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK;
+  static constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+  static constexpr int TMEM_COLS = S * BN <= 64 ? 64 : S * BN <= 128 ? 128 : S * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static_assert(S >= 1 && S * BN <= 512, "S group accumulators of BN columns must fit the 512 TMEM columns");
+  static_assert(STAGES >= 2, "need at least two stages");
+};
+
+struct Args {
+  double* C; long ldc;           // C(i,j) at C[i + j*ldc]
+  int m, n;                      // tile grid: m % 128 == 0, n % 64 == 0
+  int a_rows, b_rows;            // rows per plane of the plane tensors (plane p, row r -> TMA row p * rows + r)
+  int a_row0, b_row0;            // plane row of C(0,.) in the A planes / of C(.,0) in the B planes
+  int k0, k1;                    // k range [k0, k1), multiples of 64 (plane byte columns)
+  int kbeg_row;                  // 1: k starts at the tile's first A row (A upper-triangular in (row, k)); a_row0 is then a k coordinate too
+  int lower_only;                // 1: skip tiles entirely above the diagonal of the global matrix (C(0,0) sits at (grow0, gcol0))
+  int grow0, gcol0;
+  int accumulate;                // 0: C = sign * A B^T, 1: C += sign * A B^T
+  double sign;
+  int a_kind, b_kind;            // SCALE_*: which power of two each operand was divided by before slicing
+  const gpss::DevParams* dP;     // device parameters (theta-dependent scale: never a launch argument, so launches can sit in a graph)
+  int32_t* dbg;                  // test hook: raw int32 group accumulators, [S][m][n] row-major (else nullptr)
+};
+
+// The exponent e with |x| < 2^e for every element of an operand of the given kind.  L: |L_ij| <= sqrt(B_ii),
+// B_ii = 1 + Sw^2 (Sigma^2 + Sigma_Bias) for all i (exp(0) = 1 on the diagonal of every kernel kind).
+__device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P)
+{
+  if (kind == SCALE_UNIT || P == nullptr) return 0;
+  int e;
+  frexp(sqrt(1.0 + P->sww * (P->var2 + P->bias)), &e);      // sqrt(B_ii) = f 2^e, f in [0.5, 1)
+  return e;
+}
+
+// ------------------------------------------------------------------ PTX helpers (sm_100a)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               :: "r"(gpss::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(gpss::smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)       // arrives on bar when all MMAs issued so far have completed
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(gpss::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 64 bytes, SWIZZLE_64B (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp:
+// start >> 4 in [0,14), LBO in [16,30) (ignored for swizzled K-major: 1), SBO = 8 rows x 64 B >> 4 = 32 in [32,46),
+// version 1 in [46,48), layout SWIZZLE_64B = 4 in [61,64)).  The tile base is 1024-byte aligned.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr)
+{
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format S32 = 2 [4,6), a/b_format INT8 = 1 [7,10) / [10,13), K-major both, N >> 3 [17,23), M >> 4 [24,29)
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int S>
+__global__ void __launch_bounds__(192, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g)
+{
+  using T = Cfg<S>;
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + T::STAGES;
+  uint64_t* acc_bar = empty_bar + T::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rasterisation as in gemm_nt_ws_kernel: super-columns of RASTER_W tile columns, tile column fastest, so that one wave of
+  // 148 CTAs shares ~19 A row-tiles x 8 B row-tiles through L2 instead of streaming every A plane once per tile column
+  const int mt = g.m / BM, nt = g.n / BN;
+  const int grp = blockIdx.x / (RASTER_W * mt), within = blockIdx.x % (RASTER_W * mt);
+  const int gcols = min(RASTER_W, nt - grp * RASTER_W);
+  const int tile_n = grp * RASTER_W + within % gcols, tile_m = within / gcols;
+  if (g.lower_only && g.gcol0 + tile_n * BN > g.grow0 + tile_m * BM + BM - 1) return;      // whole CTA, before any barrier
+  int kb = g.k0;
+  if (g.kbeg_row) { const int kr = (g.a_row0 + tile_m * BM) & ~(BK - 1); if (kr > kb) kb = kr; }
+  const int nk = g.k1 > kb ? (g.k1 - kb) / BK : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T::STAGES; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
+    gpss::mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(gpss::smem_u32(tmem_slot)), "r"((uint32_t)T::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; kc++) {
+        const int st = kc % T::STAGES;
+        const uint32_t ph = (uint32_t)(kc / T::STAGES) & 1u;
+        gpss::mbar_wait(empty_bar + st, ph ^ 1u);
+        gpss::mbar_arrive_expect_tx(full_bar + st, (uint32_t)T::STAGE_BYTES);
+        uint8_t* sa = smem + st * T::STAGE_BYTES;
+        uint8_t* sb = sa + S * T::A_BYTES;
+        const int kq = kb + kc * BK;
+#pragma unroll
+        for (int p = 0; p < S; p++) {
+          tma_load_2d(sa + p * T::A_BYTES, &tmA, full_bar + st, kq, p * g.a_rows + g.a_row0 + tile_m * BM);
+          tma_load_2d(sb + p * T::B_BYTES, &tmB, full_bar + st, kq, p * g.b_rows + g.b_row0 + tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0 && nk > 0) {
+      for (int kc = 0; kc < nk; kc++) {
+        const int st = kc % T::STAGES;
+        const uint32_t ph = (uint32_t)(kc / T::STAGES) & 1u;
+        gpss::mbar_wait(full_bar + st, ph);
+        tc_fence_after();
+        const uint32_t sa = gpss::smem_u32(smem + st * T::STAGE_BYTES);
+        const uint32_t sb = sa + S * T::A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ks++) {
+#pragma unroll
+          for (int i = 0; i < S; i++) {
+            const uint64_t ad = smem_desc_sw64(sa + i * T::A_BYTES + ks * UMMA_K);
+#pragma unroll
+            for (int j = 0; j < S - i; j++) {
+              const uint64_t bd = smem_desc_sw64(sb + j * T::B_BYTES + ks * UMMA_K);
+              // group i + j: the first product that reaches it (i == 0 of the first k-step) overwrites, the rest accumulate
+              mma_i8(tmem_base + (uint32_t)((i + j) * BN), ad, bd, IDESC_I8, (kc > 0 || ks > 0 || i > 0) ? 1u : 0u);
+            }
+          }
+        }
+        tc_commit(empty_bar + st);         // stage reusable once these MMAs have read it
+      }
+      tc_commit(acc_bar);                  // accumulators complete
+    }
+  } else {
+    // ------------------------------------------------ epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows of the tile
+    if (nk > 0) {
+      gpss::mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
+    const int row = tile_m * BM + warp * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const double w = 1.0 / (double)(1 << DIGIT_BITS);
+    const double scale = g.sign * ldexp(1.0, oz_exponent(g.a_kind, g.dP) + oz_exponent(g.b_kind, g.dP) - 2 * (DIGIT_BITS - 1));
+    for (int c0 = 0; c0 < BN; c0 += 8) {
+      uint32_t v[S][8];
+      if (nk > 0) {
+#pragma unroll
+        for (int gi = 0; gi < S; gi++) tmem_ld8(lane_base + (uint32_t)(gi * BN + c0), v[gi]);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int gi = 0; gi < S; gi++)
+#pragma unroll
+          for (int c = 0; c < 8; c++) v[gi][c] = 0u;
+      }
+      if (g.dbg) {
+#pragma unroll
+        for (int gi = 0; gi < S; gi++)
+#pragma unroll
+          for (int c = 0; c < 8; c++) g.dbg[((size_t)gi * g.m + row) * g.n + tile_n * BN + c0 + c] = (int32_t)v[gi][c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int gi = S - 1; gi >= 0; gi--) acc = acc * w + (double)(int32_t)v[gi][c];     // sum_g 2^(-7g) G_g, smallest first
+        double* cp = g.C + row + (size_t)(tile_n * BN + c0 + c) * g.ldc;
+        *cp = g.accumulate ? (*cp + scale * acc) : (scale * acc);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"((uint32_t)T::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ slicing: FP64 column-major -> S K-major int8 planes
+// X is addressed by GLOBAL (row, k): X[row + k * ldx].  The block [row0, row0 + rows) x [k0, k0 + kcnt) goes to
+// planes[p][row * kpad + k] (plane p starts at p * plane_rows * kpad).  mask: MASK_LOWER keeps k <= row (L), MASK_UPPER keeps
+// k >= row (U); everything else is written as 0, so the GEMM may run its k-ranges in whole 64-byte chunks over the
+// triangle's edge.  32 x 32 tiles through shared memory: coalesced FP64 reads along rows, 32-byte row segments written.
+template <int S>
+__global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask,
+                                const gpss::DevParams* dP, int8_t* __restrict__ planes, long plane_rows, long kpad)
+{
+  __shared__ int8_t tile[S][32][33];
+  const int r = row0 + blockIdx.x * 32 + threadIdx.x;
+  const double lim = (double)(1ll << (DIGIT_BITS * S - 1));
+  const double mul = ldexp(lim, -oz_exponent(kind, dP));               // exact power of two
+  for (int ky = threadIdx.y; ky < 32; ky += blockDim.y) {
+    const int kq = k0 + blockIdx.y * 32 + ky;
+    int d[S];
+#pragma unroll
+    for (int p = 0; p < S; p++) d[p] = 0;
+    const bool keep = (mask == MASK_NONE) || (mask == MASK_LOWER && kq <= r) || (mask == MASK_UPPER && kq >= r);
+    if (r < row0 + rows && kq < k0 + kcnt && keep) {
+      double sc = X[r + (size_t)kq * ldx] * mul;
+      sc = fmin(fmax(sc, -lim), lim);                                  // |x| <= 2^e by construction; guards rounding excess
+      long long v = __double2ll_rn(sc);
+#pragma unroll
+      for (int p = S - 1; p >= 1; p--) {
+        const int dg = (int)((v + 64) & 127) - 64;                    // [-64, 63], exact remainder
+        v = (v - dg) >> DIGIT_BITS;
+        d[p] = dg;
+      }
+      d[0] = (int)v;                                                   // |v| <= 64
+    }
+#pragma unroll
+    for (int p = 0; p < S; p++) tile[p][threadIdx.x][ky] = (int8_t)d[p];
+  }
+  __syncthreads();
+  for (int ry = threadIdx.y; ry < 32; ry += blockDim.y) {
+    const int rr = row0 + blockIdx.x * 32 + ry, kq = k0 + blockIdx.y * 32 + threadIdx.x;
+    if (rr < row0 + rows && kq < k0 + kcnt) {
+#pragma unroll
+      for (int p = 0; p < S; p++) planes[((size_t)p * plane_rows + rr) * kpad + kq] = tile[p][ry][threadIdx.x];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static inline EncodeTiledFn encode_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// planes: [total_rows][kpad] bytes, K contiguous; box = 64 bytes of k x box_rows rows, SWIZZLE_64B.  Returns 0 on success.
+static inline int make_plane_map(CUtensorMap* tm, const int8_t* planes, long total_rows, long kpad, int box_rows)
+{
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int S>
+static inline cudaError_t configure()
+{
+  return cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S>::SMEM_BYTES);
+}
+
+template <int S>
+static inline void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& g, cudaStream_t st)
+{
+  oz_gemm_kernel<S><<<(unsigned)((g.m / BM) * (g.n / BN)), 192, Cfg<S>::SMEM_BYTES, st>>>(ta, tb, g);
+}
+
+template <int S>
+static inline void slice(const double* X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask, const gpss::DevParams* dP,
+                         int8_t* planes, long plane_rows, long kpad, cudaStream_t st)
+{
+  if (rows <= 0 || kcnt <= 0) return;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((kcnt + 31) / 32)), block(32, 8);
+  oz_slice_kernel<S><<<grid, block, 0, st>>>(X, ldx, row0, rows, k0, kcnt, kind, mask, dP, planes, plane_rows, kpad);
+}
+
+}  // namespace oz

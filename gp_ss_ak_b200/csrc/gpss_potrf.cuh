@@ -143,8 +143,20 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   // staging layout of one broadcast: [panel rows T0.. x nbT | the panel's 128x128 diagonal inverses | their log-dets]
   const size_t stage_need = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
   if (P > 1) RET(ensure_stage(c, stage_need));
+  // opt-in int8 path (gpss_ozaki.cuh): every finished block column is cut into digit planes on the main stream, and the long-k
+  // look-ahead update U1 reads those planes through the tcgen05 kernel; U2 (k = NBO, critical path) and the panel stay on DMMA
+  const bool ozk = oz_active(c) && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad;
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
+    if (ozk && stream != c->st) {
+      oz::Args a;
+      memset(&a, 0, sizeof a);
+      a.C = A + (long)T0 * ld + T0; a.ldc = ld; a.m = n_pad - T0; a.n = nbT;
+      a.a_row0 = T0; a.b_row0 = T0; a.k0 = kbeg; a.k1 = kbeg + klen;
+      a.lower_only = 1; a.grow0 = T0; a.gcol0 = T0;
+      a.accumulate = 1; a.sign = -1.0; a.a_kind = oz::SCALE_CHOL; a.b_kind = oz::SCALE_CHOL;
+      return oz_gemm_on(c, c->oz_tmL[0], c->oz_tmL[1], a, stream);
+    }
     const double* Lp = A + (long)kbeg * ld + T0;
     GemmArgs g = gemm_args(Lp, ld, Lp, ld, A + (long)T0 * ld + T0, ld, n_pad - T0, nbT, klen);
     g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
@@ -313,6 +325,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
     if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
     RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
+    if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));   // planes of panel t
     CU(cudaEventRecord(evP, c->st));
     // issue U1(t+1) = panels 0..t-1 applied to block column t+1; needs panel t-1 (complete: main stream order) --
     // here, right after panel t was ENQUEUED, the side stream must only wait for panel t-1.
