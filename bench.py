@@ -40,6 +40,18 @@ GEMM_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 =
                      "algorithmic 4.8 GB because operand slabs are re-fetched per wave through L2 (hit rate 83 %), yet only 4 % of the HBM peak: "
                      "the kernel runs at 96.7 % DMMA-pipe activity (profiles/r01_gemm_ws_ncu_full_summary.txt)")
 FP64_PEAK_FALLBACK_TFLOPS = 37.13   # profiles/r01_fp64_peak_microbench.txt (DMMA.8x8x4 register loop on this pool's B200)
+BF16_SUSTAINED_FALLBACK_TFLOPS = 1400.0   # /opt/skills/guides/B200_PROFILING.md: "sustained it settles near 1.4 PFLOP/s" (used "of fallback")
+
+
+def int8_tensor_peak():
+    """Dense int8 tensor peak in TOP/s for a kernel timed inside a long step: MEASURED_PEAKS.json has no int8 entry, so
+    2 x its sustained bf16 cuBLAS figure (B200: dense int8 = 2 x dense bf16, 4.5 vs 2.25 POP/s nominal)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return 2.0 * float(pk["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (of measured; the file has no int8 entry)"
+    except Exception:
+        return 2.0 * BF16_SUSTAINED_FALLBACK_TFLOPS, "2 x the 1.4 PFLOP/s sustained bf16 figure of B200_PROFILING.md (of fallback)"
 
 
 def theta_probe(k):
@@ -254,6 +266,7 @@ def main():
         peak = FP64_PEAK_FALLBACK_TFLOPS
         peak_src = "profiles/r01_fp64_peak_microbench.txt"
     achieved = alg_flops / (gemm_ms * 1e-3) * 1e-12
+    oz_s = model.ozaki_slices()                   # 0: FP64 DMMA; 6 | 7 | 8: int8 tensor cores, that many 7-bit slices (gpss_ozaki.cuh)
 
     # ---- prediction leg (BASELINE metric iii): mean + variance of block-model centroids, test points split over the GPUs,
     #      L / alpha replicated; host buffers in, host buffers out (the public call), device time from the handle's events ----
@@ -303,25 +316,43 @@ def main():
                    "row-sliced triangular inverse / B^-1, all-reduced gradient partials" % world)
         else:
             par = "replicas x%d (independent evaluations)" % world
+        note = ("achieved = n_pad^3%s algorithmic flops (potrf+trtri+lauum) / device time of those phases on rank 0"
+                % (" / %d GPUs" % world if distributed else ""))
+        if oz_s:
+            pairs = oz_s * (oz_s + 1) // 2
+            i8_peak, i8_src = int8_tensor_peak()
+            roofline = {"bound": "tensor", "achieved": achieved * pairs, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
+                        "frac": achieved * pairs / i8_peak, "traffic": None,
+                        "traffic_note": "no ncu capture of oz_gemm_kernel yet: the path was built after the round's ncu runs (profiles/ holds the DMMA captures)",
+                        "kernel": "oz_gemm_kernel<%d> (tcgen05.mma kind::i8, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; %d int8 "
+                                  "products per FP64 product)" % (oz_s, pairs),
+                        "peak_source": i8_src,
+                        "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": peak, "frac_of_fp64_dmma_peak": achieved / peak,
+                        "note": note + "; executed int8 op/s = %d x the FP64-equivalent rate; the phases also contain the k = 512 panel work that stays on "
+                                       "DMMA and the digit slicing, so the kernel itself runs faster than this" % pairs}
+            dtype = "f64 (long-k products as %d x 7-bit int8 slices on the tensor cores, int32 accumulation, FP64 recombination)" % oz_s
+            gemm_path = "int8 tensor cores, Ozaki splitting, %d slices (GPSS_OZAKI; 0 = FP64 DMMA)" % oz_s
+        else:
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE,
+                        "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
+                        "peak_source": peak_src, "note": note}
+            dtype = "f64"
+            gemm_path = "FP64 DMMA"
         line = {
             "metric": "ExpAns LML+grad evals/s at n=%dk" % (n // 1000), "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d, theta differs every step"
                                    % n, "n": n, "n_pad": n_pad, "l2_policy": "inputs larger than L2 (K, L, B^-1 = %.1f GB each)"
-                                   % (n_pad * n_pad * 8 / 1e9), "parallelism": par},
+                                   % (n_pad * n_pad * 8 / 1e9), "parallelism": par, "gemm_path": gemm_path},
             "wall_ms_per_step": wall / args.steps * 1e3,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(n * 4 * 8 + 80) * (world if world > 1 else 1),
                     "d2h_bytes_per_step": 88 * (world if world > 1 else 1)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE,
-                         "kernel": "gemm_nt_ws_kernel<GemmTileWS<128,64,2,2,2,4>> (FP64 DMMA, bulk-copy producer warp + mbarrier ring)",
-                         "peak_source": peak_src,
-                         "note": "achieved = n_pad^3%s algorithmic flops (potrf+trtri+lauum) / device time of those phases on rank 0"
-                                 % (" / %d GPUs" % world if distributed else "")},
+            "roofline": roofline,
             "phases_ms": {"kbuild": ph[0], "potrf": ph[1], "solve_objective": ph[2], "trtri": ph[3], "lauum": ph[4], "grad_pass": ph[5],
                           "gather_U": ph[8]},
             "cholesky_tflops": (float(n_pad) ** 3 / 3) / (ph[1] * 1e-3) * 1e-12,

@@ -76,6 +76,7 @@ def load_library():
         "gpss_get_launch_count": (I, [H, ctypes.POINTER(L)]),
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
+        "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
         "gpss_test_gemm_nt": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_potrf": (I, [I, I, P, P, P]),
     }
@@ -222,6 +223,12 @@ class GpssModel:
     def launch_count(self):
         v = ctypes.c_long(0)
         _check(self._lib.gpss_get_launch_count(self._h, ctypes.byref(v)))
+        return v.value
+
+    def ozaki_slices(self):
+        """0 = the long-k contractions run on the FP64 DMMA pipe; 6 | 7 | 8 = on the int8 tensor cores with that many slices."""
+        v = ctypes.c_int(0)
+        _check(self._lib.gpss_get_ozaki(self._h, ctypes.byref(v)))
         return v.value
 
     def padded_n(self):

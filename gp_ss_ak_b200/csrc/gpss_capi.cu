@@ -343,12 +343,20 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     ncclResult_t nr = g_nccl.CommInitRank(&c->comm, part_world, id, part_rank);
     if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __FILE__, __LINE__));
   }
-  // opt-in int8 tensor-core path (gpss_ozaki.cuh): GPSS_OZAKI = number of 7-bit slices (6, 7 or 8); single-GPU handles only
-  if (const char* e = getenv("GPSS_OZAKI")) {
-    const int v = atoi(e);
-    if (v != 0 && part_world <= 1) {
-      if (v < 6 || v > 8) return fail(fail_arg("GPSS_OZAKI must be 6, 7 or 8 (7-bit slices per operand)"));
-      if (c->n_pad > 65536) return fail(fail_arg("GPSS_OZAKI: int32 accumulation is exact up to n = 65 536 only"));
+  // int8 tensor-core path of the three long-k contractions (gpss_ozaki.cuh), single-GPU handles only.
+  //   GPSS_OZAKI unset : 8 slices (operands carried to 2^-55 of their a-priori bound: at or below the rounding of the DMMA
+  //                      path) for 8192 < n_pad <= 57 344, i.e. where an evaluation is GEMM-bound and the two extra
+  //                      n_pad^2-byte x 8 plane buffers still fit beside L, U and B^-1 in 180 GB; the DMMA path otherwise
+  //   GPSS_OZAKI=0     : always the FP64 DMMA path
+  //   GPSS_OZAKI=6|7|8 : that many 7-bit slices, for every n (7: 1.3x faster than 8; nlml 1e-11, alpha 4e-10 at n = 5 000..50 000)
+  if (part_world <= 1) {
+    int v = (c->n_pad > 8192 && c->n_pad <= 57344) ? 8 : 0;
+    if (const char* e = getenv("GPSS_OZAKI")) {
+      v = atoi(e);
+      if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (7-bit slices per operand)"));
+      if (v != 0 && c->n_pad > 65536) return fail(fail_arg("GPSS_OZAKI: int32 accumulation is exact up to n = 65 536 only"));
+    }
+    if (v != 0) {
       c->oz_s = v;
       r = oz_configure();
       if (r == GPSS_OK) r = oz_ensure_planes(c, &c->ozL, c->oz_tmL);
@@ -558,7 +566,9 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
-  c->oz_s = 0;                                           // the int8 path is single-GPU only (oz_active)
+  c->oz_s = 0;                                           // the int8 path is single-GPU only (oz_active): give its planes back
+  if (c->ozL) { cudaFree(c->ozL); c->ozL = nullptr; }
+  if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
   std::vector<int> b;
   balanced_rows(c->n_pad, world, 0, b);
   c->urow0 = b[rank]; c->urow1 = b[rank + 1];
@@ -954,6 +964,13 @@ int gpss_get_launch_count(gpss_handle c, long* launches)
 {
   if (!c || !launches) return fail_arg("gpss_get_launch_count: null");
   *launches = c->launches;
+  return GPSS_OK;
+}
+
+int gpss_get_ozaki(gpss_handle c, int* slices)
+{
+  if (!c || !slices) return fail_arg("gpss_get_ozaki: null");
+  *slices = oz_active(c);
   return GPSS_OK;
 }
 

@@ -147,6 +147,10 @@ int gpss_get_launch_count(gpss_handle h, long* launches);
 /* Raw device pointer to the n_pad x n_pad factor / inverse and the padded size (tests only). */
 int gpss_debug_fetch(gpss_handle h, int which, double* host_out, long count);
 int gpss_padded_n(gpss_handle h, int* n_pad);
+/* Which pipe runs the three long-k contractions of this handle (potrf look-ahead update, bulk product of the triangular
+ * inverse, B^-1 = U U^T): 0 = FP64 DMMA (gemm_nt_ws_kernel), 6 | 7 | 8 = int8 tensor cores with that many 7-bit Ozaki slices
+ * (oz_gemm_kernel, csrc/gpss_ozaki.cuh).  Chosen at gpss_create from n and the GPSS_OZAKI environment variable. */
+int gpss_get_ozaki(gpss_handle h, int* slices);
 
 /* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
 /* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised

@@ -368,6 +368,7 @@ def test_large_n_properties(gpss):
     Xs, ys, _ = datagen.standardise_symmetric(X, y)
     th = O.THETA0.copy()
     m = gpss.GpssModel(Xs, ys)
+    assert m.ozaki_slices() == 8          # n_pad > 8192: the long-k contractions run on the int8 tensor cores (csrc/gpss_ozaki.cuh)
     m.set_theta(th)
     L, g = m.nlml_grad()
     a, f = m.alpha(), m.yhat()
@@ -386,4 +387,24 @@ def test_large_n_properties(gpss):
     Lm = m.nlml()
     fd = (Lp - Lm) / (2 * h)
     assert abs(g[6] / fd - 2.0) < 1e-4
+    m.close()
+
+
+@pytest.mark.parametrize("slices,n,seed", [(8, 2000, 0), (7, 2000, 0), (8, 700, 4), (8, 2100, 6)])
+def test_int8_tensor_core_path_parity_with_oracle(gpss, monkeypatch, slices, n, seed):
+    """The int8 tensor-core evaluation of the three long-k contractions (csrc/gpss_ozaki.cuh: Ozaki splitting into 7-bit slices,
+    tcgen05 kind::i8, exact int32 accumulation) is the default for 8192 < n_pad <= 57 344; GPSS_OZAKI forces it at sizes the
+    oracle finishes in seconds.  Same tolerances as the FP64 DMMA path (which the same sizes run by default, above)."""
+    monkeypatch.setenv("GPSS_OZAKI", str(slices))
+    X, y = datagen.drillholes(n, seed)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt_raw, _ = datagen.drillholes(150, seed + 100)
+    Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
+    m = gpss.GpssModel(Xs, ys)
+    assert m.ozaki_slices() == slices
+    m.close()
+    _check_against_oracle(gpss, Xs, ys, O.THETA0.copy(), Xt)
+    monkeypatch.setenv("GPSS_OZAKI", "0")
+    m = gpss.GpssModel(Xs, ys)
+    assert m.ozaki_slices() == 0
     m.close()
