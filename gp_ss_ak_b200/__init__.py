@@ -78,6 +78,7 @@ def load_library():
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
         "gpss_test_gemm_nt": (I, [I, I, I, I, I, P, P, P, I, P]),
+        "gpss_test_oz_gemm": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_potrf": (I, [I, I, P, P, P]),
     }
     for name, (res, args) in protos.items():
@@ -315,6 +316,20 @@ def test_gemm_nt(A, B, C=None, tile=0, device=0):
     Cc = _colmajor(C).copy(order="F") if sub else np.zeros((M, N), order="F")
     ms = ctypes.c_double(0.0)
     _check(lib.gpss_test_gemm_nt(device, tile, M, N, K, _dp(A), _dp(B), _dp(Cc), 1 if sub else 0, ctypes.byref(ms)))
+    return Cc, ms.value
+
+
+def test_oz_gemm(A, B, C=None, slices=8, device=0):
+    """C = A @ B.T (or C - A @ B.T when C is given) through the int8 tensor-core kernel; |A|, |B| <= 1; returns (C, ms)."""
+    lib = load_library()
+    A = _colmajor(A)
+    B = _colmajor(B)
+    M, K = A.shape
+    N = B.shape[0]
+    sub = C is not None
+    Cc = _colmajor(C).copy(order="F") if sub else np.zeros((M, N), order="F")
+    ms = ctypes.c_double(0.0)
+    _check(lib.gpss_test_oz_gemm(device, slices, M, N, K, _dp(A), _dp(B), _dp(Cc), 1 if sub else 0, ctypes.byref(ms)))
     return Cc, ms.value
 
 

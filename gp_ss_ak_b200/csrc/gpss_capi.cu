@@ -354,7 +354,8 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     if (const char* e = getenv("GPSS_OZAKI")) {
       v = atoi(e);
       if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (7-bit slices per operand)"));
-      if (v != 0 && c->n_pad > 65536) return fail(fail_arg("GPSS_OZAKI: int32 accumulation is exact up to n = 65 536 only"));
+      // |G_g| <= S n_pad 64^2 must stay below 2^31 (S = 8: n_pad < 65 536)
+      if (v != 0 && (long long)v * c->n_pad * 4096 >= (1ll << 31)) return fail(fail_arg("GPSS_OZAKI: n too large for exact int32 accumulation with this many slices"));
     }
     if (v != 0) {
       c->oz_s = v;
@@ -1037,6 +1038,58 @@ int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A
   if (ms_out) *ms_out = ms;
   CU(cudaMemcpy(C, dC, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dparts);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return GPSS_OK;
+}
+
+// C <- C - A B^T (subtract_from_C) or C <- A B^T through the int8 tensor-core kernel with `slices` 7-bit digits per operand; host
+// buffers, column-major, |A|, |B| <= 1 (unit scale), M % 128 == 0, N % 64 == 0, K % 64 == 0.  The result is reproduced to the last
+// bit by the numpy restatement the tests hold (exact integer accumulation, fixed-order FP64 recombination).
+int gpss_test_oz_gemm(int device, int slices, int M, int N, int K, const double* A, const double* B, double* C, int subtract_from_C,
+                      double* ms_out)
+{
+  if (!A || !B || !C) return fail_arg("gpss_test_oz_gemm: null");
+  if (slices < 6 || slices > 8) return fail_arg("gpss_test_oz_gemm: slices must be 6, 7 or 8");
+  if (M <= 0 || N <= 0 || K <= 0 || M % oz::BM || N % oz::BN || K % oz::BK) return fail_arg("gpss_test_oz_gemm: M % 128, N % 64, K % 64 must be 0");
+  CU(cudaSetDevice(device));
+  RET(oz_configure());
+  gpss_ctx tmp;
+  tmp.st = nullptr;
+  tmp.oz_s = slices;
+  tmp.n_pad = K;                                  // plane geometry of the helpers below: kpad = plane_rows = n_pad
+  double *dA, *dB, *dC;
+  int8_t *pa, *pb;
+  const long R = (M > N ? M : N);
+  if (R > K) return fail_arg("gpss_test_oz_gemm: M, N <= K (the planes are K x K)");
+  CU(cudaMalloc(&dA, sizeof(double) * (size_t)M * K));
+  CU(cudaMalloc(&dB, sizeof(double) * (size_t)N * K));
+  CU(cudaMalloc(&dC, sizeof(double) * (size_t)M * N));
+  CU(cudaMalloc(&pa, (size_t)slices * K * K));
+  CU(cudaMalloc(&pb, (size_t)slices * K * K));
+  CU(cudaMemcpy(dA, A, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dB, B, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dC, C, sizeof(double) * (size_t)M * N, cudaMemcpyHostToDevice));
+  CUtensorMap ta, tb;
+  if (oz::make_plane_map(&ta, pa, (long)slices * K, K, oz::BM) != 0 || oz::make_plane_map(&tb, pb, (long)slices * K, K, oz::BN) != 0)
+    return fail_arg("gpss_test_oz_gemm: cuTensorMapEncodeTiled failed");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  RET(oz_slice_on(&tmp, dA, M, 0, M, 0, K, oz::SCALE_UNIT, oz::MASK_NONE, pa, tmp.st));
+  RET(oz_slice_on(&tmp, dB, N, 0, N, 0, K, oz::SCALE_UNIT, oz::MASK_NONE, pb, tmp.st));
+  oz::Args a;
+  memset(&a, 0, sizeof a);
+  a.C = dC; a.ldc = M; a.m = M; a.n = N; a.k0 = 0; a.k1 = K;
+  a.accumulate = subtract_from_C ? 1 : 0; a.sign = subtract_from_C ? -1.0 : 1.0;
+  CU(cudaEventRecord(e0, 0));
+  RET(oz_gemm_on(&tmp, ta, tb, a, tmp.st));
+  CU(cudaEventRecord(e1, 0));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms;
+  CU(cudaMemcpy(C, dC, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(pa); cudaFree(pb);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GPSS_OK;
 }

@@ -159,6 +159,11 @@ int gpss_get_ozaki(gpss_handle h, int* slices);
  * distributed triangular inverse uses to fill the machine from a narrow row slice. */
 int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C,
                       int subtract_from_C, double* ms_out);
+/* C(MxN) = A B^T, or C - A B^T, with host buffers through the int8 tensor-core kernel (csrc/gpss_ozaki.cuh) with `slices` in
+ * {6,7,8} 7-bit digits per operand; |A|, |B| <= 1; M % 128 == N % 64 == K % 64 == 0, M, N <= K.  Bit-exact against the numpy
+ * restatement oracle/ozaki_oracle.py::oz_gemm_nt. */
+int gpss_test_oz_gemm(int device, int slices, int M, int N, int K, const double* A, const double* B, double* C,
+                      int subtract_from_C, double* ms_out);
 /* In-place blocked Cholesky of a host n x n SPD matrix (lower), through the full potrf driver. */
 int gpss_test_potrf(int device, int n, double* A_colmajor, double* logdet_half, double* ms_out);
 

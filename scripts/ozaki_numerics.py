@@ -6,7 +6,7 @@ GPU time is spent: how many 7-bit slices does the path need so that nlml / alpha
 tolerances of DESIGN.md section 4 (nlml 1e-9, g 1e-7 of max|g|, alpha 1e-8)?  Integer products are evaluated in
 float64, which is exact here (|sum| < 2^53), so the arithmetic is bit-identical to int8 x int8 -> int32 MMA.
 
-    python scripts/ozaki_numerics.py [n] [nb] [fixed]
+    python scripts/ozaki_numerics.py [n] [nb] [row | fixed | kernel]
 
 Slicing (per ROW of each operand, i.e. along k): t = a / 2^e, e = ceil(log2 max|row|); slice l = round-to-nearest of
 the running remainder scaled by 2^(7l-1): |q| <= 64, remainder <= 2^-(7l).  Pair (i, j) is kept when i + j <= s + 1
@@ -29,7 +29,10 @@ BITS = 7
 # "fixed" as third argument: ONE a-priori exponent per operand instead of the row maxima (|L_ij| <= sqrt(max B_ii) and
 # |W_ij| <= 1 because B = I + K / sn2 >= I) -- what a GPU implementation wants: slices of L / W are then produced once,
 # block column by block column, and every product that reads them shares the scale.
-FIXED_SCALE = len(sys.argv) > 3 and sys.argv[3] == "fixed"
+# "kernel": the arithmetic of the shipped kernel, operation by operation (oracle/ozaki_oracle.py: a-priori exponent, ONE rounding
+# to the 2^-(7S-1) grid, signed base-128 digits, Horner recombination) -- bit-identical to csrc/gpss_ozaki.cuh.
+FIXED_SCALE = len(sys.argv) > 3 and sys.argv[3] in ("fixed", "kernel")
+KERNEL_ARITH = len(sys.argv) > 3 and sys.argv[3] == "kernel"
 FIXED_BOUND = [1.0]
 
 
@@ -69,7 +72,18 @@ def oz_gemm_nt(A, B, s):
 
 def gemm_nt(A, B, s, bound=1.0):
     FIXED_BOUND[0] = bound
+    if s and KERNEL_ARITH:
+        # operand kinds as on the GPU: rows of L carry the bound sqrt(max B_ii), rows of U = L^-T the bound 1
+        import math
+        from oracle import ozaki_oracle as Z
+        eL = math.frexp(bound)[1]
+        eA = eL if KERNEL_OPERANDS[0] else 0
+        eB = eL if KERNEL_OPERANDS[1] else 0
+        return Z.oz_gemm_nt(A, B, s, eA, eB)
     return A @ B.T if s == 0 else oz_gemm_nt(A, B, s)
+
+
+KERNEL_OPERANDS = [True, True]        # which operands of the current product are rows of L (set by the callers below)
 
 
 def potrf_blocked(Bm, nb, s):
@@ -81,11 +95,15 @@ def potrf_blocked(Bm, nb, s):
     for j0 in range(0, n, nb):
         j1 = min(j0 + nb, n)
         if j0 > 0:
+            KERNEL_OPERANDS[:] = [True, True]
             L[j0:, j0:j1] -= gemm_nt(L[j0:, :j0], L[j0:j1, :j0], s, bound)
         L[j0:j1, j0:j1] = np.linalg.cholesky(np.tril(L[j0:j1, j0:j1]) + np.tril(L[j0:j1, j0:j1], -1).T)
         if j1 < n:
             L[j1:, j0:j1] = sla.solve_triangular(L[j0:j1, j0:j1], L[j1:, j0:j1].T, lower=True).T
     return L
+
+
+TRTRI_BOUND = [1.0]
 
 
 def trtri_blocked(L, nb, s):
@@ -98,13 +116,15 @@ def trtri_blocked(L, nb, s):
     for i0 in range(nb, n, nb):                        # block ROW i of W from the rows above it
         i1 = min(i0 + nb, n)
         # W[I, 0:i0] = -W[I,I] (L[I, 0:i0] W[0:i0, 0:i0]) : (nb x i0) @ (i0 x i0), contraction over i0
-        T = gemm_nt(L[i0:i1, :i0], W[:i0, :i0].T.copy(), s)
+        KERNEL_OPERANDS[:] = [True, False]
+        T = gemm_nt(L[i0:i1, :i0], W[:i0, :i0].T.copy(), s, TRTRI_BOUND[0])
         W[i0:i1, :i0] = -W[i0:i1, i0:i1] @ T
     return W
 
 
 def lauum_blocked(W, s):
     """B^-1 = W^T W (one contraction over rows, like the product's single lauum launch)."""
+    KERNEL_OPERANDS[:] = [False, False]
     return gemm_nt(W.T.copy(), W.T.copy(), s)
 
 
@@ -112,6 +132,7 @@ def evaluate(X, y, theta, K, D2, nb, s):
     n = X.shape[0]
     sn2 = theta[9]
     Bm = np.eye(n) + K / sn2
+    TRTRI_BOUND[0] = float(np.sqrt(np.diag(Bm).max()))
     L = potrf_blocked(Bm, nb, s)
     logdet = float(np.log(np.diag(L)).sum())
     z = sla.solve_triangular(L, y / sn2, lower=True)

@@ -1,0 +1,117 @@
+"""CPU tests of the numpy restatement of the int8 tensor-core product (oracle/ozaki_oracle.py restates
+gp_ss_ak_b200/csrc/gpss_ozaki.cuh operation by operation): digit arithmetic, exactness of the integer accumulation, error
+bounds of the FP64 result, and the numerics of the whole blocked path (which products run through it) against the oracle's
+tolerances.  The GPU side of the same statement is tests/test_gpu_parity.py::test_int8_*."""
+import math
+from fractions import Fraction
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from gp_ss_ak_b200 import datagen
+from oracle import gpss_oracle as O
+from oracle import ozaki_oracle as Z
+
+
+@pytest.mark.parametrize("S", [6, 7, 8])
+def test_digits_are_an_exact_fixed_point_expansion(S):
+    rng = np.random.default_rng(S)
+    e = 3
+    x = np.concatenate([rng.uniform(-8, 8, 4000) * 2.0 ** -rng.integers(0, 40, 4000), [8.0, -8.0, 0.0, 7.999999999999999, 2.0 ** -60]])
+    d = Z.oz_digits(x.reshape(1, -1), e, S)
+    assert d.min() >= -64 and d.max() <= 64                      # int8 range, top digit reaches +-64 only at |x| = 2^e
+    assert np.all(d[1:] <= 63)
+    # the digits reproduce v = rint(x 2^(7S-1-e)) exactly (python integers: no rounding anywhere)
+    for k in range(x.size):
+        v = sum(int(d[p, 0, k]) * 128 ** (S - 1 - p) for p in range(S))
+        exact = Fraction(float(x[k])) * Fraction(2) ** (7 * S - 1 - e)
+        assert abs(Fraction(v) - exact) <= Fraction(1, 2)
+    # and stand for x to half a unit of the grid 2^(e-7S+1)
+    if S <= 7:
+        assert np.abs(Z.oz_undigits(d, e)[0] - x).max() <= 2.0 ** (e - 7 * S)
+
+
+def test_values_beyond_the_bound_are_clamped_not_wrapped():
+    d = Z.oz_digits(np.array([[1.0000001, -3.0]]), 0, 7)
+    assert d.min() >= -64 and d.max() <= 64
+    assert np.array_equal(Z.oz_undigits(d, 0)[0], [1.0, -1.0])
+
+
+@pytest.mark.parametrize("S,k", [(7, 512), (8, 1024)])
+def test_product_error_bound_and_int32_range(S, k):
+    rng = np.random.default_rng(11)
+    A = rng.uniform(-1, 1, (48, k)) * 2.0 ** -rng.integers(0, 12, (48, k))
+    B = rng.uniform(-1, 1, (40, k)) * 2.0 ** -rng.integers(0, 12, (40, k))
+    C = Z.oz_gemm_nt(A, B, S)
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    # each operand is off by <= 2^-(7S) (half a grid unit), every dropped pair i + j >= S is below 2^-(7S-1) per term
+    assert np.abs(C - ref).max() <= 3 * k * 2.0 ** -(7 * S - 1)
+    # worst-case digits still fit the int32 accumulators at the sizes the library admits (S n_pad 4096 < 2^31)
+    big = np.full((1, 57344), 1.0)
+    G = Z.oz_groups(Z.oz_digits(big, 0, 8), Z.oz_digits(big, 0, 8))
+    assert max(int(np.abs(g).max()) for g in G) < 2 ** 31
+
+
+def test_eight_slices_beat_plain_fp64_accumulation():
+    """S = 8 rounds each operand once at 2^-55 of its bound and accumulates EXACTLY; a chain of k FP64 FMAs does not."""
+    rng = np.random.default_rng(3)
+    k = 4096
+    A = rng.uniform(-1, 1, (32, k))
+    B = rng.uniform(-1, 1, (32, k))
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    e_oz = np.abs(Z.oz_gemm_nt(A, B, 8) - ref).max()
+    seq = np.zeros((32, 32))
+    for q in range(k):                                          # the order a single accumulator sees
+        seq += np.outer(A[:, q], B[:, q])
+    assert e_oz <= np.abs(seq - ref).max()
+
+
+def test_subtract_form_and_scales():
+    rng = np.random.default_rng(5)
+    A = rng.uniform(-7, 7, (16, 128))
+    B = rng.uniform(-0.9, 0.9, (24, 128))
+    C0 = rng.uniform(-1, 1, (16, 24))
+    out = Z.oz_gemm_nt(A, B, 8, eA=3, eB=0, C=C0, sign=-1.0)
+    assert np.abs(out - (C0 - A @ B.T)).max() <= 128 * 8 * 2.0 ** -54
+    assert Z.oz_exponent(Z.SCALE_UNIT) == 0
+    th = O.THETA0
+    e = Z.oz_exponent(Z.SCALE_CHOL, theta=th)
+    bii = 1.0 + (th[6] ** 2 + th[8]) / th[9]
+    assert 2.0 ** (e - 1) <= math.sqrt(bii) < 2.0 ** e
+
+
+@pytest.mark.parametrize("S,ok", [(8, True), (7, True), (4, False)])
+def test_blocked_path_numerics_against_oracle_tolerances(S, ok):
+    """The device path's structure (long-k updates of potrf / trtri / lauum through the int8 product with a-priori scales,
+    diagonal blocks and panel solves in FP64) at n = 600: S = 7 and 8 stay inside the parity tolerances of
+    tests/test_gpu_parity.py, S = 4 does not (the check is not vacuous)."""
+    n, nb = 600, 128
+    X, y = datagen.drillholes(n, 0)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    th = O.THETA0.copy()
+    K, D2 = O.compute_K(Xs, Xs, th)
+    sn2 = th[9]
+    Bm = np.eye(n) + K / sn2
+    eL = Z.oz_exponent(Z.SCALE_CHOL, theta=th)
+    assert np.sqrt(np.diag(Bm).max()) < 2.0 ** eL
+
+    def prod(A, B, ka, kb):
+        return Z.oz_gemm_nt(A, B, S, eL if ka == Z.SCALE_CHOL else 0, eL if kb == Z.SCALE_CHOL else 0)
+
+    def evaluate(p):
+        L = Z.potrf_blocked(Bm, nb, p)
+        alpha = sla.solve_triangular(L.T, sla.solve_triangular(L, ys / sn2, lower=True), lower=False)
+        U = Z.trtri_blocked(L, nb, p)
+        assert np.abs(U).max() <= 1.0                            # the a-priori bound the UNIT scale rests on (B >= I)
+        Q = np.tril(Z.lauum(U, p))
+        Q = Q + np.tril(Q, -1).T
+        nlml = 0.5 * float(ys @ alpha) + float(np.log(np.diag(L)).sum()) + 0.5 * n * math.log(2 * math.pi * sn2)
+        g = O.expans_gradients_fused(Xs, th, Q / sn2 - np.outer(alpha, alpha), D2)
+        return nlml, alpha, g
+
+    L0, a0, g0 = evaluate(lambda A, B, ka, kb: A @ B.T)
+    L1, a1, g1 = evaluate(prod)
+    errs = (abs(L1 - L0) / abs(L0), np.linalg.norm(a1 - a0) / np.linalg.norm(a0), np.abs(g1 - g0).max() / np.abs(g0).max())
+    inside = errs[0] <= 1e-9 and errs[1] <= 1e-8 and errs[2] <= 1e-7
+    assert inside == ok, errs
