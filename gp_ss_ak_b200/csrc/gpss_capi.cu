@@ -246,6 +246,8 @@ int gpss_destroy(gpss_handle c)
   if (c->pgather) cudaFree(c->pgather);
   if (c->ozL) cudaFree(c->ozL);
   if (c->ozU) cudaFree(c->ozU);
+  if (c->ozW) cudaFree(c->ozW);
+  if (c->ozB) cudaFree(c->ozB);
   if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -359,6 +361,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     }
     if (v != 0) {
       c->oz_s = v;
+      if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;
       r = oz_configure();
       if (r == GPSS_OK) r = oz_ensure_planes(c, &c->ozL, c->oz_tmL);
       if (r != GPSS_OK) return fail(r);
@@ -615,6 +618,7 @@ static int ensure_W(gpss_ctx* c)
   c->launches++;
   CU(cudaGetLastError());
   c->qstate = Q_IS_W;
+  c->ozW_valid = false;                                        // digit planes of W are cut on first use (predict_core)
   return GPSS_OK;
 }
 
@@ -672,9 +676,48 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
     if (var) {
       PhaseTimer t(c, 7);
       // V = L^-1 (Sw o kX): A = W (lower), B = Bm (test index contiguous)
-      GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
-      g.kend_row = 1; g.rev_order = 1;
-      RET(gemm(c, g));
+      if (oz_active(c) && c->oz_predict) {
+        // opt-in: the same product on the int8 tensor cores -- planes of W once per factor, planes of the batch per batch
+        if (!c->ozW) {
+          const size_t wb = (size_t)c->oz_s * n_pad * n_pad, bb = (size_t)c->oz_s * cap * n_pad;
+          CU(cudaMalloc(&c->ozW, wb));
+          CU(cudaMalloc(&c->ozB, bb));
+          CU(cudaMemsetAsync(c->ozB, 0, bb, c->st));
+          if (oz::make_plane_map(&c->oz_tmW[0], c->ozW, (long)c->oz_s * n_pad, n_pad, oz::BM) != 0 ||
+              oz::make_plane_map(&c->oz_tmB[1], c->ozB, (long)c->oz_s * cap, n_pad, oz::BN) != 0)
+            return fail_arg("GPSS_OZAKI_PREDICT: cuTensorMapEncodeTiled failed");
+          c->ozW_valid = false;
+        }
+        if (!c->ozW_valid) {
+          RET(oz_slice_on(c, c->Qm, n_pad, 0, n_pad, 0, n_pad, oz::SCALE_UNIT, oz::MASK_LOWER, c->ozW, c->st));
+          c->ozW_valid = true;
+        }
+        // batch planes: rows = test index (plane_rows = cap), k = training index; Bm(j, k) at Bm[j + k * m_pad]
+        switch (c->oz_s) {
+          case 6: oz::slice<6>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
+          case 7: oz::slice<7>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
+          default: oz::slice<8>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+        oz::Args a;
+        memset(&a, 0, sizeof a);
+        a.C = c->Vm; a.ldc = n_pad; a.m = n_pad; a.n = m_pad;
+        a.a_rows = n_pad; a.b_rows = cap; a.k0 = 0; a.k1 = n_pad; a.kend_row = 1; a.rev_order = 1;
+        a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CROSS;
+        a.dP = c->dP + 1;
+        switch (c->oz_s) {
+          case 6: oz::launch<6>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
+          case 7: oz::launch<7>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
+          default: oz::launch<8>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+      } else {
+        GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
+        g.kend_row = 1; g.rev_order = 1;
+        RET(gemm(c, g));
+      }
       var_finish_kernel<<<(mb + 7) / 8, 256, 0, c->st>>>(c->Vm, n_pad, n_pad, mb, kD, c->dvar);
       c->launches++;
       CU(cudaGetLastError());

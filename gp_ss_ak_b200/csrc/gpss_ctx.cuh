@@ -124,6 +124,11 @@ struct gpss_ctx {
   int oz_s = 0;
   int8_t *ozL = nullptr, *ozU = nullptr;
   CUtensorMap oz_tmL[2], oz_tmU[2];
+  // GPSS_OZAKI_PREDICT=1 (opt-in, not yet measured): the prediction GEMM V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
+  // (cut once per factor) and of the cross-covariance batch (PRED_BATCH rows, cut per batch)
+  bool oz_predict = false, ozW_valid = false;
+  int8_t *ozW = nullptr, *ozB = nullptr;
+  CUtensorMap oz_tmW[2], oz_tmB[2];
   // host state
   double theta[GPSS_NPAR];
   double sums_train[4];

@@ -31,7 +31,9 @@ constexpr int UMMA_K = 32;                       // kind::i8: 32 bytes of k per 
 constexpr int DIGIT_BITS = 7;
 constexpr int RASTER_W = 8;
 
-enum { SCALE_UNIT = 0, SCALE_CHOL = 1 };         // operand kinds: |x| <= 1 (U = L^-T: B >= I), |x| <= sqrt(max B_ii) (L)
+// operand kinds: |x| <= 1 (U = L^-T and W = L^-1: B >= I), |x| <= sqrt(max B_ii) (L), |x| <= Sw (Sigma^2 + Sigma_Bias) (the scaled
+// cross-covariance tile of the prediction)
+enum { SCALE_UNIT = 0, SCALE_CHOL = 1, SCALE_CROSS = 2 };
 enum { MASK_NONE = 0, MASK_LOWER = 1, MASK_UPPER = 2 };
 
 template <int S>
@@ -54,6 +56,8 @@ struct Args {
   int a_row0, b_row0;            // plane row of C(0,.) in the A planes / of C(.,0) in the B planes
   int k0, k1;                    // k range [k0, k1), multiples of 64 (plane byte columns)
   int kbeg_row;                  // 1: k starts at the tile's first A row (A upper-triangular in (row, k)); a_row0 is then a k coordinate too
+  int kend_row;                  // 1: k ends after the tile's last A row (A lower-triangular in (row, k))
+  int rev_order;                 // 1: last tile row first (kend_row products: longest k-ranges first)
   int lower_only;                // 1: skip tiles entirely above the diagonal of the global matrix (C(0,0) sits at (grow0, gcol0))
   int grow0, gcol0;
   int accumulate;                // 0: C = sign * A B^T, 1: C += sign * A B^T
@@ -69,7 +73,8 @@ __device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P)
 {
   if (kind == SCALE_UNIT || P == nullptr) return 0;
   int e;
-  frexp(sqrt(1.0 + P->sww * (P->var2 + P->bias)), &e);      // sqrt(B_ii) = f 2^e, f in [0.5, 1)
+  if (kind == SCALE_CROSS) frexp(P->sw * (P->var2 + P->bias), &e);
+  else frexp(sqrt(1.0 + P->sww * (P->var2 + P->bias)), &e);  // sqrt(B_ii) = f 2^e, f in [0.5, 1)
   return e;
 }
 
@@ -129,11 +134,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int mt = g.m / BM, nt = g.n / BN;
   const int grp = blockIdx.x / (RASTER_W * mt), within = blockIdx.x % (RASTER_W * mt);
   const int gcols = min(RASTER_W, nt - grp * RASTER_W);
-  const int tile_n = grp * RASTER_W + within % gcols, tile_m = within / gcols;
+  const int tile_n = grp * RASTER_W + within % gcols, tile_m = g.rev_order ? mt - 1 - within / gcols : within / gcols;
   if (g.lower_only && g.gcol0 + tile_n * BN > g.grow0 + tile_m * BM + BM - 1) return;      // whole CTA, before any barrier
   int kb = g.k0;
   if (g.kbeg_row) { const int kr = (g.a_row0 + tile_m * BM) & ~(BK - 1); if (kr > kb) kb = kr; }
-  const int nk = g.k1 > kb ? (g.k1 - kb) / BK : 0;
+  int ke = g.k1;
+  if (g.kend_row) { const int kr = g.a_row0 + tile_m * BM + BM; if (kr < ke) ke = kr; }
+  const int nk = ke > kb ? (ke - kb) / BK : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T::STAGES; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
