@@ -570,9 +570,12 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
-  c->oz_s = 0;                                           // the int8 path is single-GPU only (oz_active): give its planes back
-  if (c->ozL) { cudaFree(c->ozL); c->ozL = nullptr; }
-  if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
+  if (const char* e = getenv("GPSS_OZAKI_DIST")) c->oz_dist = atoi(e) != 0;
+  if (!c->oz_dist) {                                     // the int8 path is single-GPU by default (oz_active): give its planes back
+    c->oz_s = 0;
+    if (c->ozL) { cudaFree(c->ozL); c->ozL = nullptr; }
+    if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
+  }
   std::vector<int> b;
   balanced_rows(c->n_pad, world, 0, b);
   c->urow0 = b[rank]; c->urow1 = b[rank + 1];

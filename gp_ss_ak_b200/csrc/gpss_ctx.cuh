@@ -126,6 +126,8 @@ struct gpss_ctx {
   CUtensorMap oz_tmL[2], oz_tmU[2];
   // GPSS_OZAKI_PREDICT=1 (opt-in, not yet measured): the prediction GEMM V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
   // (cut once per factor) and of the cross-covariance batch (PRED_BATCH rows, cut per batch)
+  // GPSS_OZAKI_DIST=1 (opt-in, not yet measured): keep the int8 path on replicated-layout multi-GPU handles (gpss_dist_init)
+  bool oz_dist = false;
   bool oz_predict = false, ozW_valid = false;
   int8_t *ozW = nullptr, *ozB = nullptr;
   CUtensorMap oz_tmW[2], oz_tmB[2];
@@ -193,9 +195,12 @@ static int gemm_legacy_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
 static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st); }
 
 // ---------------------------------------------------------------------------------------------------
-// opt-in int8 (Ozaki) path: active on single-GPU, replicated-storage handles with the look-ahead streams
+// int8 (Ozaki) path: active on replicated-storage handles with the look-ahead streams -- single-GPU, or multi-GPU with GPSS_OZAKI_DIST=1
 // ---------------------------------------------------------------------------------------------------
-static int oz_active(const gpss_ctx* c) { return (c->oz_s > 0 && c->world == 1 && !c->partitioned && c->st2) ? c->oz_s : 0; }
+static int oz_active(const gpss_ctx* c)
+{
+  return (c->oz_s > 0 && !c->partitioned && c->st2 && (c->world == 1 || c->oz_dist)) ? c->oz_s : 0;
+}
 
 static int oz_configure()
 {

@@ -258,11 +258,13 @@ static int trtri_upper(gpss_ctx* c)
     double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
     // (1) the diagonal NBO-block of U in 128-steps
     RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj));
+    // rows of block column t this rank reads as digit planes later: its own rows above the block and its share of the diagonal block
+    const int sr0 = R0, sr1 = (R1 < J0 + nbj) ? R1 : (J0 + nbj);
     if (t == 0) {
-      if (ozk) {                                             // digit planes of block column 0 (only its diagonal block)
+      if (ozk && sr1 > sr0) {                                // digit planes of block column 0 (only its diagonal block)
         CU(cudaEventRecord(c->ev_pool[0], c->st));
         CU(cudaStreamWaitEvent(c->st2, c->ev_pool[0], 0));
-        RET(oz_slice_on(c, U, ld, 0, nbj, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
+        RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
       }
       continue;
     }
@@ -273,7 +275,10 @@ static int trtri_upper(gpss_ctx* c)
     CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
     CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
     const int ra = R0, rb = (R1 < J0) ? R1 : J0;             // my rows above this block column
-    if (rb <= ra) continue;
+    if (rb <= ra) {                                          // no rows above this block column: only my share of the diagonal block
+      if (ozk && sr1 > sr0) RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
+      continue;
+    }
     // (3) T[ra:rb] = U[ra:rb, 0:J0] * L[Jblk, 0:J0]^T      (k starts at each tile's own row: U is upper triangular)
     GemmArgs g = gemm_args(U + ra, ld, L + J0, ld, c->Tpanel + ra, ld, rb - ra, nbj, J0);
     g.kbeg_row = 1; g.krow_off = ra;
@@ -283,14 +288,14 @@ static int trtri_upper(gpss_ctx* c)
     if (ozk) {
       oz::Args a;
       memset(&a, 0, sizeof a);
-      a.C = c->Tpanel; a.ldc = ld; a.m = J0; a.n = nbj;
-      a.a_row0 = 0; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
+      a.C = c->Tpanel + ra; a.ldc = ld; a.m = rb - ra; a.n = nbj;
+      a.a_row0 = ra; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
       a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
       RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, c->st2));
-      GemmArgs g2 = gemm_args(c->Tpanel, ld, Wjj, NBO, U + (long)J0 * ld, ld, J0, nbj, nbj);
+      GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
       g2.negate_out = 1; g2.kend_col = 1;
       RET(gemm_ws_on(c, g2, c->st2));
-      RET(oz_slice_on(c, U, ld, 0, J0 + nbj, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));   // planes of block column t
+      RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));   // planes of block column t
       continue;
     }
     int S = 1;
@@ -347,9 +352,11 @@ static int lauum_lower(gpss_ctx* c)
   if (oz_active(c) && c->ozU) {                              // opt-in int8 path: both operands are the digit planes of U
     oz::Args a;
     memset(&a, 0, sizeof a);
-    a.C = c->Qm; a.ldc = ld; a.m = c->n_pad; a.n = c->n_pad;
-    a.a_row0 = 0; a.b_row0 = 0; a.k0 = 0; a.k1 = c->n_pad; a.kbeg_row = 1;
-    a.lower_only = 1; a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_UNIT;
+    // distributed: the slices of the other ranks arrived as FP64 (allgather_U); cut every row a tile of mine can meet
+    if (c->world > 1) RET(oz_slice_on(c, c->Um, ld, 0, q1, 0, c->n_pad, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st));
+    a.C = c->Qm + q0; a.ldc = ld; a.m = q1 - q0; a.n = q1;
+    a.a_row0 = q0; a.b_row0 = 0; a.k0 = 0; a.k1 = c->n_pad; a.kbeg_row = 1;
+    a.lower_only = 1; a.grow0 = q0; a.gcol0 = 0; a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_UNIT;
     return oz_gemm_on(c, c->oz_tmU[0], c->oz_tmU[1], a, c->st);
   }
   GemmArgs g = gemm_args(c->Um + q0, ld, c->Um, ld, c->Qm + q0, ld, q1 - q0, q1, c->n_pad);

@@ -145,10 +145,12 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   if (P > 1) RET(ensure_stage(c, stage_need));
   // opt-in int8 path (gpss_ozaki.cuh): every finished block column is cut into digit planes on the main stream, and the long-k
   // look-ahead update U1 reads those planes through the tcgen05 kernel; U2 (k = NBO, critical path) and the panel stay on DMMA
-  const bool ozk = oz_active(c) && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad;
+  const bool pipe_env = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
+  const bool ozk = oz_active(c) && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
-    if (ozk && stream != c->st) {
+    // (distributed: only the long chunks -- a single received panel, k = NBO, stays on DMMA)
+    if (ozk && stream != c->st && (P == 1 || klen >= 4 * NBO)) {
       oz::Args a;
       memset(&a, 0, sizeof a);
       a.C = A + (long)T0 * ld + T0; a.ldc = ld; a.m = n_pad - T0; a.n = nbT;
@@ -275,6 +277,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
             CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             c->launches++;
           }
+          if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));   // planes of panel op.col
           CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));            // panel op.col is complete on this rank
           if (!mine) mark(6);
           break;

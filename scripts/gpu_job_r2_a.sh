@@ -17,3 +17,6 @@ bench_micro/ozaki_gemm bench 16384 16384 8192 8 > gpurun_out/r2a_oz_plain.log 2>
 ncu --set full --clock-control none --import-source on -k regex:oz_gemm_kernel -c 1 -o gpurun_out/r2a_oz_gemm_full \
     bench_micro/ozaki_gemm bench 16384 16384 8192 8 > gpurun_out/r2a_ncu_oz.log 2>&1
 ls -la gpurun_out | tail -12
+# 5. (2 GPUs, separate call: gpurun --gpus 2) the opt-in distributed int8 path against one GPU:
+#    GPSS_OZAKI=8 GPSS_OZAKI_DIST=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py 3000 20000
+#    GPSS_OZAKI_DIST=1 python -m torch.distributed.run ... bench.py --gpus 2 --steps 1 --warmup 1 --no-cpu-baseline
