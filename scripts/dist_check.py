@@ -30,7 +30,14 @@ for n in sizes:
     m.dist_init(rank, world, ids[0])
     ref = None
     if rank == 0 and n <= 20000:
+        # same pipe for the long-k products as the multi-GPU handle (DMMA unless GPSS_OZAKI_DIST=1 kept the int8 path)
+        prev = os.environ.get("GPSS_OZAKI")
+        os.environ["GPSS_OZAKI"] = str(m.ozaki_slices())
         ms = G.GpssModel(Xs, ys, device=local)
+        if prev is None:
+            os.environ.pop("GPSS_OZAKI", None)
+        else:
+            os.environ["GPSS_OZAKI"] = prev
         ms.set_theta(base)
         ref = ms.nlml_grad() + (ms.alpha(),)
         ms.close()

@@ -33,7 +33,14 @@ for n in sizes:
     n_pad = m.padded_n()
     ref = None
     if rank == 0 and n <= 20000:
+        # same pipe for the long-k products as the multi-GPU handle (DMMA unless GPSS_OZAKI_DIST=1 kept the int8 path)
+        prev = os.environ.get("GPSS_OZAKI")
+        os.environ["GPSS_OZAKI"] = str(m.ozaki_slices())
         ms = G.GpssModel(Xs, ys, device=local)
+        if prev is None:
+            os.environ.pop("GPSS_OZAKI", None)
+        else:
+            os.environ["GPSS_OZAKI"] = prev
         ms.set_theta(base)
         ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1])
         ms.close()
