@@ -353,7 +353,9 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
   //   GPSS_OZAKI=6|7|8 : that many 7-bit slices, for every n (7: 1.3x faster than 8; nlml 1e-11, alpha 4e-10 at n = 5 000..50 000)
   if (part_world <= 1) {
     int v = (c->n_pad > 8192 && c->n_pad <= 57344) ? 8 : 0;
+    c->oz_auto = true;
     if (const char* e = getenv("GPSS_OZAKI")) {
+      c->oz_auto = false;
       v = atoi(e);
       if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (7-bit slices per operand)"));
       // |G_g| <= S n_pad 64^2 must stay below 2^31 (S = 8: n_pad < 65 536)
@@ -365,6 +367,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
       r = oz_configure();
       if (r == GPSS_OK) r = oz_ensure_planes(c, &c->ozL, c->oz_tmL);
       if (r != GPSS_OK) return fail(r);
+      if (!c->ozL) c->oz_s = 0;                              // size rule only: the planes did not fit, stay on the DMMA path
     }
   }
   *out = c;

@@ -122,6 +122,7 @@ struct gpss_ctx {
   // opt-in int8 tensor-core path (GPSS_OZAKI = 6 | 7 | 8, gpss_ozaki.cuh): signed base-128 digit planes of L and of U = L^-T,
   // [oz_s][n_pad rows][n_pad bytes of k] each, and their TMA descriptors ([0] 128-row box = A operand, [1] 64-row box = B operand)
   int oz_s = 0;
+  bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
   CUtensorMap oz_tmL[2], oz_tmU[2];
   // GPSS_OZAKI_PREDICT=1 (opt-in, not yet measured): the prediction GEMM V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
@@ -215,7 +216,11 @@ static int oz_ensure_planes(gpss_ctx* c, int8_t** planes, CUtensorMap* tm)
 {
   if (*planes) return GPSS_OK;
   const size_t bytes = (size_t)c->oz_s * c->n_pad * c->n_pad;
-  CU(cudaMalloc(planes, bytes));
+  if (c->oz_auto) {                                            // not asked for explicitly: no room means the DMMA path, not an error
+    if (cudaMalloc(planes, bytes) != cudaSuccess) { cudaGetLastError(); *planes = nullptr; return GPSS_OK; }
+  } else {
+    CU(cudaMalloc(planes, bytes));
+  }
   CU(cudaMemsetAsync(*planes, 0, bytes, c->st));
   if (oz::make_plane_map(&tm[0], *planes, (long)c->oz_s * c->n_pad, c->n_pad, oz::BM) != 0 ||
       oz::make_plane_map(&tm[1], *planes, (long)c->oz_s * c->n_pad, c->n_pad, oz::BN) != 0)

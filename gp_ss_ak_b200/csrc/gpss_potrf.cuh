@@ -146,7 +146,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   // opt-in int8 path (gpss_ozaki.cuh): every finished block column is cut into digit planes on the main stream, and the long-k
   // look-ahead update U1 reads those planes through the tcgen05 kernel; U2 (k = NBO, critical path) and the panel stay on DMMA
   const bool pipe_env = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
-  const bool ozk = oz_active(c) && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
+  const bool ozk = oz_active(c) && c->ozL && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
     // (distributed: only the long chunks -- a single received panel, k = NBO, stays on DMMA)
