@@ -359,11 +359,17 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
       v = atoi(e);
       if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (7-bit slices per operand)"));
       // |G_g| <= S n_pad 64^2 must stay below 2^31 (S = 8: n_pad < 65 536)
-      if (v != 0 && (long long)v * c->n_pad * 4096 >= (1ll << 31)) return fail(fail_arg("GPSS_OZAKI: n too large for exact int32 accumulation with this many slices"));
+      const char* eb = getenv("GPSS_OZAKI_BITS");
+      if (v != 0 && !(eb && atoi(eb) == 8) && (long long)v * c->n_pad * 4096 >= (1ll << 31)) return fail(fail_arg("GPSS_OZAKI: n too large for exact int32 accumulation with this many slices"));
     }
     if (v != 0) {
       c->oz_s = v;
       if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;
+      if (const char* e = getenv("GPSS_OZAKI_BITS")) {
+        if (atoi(e) != 7 && atoi(e) != 8) return fail(fail_arg("GPSS_OZAKI_BITS must be 7 or 8"));
+        if (atoi(e) == 8 && v == 8) return fail(fail_arg("GPSS_OZAKI_BITS=8 takes GPSS_OZAKI=6 or 7 (7 x 8 bits already exceed FP64)"));
+        c->oz_bits = atoi(e);
+      }
       r = oz_configure();
       if (r == GPSS_OK) r = oz_ensure_planes(c, &c->ozL, c->oz_tmL);
       if (r != GPSS_OK) return fail(r);
@@ -700,9 +706,9 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
         }
         // batch planes: rows = test index (plane_rows = cap), k = training index; Bm(j, k) at Bm[j + k * m_pad]
         switch (c->oz_s) {
-          case 6: oz::slice<6>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
-          case 7: oz::slice<7>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
-          default: oz::slice<8>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st); break;
+          case 6: oz::slice<6>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st, c->oz_bits); break;
+          case 7: oz::slice<7>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st, c->oz_bits); break;
+          default: oz::slice<8>(c->Bm, m_pad, 0, m_pad, 0, n_pad, oz::SCALE_CROSS, oz::MASK_NONE, c->dP + 1, c->ozB, cap, n_pad, c->st, c->oz_bits); break;
         }
         c->launches++;
         CU(cudaGetLastError());
@@ -712,13 +718,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
         a.a_rows = n_pad; a.b_rows = cap; a.k0 = 0; a.k1 = n_pad; a.kend_row = 1; a.rev_order = 1;
         a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CROSS;
         a.dP = c->dP + 1;
-        switch (c->oz_s) {
-          case 6: oz::launch<6>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
-          case 7: oz::launch<7>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
-          default: oz::launch<8>(c->oz_tmW[0], c->oz_tmB[1], a, c->st); break;
-        }
-        c->launches++;
-        CU(cudaGetLastError());
+        RET(oz_gemm_on(c, c->oz_tmW[0], c->oz_tmB[1], a, c->st));
       } else {
         GemmArgs g = gemm_args(c->Qm, n_pad, c->Bm, m_pad, c->Vm, n_pad, n_pad, m_pad, n_pad);
         g.kend_row = 1; g.rev_order = 1;
@@ -1105,6 +1105,7 @@ int gpss_test_oz_gemm(int device, int slices, int M, int N, int K, const double*
   gpss_ctx tmp;
   tmp.st = nullptr;
   tmp.oz_s = slices;
+  if (const char* e = getenv("GPSS_OZAKI_BITS")) tmp.oz_bits = atoi(e) == 8 ? 8 : 7;
   tmp.n_pad = K;                                  // plane geometry of the helpers below: kpad = plane_rows = n_pad
   double *dA, *dB, *dC;
   int8_t *pa, *pb;

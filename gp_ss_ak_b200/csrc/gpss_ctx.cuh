@@ -122,6 +122,7 @@ struct gpss_ctx {
   // opt-in int8 tensor-core path (GPSS_OZAKI = 6 | 7 | 8, gpss_ozaki.cuh): signed base-128 digit planes of L and of U = L^-T,
   // [oz_s][n_pad rows][n_pad bytes of k] each, and their TMA descriptors ([0] 128-row box = A operand, [1] 64-row box = B operand)
   int oz_s = 0;
+  int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
   bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
   CUtensorMap oz_tmL[2], oz_tmU[2];
@@ -232,16 +233,30 @@ static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
 {
   if (a.m <= 0 || a.n <= 0) return GPSS_OK;
   if (a.m % oz::BM || a.n % oz::BN || a.k0 % oz::BK || a.k1 % oz::BK) return fail_arg("oz_gemm: dimensions not tile multiples");
-  a.a_rows = a.b_rows = c->n_pad;
-  a.dP = c->dP;
-  switch (c->oz_s) {
-    case 6: oz::launch<6>(ta, tb, a, st); break;
-    case 7: oz::launch<7>(ta, tb, a, st); break;
-    case 8: oz::launch<8>(ta, tb, a, st); break;
-    default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
+  if (!a.a_rows) a.a_rows = c->n_pad;
+  if (!a.b_rows) a.b_rows = c->n_pad;
+  if (!a.dP) a.dP = c->dP;
+  a.digit_bits = c->oz_bits;
+  // one launch per k-segment an int32 accumulation can hold exactly (7-bit digits: always one launch); every launch visits every tile,
+  // so the first one initialises C in overwrite mode even where its own k-range is empty, and the rest accumulate
+  const int seg = oz::kseg(c->oz_s, c->oz_bits);
+  const int k0 = a.k0, k1 = a.k1;
+  bool first = true;
+  for (int s0 = (k0 / seg) * seg; s0 < k1 || first; s0 += seg) {
+    a.k0 = s0 > k0 ? s0 : k0;
+    a.k1 = (s0 + seg < k1) ? s0 + seg : k1;
+    if (!first) a.accumulate = 1;
+    switch (c->oz_s) {
+      case 6: oz::launch<6>(ta, tb, a, st); break;
+      case 7: oz::launch<7>(ta, tb, a, st); break;
+      case 8: oz::launch<8>(ta, tb, a, st); break;
+      default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    first = false;
+    if (seg >= (1 << 30)) break;
   }
-  c->launches++;
-  CU(cudaGetLastError());
   return GPSS_OK;
 }
 
@@ -251,9 +266,9 @@ static int oz_slice_on(gpss_ctx* c, const double* X, long ldx, int row0, int row
 {
   if (rows <= 0 || kcnt <= 0) return GPSS_OK;
   switch (c->oz_s) {
-    case 6: oz::slice<6>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
-    case 7: oz::slice<7>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
-    case 8: oz::slice<8>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st); break;
+    case 6: oz::slice<6>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
+    case 7: oz::slice<7>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
+    case 8: oz::slice<8>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
     default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
   }
   c->launches++;

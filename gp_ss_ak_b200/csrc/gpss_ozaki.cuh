@@ -5,6 +5,8 @@
 // 83.7 FP64-equivalent TFLOP/s with S = 7 slices, 69.0 with S = 8, against 35.9 for gemm_nt_ws_kernel; error of S = 8
 // against a long-double reference 1.3e-15 (DMMA: 1.4e-14).  Numerics of the whole path: scripts/ozaki_numerics.py.
 //
+// (GPSS_OZAKI_BITS=8, opt-in and not yet measured: base-256 digits in [-128, 127] -- 7 slices then carry the 55 bits that take 8 slices
+//  of 7 bits, 28 products instead of 36; the k-range of one int32 accumulation shrinks to 18 688, see kseg.)
 //   operand x -> t = x / 2^e (ONE a-priori exponent per operand kind, see oz_exponent), v = rint(t 2^(7S-1)),
 //   signed base-128 digits d_0 .. d_{S-1} in [-64, 64]:  t = sum_p d_p 2^-(7p+6)          (oz_slice_kernel, K-major int8 planes)
 //   A B^T = 2^(eA+eB-12) sum_g 2^(-7g) G_g,  G_g = sum_{i+j=g} A_i B_j^T  exact in int32 (|G_g| <= (g+1) k 2^12 < 2^31 for
@@ -63,18 +65,24 @@ struct Args {
   int accumulate;                // 0: C = sign * A B^T, 1: C += sign * A B^T
   double sign;
   int a_kind, b_kind;            // SCALE_*: which power of two each operand was divided by before slicing
+  int digit_bits;                // 0 or 7: base-128 digits in [-64, 64] (default); 8: base-256 digits in [-128, 127] (GPSS_OZAKI_BITS=8)
   const gpss::DevParams* dP;     // device parameters (theta-dependent scale: never a launch argument, so launches can sit in a graph)
   int32_t* dbg;                  // test hook: raw int32 group accumulators, [S][m][n] row-major (else nullptr)
 };
 
 // The exponent e with |x| < 2^e for every element of an operand of the given kind.  L: |L_ij| <= sqrt(B_ii),
 // B_ii = 1 + Sw^2 (Sigma^2 + Sigma_Bias) for all i (exp(0) = 1 on the diagonal of every kernel kind).
-__device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P)
+// 8-bit digits: the signed base-256 expansion of v needs |v| < 127.5 x 256^(S-1) for its top digit to fit int8, so the bound is
+// widened by 128 / 127.5 before its exponent is taken (one bit less for the unit-bound operands, rarely one for the others).
+__device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P, int bits = DIGIT_BITS)
 {
-  if (kind == SCALE_UNIT || P == nullptr) return 0;
+  if (bits != 8 && (kind == SCALE_UNIT || P == nullptr)) return 0;
+  double bound = 1.0;
+  if (kind == SCALE_CROSS && P) bound = P->sw * (P->var2 + P->bias);
+  else if (kind == SCALE_CHOL && P) bound = sqrt(1.0 + P->sww * (P->var2 + P->bias));
+  if (bits == 8) bound *= 128.0 / 127.5;
   int e;
-  if (kind == SCALE_CROSS) frexp(P->sw * (P->var2 + P->bias), &e);
-  else frexp(sqrt(1.0 + P->sww * (P->var2 + P->bias)), &e);  // sqrt(B_ii) = f 2^e, f in [0.5, 1)
+  frexp(bound, &e);                                           // bound = f 2^e, f in [0.5, 1)
   return e;
 }
 
@@ -209,8 +217,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const int row = tile_m * BM + warp * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const double w = 1.0 / (double)(1 << DIGIT_BITS);
-    const double scale = g.sign * ldexp(1.0, oz_exponent(g.a_kind, g.dP) + oz_exponent(g.b_kind, g.dP) - 2 * (DIGIT_BITS - 1));
+    const int bits = g.digit_bits ? g.digit_bits : DIGIT_BITS;
+    const double w = ldexp(1.0, -bits);
+    const double scale = g.sign * ldexp(1.0, oz_exponent(g.a_kind, g.dP, bits) + oz_exponent(g.b_kind, g.dP, bits) - 2 * (bits - 1));
     for (int c0 = 0; c0 < BN; c0 += 8) {
       uint32_t v[S][8];
       if (nk > 0) {
@@ -254,12 +263,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // triangle's edge.  32 x 32 tiles through shared memory: coalesced FP64 reads along rows, 32-byte row segments written.
 template <int S>
 __global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask,
-                                const gpss::DevParams* dP, int8_t* __restrict__ planes, long plane_rows, long kpad)
+                                const gpss::DevParams* dP, int8_t* __restrict__ planes, long plane_rows, long kpad, int bits)
 {
   __shared__ int8_t tile[S][32][33];
   const int r = row0 + blockIdx.x * 32 + threadIdx.x;
-  const double lim = (double)(1ll << (DIGIT_BITS * S - 1));
-  const double mul = ldexp(lim, -oz_exponent(kind, dP));               // exact power of two
+  const double lim = (double)(1ll << (bits * S - 1));
+  const long long half = 1ll << (bits - 1), dmask = (1ll << bits) - 1;
+  // base 256: [127, 127, ..., 127] is the largest value whose digits fit int8 (S <= 7); never reached given oz_exponent's margin
+  const long long vmax = bits == 8 ? 127ll * (((1ll << (8 * (S < 8 ? S : 7))) - 1) / 255) : (1ll << (DIGIT_BITS * S - 1));
+  const double mul = ldexp(lim, -oz_exponent(kind, dP, bits));         // exact power of two
   for (int ky = threadIdx.y; ky < 32; ky += blockDim.y) {
     const int kq = k0 + blockIdx.y * 32 + ky;
     int d[S];
@@ -270,13 +282,14 @@ __global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0
       double sc = X[r + (size_t)kq * ldx] * mul;
       sc = fmin(fmax(sc, -lim), lim);                                  // |x| <= 2^e by construction; guards rounding excess
       long long v = __double2ll_rn(sc);
+      v = v > vmax ? vmax : (v < -vmax ? -vmax : v);
 #pragma unroll
       for (int p = S - 1; p >= 1; p--) {
-        const int dg = (int)((v + 64) & 127) - 64;                    // [-64, 63], exact remainder
-        v = (v - dg) >> DIGIT_BITS;
+        const int dg = (int)(((v + half) & dmask) - half);            // [-2^(b-1), 2^(b-1) - 1], exact remainder
+        v = (v - dg) >> bits;
         d[p] = dg;
       }
-      d[0] = (int)v;                                                   // |v| <= 64
+      d[0] = (int)v;                                                   // |v| <= 2^(b-1) (b = 8: <= 127 by the clamp)
     }
 #pragma unroll
     for (int p = 0; p < S; p++) tile[p][threadIdx.x][ky] = (int8_t)d[p];
@@ -336,11 +349,16 @@ static inline void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Ar
 
 template <int S>
 static inline void slice(const double* X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask, const gpss::DevParams* dP,
-                         int8_t* planes, long plane_rows, long kpad, cudaStream_t st)
+                         int8_t* planes, long plane_rows, long kpad, cudaStream_t st, int bits = DIGIT_BITS)
 {
   if (rows <= 0 || kcnt <= 0) return;
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((kcnt + 31) / 32)), block(32, 8);
-  oz_slice_kernel<S><<<grid, block, 0, st>>>(X, ldx, row0, rows, k0, kcnt, kind, mask, dP, planes, plane_rows, kpad);
+  oz_slice_kernel<S><<<grid, block, 0, st>>>(X, ldx, row0, rows, k0, kcnt, kind, mask, dP, planes, plane_rows, kpad, bits);
 }
+
+// Longest k-range ONE int32 accumulation may cover: |G_g| <= S k 2^(2 (bits - 1)) < 2^31.  7-bit digits: 65 536 / S x 8 >= n_pad
+// for every admitted size (one launch); 8-bit digits: 18 688 at S = 7 -- the caller cuts the k-range into launches of this length,
+// the later ones accumulating into C in FP64 (a handful of roundings instead of none, against k of them on the DMMA pipe).
+static inline int kseg(int S, int bits) { return bits == 8 ? ((1 << 17) / S - 1) / 64 * 64 : (1 << 30); }
 
 }  // namespace oz

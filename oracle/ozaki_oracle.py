@@ -22,38 +22,48 @@ DIGIT_BITS = 7
 SCALE_UNIT, SCALE_CHOL = 0, 1
 
 
-def oz_exponent(kind, theta=None, sigma2=None, bias=None, sn2=None):
-    """e with |x| < 2^e for every element of the operand: 0 for U = L^-T (B >= I), frexp exponent of sqrt(B_ii) for L."""
-    if kind == SCALE_UNIT:
+def oz_exponent(kind, theta=None, sigma2=None, bias=None, sn2=None, bits=DIGIT_BITS):
+    """e with |x| < 2^e for every element of the operand: 0 for U = L^-T (B >= I), frexp exponent of sqrt(B_ii) for L.
+    8-bit digits: the bound is widened by 128 / 127.5 first, so that the top base-256 digit stays <= 127."""
+    bound = 1.0
+    if kind != SCALE_UNIT:
+        if theta is not None:
+            sigma2, bias, sn2 = theta[6] ** 2, theta[8], theta[9]
+        sw = math.sqrt(1.0 / sn2)
+        sww = sw * sw                                    # DevParams.sww = fl(Sw * Sw) (gpss_ctx.cuh fill_params)
+        bound = math.sqrt(1.0 + sww * (sigma2 + bias))
+    elif bits != 8:
         return 0
-    if theta is not None:
-        sigma2, bias, sn2 = theta[6] ** 2, theta[8], theta[9]
-    sw = math.sqrt(1.0 / sn2)
-    sww = sw * sw                                        # DevParams.sww = fl(Sw * Sw) (gpss_ctx.cuh fill_params)
-    _, e = math.frexp(math.sqrt(1.0 + sww * (sigma2 + bias)))
-    return e
+    if bits == 8:
+        bound *= 128.0 / 127.5
+    return math.frexp(bound)[1]
 
 
-def oz_digits(X, e, S):
-    """[S, rows, k] int64 digits d_p with  x ~= 2^e sum_p d_p 2^-(7p+6)  (one rounding, at 2^(e-7S+1))."""
-    lim = float(1 << (DIGIT_BITS * S - 1))
+def oz_digits(X, e, S, bits=DIGIT_BITS):
+    """[S, rows, k] int64 digits d_p with  x ~= 2^e sum_p d_p 2^-(b p + b - 1)  (one rounding, at 2^(e - b S + 1)).
+    bits = 7 (shipped default): digits in [-64, 64].  bits = 8 (GPSS_OZAKI_BITS=8): the full int8 range [-128, 127]; the top
+    digit fits only for |v| < 127.5 x 256^(S-1), which oz_exponent(bits=8) guarantees (v is also saturated at [127, ..., 127])."""
+    lim = float(1 << (bits * S - 1))
     v = np.rint(np.clip(np.asarray(X, dtype=np.float64) * math.ldexp(lim, -e), -lim, lim)).astype(np.int64)
+    vmax = 127 * (((1 << (8 * min(S, 7))) - 1) // 255) if bits == 8 else 1 << (DIGIT_BITS * S - 1)
+    v = np.clip(v, -vmax, vmax)
+    half, mask = 1 << (bits - 1), (1 << bits) - 1
     d = np.empty((S,) + v.shape, dtype=np.int64)
     for p in range(S - 1, 0, -1):
-        dg = ((v + 64) & 127) - 64
-        v = (v - dg) >> DIGIT_BITS
+        dg = ((v + half) & mask) - half
+        v = (v - dg) >> bits
         d[p] = dg
     d[0] = v
     return d
 
 
-def oz_undigits(d, e):
-    """The value the digits stand for (exact in FP64 for S <= 7; for tests)."""
+def oz_undigits(d, e, bits=DIGIT_BITS):
+    """The value the digits stand for (exact in FP64 while bits * S <= 53; for tests)."""
     S = d.shape[0]
     v = np.zeros(d.shape[1:], dtype=np.int64)
     for p in range(S):
-        v = v * 128 + d[p]
-    return v.astype(np.float64) * math.ldexp(1.0, e - (DIGIT_BITS * S - 1))
+        v = v * (1 << bits) + d[p]
+    return v.astype(np.float64) * math.ldexp(1.0, e - (bits * S - 1))
 
 
 def oz_groups(Ad, Bd):
@@ -70,15 +80,26 @@ def oz_groups(Ad, Bd):
     return out
 
 
-def oz_gemm_nt(A, B, S, eA=0, eB=0, C=None, sign=1.0):
-    """sign * A B^T (C given: C + sign * A B^T) exactly as oz_gemm_kernel<S> evaluates it."""
-    G = oz_groups(oz_digits(A, eA, S), oz_digits(B, eB, S))
-    w = 1.0 / (1 << DIGIT_BITS)
-    acc = np.zeros(G[0].shape)
-    for g in range(S - 1, -1, -1):
-        acc = acc * w + G[g].astype(np.float64)
-    scale = sign * math.ldexp(1.0, eA + eB - 2 * (DIGIT_BITS - 1))
-    return scale * acc if C is None else C + scale * acc
+def oz_kseg(S, bits=DIGIT_BITS):
+    """Longest k-range one int32 accumulation may cover: |G_g| <= S k 2^(2 (bits - 1)) < 2^31, rounded down to a multiple of 64."""
+    return ((1 << (31 - 2 * (bits - 1))) // S - 1) // 64 * 64 if bits == 8 else 1 << 30
+
+
+def oz_gemm_nt(A, B, S, eA=0, eB=0, C=None, sign=1.0, bits=DIGIT_BITS):
+    """sign * A B^T (C given: C + sign * A B^T) exactly as oz_gemm_kernel<S> evaluates it.  With 8-bit digits the k-range is cut
+    into segments of oz_kseg (one launch each, the later ones accumulating into C in FP64), as oz_gemm_on does."""
+    Ad, Bd = oz_digits(A, eA, S, bits), oz_digits(B, eB, S, bits)
+    w = math.ldexp(1.0, -bits)
+    scale = sign * math.ldexp(1.0, eA + eB - 2 * (bits - 1))
+    out = None if C is None else np.array(C, dtype=np.float64)
+    kseg = oz_kseg(S, bits)
+    for k0 in range(0, Ad.shape[2], kseg):
+        G = oz_groups(Ad[:, :, k0:k0 + kseg], Bd[:, :, k0:k0 + kseg])
+        acc = np.zeros(G[0].shape)
+        for g in range(S - 1, -1, -1):
+            acc = acc * w + G[g].astype(np.float64)
+        out = scale * acc if out is None else out + scale * acc
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -32,6 +32,34 @@ def test_digits_are_an_exact_fixed_point_expansion(S):
         assert np.abs(Z.oz_undigits(d, e)[0] - x).max() <= 2.0 ** (e - 7 * S)
 
 
+@pytest.mark.parametrize("S", [6, 7])
+def test_eight_bit_digits_use_the_full_int8_range(S):
+    """GPSS_OZAKI_BITS=8: base-256 signed digits; 7 of them carry the bits that take 8 digits of 7 bits.  The top digit fits int8
+    only below 127.5/128 of the scale, which the widened exponent guarantees for every value up to the operand's bound."""
+    rng = np.random.default_rng(S)
+    e = Z.oz_exponent(Z.SCALE_UNIT, bits=8)
+    assert e == 1
+    x = np.concatenate([rng.uniform(-1, 1, 4000) * 2.0 ** -rng.integers(0, 40, 4000), [1.0, -1.0, 0.0, 0.9999999999999999]])
+    d = Z.oz_digits(x.reshape(1, -1), e, S, bits=8)
+    assert d.min() >= -128 and d.max() <= 127
+    for k in range(x.size):
+        v = sum(int(d[p, 0, k]) * 256 ** (S - 1 - p) for p in range(S))
+        exact = Fraction(float(x[k])) * Fraction(2) ** (8 * S - 1 - e)
+        assert abs(Fraction(v) - exact) <= Fraction(1, 2)
+    # a Cholesky-kind bound just below a power of two takes the next exponent, one well below it does not
+    assert Z.oz_exponent(Z.SCALE_CHOL, sigma2=62.9 * 0.016, bias=0.0, sn2=0.016, bits=8) == Z.oz_exponent(Z.SCALE_CHOL, sigma2=62.9 * 0.016, bias=0.0, sn2=0.016) + 1
+    assert Z.oz_exponent(Z.SCALE_CHOL, theta=O.THETA0, bits=8) == Z.oz_exponent(Z.SCALE_CHOL, theta=O.THETA0)
+    # values that would break the bound saturate at [127, ..., 127] instead of wrapping
+    d = Z.oz_digits(np.array([[3.0, -3.0]]), 0, S, bits=8)
+    assert d.min() >= -128 and d.max() <= 127
+    A = rng.uniform(-1, 1, (24, 40000))
+    B = rng.uniform(-1, 1, (16, 40000))
+    assert Z.oz_kseg(S, 8) % 64 == 0 and S * Z.oz_kseg(S, 8) * 2 ** 14 < 2 ** 31
+    C = Z.oz_gemm_nt(A, B, S, e, e, bits=8)                          # three k-segments, each exact in int32 (asserted inside)
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    assert np.abs(C - ref).max() <= 3 * 40000 * 2.0 ** (2 * e - (8 * S - 1)) + 4 * 2.0 ** -53 * np.abs(ref).max()
+
+
 def test_values_beyond_the_bound_are_clamped_not_wrapped():
     d = Z.oz_digits(np.array([[1.0000001, -3.0]]), 0, 7)
     assert d.min() >= -64 and d.max() <= 64
@@ -81,8 +109,8 @@ def test_subtract_form_and_scales():
     assert 2.0 ** (e - 1) <= math.sqrt(bii) < 2.0 ** e
 
 
-@pytest.mark.parametrize("S,ok", [(8, True), (7, True), (4, False)])
-def test_blocked_path_numerics_against_oracle_tolerances(S, ok):
+@pytest.mark.parametrize("S,bits,ok", [(8, 7, True), (7, 7, True), (4, 7, False), (7, 8, True), (6, 8, True)])
+def test_blocked_path_numerics_against_oracle_tolerances(S, bits, ok):
     """The device path's structure (long-k updates of potrf / trtri / lauum through the int8 product with a-priori scales,
     diagonal blocks and panel solves in FP64) at n = 600: S = 7 and 8 stay inside the parity tolerances of
     tests/test_gpu_parity.py, S = 4 does not (the check is not vacuous)."""
@@ -93,11 +121,11 @@ def test_blocked_path_numerics_against_oracle_tolerances(S, ok):
     K, D2 = O.compute_K(Xs, Xs, th)
     sn2 = th[9]
     Bm = np.eye(n) + K / sn2
-    eL = Z.oz_exponent(Z.SCALE_CHOL, theta=th)
+    eL, eU = Z.oz_exponent(Z.SCALE_CHOL, theta=th, bits=bits), Z.oz_exponent(Z.SCALE_UNIT, bits=bits)
     assert np.sqrt(np.diag(Bm).max()) < 2.0 ** eL
 
     def prod(A, B, ka, kb):
-        return Z.oz_gemm_nt(A, B, S, eL if ka == Z.SCALE_CHOL else 0, eL if kb == Z.SCALE_CHOL else 0)
+        return Z.oz_gemm_nt(A, B, S, eL if ka == Z.SCALE_CHOL else eU, eL if kb == Z.SCALE_CHOL else eU, bits=bits)
 
     def evaluate(p):
         L = Z.potrf_blocked(Bm, nb, p)
