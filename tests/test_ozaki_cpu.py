@@ -143,3 +143,43 @@ def test_blocked_path_numerics_against_oracle_tolerances(S, bits, ok):
     errs = (abs(L1 - L0) / abs(L0), np.linalg.norm(a1 - a0) / np.linalg.norm(a0), np.abs(g1 - g0).max() / np.abs(g0).max())
     inside = errs[0] <= 1e-9 and errs[1] <= 1e-8 and errs[2] <= 1e-7
     assert inside == ok, errs
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_digit_plane_coverage_of_the_row_sliced_inverse(world):
+    """Host logic of the int8 path in trtri_upper / lauum_lower (csrc/gpss_inverse.cuh), replayed for every rank: each k-chunk of
+    U planes a product reads must have been cut before, from rows the rank owns or computes redundantly (the diagonal blocks).
+    world = 1 is the shipped single-GPU path, world > 1 the opt-in GPSS_OZAKI_DIST layout."""
+    import gp_ss_ak_b200 as G
+    NBO, BM = 512, 128
+    n_pad = 20096                                                    # 39 full block columns + a 128-wide remainder
+    nblk_o = (n_pad + NBO - 1) // NBO
+    ub = G.dist_partition(n_pad, world, 0) if world > 1 else [0, n_pad]
+    qb = G.dist_partition(n_pad, world, 1) if world > 1 else [0, n_pad]
+    for r in range(world):
+        R0, R1 = ub[r], ub[r + 1]
+        assert R0 % BM == 0 and R1 % BM == 0
+        cut = np.zeros((n_pad // BM, nblk_o), dtype=bool)            # [row tile, block column of k] of the U planes on this rank
+        for t in range(nblk_o):
+            J0 = t * NBO
+            nbj = min(NBO, n_pad - J0)
+            sr0, sr1 = R0, min(R1, J0 + nbj)
+            ra, rb = R0, min(R1, J0)
+            if t > 0 and rb > ra:
+                # product (3): rows [ra, rb), k from each row tile's own first row up to J0
+                for rt in range(ra // BM, rb // BM):
+                    for kb in range((rt * BM) // NBO, t):
+                        assert cut[rt, kb], "rank %d step %d reads uncut planes (row tile %d, block column %d)" % (r, t, rt, kb)
+            if sr1 > sr0:
+                cut[sr0 // BM:(sr1 + BM - 1) // BM, t] = True        # slice of block column t after (4) / of the diagonal block
+        # B^-1 rows [q0, q1): distributed handles re-cut every row below q1 after the all-gather
+        q0, q1 = qb[r], qb[r + 1]
+        if world > 1:
+            cut[:q1 // BM, :] = True
+        for rt in range(q0 // BM, q1 // BM):
+            for kb in range((rt * BM) // NBO, nblk_o):
+                assert cut[rt, kb]                                   # A rows
+        # B rows 0 .. q1 meet the same k-range as the A tile they are paired with (k >= the A tile's first row >= their own)
+        for rt in range(0, q1 // BM):
+            for kb in range((max(rt, q0 // BM) * BM) // NBO, nblk_o):
+                assert cut[rt, kb]
