@@ -125,6 +125,7 @@ struct gpss_ctx {
   int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
   bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
+  bool ozL_valid = false, ozU_valid = false;                   // the planes hold the CURRENT factor / inverse (set by the drivers that cut them)
   CUtensorMap oz_tmL[2], oz_tmU[2];
   // GPSS_OZAKI_PREDICT=1 (opt-in, not yet measured): the prediction GEMM V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
   // (cut once per factor) and of the cross-covariance batch (PRED_BATCH rows, cut per batch)

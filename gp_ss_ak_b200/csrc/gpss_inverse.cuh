@@ -248,7 +248,8 @@ static int trtri_upper(gpss_ctx* c)
   const int R0 = c->urow0, R1 = c->urow1;
   // opt-in int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
   // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
-  const bool ozk = oz_active(c) && c->ozL && c->ozU;
+  const bool ozk = oz_active(c) && c->ozL && c->ozU && c->ozL_valid;
+  c->ozU_valid = ozk;
   // the side stream must not start before the factor is complete on the main stream
   CU(cudaEventRecord(c->ev_main, c->st));
   CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
@@ -349,7 +350,7 @@ static int lauum_lower(gpss_ctx* c)
   const long ld = c->n_pad;
   const int q0 = c->qrow0, q1 = c->qrow1;
   if (q1 <= q0) return GPSS_OK;
-  if (oz_active(c) && c->ozU) {                              // opt-in int8 path: both operands are the digit planes of U
+  if (oz_active(c) && c->ozU && (c->ozU_valid || c->world > 1)) {   // int8 path: both operands are the digit planes of U
     oz::Args a;
     memset(&a, 0, sizeof a);
     // distributed: the slices of the other ranks arrived as FP64 (allgather_U); cut every row a tile of mine can meet

@@ -147,6 +147,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   // look-ahead update U1 reads those planes through the tcgen05 kernel; U2 (k = NBO, critical path) and the panel stay on DMMA
   const bool pipe_env = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
   const bool ozk = oz_active(c) && c->ozL && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
+  if (A == c->Lm) c->ozL_valid = ozk;                          // every panel is cut below iff ozk; the inverse must not read stale planes
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
     // (distributed: only the long chunks -- a single received panel, k = NBO, stays on DMMA)
