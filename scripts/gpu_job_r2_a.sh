@@ -12,6 +12,8 @@ GPSS_OZAKI_PREDICT=1 timeout 120 python scripts/oz_predict_check.py > gpurun_out
 OZ_TIME_S=7,8 timeout 120 python scripts/oz_check.py 700 -- 50000 > gpurun_out/r2a_oz_50k.log 2>&1; tail -3 gpurun_out/r2a_oz_50k.log
 # 8-bit digits (GPSS_OZAKI_BITS=8): 7 slices = the accuracy of 8 x 7 bits with 28 products instead of 36 (CPU study: tests/test_ozaki_cpu.py)
 GPSS_OZAKI_BITS=8 OZ_CHECK_S=7,6 OZ_TIME_S=7,6 timeout 150 python scripts/oz_check.py 2000 5000 -- 20000 50000 > gpurun_out/r2a_oz_bits8.log 2>&1; tail -8 gpurun_out/r2a_oz_bits8.log
+# BASELINE configs[2] on one GPU: the command line's LBFGS fit at n = 50 000, 3 iterations, end to end
+timeout 400 python scripts/fit_n50k.py 50000 3 > gpurun_out/r2a_fit_n50k.log 2>&1; tail -2 gpurun_out/r2a_fit_n50k.log
 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --pred-m 0 > gpurun_out/r2a_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2a_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --pred-m 0 > gpurun_out/r2a_ncu_launches.log 2>&1
