@@ -365,6 +365,7 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     if (v != 0) {
       c->oz_s = v;
       if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;
+      if (const char* e = getenv("GPSS_OZAKI_GRAD")) { const int sg = atoi(e); if (sg >= 6 && sg < v) c->oz_s_grad = sg; }
       if (const char* e = getenv("GPSS_OZAKI_BITS")) {
         if (atoi(e) != 7 && atoi(e) != 8) return fail(fail_arg("GPSS_OZAKI_BITS must be 7 or 8"));
         if (atoi(e) == 8 && v == 8) return fail(fail_arg("GPSS_OZAKI_BITS=8 takes GPSS_OZAKI=6 or 7 (7 x 8 bits already exceed FP64)"));

@@ -122,6 +122,8 @@ struct gpss_ctx {
   // opt-in int8 tensor-core path (GPSS_OZAKI = 6 | 7 | 8, gpss_ozaki.cuh): signed base-128 digit planes of L and of U = L^-T,
   // [oz_s][n_pad rows][n_pad bytes of k] each, and their TMA descriptors ([0] 128-row box = A operand, [1] 64-row box = B operand)
   int oz_s = 0;
+  int oz_s_grad = 0;                                           // GPSS_OZAKI_GRAD=6|7 (opt-in, not yet measured): fewer slices for the inverse / B^-1
+                                                               // products (they feed the gradient only), read from the TOP planes of the same tensors
   int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
   bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
@@ -230,8 +232,11 @@ static int oz_ensure_planes(gpss_ctx* c, int8_t** planes, CUtensorMap* tm)
   return GPSS_OK;
 }
 
-static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, oz::Args a, cudaStream_t st)
+// slices = 0: the handle's slice count; otherwise the product reads only the top `slices` planes of the (oz_s-plane) tensors -- the
+// leading digits of a signed-digit expansion are the expansion of the value rounded to fewer digits
+static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, oz::Args a, cudaStream_t st, int slices = 0)
 {
+  const int s_use = (slices > 0 && slices < c->oz_s) ? slices : c->oz_s;
   if (a.m <= 0 || a.n <= 0) return GPSS_OK;
   if (a.m % oz::BM || a.n % oz::BN || a.k0 % oz::BK || a.k1 % oz::BK) return fail_arg("oz_gemm: dimensions not tile multiples");
   if (!a.a_rows) a.a_rows = c->n_pad;
@@ -240,14 +245,14 @@ static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
   a.digit_bits = c->oz_bits;
   // one launch per k-segment an int32 accumulation can hold exactly (7-bit digits: always one launch); every launch visits every tile,
   // so the first one initialises C in overwrite mode even where its own k-range is empty, and the rest accumulate
-  const int seg = oz::kseg(c->oz_s, c->oz_bits);
+  const int seg = oz::kseg(s_use, c->oz_bits);
   const int k0 = a.k0, k1 = a.k1;
   bool first = true;
   for (int s0 = (k0 / seg) * seg; s0 < k1 || first; s0 += seg) {
     a.k0 = s0 > k0 ? s0 : k0;
     a.k1 = (s0 + seg < k1) ? s0 + seg : k1;
     if (!first) a.accumulate = 1;
-    switch (c->oz_s) {
+    switch (s_use) {
       case 6: oz::launch<6>(ta, tb, a, st); break;
       case 7: oz::launch<7>(ta, tb, a, st); break;
       case 8: oz::launch<8>(ta, tb, a, st); break;

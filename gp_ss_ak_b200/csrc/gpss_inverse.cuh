@@ -292,7 +292,7 @@ static int trtri_upper(gpss_ctx* c)
       a.C = c->Tpanel + ra; a.ldc = ld; a.m = rb - ra; a.n = nbj;
       a.a_row0 = ra; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
       a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
-      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, c->st2));
+      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, c->st2, c->oz_s_grad));
       GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
       g2.negate_out = 1; g2.kend_col = 1;
       RET(gemm_ws_on(c, g2, c->st2));
@@ -358,7 +358,7 @@ static int lauum_lower(gpss_ctx* c)
     a.C = c->Qm + q0; a.ldc = ld; a.m = q1 - q0; a.n = q1;
     a.a_row0 = q0; a.b_row0 = 0; a.k0 = 0; a.k1 = c->n_pad; a.kbeg_row = 1;
     a.lower_only = 1; a.grow0 = q0; a.gcol0 = 0; a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_UNIT;
-    return oz_gemm_on(c, c->oz_tmU[0], c->oz_tmU[1], a, c->st);
+    return oz_gemm_on(c, c->oz_tmU[0], c->oz_tmU[1], a, c->st, c->oz_s_grad);
   }
   GemmArgs g = gemm_args(c->Um + q0, ld, c->Um, ld, c->Qm + q0, ld, q1 - q0, q1, c->n_pad);
   g.lower_only = 1; g.kbeg_row = 1; g.krow_off = q0; g.grow0 = q0; g.gcol0 = 0;

@@ -10,6 +10,7 @@ GPSS_TEST_ROUND2=1 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/
 timeout 300 python bench.py > gpurun_out/r2a_bench_n1.json 2> gpurun_out/r2a_bench_n1.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/r2a_bench_n1.json
 GPSS_OZAKI_PREDICT=1 timeout 120 python scripts/oz_predict_check.py > gpurun_out/r2a_oz_predict.log 2>&1; echo "predict rc=$?"; tail -6 gpurun_out/r2a_oz_predict.log
 OZ_TIME_S=7,8 timeout 120 python scripts/oz_check.py 700 -- 50000 > gpurun_out/r2a_oz_50k.log 2>&1; tail -3 gpurun_out/r2a_oz_50k.log
+GPSS_OZAKI_GRAD=7 OZ_CHECK_S=8 OZ_TIME_S=8 timeout 120 python scripts/oz_check.py 2000 5000 -- 50000 > gpurun_out/r2a_oz_grad7.log 2>&1; tail -5 gpurun_out/r2a_oz_grad7.log
 # 8-bit digits (GPSS_OZAKI_BITS=8): 7 slices = the accuracy of 8 x 7 bits with 28 products instead of 36 (CPU study: tests/test_ozaki_cpu.py)
 GPSS_OZAKI_BITS=8 OZ_CHECK_S=7,6 OZ_TIME_S=7,6 timeout 150 python scripts/oz_check.py 2000 5000 -- 20000 50000 > gpurun_out/r2a_oz_bits8.log 2>&1; tail -8 gpurun_out/r2a_oz_bits8.log
 # BASELINE configs[2] on one GPU: the command line's LBFGS fit at n = 50 000, 3 iterations, end to end

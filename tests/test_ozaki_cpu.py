@@ -183,3 +183,15 @@ def test_digit_plane_coverage_of_the_row_sliced_inverse(world):
         for rt in range(0, q1 // BM):
             for kb in range((max(rt, q0 // BM) * BM) // NBO, nblk_o):
                 assert cut[rt, kb]
+
+
+def test_leading_digits_are_the_shorter_expansion():
+    """GPSS_OZAKI_GRAD: a product may read only the top planes of a tensor cut with more slices -- the leading 7 digits of the
+    8-digit signed expansion stand for the value rounded to 7 digits (to within the second rounding)."""
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, 5000) * 2.0 ** -rng.integers(0, 30, 5000)
+    d8 = Z.oz_digits(x.reshape(1, -1), 0, 8)
+    top7 = Z.oz_undigits(d8[:7], 0)[0]
+    assert np.abs(top7 - x).max() <= (0.5 + 1.0 / 128) * 2.0 ** -48
+    d7 = Z.oz_digits(x.reshape(1, -1), 0, 7)
+    assert (np.abs(d8[:7] - d7).sum(axis=0) != 0).mean() < 0.02          # they differ only where the 8th digit sits on a tie
