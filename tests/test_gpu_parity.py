@@ -421,6 +421,8 @@ def test_int8_gemm_bit_exact_against_numpy_restatement(gpss, slices):
     B = rng.uniform(-1, 1, (192, 512)) * 2.0 ** -rng.integers(0, 20, (192, 512))
     C0 = rng.uniform(-1, 1, (256, 192))
     bits = 8 if os.environ.get("GPSS_OZAKI_BITS") == "8" else 7
+    if bits == 8 and slices == 8:
+        pytest.skip("8-bit digits take at most 7 slices")
     e = Z.oz_exponent(Z.SCALE_UNIT, bits=bits)          # 0, or 1 with 8-bit digits (the widened unit bound)
     C, _ = gpss.test_oz_gemm(A, B, slices=slices)
     assert np.array_equal(C, Z.oz_gemm_nt(A, B, slices, e, e, bits=bits))
