@@ -231,7 +231,8 @@ def test_isotropic_kernels_parity_with_oracle(gpss, kernel, seed):
         assert np.array_equal(D2, D2o) and np.abs(K - Ko).max() <= 4 * np.finfo(float).eps
 
 
-@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_n2000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz"])
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_n2000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz",
+                                  "ref_rock_n1000.npz", "ref_exp_n1000.npz", "ref_rbf_n1000.npz"])
 def test_against_compiled_reference(gpss, name):
     """The CUDA path against numbers computed by the UNMODIFIED reference classes (tests/golden/make_ref_golden.py).
     Tolerances = the reference's own BLAS-dependent reproducibility floor (oracle/gpss_oracle.py header); for the Exp kernel

@@ -27,7 +27,7 @@ def _parse(text):
     return rec
 
 
-@pytest.mark.parametrize("fixture", ["ref_n300.npz", "ref_n2000.npz"])
+@pytest.mark.parametrize("fixture", ["ref_n300.npz", "ref_n2000.npz", "ref_rock_n1000.npz", "ref_exp_n1000.npz", "ref_rbf_n1000.npz"])
 def test_lbfgs_replays_reference_trace(host_built, tmp_path, fixture):
     """Every ObjVal / Grad_Values probe of a 30-iteration fit by the UNMODIFIED reference (recorded in
     tests/golden/ref_n300.npz; ref_n2000.npz = BASELINE.json configs[0], 4 iterations / 63 probes) must be requested by the
@@ -40,7 +40,8 @@ def test_lbfgs_replays_reference_trace(host_built, tmp_path, fixture):
             g = np.nan_to_num(z["probe_g"][k], nan=0.0)
             f.write("%d " % int(z["probe_kind"][k]) + " ".join("%.17g" % v for v in z["probe_theta"][k]) + " %.17g " % z["probe_f"][k]
                     + " ".join("%.17g" % v for v in g) + "\n")
-    out = subprocess.run([os.path.join(host_built, "tests", "replay_lbfgs"), str(trace), str(int(z["lbfgs_iters"])), "1e-12"],
+    npar = z["probe_theta"].shape[1]                       # 10: Hyb{ExpAns, Bias}; 4 / 5: Hyb{Exp | RBF, Bias}
+    out = subprocess.run([os.path.join(host_built, "tests", "replay_lbfgs"), str(trace), str(int(z["lbfgs_iters"])), "1e-12", "LBFGS", str(npar)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "REPLAY OK probes %d of %d" % (len(z["probe_f"]), len(z["probe_f"])) in out.stdout

@@ -119,7 +119,8 @@ def test_oracle_reproduces_golden(name, nth):
 REF_TOL_NLML, REF_TOL_G, REF_TOL_ALPHA, REF_TOL_MU, REF_TOL_VAR = 2e-7, 5e-7, 5e-7, 5e-7, 1e-7
 
 
-@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_n2000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz"])
+@pytest.mark.parametrize("name", ["ref_n300.npz", "ref_n1000.npz", "ref_n2000.npz", "ref_rock_n300.npz", "ref_exp_n300.npz", "ref_rbf_n300.npz",
+                                  "ref_rock_n1000.npz", "ref_exp_n1000.npz", "ref_rbf_n1000.npz"])
 def test_oracle_matches_compiled_reference(name):
     """The restatement against numbers produced by the unmodified reference classes (tests/golden/make_ref_golden.py;
     ref_n2000.npz = BASELINE.json configs[0], tests/golden/make_ref_n2000.py)."""
@@ -132,7 +133,7 @@ def test_oracle_matches_compiled_reference(name):
     # Exp kernel: the reference's own diagonal residue (expansion-form D2 then sqrt) is amplified by 1/hyp^2 ~ 4..6 and its
     # K_diag is off by 5e-8..7e-8 from Sigma^2 + Sigma_Bias at the perturbed thetas, so the floor is 10x higher there; in the
     # reference's own (BLAS) operation order the restatement agrees to 1e-13 (asserted below).  RBF has no sqrt: 1e-12.
-    loose = 10.0 if name == "ref_exp_n300.npz" else 1.0
+    loose = 10.0 if name.startswith("ref_exp_") else 1.0
     for k in range(int(z["n_theta"])):
         th = z["theta_%d" % k].reshape(-1)
         L, g, gp = O.nlml_and_grad(z["Xs"], z["ys"].reshape(-1), th, dist="defined", literal=True)
@@ -140,7 +141,8 @@ def test_oracle_matches_compiled_reference(name):
         assert abs(float(z["nlml_grad_%d" % k]) - Lr) <= 1e-12 * abs(Lr)                   # GradLL re-evaluates from a warm Alpha
         if len(th) != 10:
             Lb, gb, _ = O.nlml_and_grad(z["Xs"], z["ys"].reshape(-1), th, dist="blas", literal=True)
-            tight = 1e-7 if name == "ref_exp_n300.npz" else 1e-11
+            # (RBF covariance matrices are the worst conditioned: at n = 1000 the two BLAS orders agree to 2e-11 instead of < 1e-11)
+            tight = 1e-7 if name.startswith("ref_exp_") else (1e-10 if z["Xs"].shape[0] >= 1000 else 1e-11)
             assert abs(Lb - Lr) <= tight * abs(Lr) and np.abs(gb - gr).max() <= tight * np.abs(gr).max()
         assert abs(L - Lr) <= loose * REF_TOL_NLML * abs(Lr)
         assert np.abs(g - gr).max() <= loose * REF_TOL_G * np.abs(gr).max()
