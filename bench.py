@@ -54,6 +54,28 @@ def int8_tensor_peak():
         return 2.0 * BF16_SUSTAINED_FALLBACK_TFLOPS, "2 x the 1.4 PFLOP/s sustained bf16 figure of B200_PROFILING.md (of fallback)"
 
 
+def int8_macs(n_pad, nbo=512):
+    """int8 multiply-accumulates PER SLICE PAIR that oz_gemm_kernel executes in one LML+gradient evaluation on one GPU, counted tile by
+    tile as the kernel runs them (128 x 64 tiles, whole tiles on the diagonal, triangular k-ranges): the look-ahead updates U1 of the
+    Cholesky, the bulk product of the triangular inverse, B^-1 = U U^T (gpss_potrf.cuh / gpss_inverse.cuh).  98.5 % of n_pad^3 / 2 at
+    n = 50 000; the rest (k = 512 updates, panels, right factors) stays on the FP64 DMMA pipe."""
+    mac = 0
+    T = (n_pad + nbo - 1) // nbo
+    for t in range(1, T - 1):                                  # U1(t + 1): rows >= T1, block column t + 1, k = 0 .. T0
+        T0, T1 = t * nbo, (t + 1) * nbo
+        nb1 = min(nbo, n_pad - T1)
+        for tm in range((n_pad - T1) // 128):
+            mac += 128 * 64 * min(nb1 // 64, (tm * 128 + 127) // 64 + 1) * T0
+    for t in range(1, T):                                      # T = U[0:J0, 0:J0] L[J, 0:J0]^T, k from each row tile's first row
+        J0 = t * nbo
+        nbj = min(nbo, n_pad - J0)
+        for tm in range(J0 // 128):
+            mac += 128 * nbj * (J0 - tm * 128)
+    for tm in range(n_pad // 128):                             # B^-1 = U U^T, lower tiles, k from the row tile's first row
+        mac += 128 * 64 * min(n_pad // 64, (tm * 128 + 127) // 64 + 1) * (n_pad - tm * 128)
+    return mac
+
+
 def theta_probe(k):
     """Deterministic theta probes around the reference's initial vector (Kernel.cpp:763-773, GP_Utils.cpp:43)."""
     base = np.array([np.pi / 3.1, 1.5, np.pi / 3.1, 1.5, np.pi / 3.1, 1.3, 0.9, 0.6, 0.2, 0.016])
@@ -321,15 +343,20 @@ def main():
         if oz_s:
             pairs = oz_s * (oz_s + 1) // 2
             i8_peak, i8_src = int8_tensor_peak()
-            roofline = {"bound": "tensor", "achieved": achieved * pairs, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
-                        "frac": achieved * pairs / i8_peak, "traffic": None,
+            # executed int8 op/s: exact tile-level count on one GPU; a partitioned evaluation is approximated by its share of n^3
+            i8_ops = 2.0 * int8_macs(n_pad) * pairs if share == 1 else alg_flops * pairs
+            i8_tops = i8_ops / (gemm_ms * 1e-3) * 1e-12
+            roofline = {"bound": "tensor", "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
+                        "frac": i8_tops / i8_peak, "traffic": None,
                         "traffic_note": "no ncu capture of oz_gemm_kernel yet: the path was built after the round's ncu runs (profiles/ holds the DMMA captures)",
                         "kernel": "oz_gemm_kernel<%d> (tcgen05.mma kind::i8, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; %d int8 "
                                   "products per FP64 product)" % (oz_s, pairs),
                         "peak_source": i8_src,
                         "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": peak, "frac_of_fp64_dmma_peak": achieved / peak,
-                        "note": note + "; executed int8 op/s = %d x the FP64-equivalent rate; the phases also contain the k = 512 panel work that stays on "
-                                       "DMMA and the digit slicing, so the kernel itself runs faster than this" % pairs}
+                        "note": "achieved = int8 ops oz_gemm_kernel executes in one evaluation (tile-level count, %.1f %% of n_pad^3, x %d slice pairs) / device "
+                                "time of the potrf + trtri + lauum phases, which also contain the k = 512 panel work on DMMA and the digit slicing: the "
+                                "kernel itself runs faster than this; fp64_equivalent_tflops = n_pad^3 / the same time"
+                                % (100.0 * i8_ops / pairs / alg_flops, pairs)}
             dtype = "f64 (long-k products as %d x 7-bit int8 slices on the tensor cores, int32 accumulation, FP64 recombination)" % oz_s
             gemm_path = "int8 tensor cores, Ozaki splitting, %d slices (GPSS_OZAKI; 0 = FP64 DMMA)" % oz_s
         else:
