@@ -195,3 +195,41 @@ def test_leading_digits_are_the_shorter_expansion():
     assert np.abs(top7 - x).max() <= (0.5 + 1.0 / 128) * 2.0 ** -48
     d7 = Z.oz_digits(x.reshape(1, -1), 0, 7)
     assert (np.abs(d8[:7] - d7).sum(axis=0) != 0).mean() < 0.02          # they differ only where the 8th digit sits on a tie
+
+
+def test_bench_int8_op_count_mirrors_the_kernel_tiles():
+    """bench.py's roofline numerator: the MACs per slice pair the three int8 launches of an evaluation execute, tile by tile."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def brute(n_pad, nbo=512):
+        mac, T = 0, (n_pad + nbo - 1) // nbo
+        for t in range(1, T - 1):                                   # oz launch of U1(t + 1): every 128 x 64 tile not above the diagonal
+            T0, T1 = t * nbo, (t + 1) * nbo
+            nb1 = min(nbo, n_pad - T1)
+            for tm in range((n_pad - T1) // 128):
+                for tn in range(nb1 // 64):
+                    if T1 + tn * 64 > T1 + tm * 128 + 127:
+                        continue
+                    mac += 128 * 64 * T0
+        for t in range(1, T):                                       # product (3) of the inverse: k from the tile's first row to J0
+            J0 = t * nbo
+            nbj = min(nbo, n_pad - J0)
+            for tm in range(J0 // 128):
+                for tn in range(nbj // 64):
+                    mac += 128 * 64 * (J0 - tm * 128)
+        for tm in range(n_pad // 128):                              # B^-1: lower tiles, k from the tile's first row to n_pad
+            for tn in range(n_pad // 64):
+                if tn * 64 > tm * 128 + 127:
+                    continue
+                mac += 128 * 64 * (n_pad - tm * 128)
+        return mac
+
+    for n_pad in (1024, 2176, 5120):
+        assert bench.int8_macs(n_pad) == brute(n_pad)
+    for n_pad in (20096, 50048):
+        share = 2.0 * bench.int8_macs(n_pad) / float(n_pad) ** 3
+        assert 0.95 < share < 1.0
