@@ -77,6 +77,7 @@ def load_library():
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
+        "gpss_get_ozaki_fallbacks": (I, [H, ctypes.POINTER(L)]),
         "gpss_test_gemm_nt": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_oz_gemm": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_potrf": (I, [I, I, P, P, P]),
@@ -230,6 +231,12 @@ class GpssModel:
         """0 = the long-k contractions run on the FP64 DMMA pipe; 6 | 7 | 8 = on the int8 tensor cores with that many slices."""
         v = ctypes.c_int(0)
         _check(self._lib.gpss_get_ozaki(self._h, ctypes.byref(v)))
+        return v.value
+
+    def ozaki_fallbacks(self):
+        """Evaluations repeated on the DMMA pipe because an int8 operand left its a-priori bound (device flag)."""
+        v = ctypes.c_long(0)
+        _check(self._lib.gpss_get_ozaki_fallbacks(self._h, ctypes.byref(v)))
         return v.value
 
     def padded_n(self):

@@ -44,7 +44,7 @@ static int enqueue_factor(gpss_ctx* c)
 {
   const int n_pad = c->n_pad;
   const long ld = n_pad;
-  CU(cudaMemsetAsync(c->dflag, 0, sizeof(int), c->st));
+  CU(cudaMemsetAsync(c->dflag, 0, 2 * sizeof(int), c->st));
   {
     PhaseTimer t(c, 0);
     transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs, ld, c->n, n_pad, c->dP);
@@ -97,6 +97,7 @@ static int enqueue_solves(gpss_ctx* c)
 // ---------------------------------------------------------------------------------------------------
 static bool graphs_enabled(const gpss_ctx* c)
 {
+  if (c->oz_s > 0 && c->oz_blocked) return false;               // the captured graphs hold the int8 launches
   if (c->world != 1 || c->partitioned || c->profiling || c->graph_failed || !c->st2) return false;
   if (getenv("GPSS_NO_GRAPH")) return false;
   int max_n = 8192;
@@ -330,7 +331,8 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
   CUF(cudaMalloc(&c->fvec, sizeof(double) * np));
   CUF(cudaMalloc(&c->red, sizeof(double) * 32));
   CUF(cudaMalloc(&c->dP, sizeof(DevParams) * 2));
-  CUF(cudaMalloc(&c->dflag, sizeof(int)));
+  CUF(cudaMalloc(&c->dflag, 2 * sizeof(int)));
+  CUF(cudaMemsetAsync(c->dflag, 0, 2 * sizeof(int), c->st));
   CUF(cudaMemsetAsync(c->alpha, 0, sizeof(double) * np, c->st));
   CUF(cudaMemsetAsync(c->fvec, 0, sizeof(double) * np, c->st));
 #undef CUF
@@ -399,6 +401,10 @@ int gpss_set_theta(gpss_handle c, const double theta[GPSS_NPAR])
   memcpy(c->theta, theta, sizeof c->theta);
   c->have_factor = c->have_alpha = c->have_U = false;   // setKUpdateStat(false) (GP_Utils.cpp:132)
   c->qstate = Q_NONE;
+  // the int8 path scales U = L^-T and W = L^-1 by the a-priori bound |L^-1_ij| <= 1, which needs B = I + K / sn2 >= I: every kernel
+  // of the path is positive semi-definite for any widths / angles, the bias term only for Sigma_Bias >= 0 (Kern_Bias uses it raw,
+  // Kernel.cpp:362-367, and no optimiser constrains it).  Outside that region this theta is evaluated on the DMMA path.
+  c->oz_blocked = theta[8] < 0.0 || !(theta[9] > 0.0);
   return GPSS_OK;
 }
 
@@ -460,26 +466,45 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
     else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, redp, c->s3, g); }
     return GPSS_OK;
   }
-  RET(ensure_gradient_buffers(c));
-  bool replayed = false;
-  if (graphs_enabled(c) && !c->have_U && c->qstate != Q_IS_BINV) {
-    const int nblk_o = (c->n_pad + NBO - 1) / NBO;
-    RET(ensure_event_pool(c, 2 * nblk_o + 2));
-    const int r = run_graph(c, 1);
-    if (r < 0) return r;
-    if (r == 0) {
-      c->have_U = true;
-      c->qstate = Q_IS_BINV;
-      replayed = true;
+  for (int attempt = 0;; attempt++) {
+    RET(ensure_gradient_buffers(c));
+    bool replayed = false;
+    if (graphs_enabled(c) && !c->have_U && c->qstate != Q_IS_BINV) {
+      const int nblk_o = (c->n_pad + NBO - 1) / NBO;
+      RET(ensure_event_pool(c, 2 * nblk_o + 2));
+      const int r = run_graph(c, 1);
+      if (r < 0) return r;
+      if (r == 0) {
+        c->have_U = true;
+        c->qstate = Q_IS_BINV;
+        replayed = true;
+      }
     }
+    if (!replayed) RET(enqueue_gradient(c));
+    double red[NGRAD];
+    int viol = 0;
+    CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
+    if (oz_active(c)) CU(cudaMemcpyAsync(&viol, c->dflag + 1, sizeof viol, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (viol && attempt == 0) {
+      // an operand of the int8 products left its a-priori bound (oz_slice_kernel): U, B^-1 and the sums above are not trustworthy.
+      // Repeat this theta on the FP64 DMMA path (oz_active() is 0 while oz_blocked is set; gpss_set_theta clears it).
+      c->oz_blocked = true;
+      c->oz_fallbacks++;
+      c->have_factor = c->have_alpha = c->have_U = false;
+      c->qstate = Q_NONE;
+      RET(ensure_objective(c));
+      *nlml = c->nlml;
+      if (c->chol_fail) {
+        for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
+        return GPSS_NOT_POSDEF;
+      }
+      continue;
+    }
+    if (c->kind == 0) combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
+    else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, red, c->s3, g); }
+    return GPSS_OK;
   }
-  if (!replayed) RET(enqueue_gradient(c));
-  double red[NGRAD];
-  CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
-  CU(cudaStreamSynchronize(c->st));
-  if (c->kind == 0) combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
-  else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, red, c->s3, g); }
-  return GPSS_OK;
 }
 
 }  // extern "C"
@@ -530,6 +555,7 @@ static int enqueue_gradient(gpss_ctx* c)
     c->launches++;
     CU(cudaGetLastError());
     if (c->world > 1) NC(g_nccl.AllReduce(c->red + 8, c->red + 8, NGRAD, ncclDouble, ncclSum, c->comm, c->st));
+    if (c->world > 1 && oz_active(c)) NC(g_nccl.AllReduce(c->dflag + 1, c->dflag + 1, 1, ncclInt, ncclMax, c->comm, c->st));   // all ranks take the same branch
   }
   return GPSS_OK;
 }
@@ -1022,6 +1048,13 @@ int gpss_get_ozaki(gpss_handle c, int* slices)
 {
   if (!c || !slices) return fail_arg("gpss_get_ozaki: null");
   *slices = oz_active(c);
+  return GPSS_OK;
+}
+
+int gpss_get_ozaki_fallbacks(gpss_handle c, long* count)
+{
+  if (!c || !count) return fail_arg("gpss_get_ozaki_fallbacks: null");
+  *count = c->oz_fallbacks;
   return GPSS_OK;
 }
 

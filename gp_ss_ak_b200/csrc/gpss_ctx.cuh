@@ -105,7 +105,7 @@ struct gpss_ctx {
   double *partial = nullptr; long partial_blocks = 0;          // gradient partial sums
   double *red = nullptr;                                       // 32 doubles of reduced scalars
   DevParams* dP = nullptr;                                     // [0] training, [1] prediction
-  int* dflag = nullptr;
+  int* dflag = nullptr;                                        // [0] Cholesky failure, [1] an int8 digit-plane operand exceeded its a-priori bound
   // prediction scratch (lazily)
   double *xt = nullptr, *zt = nullptr, *zsp = nullptr, *Bm = nullptr, *Vm = nullptr, *mu_part = nullptr, *dmu = nullptr, *dvar = nullptr;
   int pred_cap = 0;
@@ -125,6 +125,9 @@ struct gpss_ctx {
   int oz_s_grad = 0;                                           // GPSS_OZAKI_GRAD=6|7 (opt-in, not yet measured): fewer slices for the inverse / B^-1
                                                                // products (they feed the gradient only), read from the TOP planes of the same tensors
   int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
+  bool oz_blocked = false;                                     // this theta stays on the DMMA path: Sigma_Bias < 0 or sn2 <= 0 (K not PSD, so |L^-1| <= 1 is not
+                                                               // guaranteed), or dflag[1] was raised by the previous attempt at this theta
+  long oz_fallbacks = 0;                                       // evaluations repeated on the DMMA path because dflag[1] was raised
   bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
   bool ozL_valid = false, ozU_valid = false;                   // the planes hold the CURRENT factor / inverse (set by the drivers that cut them)
@@ -204,7 +207,7 @@ static int gemm(gpss_ctx* c, const GemmArgs& g) { return gemm_ws_on(c, g, c->st)
 // ---------------------------------------------------------------------------------------------------
 static int oz_active(const gpss_ctx* c)
 {
-  return (c->oz_s > 0 && !c->partitioned && c->st2 && (c->world == 1 || c->oz_dist)) ? c->oz_s : 0;
+  return (c->oz_s > 0 && !c->oz_blocked && !c->partitioned && c->st2 && (c->world == 1 || c->oz_dist)) ? c->oz_s : 0;
 }
 
 static int oz_configure()
@@ -272,9 +275,9 @@ static int oz_slice_on(gpss_ctx* c, const double* X, long ldx, int row0, int row
 {
   if (rows <= 0 || kcnt <= 0) return GPSS_OK;
   switch (c->oz_s) {
-    case 6: oz::slice<6>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
-    case 7: oz::slice<7>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
-    case 8: oz::slice<8>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits); break;
+    case 6: oz::slice<6>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits, c->dflag ? c->dflag + 1 : nullptr); break;
+    case 7: oz::slice<7>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits, c->dflag ? c->dflag + 1 : nullptr); break;
+    case 8: oz::slice<8>(X, ldx, row0, rows, k0, kcnt, kind, mask, c->dP, planes, c->n_pad, c->n_pad, st, c->oz_bits, c->dflag ? c->dflag + 1 : nullptr); break;
     default: return fail_arg("GPSS_OZAKI must be 6, 7 or 8");
   }
   c->launches++;

@@ -1,4 +1,5 @@
-// gpss_ozaki.cuh -- OPT-IN (GPSS_OZAKI=6|7|8, single-GPU handles; default off): the three long-k FP64 contractions of the
+// gpss_ozaki.cuh -- the DEFAULT pipe for 8192 < n_pad <= 57 344 (GPSS_OZAKI=0 restores DMMA everywhere, GPSS_OZAKI=6|7|8 forces
+// it for every n; size rule in gpss_create): the three long-k FP64 contractions of the
 // path (look-ahead update of the Cholesky, bulk product of the triangular inverse, B^-1 = U U^T) evaluated on the int8
 // tensor cores of sm_100a -- tcgen05.mma kind::i8, operands by TMA, int32 accumulators in TMEM -- with the Ozaki splitting,
 // instead of the 37 TFLOP/s DMMA pipe.  Measured on B200 (profiles/r01_ozaki_int8_gemm_microbench.txt, 16384^2 x 8192):
@@ -28,7 +29,7 @@
 
 namespace oz {
 
-constexpr int BM = 128, BN = 64, BK = 64;        // BK in bytes (= int8 elements) per stage and plane: one SWIZZLE_64B row
+constexpr int BM = 128, BN = 64, BK = 64;        // BK: granularity of every k-range in bytes (= int8 elements); a stage holds BKB = 64 or 32 of them
 constexpr int UMMA_K = 32;                       // kind::i8: 32 bytes of k per instruction
 constexpr int DIGIT_BITS = 7;
 constexpr int RASTER_W = 8;
@@ -38,13 +39,23 @@ constexpr int RASTER_W = 8;
 enum { SCALE_UNIT = 0, SCALE_CHOL = 1, SCALE_CROSS = 2 };
 enum { MASK_NONE = 0, MASK_LOWER = 1, MASK_UPPER = 2 };
 
-template <int S>
+// Kernel variants (oz::variant(), GPSS_OZ_VARIANT; A/B-measured in profiles/r02_oz_gemm_variants.txt):
+//   0: 64-byte stages (SWIZZLE_64B), one MMA of N = 64 per slice pair                       -- the round-1 kernel
+//   1: 64-byte stages, MERGED MMAs: the B planes of a stage are contiguous in shared memory (64 rows each) and group i + j sits in
+//      TMEM columns [64 (i + j), +64), so A_i x [B_j .. B_j+c-1] is ONE instruction of N = 64 c <= 256 whose accumulator columns
+//      are exactly the groups i + j .. i + j + c - 1: 12 instructions instead of 36 per 32 bytes of k at S = 8, and the A tile is
+//      read from shared memory 12 times instead of 36 (the round-1 kernel ran at the 128 B/clk shared-memory limit:
+//      36 x (4 KB + 2 KB) per 32 clk of tensor work)
+//   2: variant 1 with 32-byte stages (SWIZZLE_32B): twice the stages in the same shared memory, finer refill granularity
+enum { VAR_PAIR64 = 0, VAR_MERGE64 = 1, VAR_MERGE32 = 2, VAR_DEFAULT = VAR_MERGE64 };
+
+template <int S, int BKB = BK>
 struct Cfg {
   static constexpr int PAIRS = S * (S + 1) / 2;
-  static constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK;
+  static constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB;
   static constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
   static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = S * BN <= 64 ? 64 : S * BN <= 128 ? 128 : S * BN <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
   static_assert(S >= 1 && S * BN <= 512, "S group accumulators of BN columns must fit the 512 TMEM columns");
@@ -114,21 +125,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-// K-major operand tile in shared memory, rows of 64 bytes, SWIZZLE_64B (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp:
-// start >> 4 in [0,14), LBO in [16,30) (ignored for swizzled K-major: 1), SBO = 8 rows x 64 B >> 4 = 32 in [32,46),
-// version 1 in [46,48), layout SWIZZLE_64B = 4 in [61,64)).  The tile base is 1024-byte aligned.
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr)
+// K-major operand tile in shared memory, rows of BKB = 64 / 32 bytes, SWIZZLE_64B / SWIZZLE_32B (cute::UMMA::SmemDescriptor,
+// mma_sm100_desc.hpp: start >> 4 in [0,14), LBO in [16,30) (ignored for swizzled K-major: 1), SBO = 8 rows x BKB bytes >> 4 in
+// [32,46), version 1 in [46,48), layout SWIZZLE_64B = 4 / SWIZZLE_32B = 6 in [61,64)).  The tile base is 1024-byte aligned.
+template <int BKB>
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr)
 {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(8 * BKB / 16) << 32) | (1ull << 46) | ((BKB == 64 ? 4ull : 6ull) << 61);
 }
 // cute::UMMA::InstrDescriptor: c_format S32 = 2 [4,6), a/b_format INT8 = 1 [7,10) / [10,13), K-major both, N >> 3 [17,23), M >> 4 [24,29)
-constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+constexpr uint32_t IDESC_I8 = idesc_i8(BN);
 
-template <int S>
+template <int S, int BKB = BK, bool MERGE = false>
 __global__ void __launch_bounds__(192, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g)
 {
-  using T = Cfg<S>;
+  using T = Cfg<S, BKB>;
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
@@ -148,7 +161,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (g.kbeg_row) { const int kr = (g.a_row0 + tile_m * BM) & ~(BK - 1); if (kr > kb) kb = kr; }
   int ke = g.k1;
   if (g.kend_row) { const int kr = g.a_row0 + tile_m * BM + BM; if (kr < ke) ke = kr; }
-  const int nk = ke > kb ? (ke - kb) / BK : 0;
+  const int nk = ke > kb ? (ke - kb) / BKB : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T::STAGES; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
@@ -174,7 +187,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         gpss::mbar_arrive_expect_tx(full_bar + st, (uint32_t)T::STAGE_BYTES);
         uint8_t* sa = smem + st * T::STAGE_BYTES;
         uint8_t* sb = sa + S * T::A_BYTES;
-        const int kq = kb + kc * BK;
+        const int kq = kb + kc * BKB;
 #pragma unroll
         for (int p = 0; p < S; p++) {
           tma_load_2d(sa + p * T::A_BYTES, &tmA, full_bar + st, kq, p * g.a_rows + g.a_row0 + tile_m * BM);
@@ -193,15 +206,31 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = gpss::smem_u32(smem + st * T::STAGE_BYTES);
         const uint32_t sb = sa + S * T::A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ks++) {
+        for (int ks = 0; ks < BKB / UMMA_K; ks++) {
 #pragma unroll
           for (int i = 0; i < S; i++) {
-            const uint64_t ad = smem_desc_sw64(sa + i * T::A_BYTES + ks * UMMA_K);
+            const uint64_t ad = smem_desc_k<BKB>(sa + i * T::A_BYTES + ks * UMMA_K);
+            // group i + j: the first product that reaches it (i == 0 of the first k-step) overwrites, the rest accumulate
+            const uint32_t acc = (kc > 0 || ks > 0 || i > 0) ? 1u : 0u;
+            if constexpr (MERGE) {
+              // B planes 0 .. S-1-i are 64 (S - i) consecutive rows of shared memory and their groups i .. S-1 are 64 (S - i)
+              // consecutive TMEM columns: ceil((S - i) / 4) instructions of N <= 256, planes split as evenly as possible
+              constexpr int MAXP = 256 / BN;
+              const int cnt = S - i, nm = (cnt + MAXP - 1) / MAXP;
+              int j0 = 0;
 #pragma unroll
-            for (int j = 0; j < S - i; j++) {
-              const uint64_t bd = smem_desc_sw64(sb + j * T::B_BYTES + ks * UMMA_K);
-              // group i + j: the first product that reaches it (i == 0 of the first k-step) overwrites, the rest accumulate
-              mma_i8(tmem_base + (uint32_t)((i + j) * BN), ad, bd, IDESC_I8, (kc > 0 || ks > 0 || i > 0) ? 1u : 0u);
+              for (int q = 0; q < nm; q++) {
+                const int len = (cnt - j0 + (nm - q) - 1) / (nm - q);
+                const uint64_t bd = smem_desc_k<BKB>(sb + j0 * T::B_BYTES + ks * UMMA_K);
+                mma_i8(tmem_base + (uint32_t)((i + j0) * BN), ad, bd, idesc_i8(len * BN), acc);
+                j0 += len;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < S - i; j++) {
+                const uint64_t bd = smem_desc_k<BKB>(sb + j * T::B_BYTES + ks * UMMA_K);
+                mma_i8(tmem_base + (uint32_t)((i + j) * BN), ad, bd, IDESC_I8, acc);
+              }
             }
           }
         }
@@ -263,7 +292,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // triangle's edge.  32 x 32 tiles through shared memory: coalesced FP64 reads along rows, 32-byte row segments written.
 template <int S>
 __global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask,
-                                const gpss::DevParams* dP, int8_t* __restrict__ planes, long plane_rows, long kpad, int bits)
+                                const gpss::DevParams* dP, int8_t* __restrict__ planes, long plane_rows, long kpad, int bits, int* viol)
 {
   __shared__ int8_t tile[S][32][33];
   const int r = row0 + blockIdx.x * 32 + threadIdx.x;
@@ -280,7 +309,11 @@ __global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0
     const bool keep = (mask == MASK_NONE) || (mask == MASK_LOWER && kq <= r) || (mask == MASK_UPPER && kq >= r);
     if (r < row0 + rows && kq < k0 + kcnt && keep) {
       double sc = X[r + (size_t)kq * ldx] * mul;
-      sc = fmin(fmax(sc, -lim), lim);                                  // |x| <= 2^e by construction; guards rounding excess
+      // |x| <= 2^e holds when B = I + K / sn2 >= I, i.e. for a positive semi-definite K; nothing constrains theta (Sigma_Bias enters
+      // raw), so an operand that exceeds its a-priori bound by more than rounding noise (2^-40 relative) raises the flag the host reads
+      // at the end of the evaluation, which is then repeated on the DMMA path (gpss_capi.cu: oz_blocked).  NaN raises it too.
+      if (viol && !(fabs(sc) <= lim * (1.0 + 0x1p-40))) *viol = 1;
+      sc = fmin(fmax(sc, -lim), lim);                                  // rounding excess only
       long long v = __double2ll_rn(sc);
       v = v > vmax ? vmax : (v < -vmax ? -vmax : v);
 #pragma unroll
@@ -322,38 +355,60 @@ static inline EncodeTiledFn encode_fn()
   return fn;
 }
 
-// planes: [total_rows][kpad] bytes, K contiguous; box = 64 bytes of k x box_rows rows, SWIZZLE_64B.  Returns 0 on success.
+// which oz_gemm_kernel variant runs (see the list above Cfg): GPSS_OZ_VARIANT = 0 | 1 | 2, read once
+static inline int variant()
+{
+  static int v = -1;
+  if (v < 0) {
+    v = VAR_DEFAULT;
+    if (const char* e = getenv("GPSS_OZ_VARIANT")) { const int x = atoi(e); if (x >= VAR_PAIR64 && x <= VAR_MERGE32) v = x; }
+  }
+  return v;
+}
+static inline int stage_k() { return variant() == VAR_MERGE32 ? 32 : 64; }
+
+// planes: [total_rows][kpad] bytes, K contiguous; box = stage_k() bytes of k x box_rows rows, SWIZZLE_64B / _32B.  Returns 0 on success.
 static inline int make_plane_map(CUtensorMap* tm, const int8_t* planes, long total_rows, long kpad, int box_rows)
 {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1;
+  const int bkb = stage_k();
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)total_rows};
   cuuint64_t strides[1] = {(cuuint64_t)kpad};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bkb, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -2;
+            bkb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -2;
 }
 
 template <int S>
 static inline cudaError_t configure()
 {
-  return cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel<S, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 64>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<S, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 64>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<S, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 32>::SMEM_BYTES);
+  return e;
 }
 
 template <int S>
 static inline void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& g, cudaStream_t st)
 {
-  oz_gemm_kernel<S><<<(unsigned)((g.m / BM) * (g.n / BN)), 192, Cfg<S>::SMEM_BYTES, st>>>(ta, tb, g);
+  const unsigned grid = (unsigned)((g.m / BM) * (g.n / BN));
+  switch (variant()) {
+    case VAR_PAIR64: oz_gemm_kernel<S, 64, false><<<grid, 192, Cfg<S, 64>::SMEM_BYTES, st>>>(ta, tb, g); break;
+    case VAR_MERGE64: oz_gemm_kernel<S, 64, true><<<grid, 192, Cfg<S, 64>::SMEM_BYTES, st>>>(ta, tb, g); break;
+    default: oz_gemm_kernel<S, 32, true><<<grid, 192, Cfg<S, 32>::SMEM_BYTES, st>>>(ta, tb, g); break;
+  }
 }
 
 template <int S>
 static inline void slice(const double* X, long ldx, int row0, int rows, int k0, int kcnt, int kind, int mask, const gpss::DevParams* dP,
-                         int8_t* planes, long plane_rows, long kpad, cudaStream_t st, int bits = DIGIT_BITS)
+                         int8_t* planes, long plane_rows, long kpad, cudaStream_t st, int bits = DIGIT_BITS, int* viol = nullptr)
 {
   if (rows <= 0 || kcnt <= 0) return;
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((kcnt + 31) / 32)), block(32, 8);
-  oz_slice_kernel<S><<<grid, block, 0, st>>>(X, ldx, row0, rows, k0, kcnt, kind, mask, dP, planes, plane_rows, kpad, bits);
+  oz_slice_kernel<S><<<grid, block, 0, st>>>(X, ldx, row0, rows, k0, kcnt, kind, mask, dP, planes, plane_rows, kpad, bits, viol);
 }
 
 // Longest k-range ONE int32 accumulation may cover: |G_g| <= S k 2^(2 (bits - 1)) < 2^31.  7-bit digits: 65 536 / S x 8 >= n_pad

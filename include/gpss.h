@@ -149,8 +149,13 @@ int gpss_debug_fetch(gpss_handle h, int which, double* host_out, long count);
 int gpss_padded_n(gpss_handle h, int* n_pad);
 /* Which pipe runs the three long-k contractions of this handle (potrf look-ahead update, bulk product of the triangular
  * inverse, B^-1 = U U^T): 0 = FP64 DMMA (gemm_nt_ws_kernel), 6 | 7 | 8 = int8 tensor cores with that many 7-bit Ozaki slices
- * (oz_gemm_kernel, csrc/gpss_ozaki.cuh).  Chosen at gpss_create from n and the GPSS_OZAKI environment variable. */
+ * (oz_gemm_kernel, csrc/gpss_ozaki.cuh).  Chosen at gpss_create from n and the GPSS_OZAKI environment variable.
+ * The answer is per theta: the int8 scaling rests on |L^-1_ij| <= 1, i.e. on B = I + K / sn2 >= I, which the reference's
+ * unconstrained parameters do not guarantee (Kern_Bias adds Sigma_Bias raw, Kernel.cpp:362-367).  A theta with Sigma_Bias < 0 or
+ * sn2 <= 0 is evaluated on the DMMA pipe (0 is returned after gpss_set_theta), and if an operand still leaves its bound the
+ * device flags it and the evaluation is repeated on the DMMA pipe: gpss_get_ozaki_fallbacks counts those repeats. */
 int gpss_get_ozaki(gpss_handle h, int* slices);
+int gpss_get_ozaki_fallbacks(gpss_handle h, long* count);
 
 /* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
 /* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised
