@@ -43,15 +43,31 @@ FP64_PEAK_FALLBACK_TFLOPS = 37.13   # profiles/r01_fp64_peak_microbench.txt (DMM
 BF16_SUSTAINED_FALLBACK_TFLOPS = 1400.0   # /opt/skills/guides/B200_PROFILING.md: "sustained it settles near 1.4 PFLOP/s" (used "of fallback")
 
 
-def int8_tensor_peak():
-    """Dense int8 tensor peak in TOP/s for a kernel timed inside a long step: MEASURED_PEAKS.json has no int8 entry, so
-    2 x its sustained bf16 cuBLAS figure (B200: dense int8 = 2 x dense bf16, 4.5 vs 2.25 POP/s nominal)."""
+INT8_PEAK_FALLBACK_TOPS = 3796.9   # profiles/r02_int8_peak_microbench.txt (sustained, N = 256 shape) -- used only if the live measurement fails
+
+# DRAM bytes (read + write) of the B^-1 = U U^T launch of oz_gemm_kernel at n_pad = 50 048, from the ncu capture of the bench command
+# (profiles/r02_oz_gemm_dram_per_launch_n50k.txt); filled in by the round's GPU job, None until then
+OZ_LAUUM_TRAFFIC_BYTES = None
+
+
+def int8_tensor_peak(device):
+    """int8 tensor-pipe micro-peak in TOP/s measured live (gpss_measure_int8_peak: tcgen05.mma kind::i8 M 128 N 256 K 32 from resident
+    shared-memory operands on all SMs).  MEASURED_PEAKS.json has no int8 entry.  The kernel is timed inside a long step, so the
+    SUSTAINED figure (~1 s back to back, under the power cap) is the denominator; the burst figure is reported beside it."""
+    import gp_ss_ak_b200 as G
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            pk = json.load(f)
-        return 2.0 * float(pk["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (of measured; the file has no int8 entry)"
-    except Exception:
-        return 2.0 * BF16_SUSTAINED_FALLBACK_TFLOPS, "2 x the 1.4 PFLOP/s sustained bf16 figure of B200_PROFILING.md (of fallback)"
+        burst, sust = G.measure_int8_peak(device)
+        return sust, burst, "gpss_measure_int8_peak, measured live in this run (sustained over ~1 s; burst = best 6 ms launch); MEASURED_PEAKS.json has no int8 entry"
+    except Exception as e:   # noqa: BLE001
+        return INT8_PEAK_FALLBACK_TOPS, None, "profiles/r02_int8_peak_microbench.txt (live measurement failed: %s)" % e
+
+
+def int8_macs_lauum(n_pad):
+    """int8 MACs per slice pair of the ONE oz_gemm_kernel launch that forms B^-1 = U U^T (lower tiles, k from the row tile's first row)."""
+    mac = 0
+    for tm in range(n_pad // 128):
+        mac += 128 * 64 * min(n_pad // 64, (tm * 128 + 127) // 64 + 1) * (n_pad - tm * 128)
+    return mac
 
 
 def int8_macs(n_pad, nbo=512):
@@ -148,32 +164,91 @@ def cpu_reference_times(n_sample, warmup, steps):
     return secs, "port"
 
 
-def cpu_sample_text(kind, n_sample, n, t_step, cores):
-    what = ("the unmodified reference (oracle/_ref/ref_driver: reference sources + Armadillo stand-in + OpenBLAS, built -O0 like "
-            "make_linux)" if kind == "reference" else "the numpy/scipy port of the reference (oracle/gpss_oracle.py, literal path)")
-    return ("%s: set_GP_Pars + Grad_Values at n=%d took %.2f s per evaluation on %d host threads; scaled by (n/n_sample)^3 = %.0f to "
-            "n=%d (the reference keeps ~34 dense n x n buffers, ~680 GB at n=%d, and cannot run the full size)"
-            % (what, n_sample, t_step, cores, (n / n_sample) ** 3, n, n))
+REF_SIZES = (750, 1500, 3000)          # reference-literal samples (the compiled reference; ~25 s of CPU work in all)
+LEAN_SIZES = (5000, 10000)             # lean samples (1 dpotrf + 1 dpotri on all cores; ~15 s); --cpu-lean-max 20000 adds a third
+
+
+def cpu_baseline_block(n, ref_samples, lean_sizes, cores):
+    """the CPU path on the box's host cores in two forms, each measured at several sizes, fitted
+    t = a n^2 + b n^3 and EXTRAPOLATED to n (no CPU code can hold n = 50 000 in the reference's ~34 dense buffers).
+      reference-literal: the unmodified reference classes (oracle/_ref/ref_driver; kind "reference") -- 3 dpotrf + 2 n x n dtrtrs
+        = 3 n^3 flop through OpenBLAS plus ~100 element-wise n x n passes compiled -O0 like make_linux.  At the sample sizes the
+        n^2 passes dominate, so the n^3 coefficient is not fitted from them: it is 3 flop / the OpenBLAS rate measured by the lean
+        run in the same process (the reference cannot run its LAPACK calls faster than that);
+      lean: the same mathematics with one dpotrf + one dpotri (oracle/lean_baseline.py): what a careful CPU implementation costs.
+    `value` (and the reference arm's line) is the reference-literal extrapolation; `lean` is printed beside it."""
+    from oracle import lean_baseline as LB
+    threads = LB.blas_threads()
+    LB.time_lean([1500])                                          # page OpenBLAS in
+    lean = LB.time_lean(list(lean_sizes))
+    gf = lean[-1][2]                                              # GFLOP/s of potrf + potri at the largest lean size
+    a_l, b_l = LB.fit_n2_n3([r[0] for r in lean], [r[1] for r in lean])
+    t_lean = a_l * n ** 2 + b_l * float(n) ** 3
+    out = {"cores": cores, "blas_threads": threads, "extrapolated": True,
+           "lean": {"what": "1 dpotrf + 1 dpotri + O(n^2) passes, scipy OpenBLAS, all cores (oracle/lean_baseline.py)",
+                    "samples": [{"n": r[0], "seconds": round(r[1], 3), "gflops_potrf_potri": round(r[2], 1)} for r in lean],
+                    "fit": {"a_n2": a_l, "b_n3": b_l}, "seconds_at_n": t_lean, "value": 1.0 / t_lean, "unit": "evals/s"}}
+    if ref_samples:
+        ns = [r[0] for r in ref_samples]
+        ts = [r[1] for r in ref_samples]
+        b_ref = 3.0 / (gf * 1e9)
+        a_ref, b_ref = LB.fit_n2_n3(ns, ts, b_fixed=b_ref)
+        t_ref = a_ref * n ** 2 + b_ref * float(n) ** 3
+        out.update({"kind": "reference", "value": 1.0 / t_ref, "unit": "evals/s",
+                    "sample": ("the unmodified reference (oracle/_ref/ref_driver: reference sources + Armadillo stand-in + OpenBLAS, built -O0 like "
+                               "make_linux), set_GP_Pars + Grad_Values at n = %s: %s s per evaluation on %d host threads; fitted t = a n^2 + b n^3 with "
+                               "b = 3 flop / the %.0f GFLOP/s OpenBLAS rate measured beside it, a = %.3g s by least squares; EXTRAPOLATED to n=%d: %.0f s "
+                               "(a n^2 = %.0f s of -O0 element-wise passes, b n^3 = %.0f s of LAPACK); the reference itself cannot hold n=%d "
+                               "(~34 dense n x n buffers = ~680 GB)"
+                               % ("/".join(str(v) for v in ns), "/".join("%.2f" % v for v in ts), cores, gf, a_ref, n, t_ref,
+                                  a_ref * n ** 2, b_ref * float(n) ** 3, n)),
+                    "reference_literal": {"samples": [{"n": a, "seconds": round(b, 3)} for a, b in ref_samples],
+                                          "fit": {"a_n2": a_ref, "b_n3": b_ref}, "seconds_at_n": t_ref}})
+    else:
+        out.update({"kind": "port", "value": 1.0 / t_lean, "unit": "evals/s",
+                    "sample": "oracle/_ref/ref_driver not present: the lean numpy/LAPACK port only (see `lean`), extrapolated to n=%d" % n})
+    return out
+
+
+def ref_samples_once(sizes):
+    """One timed evaluation of the compiled reference per size (after one untimed one at the smallest size)."""
+    if not os.path.exists(REF_DRIVER):
+        return []
+    cpu_reference_times(sizes[0], 0, 1)
+    out = []
+    for ns in sizes:
+        secs, _ = cpu_reference_times(ns, 0, 1)
+        out.append((ns, float(np.mean(secs))))
+    return out
 
 
 def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: the reference's own CPU implementation on the host cores.  Each of the W + K steps is ONE
+    LML+gradient evaluation of the compiled reference at one of REF_SIZES (cycled); the K timed ones are averaged per size, fitted
+    and extrapolated to n as cpu_baseline_block documents.  ms_per_step is the extrapolated time of one evaluation at n."""
     if rank != 0:
         return
-    n_sample = args.cpu_n
     cores = os.cpu_count()
-    secs, kind = cpu_reference_times(n_sample, args.warmup, args.steps)
-    t_step = float(np.mean(secs))
-    scale = (args.n / n_sample) ** 3
-    value = 1.0 / (t_step * scale)
+    sizes = REF_SIZES if os.path.exists(REF_DRIVER) else ()
+    per = {ns: [] for ns in sizes}
+    for k in range(args.warmup + args.steps):
+        if not sizes:
+            break
+        ns = sizes[k % len(sizes)]
+        secs, _ = cpu_reference_times(ns, 0, 1)
+        if k >= args.warmup:
+            per[ns].append(secs[0])
+    samples = [(ns, float(np.mean(v))) for ns, v in per.items() if v]
+    cb = cpu_baseline_block(args.n, samples, LEAN_SIZES, cores)
+    value = cb["value"]
     line = {
         "impl": "reference", "metric": "ExpAns LML+grad evals/s at n=%dk" % (args.n // 1000), "value": value, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * scale * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d; each step is a bounded "
-                               "sample: one evaluation at n=%d, scaled by (n/n_sample)^3" % (args.n, n_sample), "n": args.n,
-                   "n_sample": n_sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
-                         "sample": cpu_sample_text(kind, n_sample, args.n, t_step, cores)},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d; each step is a bounded sample: one "
+                               "evaluation of the compiled reference at n in %s (cycled), fitted a n^2 + b n^3 and extrapolated to n=%d"
+                               % (args.n, list(sizes), args.n), "n": args.n, "n_samples": list(sizes)},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -188,7 +263,7 @@ def main():
     ap.add_argument("--impl", default="gpss")
     ap.add_argument("--mode", default="distributed", choices=["distributed", "replicas"],
                     help="N > 1: one evaluation partitioned over all GPUs (default), or one independent evaluation stream per GPU")
-    ap.add_argument("--cpu-n", type=int, default=1500, help="sample size of the CPU baseline / reference-arm evaluation")
+    ap.add_argument("--cpu-lean-max", type=int, default=0, help="largest extra size of the lean CPU baseline (e.g. 20000; default: 5000 and 10000 only)")
     ap.add_argument("--pred-m", type=int, default=32768, help="test points PER GPU of the prediction leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -272,7 +347,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- roofline of the dominant kernel (DMMA GEMM-NT) from a profiled evaluation ----
+    # ---- roofline of the dominant kernel (oz_gemm_kernel on the default int8 pipe, gemm_nt_ws_kernel with GPSS_OZAKI=0) from a profiled evaluation ----
     model.set_profiling(True)
     model.set_theta(theta_probe(stream_id * 7919 + 300))
     checked_eval()
@@ -342,23 +417,32 @@ def main():
                 % (" / %d GPUs" % world if distributed else ""))
         if oz_s:
             pairs = oz_s * (oz_s + 1) // 2
-            i8_peak, i8_src = int8_tensor_peak()
+            i8_peak, i8_burst, i8_src = int8_tensor_peak(local_rank)
             # executed int8 op/s: exact tile-level count on one GPU; a partitioned evaluation is approximated by its share of n^3
             i8_ops = 2.0 * int8_macs(n_pad) * pairs if share == 1 else alg_flops * pairs
             i8_tops = i8_ops / (gemm_ms * 1e-3) * 1e-12
-            roofline = {"bound": "tensor", "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
-                        "frac": i8_tops / i8_peak, "traffic": None,
-                        "traffic_note": "no ncu capture of oz_gemm_kernel yet: the path was built after the round's ncu runs (profiles/ holds the DMMA captures)",
-                        "kernel": "oz_gemm_kernel<%d> (tcgen05.mma kind::i8, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; %d int8 "
-                                  "products per FP64 product)" % (oz_s, pairs),
-                        "peak_source": i8_src,
+            # the kernel alone: the lauum phase is oz_gemm_kernel launches and nothing else (one launch with 7-bit digits)
+            lau_ops = 2.0 * int8_macs_lauum(n_pad) * pairs / share
+            lau_tops = lau_ops / (float(ph[4]) * 1e-3) * 1e-12
+            roofline = {"bound": "tensor", "achieved": lau_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
+                        "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES,
+                        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from the ncu pass over the bench "
+                                        "command (profiles/r02_oz_gemm_dram_per_launch_n50k.txt); algorithmic: the digit planes of U (upper triangle, %d planes) read "
+                                        "once + the lower triangle of B^-1 written = %.1f GB" % (oz_s, (oz_s * n_pad * n_pad / 2 + 4.0 * n_pad * n_pad) / 1e9),
+                        "kernel": "oz_gemm_kernel<%d, 64, merged> (tcgen05.mma kind::i8 M 128 N <= 256, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; "
+                                  "%d int8 products per FP64 product)" % (oz_s, pairs),
+                        "launch": "B^-1 = U U^T (lauum phase: oz_gemm_kernel launches only), %.3e int8 op in %.1f ms, CUDA events on the handle's stream"
+                                  % (lau_ops, float(ph[4])),
+                        "peak_source": i8_src, "peak_burst": i8_burst, "frac_of_burst": (lau_tops / i8_burst) if i8_burst else None,
+                        "all_gemm_phases": {"achieved": i8_tops, "frac": i8_tops / i8_peak,
+                                            "note": "int8 ops of ALL oz_gemm_kernel launches of one evaluation (tile-level count, %.1f %% of n_pad^3, x %d slice pairs) / device "
+                                                    "time of the potrf + trtri + lauum phases, which also hold the k = 512 panel work on the DMMA pipe and the digit slicing"
+                                                    % (100.0 * i8_ops / pairs / alg_flops, pairs)},
                         "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": peak, "frac_of_fp64_dmma_peak": achieved / peak,
-                        "note": "achieved = int8 ops oz_gemm_kernel executes in one evaluation (tile-level count, %.1f %% of n_pad^3, x %d slice pairs) / device "
-                                "time of the potrf + trtri + lauum phases, which also contain the k = 512 panel work on DMMA and the digit slicing: the "
-                                "kernel itself runs faster than this; fp64_equivalent_tflops = n_pad^3 / the same time"
-                                % (100.0 * i8_ops / pairs / alg_flops, pairs)}
-            dtype = "f64 (long-k products as %d x 7-bit int8 slices on the tensor cores, int32 accumulation, FP64 recombination)" % oz_s
-            gemm_path = "int8 tensor cores, Ozaki splitting, %d slices (GPSS_OZAKI; 0 = FP64 DMMA)" % oz_s
+                        "note": "achieved = int8 ops of the B^-1 = U U^T launch / its duration; fp64_equivalent_tflops = n_pad^3 / (potrf + trtri + lauum time)"}
+            oz_bits = model.ozaki_digit_bits()
+            dtype = "f64 (long-k products as %d x %d-bit int8 slices on the tensor cores, int32 accumulation, FP64 recombination)" % (oz_s, oz_bits)
+            gemm_path = "int8 tensor cores, Ozaki splitting, %d slices of %d bits (GPSS_OZAKI / GPSS_OZAKI_BITS; GPSS_OZAKI=0: FP64 DMMA)" % (oz_s, oz_bits)
         else:
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                         "traffic": GEMM_TRAFFIC_BYTES, "traffic_note": GEMM_TRAFFIC_NOTE,
@@ -369,7 +453,7 @@ def main():
         line = {
             "metric": "ExpAns LML+grad evals/s at n=%dk" % (n // 1000), "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": dtype,
+            "higher_is_better": True, "scaling": "strong" if (distributed or world == 1) else "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": "LML+gradient evaluation (set_GP_Pars + Grad_Values), ExpAns+Bias 3-D, n=%d, theta differs every step"
                                    % n, "n": n, "n_pad": n_pad, "l2_policy": "inputs larger than L2 (K, L, B^-1 = %.1f GB each)"
@@ -398,11 +482,8 @@ def main():
                                             "note": "n_pad^2 flop per test point (triangular k-range of W = L^-1), per GPU"},
                                "sharding": "test points split over %d GPUs, L / alpha replicated" % world}
         if not args.no_cpu_baseline:
-            cores = os.cpu_count()
-            secs, kind = cpu_reference_times(args.cpu_n, 1, 3)
-            t_cpu = float(np.mean(secs))
-            line["cpu_baseline"] = {"value": 1.0 / (t_cpu * (n / args.cpu_n) ** 3), "unit": "evals/s", "cores": cores, "kind": kind,
-                                    "sample": cpu_sample_text(kind, args.cpu_n, n, t_cpu, cores)}
+            lean_sizes = LEAN_SIZES + ((args.cpu_lean_max,) if args.cpu_lean_max > LEAN_SIZES[-1] else ())
+            line["cpu_baseline"] = cpu_baseline_block(n, ref_samples_once(REF_SIZES), lean_sizes, os.cpu_count())
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:

@@ -10,50 +10,7 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-// shared memory: A tile 128 rows x 64 B (SWIZZLE_64B layout, 8 KB) + B tile 256 rows x 64 B (16 KB), filled with pseudo-random bytes
-// (all-zero operands would flatter the clocks: tensor power is data dependent)
-template <int N>
-__global__ void __launch_bounds__(128, 1) int8_peak_kernel(int iters, unsigned long long* cycles)
-{
-  extern __shared__ uint8_t raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 24 * 1024);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-  unsigned s = 1234567u + blockIdx.x * 7919u + threadIdx.x;
-  for (int i = threadIdx.x; i < 24 * 1024; i += blockDim.x) { s = s * 1664525u + 1013904223u; smem[i] = (uint8_t)((int)((s >> 16) % 129u) - 64); }
-  if (threadIdx.x == 0) { gpss::mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(gpss::smem_u32(slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic-proxy writes of the operands -> visible to the tensor core
-  oz::tc_fence_before();
-  __syncthreads();
-  oz::tc_fence_after();
-  const uint32_t tmem = *slot;
-  if (threadIdx.x == 0) {
-    const uint32_t sa = gpss::smem_u32(smem), sb = sa + 8 * 1024;
-    const long long t0 = clock64();
-    constexpr int ACC = 512 / N;                  // independent accumulators of N columns (N = 192: 2)
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int q = 0; q < ACC; q++) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++)
-          oz::mma_i8(tmem + (uint32_t)(q * N), oz::smem_desc_k<64>(sa + ks * 32), oz::smem_desc_k<64>(sb + ks * 32), oz::idesc_i8(N), it > 0 || ks > 0);
-      }
-    }
-    oz::tc_commit(bar);
-    gpss::mbar_wait(bar, 0);
-    if (blockIdx.x == 0) *cycles = (unsigned long long)(clock64() - t0);
-  }
-  oz::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    oz::tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
-  }
-}
+using oz::int8_peak_kernel;
 
 template <int N>
 static double run(int iters, int sms)

@@ -73,11 +73,13 @@ def load_library():
         "gpss_get_phase_ms": (I, [H, P]),
         "gpss_get_last_call_ms": (I, [H, P]),
         "gpss_measure_fp64_peak": (I, [I, P]),
+        "gpss_measure_int8_peak": (I, [I, P, P]),
         "gpss_get_launch_count": (I, [H, ctypes.POINTER(L)]),
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki_fallbacks": (I, [H, ctypes.POINTER(L)]),
+        "gpss_get_ozaki_bits": (I, [H, ctypes.POINTER(I)]),
         "gpss_test_gemm_nt": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_oz_gemm": (I, [I, I, I, I, I, P, P, P, I, P]),
         "gpss_test_potrf": (I, [I, I, P, P, P]),
@@ -233,6 +235,11 @@ class GpssModel:
         _check(self._lib.gpss_get_ozaki(self._h, ctypes.byref(v)))
         return v.value
 
+    def ozaki_digit_bits(self):
+        v = ctypes.c_int(0)
+        _check(self._lib.gpss_get_ozaki_bits(self._h, ctypes.byref(v)))
+        return v.value
+
     def ozaki_fallbacks(self):
         """Evaluations repeated on the DMMA pipe because an int8 operand left its a-priori bound (device flag)."""
         v = ctypes.c_long(0)
@@ -285,6 +292,13 @@ def measure_fp64_peak(device=0):
     v = ctypes.c_double(0.0)
     _check(load_library().gpss_measure_fp64_peak(device, ctypes.byref(v)))
     return v.value
+
+
+def measure_int8_peak(device=0):
+    """(burst, sustained) int8 tensor-pipe micro-peak in TOP/s (tcgen05 kind::i8, M 128 N 256 K 32, operands resident in shared memory)."""
+    b, s = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    _check(load_library().gpss_measure_int8_peak(device, ctypes.byref(b), ctypes.byref(s)))
+    return b.value, s.value
 
 
 def compute_K(theta, X1, X2, want_K=True, want_D2=True, device=0):

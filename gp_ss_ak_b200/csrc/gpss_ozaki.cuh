@@ -249,8 +249,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int bits = g.digit_bits ? g.digit_bits : DIGIT_BITS;
     const double w = ldexp(1.0, -bits);
     const double scale = g.sign * ldexp(1.0, oz_exponent(g.a_kind, g.dP, bits) + oz_exponent(g.b_kind, g.dP, bits) - 2 * (bits - 1));
+    // C is read-modify-written in place: the 8 loads of a column group are issued together, BEFORE the TMEM read-back and the Horner
+    // sums, and the next group's loads before this group's stores (one round trip to L2 / HBM per group instead of one per column --
+    // the first version's 64 dependent load -> FMA -> store chains cost ~30 us per tile, profiles/r02_oz_gemm_variants.txt)
+    double* const crow = g.C + row + (size_t)(tile_n * BN) * g.ldc;
+    double cin[8], cnx[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) cnx[c] = g.accumulate ? __ldcg(crow + (size_t)c * g.ldc) : 0.0;
     for (int c0 = 0; c0 < BN; c0 += 8) {
       uint32_t v[S][8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) cin[c] = cnx[c];
+      if (g.accumulate && c0 + 8 < BN) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) cnx[c] = __ldcg(crow + (size_t)(c0 + 8 + c) * g.ldc);
+      }
       if (nk > 0) {
 #pragma unroll
         for (int gi = 0; gi < S; gi++) tmem_ld8(lane_base + (uint32_t)(gi * BN + c0), v[gi]);
@@ -267,14 +280,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 8; c++) g.dbg[((size_t)gi * g.m + row) * g.n + tile_n * BN + c0 + c] = (int32_t)v[gi][c];
       }
+      double outv[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         double acc = 0.0;
 #pragma unroll
         for (int gi = S - 1; gi >= 0; gi--) acc = acc * w + (double)(int32_t)v[gi][c];     // sum_g 2^(-7g) G_g, smallest first
-        double* cp = g.C + row + (size_t)(tile_n * BN + c0 + c) * g.ldc;
-        *cp = g.accumulate ? (*cp + scale * acc) : (scale * acc);
+        outv[c] = g.accumulate ? (cin[c] + scale * acc) : (scale * acc);
       }
+#pragma unroll
+      for (int c = 0; c < 8; c++) crow[(size_t)(c0 + c) * g.ldc] = outv[c];
     }
     tc_fence_before();
   }
@@ -282,6 +297,55 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"((uint32_t)T::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ int8 tensor-pipe micro-peak (roofline denominator)
+// tcgen05.mma kind::i8 (M 128, K 32, N = 64 | 128 | 256) issued back to back from operands that stay in shared memory -- no TMA, no
+// epilogue -- one CTA per SM: what the pipe delivers for the instruction shapes oz_gemm_kernel uses (bench_micro/int8_peak.cu prints
+// the table, gpss_measure_int8_peak times the N = 256 shape for bench.py; MEASURED_PEAKS.json has no int8 entry).
+// shared memory: A tile 128 rows x 64 B (SWIZZLE_64B layout, 8 KB) + B tile 256 rows x 64 B (16 KB), filled with pseudo-random bytes
+// (all-zero operands would flatter the clocks: tensor power is data dependent)
+template <int N>
+__global__ void __launch_bounds__(128, 1) int8_peak_kernel(int iters, unsigned long long* cycles)
+{
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 24 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  unsigned s = 1234567u + blockIdx.x * 7919u + threadIdx.x;
+  for (int i = threadIdx.x; i < 24 * 1024; i += blockDim.x) { s = s * 1664525u + 1013904223u; smem[i] = (uint8_t)((int)((s >> 16) % 129u) - 64); }
+  if (threadIdx.x == 0) { gpss::mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(gpss::smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic-proxy writes of the operands -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t sa = gpss::smem_u32(smem), sb = sa + 8 * 1024;
+    const long long t0 = clock64();
+    constexpr int ACC = 512 / N;                  // independent accumulators of N columns (N = 192: 2)
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int q = 0; q < ACC; q++) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++)
+          mma_i8(tmem + (uint32_t)(q * N), smem_desc_k<64>(sa + ks * 32), smem_desc_k<64>(sb + ks * 32), idesc_i8(N), it > 0 || ks > 0);
+      }
+    }
+    tc_commit(bar);
+    gpss::mbar_wait(bar, 0);
+    if (blockIdx.x == 0) *cycles = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
   }
 }
 

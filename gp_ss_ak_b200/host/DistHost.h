@@ -17,6 +17,9 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <ctime>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace gpss_host {
@@ -53,26 +56,45 @@ inline std::string id_file(int seq)
   name += job ? std::string(job) : std::to_string((long)getppid());
   return name + "_" + std::to_string(seq);
 }
+// A job that died between publish_id and rank 0's remove leaves its file behind, and the key repeats (MASTER_PORT is constant
+// under torchrun, pids are recycled).  So: (1) rank 0 removes any leftover of its key at start-up (clear_stale_ids, called before
+// anything is published) and creates the file with O_EXCL under a temporary name before renaming it in; (2) readers accept only a
+// file written after their own process started (minus the launch skew between ranks) -- a leftover is older than that.
+inline time_t process_start() { static const time_t t0 = std::time(nullptr); return t0; }
+inline void clear_stale_ids()
+{
+  process_start();
+  if (world() <= 1 || rank() != 0) return;
+  for (int seq = 0; seq < 8; seq++) { std::remove(id_file(seq).c_str()); std::remove((id_file(seq) + ".tmp").c_str()); }
+}
 inline bool publish_id(const std::string& path, const unsigned char id[128])
 {
   const std::string tmp = path + ".tmp";
-  FILE* f = std::fopen(tmp.c_str(), "wb");
-  if (!f) return false;
-  const bool ok = std::fwrite(id, 1, 128, f) == 128;
-  std::fclose(f);
+  std::remove(tmp.c_str());
+  std::remove(path.c_str());
+  const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+  if (fd < 0) return false;
+  const bool ok = ::write(fd, id, 128) == 128;
+  ::close(fd);
   return ok && std::rename(tmp.c_str(), path.c_str()) == 0;
 }
-inline bool fetch_id(const std::string& path, unsigned char id[128], int timeout_s = 300)
+inline bool fetch_id(const std::string& path, unsigned char id[128], int timeout_s = 300, int launch_skew_s = 30)
 {
+  const time_t oldest = process_start() - launch_skew_s;
   for (int waited_ms = 0; waited_ms < timeout_s * 1000; waited_ms += 20) {
-    FILE* f = std::fopen(path.c_str(), "rb");
-    if (f) {
-      const size_t got = std::fread(id, 1, 128, f);
-      std::fclose(f);
-      if (got == 128) return true;
+    struct stat sb;
+    if (::stat(path.c_str(), &sb) == 0 && sb.st_mtime >= oldest) {
+      FILE* f = std::fopen(path.c_str(), "rb");
+      if (f) {
+        const size_t got = std::fread(id, 1, 128, f);
+        std::fclose(f);
+        if (got == 128) return true;
+      }
     }
     usleep(20000);
   }
+  std::fprintf(stderr, "gp_ss_ak: rank %d timed out after %d s waiting for the NCCL id file %s (is rank 0 running? a file older than this "
+               "process is ignored as a leftover)\n", rank(), timeout_s, path.c_str());
   return false;
 }
 

@@ -25,6 +25,7 @@ using std::string;
 int main(int argc, char* argv[])
 {
   gpss_host::silence_other_ranks();      // multi-GPU launch: rank 0 alone prints and writes files (DistHost.h)
+  gpss_host::clear_stale_ids();          // rank 0: remove rendezvous files a crashed earlier job with the same key left behind
   GP_Cntrl cmd(argc, argv);
   cmd.setFlgs(true);
   cmd.setprepM(1);          // 0: mean/std, 1: symmetric, 2: "0..1"

@@ -142,6 +142,10 @@ int gpss_get_phase_ms(gpss_handle h, double ms[16]);
 int gpss_get_last_call_ms(gpss_handle h, double* ms);
 /* FP64 tensor-pipe (DMMA.8x8x4) micro-peak in TFLOP/s, measured live: the roofline denominator. */
 int gpss_measure_fp64_peak(int device, double* tflops);
+/* int8 tensor-pipe micro-peak in TOP/s, measured live: tcgen05.mma kind::i8 (M 128, N 256, K 32) from operands resident in
+ * shared memory on every SM -- burst (best ~6 ms launch) and sustained (~1 s back to back, under the power cap).  The roofline
+ * denominator of oz_gemm_kernel (MEASURED_PEAKS.json carries no int8 figure). */
+int gpss_measure_int8_peak(int device, double* tops_burst, double* tops_sustained);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int gpss_get_launch_count(gpss_handle h, long* launches);
 /* Raw device pointer to the n_pad x n_pad factor / inverse and the padded size (tests only). */
@@ -156,6 +160,8 @@ int gpss_padded_n(gpss_handle h, int* n_pad);
  * device flags it and the evaluation is repeated on the DMMA pipe: gpss_get_ozaki_fallbacks counts those repeats. */
 int gpss_get_ozaki(gpss_handle h, int* slices);
 int gpss_get_ozaki_fallbacks(gpss_handle h, long* count);
+/* Width of the signed digits the int8 pipe cuts operands into: 7 (base 128, digits in [-64, 64]) or 8 (base 256, [-128, 127]). */
+int gpss_get_ozaki_bits(gpss_handle h, int* bits);
 
 /* kernel-level test hooks (tests/ only) ------------------------------------------------------------ */
 /* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised

@@ -22,10 +22,10 @@ base = np.array([np.pi / 3.1, 1.5, np.pi / 3.1, 1.5, np.pi / 3.1, 1.3, 0.9, 0.6,
 
 
 def model(Xs, ys, s):
-    if s:
-        os.environ["GPSS_OZAKI"] = str(s)
+    if s >= 0:
+        os.environ["GPSS_OZAKI"] = str(s)             # 0: the FP64 DMMA pipe, 6 | 7 | 8: that many int8 slices
     else:
-        os.environ.pop("GPSS_OZAKI", None)
+        os.environ.pop("GPSS_OZAKI", None)            # -1: the library's own size rule
     m = G.GpssModel(Xs, ys)
     os.environ.pop("GPSS_OZAKI", None)
     return m
@@ -82,11 +82,13 @@ for n in tim_sizes:
         ms = m.last_call_ms()
         m.set_theta(base * 1.01)
         L, g = m.nlml_grad()
+        a = m.alpha()
         if ref is None:
-            ref = (L, g)
+            ref = (L, g, a)
         f3 = float(npad) ** 3 / 3
-        print("time n %d S %d: nlml %.9f (rel to first %.1e, g %.1e) | eval %.1f ms = %.1f FP64-eq TFLOP/s | potrf %.1f (%.1f) trtri %.1f (%.1f) lauum %.1f (%.1f) "
-              "kbuild %.1f solve %.1f grad %.1f" % (n, s, L, abs(L - ref[0]) / abs(ref[0]), np.abs(g - ref[1]).max() / np.abs(ref[1]).max(), ms,
+        print("time n %d S %d bits %s: nlml %.9f (rel to first %.1e, g/max|g| %.1e, alpha %.1e) | eval %.1f ms = %.1f FP64-eq TFLOP/s | potrf %.1f (%.1f) trtri %.1f (%.1f) lauum %.1f (%.1f) "
+              "kbuild %.1f solve %.1f grad %.1f" % (n, s, os.environ.get("GPSS_OZAKI_BITS", "7"), L, abs(L - ref[0]) / abs(ref[0]), np.abs(g - ref[1]).max() / np.abs(ref[1]).max(),
+                                                   np.linalg.norm(a - ref[2]) / np.linalg.norm(ref[2]), ms,
                                                    3 * f3 / ms * 1e-9, ph[1], f3 / ph[1] * 1e-9, ph[3], f3 / ph[3] * 1e-9, ph[4], f3 / ph[4] * 1e-9,
                                                    ph[0], ph[2], ph[5]), flush=True)
         m.close()

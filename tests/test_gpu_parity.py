@@ -411,8 +411,6 @@ def test_int8_tensor_core_path_parity_with_oracle(gpss, monkeypatch, slices, n, 
     m.close()
 
 
-@pytest.mark.skipif(os.environ.get("GPSS_TEST_ROUND2") is None,
-                    reason="gpss_test_oz_gemm was written after the round's last GPU second; first run scheduled for round 2 (GPSS_TEST_ROUND2=1)")
 @pytest.mark.parametrize("slices", [7, 8])
 def test_int8_gemm_bit_exact_against_numpy_restatement(gpss, slices):
     """Integer work is exact, the FP64 recombination has a fixed order: the kernel must equal oracle/ozaki_oracle.py bit for bit."""
@@ -429,3 +427,134 @@ def test_int8_gemm_bit_exact_against_numpy_restatement(gpss, slices):
     assert np.array_equal(C, Z.oz_gemm_nt(A, B, slices, e, e, bits=bits))
     C, _ = gpss.test_oz_gemm(A, B, C=C0, slices=slices)
     assert np.array_equal(C, Z.oz_gemm_nt(A, B, slices, e, e, C=C0, sign=-1.0, bits=bits))
+
+
+def test_int8_gemm_exact_at_the_int32_bound(gpss):
+    """The admitted maximum of the default pipe: k = 57 344 (n_pad <= 57 344), S = 8, every digit at its extreme.  The largest value
+    the slicer can emit below the clamp has digits [63, 64, ..., 64]; with all k products of one sign group 7 reaches
+    (6 x 64^2 + 2 x 63 x 64) x 57 344 = 1.87e9 < 2^31.  The kernel must still equal the integer restatement bit for bit -- an int32
+    wrap-around or a saturating accumulator would show here and nowhere else."""
+    from oracle import ozaki_oracle as Z
+    S, K = 8, 57344
+    v = 63 * 128 ** 7 + 64 * (128 ** 7 - 1) // 127
+    x = float(v) * 2.0 ** -55
+    assert int(x * 2.0 ** 55) == v                                  # exactly representable
+    d = Z.oz_digits(np.array([[x, -x]]), 0, S)[:, 0, :]
+    # digits live in [-64, 63] below the top one: -x is [-63, -64, ..., -64] (the extreme), +x is [64, -63, ..., -63, -64]
+    assert d[:, 1].tolist() == [-63] + [-64] * 7 and d[0, 0] == 64
+    A = np.full((128, K), -x)
+    B = np.full((64, K), -x)                                        # even columns of C: every product of group 7 at +64^2 / +63 x 64
+    B[1::2] = x                                                     # odd columns: the mixed-sign digit pattern
+    B[2, ::2] = x                                                   # one column whose accumulators swing up and down along k
+    G = Z.oz_groups(Z.oz_digits(A[:1], 0, S), Z.oz_digits(B[:2], 0, S))
+    assert int(G[7][0, 0]) == (6 * 4096 + 2 * 63 * 64) * K and int(G[7][0, 0]) > 0.87 * 2 ** 31
+    C, _ = gpss.test_oz_gemm(A, B, slices=S)
+    ref = Z.oz_gemm_nt(A, B, S, 0, 0)
+    assert np.array_equal(C, ref)
+    assert C[0, 0] == -C[0, 1]
+    assert abs(C[0, 0] - K * x * x) <= 1e-15 * K                    # and it is the FP64 product to rounding
+
+
+@pytest.mark.parametrize("n,seed", [(10000, 3)])
+def test_default_pipe_above_8192_against_oracle_and_dmma(gpss, monkeypatch, n, seed):
+    """No environment override: n_pad > 8192 selects the int8 tensor-core pipe (gpss_create's size rule).  nlml / alpha against the
+    oracle's direct solve (GP_Utils.cpp:881-915: the fixed point of the IRLS loop), g / mu / var against the FP64 DMMA handle of the
+    same library (GPSS_OZAKI=0), whose parity with the oracle and the compiled reference the tests above establish.
+    Covers the size rule, plane allocation, int32 accumulation over ~20 block columns and the triangular k-ranges over many chunks."""
+    monkeypatch.delenv("GPSS_OZAKI", raising=False)
+    X, y = datagen.drillholes(n, seed)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt_raw, _ = datagen.drillholes(200, seed + 100)
+    Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
+    th = O.THETA0.copy()
+    m = gpss.GpssModel(Xs, ys)
+    assert m.padded_n() > 8192 and m.ozaki_slices() == 8
+    m.set_theta(th)
+    L, g = m.nlml_grad()
+    a = m.alpha()
+    mu, var = m.predict(Xt)
+    assert m.ozaki_fallbacks() == 0
+    m.close()
+    Lo, ao = O.nlml_direct(Xs, ys, th)
+    assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+    assert np.linalg.norm(a - ao) <= TOL_ALPHA * np.linalg.norm(ao)
+    monkeypatch.setenv("GPSS_OZAKI", "0")
+    m = gpss.GpssModel(Xs, ys)
+    assert m.ozaki_slices() == 0
+    m.set_theta(th)
+    L0, g0 = m.nlml_grad()
+    a0 = m.alpha()
+    mu0, var0 = m.predict(Xt)
+    m.close()
+    assert abs(L0 - Lo) <= TOL_NLML * abs(Lo)
+    assert np.abs(g - g0).max() <= TOL_G * np.abs(g0).max()
+    assert np.linalg.norm(a - a0) <= TOL_ALPHA * np.linalg.norm(a0)
+    assert np.abs(mu - mu0).max() <= TOL_MU and np.abs(var - var0).max() <= TOL_VAR
+
+
+def test_config2_n20000_default_pipe_against_dmma(gpss, monkeypatch):
+    """BASELINE configs[1] (n = 20 000, one B200): the default (int8) handle against the FP64 DMMA handle on every output --
+    nlml, all 10 gradient entries, alpha, predictive mean / variance -- at the tolerances of the header."""
+    monkeypatch.delenv("GPSS_OZAKI", raising=False)
+    n = 20000
+    X, y = datagen.drillholes(n, 1)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt_raw, _ = datagen.drillholes(300, 77)
+    Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
+    out = []
+    for env in (None, "0"):
+        if env is not None:
+            monkeypatch.setenv("GPSS_OZAKI", env)
+        m = gpss.GpssModel(Xs, ys)
+        assert m.ozaki_slices() == (8 if env is None else 0)
+        res = []
+        for th in (O.THETA0, O.THETA0 * np.array([1.05, 0.9, 0.97, 1.1, 1.02, 0.85, 1.1, 1.0, 0.7, 1.3])):
+            m.set_theta(th)
+            L, g = m.nlml_grad()
+            res.append((L, g, m.alpha(), *m.predict(Xt)))
+        assert m.ozaki_fallbacks() == 0
+        m.close()
+        out.append(res)
+    for (L, g, a, mu, var), (L0, g0, a0, mu0, var0) in zip(*out):
+        assert abs(L - L0) <= TOL_NLML * abs(L0)
+        assert np.abs(g - g0).max() <= TOL_G * np.abs(g0).max()
+        assert np.linalg.norm(a - a0) <= TOL_ALPHA * np.linalg.norm(a0)
+        assert np.abs(mu - mu0).max() <= TOL_MU and np.abs(var - var0).max() <= TOL_VAR
+
+
+@pytest.mark.parametrize("trust_theta", [False, True])
+def test_int8_path_leaves_thetas_without_its_operand_bound_to_dmma(gpss, monkeypatch, trust_theta):
+    """The int8 scaling assumes |L^-1_ij| <= 1, i.e. B = I + K / sn2 >= I, which holds for a PSD K only; the reference constrains
+    nothing (Kern_Bias adds Sigma_Bias raw, Kernel.cpp:362-367).  With Sigma_Bias < 0 the handle must evaluate that theta on the DMMA
+    pipe (host rule in gpss_set_theta; with the rule switched off by the test hook, the device flag raised by oz_slice_kernel and the
+    repeat) -- never return clamped products."""
+    n = 2000
+    X, y = datagen.drillholes(n, 5)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    th = O.THETA0.copy()
+    th[8] = -0.004
+    monkeypatch.setenv("GPSS_OZAKI", "0")
+    m = gpss.GpssModel(Xs, ys)
+    m.set_theta(th)
+    L0, g0 = m.nlml_grad()
+    U0 = m.debug_fetch(1)
+    m.close()
+    assert np.isfinite(L0)
+    monkeypatch.setenv("GPSS_OZAKI", "8")
+    if trust_theta:
+        monkeypatch.setenv("GPSS_OZAKI_TRUST_THETA", "1")
+    m = gpss.GpssModel(Xs, ys)
+    m.set_theta(th)
+    assert m.ozaki_slices() == (8 if trust_theta else 0)
+    L, g = m.nlml_grad()
+    if trust_theta:
+        exceeded = np.abs(U0).max() > 1.0 + 1e-9
+        assert (m.ozaki_fallbacks() > 0) == exceeded       # the flag is raised exactly when an entry of U = L^-T leaves [-1, 1]
+        if exceeded:
+            assert L == L0 and np.array_equal(g, g0)       # repeated on the DMMA pipe
+    else:
+        assert L == L0 and np.array_equal(g, g0) and m.ozaki_fallbacks() == 0
+    assert abs(L - L0) <= TOL_NLML * abs(L0) and np.abs(g - g0).max() <= TOL_G * np.abs(g0).max()
+    m.set_theta(O.THETA0)                                  # the next admissible theta is back on the int8 pipe
+    assert m.ozaki_slices() == 8
+    m.close()

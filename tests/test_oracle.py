@@ -178,3 +178,21 @@ def test_var_postprocess_is_index_arithmetic():
     assert np.allclose(v, [0.0, 0.25])
     with pytest.raises(IndexError):
         O.var_postprocess(np.array([-0.5]), 0.01)
+
+
+def test_lean_baseline_matches_oracle():
+    """oracle/lean_baseline.py (bench.py's `lean` CPU baseline: 1 dpotrf + 1 dpotri) computes the same objective and the same Sigma /
+    Sigma_Bias / sn2 gradient entries as the literal restatement (3 factorisations + 2 triangular solves, GP_Utils.cpp:872-915,1202-1233)."""
+    from oracle import lean_baseline as LB
+    X, y = datagen.drillholes(600, 2)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    L, g, _ = O.nlml_and_grad(Xs, ys, O.THETA0, dist="blas", literal=True)
+    tm = {}
+    Ll, gl = LB.lean_eval(Xs, ys, O.THETA0, tm)
+    assert abs(L - Ll) <= 1e-10 * abs(L)
+    assert np.abs(gl - g[[6, 8, 9]]).max() <= 1e-8 * np.abs(g).max()
+    assert tm["total"] > 0
+    a, b = LB.fit_n2_n3([1000, 2000, 4000], [2e-6 * n * n + 1e-11 * n ** 3 for n in (1000, 2000, 4000)])
+    assert abs(a - 2e-6) < 1e-9 and abs(b - 1e-11) < 1e-14
+    a, b = LB.fit_n2_n3([1000, 2000], [3e-6 * n * n + 1e-11 * n ** 3 for n in (1000, 2000)], b_fixed=1e-11)
+    assert abs(a - 3e-6) < 1e-12 and b == 1e-11
