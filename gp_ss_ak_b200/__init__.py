@@ -77,6 +77,7 @@ def load_library():
         "gpss_get_launch_count": (I, [H, ctypes.POINTER(L)]),
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
+        "gpss_set_white": (I, [H, D, I]),
         "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki_fallbacks": (I, [H, ctypes.POINTER(L)]),
         "gpss_get_ozaki_bits": (I, [H, ctypes.POINTER(I)]),
@@ -234,6 +235,10 @@ class GpssModel:
         v = ctypes.c_int(0)
         _check(self._lib.gpss_get_ozaki(self._h, ctypes.byref(v)))
         return v.value
+
+    def set_white(self, sigma_white, cross_diagonal=False):
+        """Sum of the White members' Sigma_White (Kernel.cpp:180-270); cross_diagonal: see include/gpss.h."""
+        _check(self._lib.gpss_set_white(self._h, float(sigma_white), 1 if cross_diagonal else 0))
 
     def ozaki_digit_bits(self):
         v = ctypes.c_int(0)

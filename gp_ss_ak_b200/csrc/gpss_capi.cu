@@ -18,7 +18,7 @@ __global__ void scale_copy_kernel(double* __restrict__ dst, const double* __rest
 static int upload_params(gpss_ctx* c, int slot, const double* centre)
 {
   DevParams P;
-  fill_params(c->theta, centre, P, c->d, c->kind);
+  fill_params(c->theta, centre, P, c->d, c->kind, c->white);
   CU(cudaMemcpyAsync(c->dP + slot, &P, sizeof P, cudaMemcpyHostToDevice, c->st));
   CU(cudaStreamSynchronize(c->st));   // P is a stack object
   return GPSS_OK;
@@ -404,7 +404,7 @@ int gpss_set_theta(gpss_handle c, const double theta[GPSS_NPAR])
   // the int8 path scales U = L^-T and W = L^-1 by the a-priori bound |L^-1_ij| <= 1, which needs B = I + K / sn2 >= I: every kernel
   // of the path is positive semi-definite for any widths / angles, the bias term only for Sigma_Bias >= 0 (Kern_Bias uses it raw,
   // Kernel.cpp:362-367, and no optimiser constrains it).  Outside that region this theta is evaluated on the DMMA path.
-  c->oz_blocked = (theta[8] < 0.0 || !(theta[9] > 0.0)) && !getenv("GPSS_OZAKI_TRUST_THETA");   // (test hook: leave it to the device flag)
+  c->oz_blocked = (theta_bias(c->kind, theta) + (c->white < 0.0 ? c->white : 0.0) < 0.0 || !(theta_sn2(c->kind, theta) > 0.0)) && !getenv("GPSS_OZAKI_TRUST_THETA");   // (test hook: leave it to the device flag)
   return GPSS_OK;
 }
 
@@ -415,6 +415,21 @@ int gpss_set_kernel(gpss_handle c, int kind)
   c->kind = kind;
   c->have_factor = c->have_alpha = c->have_U = false;
   c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+// White members of the Hyb covariance (Kern_White, Kernel.cpp:180-270): K_ii += sigma_white for the training covariance and the prior
+// variance; its gradient entry is 0 (getGradParam, Kernel.cpp:266-270), so the host never asks the device for it.
+int gpss_set_white(gpss_handle c, double sigma_white, int cross_diagonal)
+{
+  if (!c) return fail_arg("gpss_set_white: null");
+  if (c->partitioned && sigma_white != 0.0) return fail_arg("gpss_set_white: not supported on partitioned handles");
+  if (c->white != sigma_white) {
+    c->white = sigma_white;
+    c->have_factor = c->have_alpha = c->have_U = false;
+    c->qstate = Q_NONE;
+  }
+  c->white_cross = cross_diagonal != 0;
   return GPSS_OK;
 }
 
@@ -662,7 +677,8 @@ static int ensure_W(gpss_ctx* c)
 }
 
 // mean and RAW variance (kD - k*' A k*, no post-processing) of one shard
-static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, long count, const double* Xs, long ldx, double* mu, double* var)
+static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, long count, const double* Xs, long ldx, double* mu, double* var,
+                        long shard_off = 0)
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
@@ -695,7 +711,8 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
   transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
   c->launches++;
   const double sig_k = theta_sigma(c->kind, c->theta);
-  const double kD = sig_k * sig_k + theta_bias(c->kind, c->theta);   // diag_Compute (Kernel.cpp:782, 449, 594, 331, 127-136)
+  const double kD = sig_k * sig_k + theta_bias(c->kind, c->theta) + c->white;   // diag_Compute (Kernel.cpp:782, 449, 594, 331, 222-225, 127-136)
+  const double white_x = (c->white_cross && m_total == c->n) ? c->white : 0.0;   // Kern_White::computeK on (X_train, X_test), Kernel.cpp:257-264
   for (long off = 0; off < count; off += cap) {
     const int mb = (int)((count - off < cap) ? (count - off) : cap);
     const int m_pad = ((mb + NB - 1) / NB) * NB;
@@ -706,7 +723,7 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
     {
       PhaseTimer t(c, 6);
       cross_build_kernel<<<dim3(m_pad / NB, c->nblk), 256, 0, c->st>>>(c->Bm, m_pad, c->zt, cap, c->zsp, n_pad, c->alpha, mb, c->n,
-                                                                    c->dP + 1, c->mu_part, cap, var ? 1 : 0);
+                                                                    c->dP + 1, c->mu_part, cap, var ? 1 : 0, white_x, shard_off + off);
       mean_finish_kernel<<<(mb + 255) / 256, 256, 0, c->st>>>(c->mu_part, cap, c->nblk, mb, c->dmu);
       c->launches += 3;
       CU(cudaGetLastError());
@@ -799,7 +816,7 @@ int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* va
     // are exchanged with one ncclBroadcast per rank and output vector, so every rank returns the full vectors.
     const long P = c->world;
     const long lo = m * c->rank / P, hi = m * (c->rank + 1) / P;
-    RET(predict_core(c, m, sums, hi - lo, Xs + lo, m, mu + lo, var ? var + lo : nullptr));
+    RET(predict_core(c, m, sums, hi - lo, Xs + lo, m, mu + lo, var ? var + lo : nullptr, lo));
     const int nvec = var ? 2 : 1;
     RET(ensure_stage(c, (size_t)nvec * m));
     if (hi > lo) {

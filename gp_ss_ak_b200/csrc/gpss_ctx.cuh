@@ -140,6 +140,8 @@ struct gpss_ctx {
   int8_t *ozW = nullptr, *ozB = nullptr;
   CUtensorMap oz_tmW[2], oz_tmB[2];
   // host state
+  double white = 0.0;                                          // sum of the White members' Sigma_White (gpss_set_white); 0 without one
+  int white_cross = 0;                                         // the next gpss_predict adds it on the cross-covariance diagonal (Kernel.cpp:261-262)
   double theta[GPSS_NPAR];
   double sums_train[4];
   bool have_factor = false, have_alpha = false, have_U = false;
@@ -322,7 +324,7 @@ struct PhaseTimer {
 // ---------------------------------------------------------------------------------------------------
 // parameters -> device
 // ---------------------------------------------------------------------------------------------------
-static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0)
+static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0, double white = 0.0)
 {
   memset(&P, 0, sizeof P);
   for (int j = 0; j < dim; j++) P.c[j] = centre[j];
@@ -341,6 +343,7 @@ static void fill_params(const double theta[GPSS_NPAR], const double* centre, Dev
   const double sig = theta_sigma(kind, theta), sn2 = theta_sn2(kind, theta);
   P.var2 = sig * sig;
   P.bias = theta_bias(kind, theta);
+  P.white = white;
   P.sn2 = sn2;
   P.inv_sn2 = 1 / sn2;
   P.sw = std::sqrt(P.inv_sn2);

@@ -30,6 +30,7 @@ struct DevParams {
   double rbf_c;       // -0.5 * inverseWidth_RBF (Kernel.cpp:486)
   double var2;        // Sigma_ExpAns^2 (Kernel.cpp:861)
   double bias;        // Sigma_Bias (Kernel.cpp:366)
+  double white;       // Sigma_White, summed over the White members: added to K_ii of the training covariance only (Kernel.cpp:257-264)
   double sn2;         // hyperlf(0) (GP_Utils.cpp:406)
   double inv_sn2;     // 1/sn2 = d2lp (GP_Utils.cpp:412-413)
   double sw;          // Sw = sqrt(d2lp) (GP_Utils.cpp:897)
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
       if (i < n && j < n) {
         const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
         v = kern_val(d2, P);
+        if (i == j) v = __dadd_rn(v, P.white);                 // Kern_White: K.diag() += Sigma_White (0 without a White member: v unchanged)
         if (!raw_K) {
           v = __dmul_rn(P.sww, v);
           if (i == j) v = __dadd_rn(v, 1.0);
@@ -555,7 +557,11 @@ __global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__
   }
   part[pp][rr] = acc;
   __syncthreads();
-  if (pp == 0 && vi) f[i] = (part[0][rr] + part[1][rr]) + (part[2][rr] + part[3][rr]);
+  if (pp == 0 && vi) {
+    double fi = (part[0][rr] + part[1][rr]) + (part[2][rr] + part[3][rr]);
+    if (P.white != 0.0) fi = fma(P.white, alpha[i], fi);        // the White members' diagonal
+    f[i] = fi;
+  }
 }
 
 // block-wide sum of NV values per thread -> out[blockIdx][NV]; 256 threads
@@ -682,7 +688,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
           g6 += mult * a;
           rk += mult * b;
           if (i == j) tr += QWij;
-          qk += mult * (qe[e] * kern_val(d2, P));
+          qk += mult * (qe[e] * ((i == j) ? __dadd_rn(kern_val(d2, P), P.white) : kern_val(d2, P)));
           continue;
         }
         const double s = sqrt(d2);
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
         if (i == j) {
           g6 += QWij * es;
           tr += QWij;
-          qk += qe[e] * Kij;
+          qk += qe[e] * __dadd_rn(Kij, P.white);
         } else {
           g6 += 2.0 * (QWij * es);
           qk += 2.0 * (qe[e] * Kij);
@@ -847,8 +853,10 @@ __global__ void zero_region_kernel(double* __restrict__ p, long ld, int rows, in
 __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ Bm, long ldb, const double* __restrict__ zt, long ldzt,
                                                           const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
                                                           int m, int n, const DevParams* __restrict__ Pp,
-                                                          double* __restrict__ mu_part, long ldmu, int write_B)
+                                                          double* __restrict__ mu_part, long ldmu, int write_B, double white_x, long goff)
 {
+  // white_x != 0: Kern_White::computeK's condition held for the whole call (X1(0) == X2(0) and equally many rows, Kernel.cpp:261-262),
+  // so element (i, i) of the n x m cross-covariance carries Sigma_White; goff = global test index of this batch's column 0.
   __shared__ double cz[NZ][NB], ca[NB];
   __shared__ double mred[4][NB];
   __shared__ DevParams P;
@@ -880,7 +888,8 @@ __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ B
       if (i < n && (j0 + e) < m) {
         // K(X_train, X_test)(i,j): first argument is the training point (GP_Utils.cpp:946-947)
         const double d2 = pair_d2(cz[0][ii], cz[1][ii], cz[2][ii], cz[3][ii], zj[e][0], zj[e][1], zj[e][2], zj[e][3], cz[4][ii], zj[e][4]);
-        const double k = kern_val(d2, P);
+        double k = kern_val(d2, P);
+        if (white_x != 0.0 && (long)i == goff + j0 + e) k = __dadd_rn(k, white_x);
         mu[e] = fma(ca[ii], k, mu[e]);
         v = __dmul_rn(k, P.sw);
       }

@@ -89,8 +89,8 @@ __device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P, i
 {
   if (bits != 8 && (kind == SCALE_UNIT || P == nullptr)) return 0;
   double bound = 1.0;
-  if (kind == SCALE_CROSS && P) bound = P->sw * (P->var2 + P->bias);
-  else if (kind == SCALE_CHOL && P) bound = sqrt(1.0 + P->sww * (P->var2 + P->bias));
+  if (kind == SCALE_CROSS && P) bound = P->sw * (P->var2 + P->bias + P->white);
+  else if (kind == SCALE_CHOL && P) bound = sqrt(1.0 + P->sww * (P->var2 + P->bias + P->white));
   if (bits == 8) bound *= 128.0 / 127.5;
   int e;
   frexp(bound, &e);                                           // bound = f 2^e, f in [0.5, 1)
@@ -162,6 +162,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   int ke = g.k1;
   if (g.kend_row) { const int kr = g.a_row0 + tile_m * BM + BM; if (kr < ke) ke = kr; }
   const int nk = ke > kb ? (ke - kb) / BKB : 0;
+  if (nk == 0 && g.accumulate) return;                                                      // nothing to add (k-segment launches of 8-bit digits)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T::STAGES; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }

@@ -151,7 +151,9 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
     // (distributed: only the long chunks -- a single received panel, k = NBO, stays on DMMA)
-    if (ozk && stream != c->st && (P == 1 || klen >= 4 * NBO)) {
+    // GPSS_OZ_U2=1 (single GPU): U2 (k = NBO, main stream) on the int8 kernel as well -- panel t-1 was cut into planes right after it was factored
+    static const bool oz_u2 = getenv("GPSS_OZ_U2") != nullptr && atoi(getenv("GPSS_OZ_U2")) != 0;
+    if (ozk && (stream != c->st || (oz_u2 && P == 1)) && (P == 1 || klen >= 4 * NBO)) {
       oz::Args a;
       memset(&a, 0, sizeof a);
       a.C = A + (long)T0 * ld + T0; a.ldc = ld; a.m = n_pad - T0; a.n = nbT;

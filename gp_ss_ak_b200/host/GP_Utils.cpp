@@ -54,6 +54,7 @@ void GP_utils::_init()
   handle = 0;
   handle_n = -1;
   kind_dev = -1;
+  white_cross = 0;
   data_stale = true;
   dirty = true;
   Chol_fail = false;
@@ -131,14 +132,41 @@ void GP_utils::device_failure(const char* what) const
   exit(1);
 }
 
+// Members of the Hyb covariance as the device sees them: at most one distance-based member (the "main" kernel of the C ABI),
+// any number of Bias members (their parameters add up in the Sigma_Bias slot) and of White members (gpss_set_white).
+struct MemberMap {
+  int main_member;          // index of the ExpAns | Exp | RBF member, -1 if none
+  int main_first;           // its first parameter in the concatenated vector
+  int kind;                 // GPSS_KERNEL_* of it (ExpAns with Sigma = 0 stands in when there is none)
+  bool ok;                  // false: something this build does not evaluate (two distance members, an unknown member)
+};
+static MemberMap map_members(const Kernels* K)
+{
+  MemberMap m = {-1, 0, GPSS_KERNEL_EXPANS, true};
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(K);
+  if (!hyb || K->getKerName() != "Hyb" || hyb->getNumKerns() < 1) { m.ok = false; return m; }
+  int first = 0;
+  for (unsigned int i = 0; i < hyb->getNumKerns(); i++) {
+    const string name = hyb->getKern(i)->getKerName();
+    const int kind = name == "ExpAns" ? GPSS_KERNEL_EXPANS : name == "Exp" ? GPSS_KERNEL_EXP : name == "RBF" ? GPSS_KERNEL_RBF : -1;
+    if (kind >= 0) {
+      if (m.main_member >= 0) m.ok = false;                  // a sum of two distance-based kernels
+      m.main_member = (int)i; m.main_first = first; m.kind = kind;
+    } else if (name != "Bias" && name != "White Noise") {
+      m.ok = false;
+    }
+    first += (int)hyb->getKern(i)->getNPars();
+  }
+  return m;
+}
+
 void GP_utils::check_supported() const
 {
   const char* why = 0;
-  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
   if (!KerenlW) why = "no kernel";
-  else if (!hyb || KerenlW->getKerName() != "Hyb" || hyb->getNumKerns() < 1 || hyb->getNumKerns() > 2 || kernel_kind() < 0 ||
-           (hyb->getNumKerns() == 2 && hyb->getKern(1)->getKerName() != "Bias"))
-    why = "the kernel must be Hyb{ExpAns | Exp | RBF [, Bias]} (train with -k ExpAns|Exp|RBF and -kn 0|1)";
+  else if (!map_members(KerenlW).ok)
+    why = "the kernel must be Hyb{at most one of ExpAns | Exp | RBF, any number of Bias and White members} (-k ExpAns|Exp|RBF|Bias|White, -kn 0|1); "
+          "a sum of two distance-based kernels is not evaluated by this build";
   else if (Xinp.n_cols != 3 && Xinp.n_cols != 4) why = "inputs must have 3 columns, or 4 with the rock-type column";
   else if (yTarg.n_cols != 1 || getOutDim() != 1) why = "exactly one output column is supported";
   else if (likelihoodType_ != likeL_Gaussian || getNumlikfpar() != 1) why = "only the Gaussian likelihood is supported";
@@ -150,23 +178,44 @@ void GP_utils::check_supported() const
   }
 }
 
-// GPSS_KERNEL_* of the Hyb kernel's first member, -1 if it is none of the three
+// GPSS_KERNEL_* of the Hyb kernel's distance-based member (ExpAns when there is none: it then runs with Sigma = 0), -1 if unsupported
 int GP_utils::kernel_kind() const
 {
-  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
-  if (!hyb || hyb->getNumKerns() < 1) return -1;
-  const string name = hyb->getKern(0)->getKerName();
-  return name == "ExpAns" ? GPSS_KERNEL_EXPANS : name == "Exp" ? GPSS_KERNEL_EXP : name == "RBF" ? GPSS_KERNEL_RBF : -1;
+  const MemberMap m = map_members(KerenlW);
+  return m.ok ? m.kind : -1;
 }
 
-// The C ABI's slot layout (include/gpss.h, gpss_set_kernel): main-kernel parameters, Sigma_Bias (0 without a Bias member), sn2.
+// sum of the White members' Sigma_White
+double GP_utils::white_now() const
+{
+  const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+  double w = 0.0;
+  for (unsigned int i = 0; i < hyb->getNumKerns(); i++)
+    if (hyb->getKern(i)->getKerName() == "White Noise") w += hyb->getKern(i)->getParam(0);
+  return w;
+}
+
+// The C ABI's slot layout (include/gpss.h, gpss_set_kernel): main-kernel parameters, Sigma_Bias (the Bias members' sum; 0 without
+// one), sn2.  Without a distance-based member the ExpAns slots hold the class defaults with Sigma = 0: K = bias (+ white).
 void GP_utils::theta_now(double theta[GPSS_NPAR]) const
 {
   const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
-  const unsigned int nk = hyb->getKern(0)->getNPars();
+  const MemberMap m = map_members(KerenlW);
   for (int i = 0; i < GPSS_NPAR; i++) theta[i] = 0.0;
-  for (unsigned int i = 0; i < nk; i++) theta[i] = KerenlW->getParam(i);
-  theta[nk] = (hyb->getNumKerns() == 2) ? KerenlW->getParam(nk) : 0.0;
+  unsigned int nk;
+  if (m.main_member >= 0) {
+    nk = hyb->getKern(m.main_member)->getNPars();
+    for (unsigned int i = 0; i < nk; i++) theta[i] = KerenlW->getParam(m.main_first + i);
+  } else {
+    Kern_ExpAnisotropic dflt;
+    nk = dflt.getNPars();
+    for (unsigned int i = 0; i < nk; i++) theta[i] = dflt.getParam(i);
+    theta[6] = 0.0;                                          // Sigma_ExpAns
+  }
+  double bias = 0.0;
+  for (unsigned int i = 0; i < hyb->getNumKerns(); i++)
+    if (hyb->getKern(i)->getKerName() == "Bias") bias += hyb->getKern(i)->getParam(0);
+  theta[nk] = bias;
   theta[nk + 1] = hyperlf(0);
 }
 
@@ -210,6 +259,7 @@ void GP_utils::sync_device() const
     kind_dev = kernel_kind();
     dirty = true;
   }
+  if (gpss_set_white(handle, white_now(), white_cross) != GPSS_OK) device_failure("gpss_set_white");   // invalidates only on change
   double theta[GPSS_NPAR];
   theta_now(theta);
   if (dirty || std::memcmp(theta, theta_dev, sizeof theta) != 0) {
@@ -263,11 +313,20 @@ double GP_utils::GradLL(mat& g) const
   if (Chol_fail) return std::numeric_limits<double>::quiet_NaN();       // g is left untouched, as in the reference (:1175-1176)
   L.zeros(1, 1);
   L[0] = nlml;
-  // same packing as GP_Utils.cpp:1243-1260: kernel entries, likelihood entry, mean entries
+  // same packing as GP_Utils.cpp:1243-1260: kernel entries member by member (HybKerns::getGradients, Kernel.cpp:156-169), likelihood
+  // entry, mean entries.  Device slots: main-kernel entries, then trace(QW) (every Bias member's entry), then the sn2 entry.
   const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
-  const unsigned int nk = hyb->getKern(0)->getNPars();
+  const MemberMap mm = map_members(KerenlW);
+  const unsigned int nk = (mm.main_member >= 0) ? hyb->getKern(mm.main_member)->getNPars() : Kern_ExpAnisotropic().getNPars();
   g_param.set_size(1, KerenlW->getNPars());
-  for (unsigned int i = 0; i < KerenlW->getNPars(); i++) g_param(i) = gv[i];      // main kernel entries, then Sigma_Bias if present
+  unsigned int at = 0;
+  for (unsigned int i = 0; i < hyb->getNumKerns(); i++) {
+    const Kernels* k = hyb->getKern(i);
+    if ((int)i == mm.main_member) for (unsigned int q = 0; q < nk; q++) g_param(at + q) = gv[q];
+    else if (k->getKerName() == "Bias") g_param(at) = gv[nk];
+    else g_param(at) = 0.0;                                  // White: getGradParam (Kernel.cpp:265-269); see Kernel.h on the reference's crash
+    at += k->getNPars();
+  }
   g_hyperlf.zeros(1, 1);
   g_hyperlf(0) = gv[nk + 1];                                                      // the slot after Sigma_Bias (include/gpss.h)
   unsigned int c = 0;
@@ -282,6 +341,7 @@ double GP_utils::GradLL(mat& g) const
 void GP_utils::posteriorMeanVar(mat& mu, mat& varSigma, const mat& X) const
 {
   if (X.n_cols != Xinp.n_cols) { cout << "GP_utils: test inputs must have as many columns as the training inputs\n"; exit(1); }
+  white_cross = (X.n_rows == Xinp.n_rows && X(0) == Xinp(0)) ? 1 : 0;        // Kern_White::computeK's test on (X_train, X_test), Kernel.cpp:261-262
   sync_device();
   mu.set_size(X.n_rows, 1);
   varSigma.set_size(X.n_rows, 1);
@@ -297,6 +357,7 @@ void GP_utils::posteriorMeanVar(mat& mu, mat& varSigma, const mat& X) const
 void GP_utils::posteriorMean(mat& mu, const mat& X) const
 {
   if (X.n_cols != Xinp.n_cols) { cout << "GP_utils: test inputs must have as many columns as the training inputs\n"; exit(1); }
+  white_cross = (X.n_rows == Xinp.n_rows && X(0) == Xinp(0)) ? 1 : 0;
   sync_device();
   mu.set_size(X.n_rows, 1);
   const int rc = gpss_predict(handle, (long)X.n_rows, X.memptr(), mu.memptr(), 0);

@@ -215,6 +215,34 @@ void Kern_Bias::getGradients(mat& g, const mat&, const mat&, const mat&, const m
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Kern_White (Kernel.cpp:180-270)
+// ---------------------------------------------------------------------------------------------------
+void Kern_White::_init()
+{
+  nParams = 1;
+  setKerName("White Noise");            // what the model file then carries -- and what ReadKerFromFile does NOT accept (it wants "white")
+  setParamName("Sigma_White", 0);
+  setInitPars();
+}
+void Kern_White::setParam(double val, unsigned int paramNo)
+{
+  if (paramNo != 0) fatal("Requested parameter doesn't exist.");
+  Sigma_White = val;
+}
+double Kern_White::getParam(unsigned int paramNo) const
+{
+  if (paramNo != 0) fatal("Requested parameter doesn't exist.");
+  return Sigma_White;
+}
+void Kern_White::computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const
+{
+  D2.zeros();
+  K.zeros();
+  if (X1(0) == X2(0) && X1.n_rows == X2.n_rows)                                   // Kernel.cpp:261-262
+    for (uword i = 0; i < K.n_rows && i < K.n_cols; i++) K(i, i) = Sigma_White;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Kern_ExpAnisotropic
 // ---------------------------------------------------------------------------------------------------
 void Kern_ExpAnisotropic::_init()
@@ -381,7 +409,7 @@ Kernels* ReadKerFromFile(std::istream& in)
   else if (name == "Hyb") k = new HybKerns();
   else if (name == "Exp") k = new Kern_Exponential();
   else if (name == "RBF") k = new Kern_RBF();
-  else if (name == "white") fatal("The " + name + " kernel is not part of the B200 hot-path build.");
+  else if (name == "white") k = new Kern_White();          // [quirk] the WRITER emits "White Noise" (getKerName), which lands in the branch below
   else fatal("Unknown kernel type ");
   k->FromFile_GP_Params(in);
   return k;

@@ -5,7 +5,8 @@
 // computeK / getGradients are COMPATIBILITY wrappers: they move host matrices through the C ABI
 // (gpss_compute_K / gpss_expans_gradients); GP_utils never uses them on the hot path -- it hands the parameter
 // vector to the device-resident handle instead.
-// Kernels outside the scope table (RBF, Exponential, White) are not provided by this build.
+// Additive members without a distance (Kern_Bias, Kern_White) may appear any number of times next to at most ONE distance-based
+// member (ExpAns | Exp | RBF); sums of two distance-based members are outside this build (GP_utils::check_supported says so).
 #ifndef GPSS_HOST_KERNEL_H
 #define GPSS_HOST_KERNEL_H
 
@@ -139,6 +140,33 @@ class Kern_Bias : public Kernels {
  private:
   void _init();
   double Sigma_Bias;
+};
+
+// white-noise kernel (reference Kernel.cpp:180-270, Kernel.h:256-282): K = Sigma_White on the diagonal, and only when computeK is
+// handed the same point set twice -- the reference tests `X1(0) == X2(0) && X1.n_rows == X2.n_rows` (:261-262).
+// [reference defect, reproduced as far as it can be] Kern_White does not override getGradients, and the base-class default calls
+// ITSELF (Kernel.h:56-59): any optimiser run with a White member overflows the stack (the compiled reference: SIGSEGV right after
+// "Log likelihood" of the initial model).  Objective and prediction work and are matched; for the gradient this build returns what
+// the class's own getGradParam returns, 0 (Kernel.cpp:265-269), so an optimiser leaves Sigma_White where it started.
+class Kern_White : public Kernels {
+ public:
+  Kern_White() : Kernels() { _init(); }
+  explicit Kern_White(unsigned int inDim) : Kernels(inDim) { _init(); setInputDim(inDim); }
+  explicit Kern_White(const mat& X) : Kernels(X) { _init(); setInputDim(X.n_cols); }
+  Kern_White* clone() const { return new Kern_White(*this); }
+
+  void setInitPars() { Sigma_White = 0.10; }                       // Kernel.cpp:217-220
+  double Diag_Kernel(const mat&, unsigned int) const { return Sigma_White; }
+  void diag_Compute(mat& d, const mat&) const { d.fill(Sigma_White); }
+  void setParam(double val, unsigned int paramNo);
+  double getParam(unsigned int paramNo) const;
+  double getGradParam(unsigned int, const mat&, const mat&, const mat&, const mat&) const { return 0.0; }
+  void computeK(const mat& X1, const mat& X2, mat& K, mat& D2) const;
+  void getGradients(mat& g, const mat&, const mat&, const mat&, const mat&) const { g[0] = 0.0; }
+
+ private:
+  void _init();
+  double Sigma_White;
 };
 
 // K_ij = Sigma^2 exp(-sqrt(D2_ij)),  D2 = (x - x')' S^2 (x - x'),  S = Rot(AngleX, AngleY, AngleZ) diag(iWx, iWy, iWz) Rot'

@@ -52,6 +52,13 @@ int gpss_destroy(gpss_handle h);
 int gpss_set_data(gpss_handle h, const double* X_colmajor, const double* y);
 /* GP_utils::set_GP_Pars (GP_Utils.cpp:130-157): stores theta and invalidates the caches; no GPU work. */
 int gpss_set_theta(gpss_handle h, const double theta[GPSS_NPAR]);
+/* Kern_White members of the additive covariance (reference Kernel.cpp:180-270): sigma_white (the sum over the White members) is
+ * added to K_ii of the training covariance (computeK fills the diagonal when both arguments are the training set, :257-264) and to
+ * the prior variance of a test point (Diag_Kernel, :222-225).  cross_diagonal != 0: the reference's condition `X1(0) == X2(0) and
+ * equal row counts` held for (X_train, X_test) of the NEXT gpss_predict, so element (i, i) of that cross-covariance carries it too
+ * (gpss_predict only; gpss_predict_shard callers own the offset bookkeeping and do not get this quirk).  The gradient entry of a
+ * White member is 0 (getGradParam, :266-270).  Invalidates the factorisation when the value changes. */
+int gpss_set_white(gpss_handle h, double sigma_white, int cross_diagonal);
 int gpss_get_theta(gpss_handle h, double theta[GPSS_NPAR]);
 /* The main kernel of the Hyb{main, Bias} covariance -- the reference's `-k` choice (gp_ss_ak.cpp:146-170; HybKerns,
  * Kernel.cpp:140-169).  theta and g keep their 10-slot arrays; the slots in use are

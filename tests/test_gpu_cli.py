@@ -126,9 +126,10 @@ def test_cli_baseline_config0_n2000(tmp_path):
 def test_cli_rejects_configurations_outside_the_hot_path(tmp_path):
     z = np.load(os.path.join(GOLD, "ref_n300.npz"))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
-    out = subprocess.run([CLI, "train", "-k", "White", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
+    # a sum of two distance-based members is the one additive combination this build does not evaluate (GP_utils::check_supported)
+    out = subprocess.run([CLI, "train", "-k", "ExpAns", "-k", "RBF", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
                          stdin=subprocess.DEVNULL, cwd=tmp_path)
-    assert out.returncode == 1 and "not part of the B200 hot-path build" in (out.stdout + out.stderr)
+    assert out.returncode == 1 and "outside the B200 hot path" in (out.stdout + out.stderr) and "no CPU fallback" in (out.stdout + out.stderr)
 
 
 def test_cli_two_gpu_launch_matches_single_gpu(tmp_path):
