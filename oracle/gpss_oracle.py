@@ -344,7 +344,10 @@ def sign_ref(v):
 class OracleGP:
     """State-carrying restatement of GP_utils for Gaussian likelihood, zero mean (GP_Utils.cpp)."""
 
-    def __init__(self, X, y, theta=None, dist="defined", literal=True):
+    def __init__(self, X, y, theta=None, dist="defined", literal=True, white=0.0):
+        # white: sum of the White members' Sigma_White (Kern_White, Kernel.cpp:180-270): K.diag() += white when computeK sees the same
+        # point set twice (`X1(0) == X2(0) && X1.n_rows == X2.n_rows`, :261-262), prior variance += white (:222-225), gradient 0
+        self.white = float(white)
         self.X = np.ascontiguousarray(X, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
         self.n = self.X.shape[0]
@@ -376,6 +379,8 @@ class OracleGP:
     def update_kernel(self):
         if not self.K_ok:
             self.K, self.D2 = compute_K(self.X, self.X, self.theta, self.dist)
+            if self.white != 0.0:
+                self.K[np.diag_indices(self.n)] += self.white
             self.K_ok = True
 
     # -- likelihood terms (GP_Utils.cpp:398-416 and 795-839) --
@@ -612,9 +617,11 @@ class OracleGP:
     def predict(self, Xs):
         Xs = np.ascontiguousarray(Xs, dtype=np.float64)
         kX, _ = compute_K(self.X, Xs, self.theta, self.dist)      # n x m, centre uses BOTH sets (Kernel.cpp:1391)
+        if self.white != 0.0 and Xs.shape[0] == self.n and Xs[0, 0] == self.X[0, 0]:      # Kern_White::computeK(X_train, X_test), Kernel.cpp:261-262
+            kX[np.diag_indices(self.n)] += self.white
         self.update_alpha()
         mu = kX.T @ self.Alpha
-        kD = np.full(Xs.shape[0], sigma_of(self.theta) ** 2 + self.theta[-2])      # diag_Compute (Kernel.cpp:782, 331, 449, 594)
+        kD = np.full(Xs.shape[0], sigma_of(self.theta) ** 2 + self.theta[-2] + self.white)      # diag_Compute (Kernel.cpp:782, 331, 449, 594, 222-225)
         self.log_likelihood()                                         # GP_Utils.cpp:980
         Wh = np.sqrt(self.d2lp)
         LKs = kX * Wh[:, None]
@@ -839,3 +846,20 @@ def nlml_direct(X, y, theta, dist="defined"):
     Lc = sla.cholesky(K + sn2 * np.eye(n), lower=True, check_finite=False)
     alpha = sla.cho_solve((Lc, True), y, check_finite=False)
     return 0.5 * float(y @ alpha) + float(np.log(np.diag(Lc)).sum()) + 0.5 * n * math.log(2 * math.pi), alpha
+
+
+def white_fixture_cases(z):
+    """(tag, k, 10-slot theta of the C ABI, white) for the parameter vectors of tests/golden/ref_white_n300.npz:
+    Hyb{White, Bias} = [Sigma_White, Sigma_Bias, sn2] (no distance member: the ExpAns slots run with Sigma = 0) and
+    Hyb{ExpAns, White, Bias} = [ExpAns x 8, Sigma_White, Sigma_Bias, sn2]."""
+    out = []
+    for tag in ("w", "ew"):
+        for k in range(2):
+            th = z["%s_foreign_theta_%d" % (tag, k)].ravel()
+            if tag == "w":
+                t10 = THETA0.copy()
+                t10[6], t10[8], t10[9] = 0.0, th[1], th[2]
+                out.append((tag, k, t10, float(th[0])))
+            else:
+                out.append((tag, k, np.concatenate([th[:8], th[9:]]), float(th[8])))
+    return out

@@ -45,15 +45,24 @@ class TraceGP : public GP_utils {
   mutable int count;
 };
 
-// The main covariance of the Hyb kernel: GPSS_REF_KERNEL = ExpAns (default) | Exp | RBF (gp_ss_ak.cpp:146-170); GPSS_REF_BIAS=0
-// drops the Bias member (-kn 0, gp_ss_ak.cpp:179-184).
+// The members of the Hyb kernel, in order: GPSS_REF_KERNEL = a '+'-separated list of ExpAns (default) | Exp | RBF | Bias | White
+// (one -k each, gp_ss_ak.cpp:146-170); GPSS_REF_BIAS=0 drops the trailing Bias member (-kn 0, gp_ss_ak.cpp:179-184).
+// GPSS_REF_NOGRAD=1 skips Grad_Values in the evaluation loop: with a White member the reference's Kernels::getGradients
+// default calls itself (Kernel.h:56-59) and the process dies of stack overflow.
 static void add_kernels(HybKerns& K, const mat& X)
 {
   const char* e = getenv("GPSS_REF_KERNEL");
-  const string name = e ? e : "ExpAns";
-  if (name == "Exp") K.addNewKernel(new Kern_Exponential(X));
-  else if (name == "RBF") K.addNewKernel(new Kern_RBF(X));
-  else K.addNewKernel(new Kern_ExpAnisotropic(X));
+  string list = e ? e : "ExpAns";
+  while (!list.empty()) {
+    const size_t plus = list.find('+');
+    const string name = list.substr(0, plus);
+    list = (plus == string::npos) ? string() : list.substr(plus + 1);
+    if (name == "Exp") K.addNewKernel(new Kern_Exponential(X));
+    else if (name == "RBF") K.addNewKernel(new Kern_RBF(X));
+    else if (name == "Bias") K.addNewKernel(new Kern_Bias(X));
+    else if (name == "White") K.addNewKernel(new Kern_White(X));
+    else K.addNewKernel(new Kern_ExpAnisotropic(X));
+  }
   const char* b = getenv("GPSS_REF_BIAS");
   if (!b || atoi(b) != 0) K.addNewKernel(new Kern_Bias(X));
 }
@@ -190,8 +199,10 @@ int main(int argc, char** argv)
     gp.set_GP_Pars(th);
     const double L = gp.logLikelihood();
     mat g(1, np);
+    g.zeros();
     gp.set_GP_Pars(th);                    // the optimiser always calls set_GP_Pars before Grad_Values (Opt_pars.cpp:266-267)
-    const double L2 = gp.Grad_Values(g);
+    const bool nograd = getenv("GPSS_REF_NOGRAD") != 0 && atoi(getenv("GPSS_REF_NOGRAD")) != 0;
+    const double L2 = nograd ? gp.logLikelihood() : gp.Grad_Values(g);
     snprintf(key, sizeof key, "theta_%d", nth); dump(key, th);
     snprintf(key, sizeof key, "nlml_%d", nth); dump(key, L);
     snprintf(key, sizeof key, "nlml_grad_%d", nth); dump(key, L2);

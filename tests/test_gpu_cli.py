@@ -200,3 +200,29 @@ def test_cli_widened_configurations_match_reference_binary(tmp_path, fixture, ke
     assert np.array_equal(mine_pred[:, 0], ref_pred[:, 0])
     assert np.allclose(mine_pred[:, 2], ref_pred[:, 2], rtol=2e-5, atol=1e-6)
     assert np.allclose(mine_pred[:, 3], ref_pred[:, 3], rtol=2e-5, atol=1e-6)
+
+
+def test_cli_white_member_trains_where_the_reference_crashes(tmp_path):
+    """`-k White` (gp_ss_ak.cpp:166-169): the reference prints the initial model and its objective and then dies in the first gradient
+    (Kernels::getGradients calls itself, Kernel.h:56-59; fixture rc != 0).  This build matches the printed objective of the initial
+    model, runs the fit with gradient entry 0 for Sigma_White (its getGradParam), and writes the model the reference's writer would
+    (KernelName=White Noise -- which its own reader then refuses, Kernel.cpp:1288: reproduced)."""
+    z = np.load(os.path.join(GOLD, "ref_white_n300.npz"))
+    (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
+    for tag, ks in (("w", ["-k", "White"]), ("ew", ["-k", "ExpAns", "-k", "White"])):
+        model = str(tmp_path / ("m_" + tag))
+        tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train"] + ks + ["-kn", "1", "-o", "LBFGS", "-#", "2", str(tmp_path / "train.txt"), model],
+                            capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path)
+        assert tr.returncode == 0, tr.stdout + tr.stderr
+        assert int(z["cli_%s_rc" % tag]) != 0
+        ref_ll = _floats_after(str(z["cli_%s_stdout" % tag]), "Log likelihood:")
+        mine_ll = _floats_after(tr.stdout, "Log likelihood:")
+        assert np.allclose(mine_ll[0], ref_ll[0], rtol=2e-5)                    # 6 significant digits printed
+        text = open(model).read()
+        assert "KernelName=White Noise" in text
+        lines = text.splitlines()
+        w = lines.index("KernelName=White Noise")
+        assert float(lines[w + 3].split()[0]) == 0.1                            # Sigma_White never moves: its gradient entry is 0
+        te = subprocess.run([CLI, "-v", "1", "-pm", "1", "test", str(tmp_path / "train.txt"), model, str(tmp_path / "train.txt")],
+                            capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path)
+        assert te.returncode == 1 and "Unknown kernel type" in (te.stdout + te.stderr)

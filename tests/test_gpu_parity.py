@@ -558,3 +558,41 @@ def test_int8_path_leaves_thetas_without_its_operand_bound_to_dmma(gpss, monkeyp
     m.set_theta(O.THETA0)                                  # the next admissible theta is back on the int8 pipe
     assert m.ozaki_slices() == 8
     m.close()
+
+
+def test_white_member_against_oracle_and_reference(gpss):
+    """Kern_White (reference Kernel.cpp:180-270) through gpss_set_white: Hyb{White, Bias} (no distance member: the ExpAns slots run with
+    Sigma = 0) and Hyb{ExpAns, White, Bias}.  Objective / Alpha / predictions against the oracle at the header's tolerances and against
+    the unmodified reference's dumps (tests/golden/ref_white_n300.npz) at the reference floor; the prediction on the training set itself
+    exercises Kern_White::computeK's cross-covariance diagonal; the gradient carries 0 for Sigma_White by construction (host side)."""
+    z = np.load(os.path.join(GOLD, "ref_white_n300.npz"))
+    Xs, ys = z["Xs"], z["ys"].ravel()
+    m = gpss.GpssModel(Xs, ys)
+    for tag, k, t10, white in O.white_fixture_cases(z):
+        gp = O.OracleGP(Xs, ys, t10, literal=True, white=white)
+        Lo = gp.log_likelihood()
+        for tset, Xq in (("foreign", z["Xt"]), ("self", Xs)):
+            m.set_white(white, cross_diagonal=(tset == "self"))
+            m.set_theta(t10)
+            L = m.nlml()
+            a = m.alpha()
+            mu, var = m.predict(Xq)
+            mu_o, var_o = gp.predict(Xq)
+            assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+            assert np.linalg.norm(a - gp.Alpha) <= TOL_ALPHA * np.linalg.norm(gp.Alpha)
+            assert np.abs(mu - mu_o).max() <= TOL_MU and np.abs(var - var_o).max() <= TOL_VAR
+            Lr = float(z["%s_%s_nlml_%d" % (tag, tset, k)])
+            assert abs(L - Lr) <= 2e-7 * abs(Lr)
+            assert np.abs(mu - z["%s_%s_mu_%d" % (tag, tset, k)].ravel()).max() <= 5e-7
+            assert np.abs(var - z["%s_%s_var_%d" % (tag, tset, k)].ravel()).max() <= 1e-7
+        # the gradient still evaluates (B^-1 with the white diagonal inside K): sn2 entry against the oracle's matrix form
+        m.set_white(white)
+        m.set_theta(t10)
+        L2, g = m.nlml_grad()
+        Q = np.linalg.inv(gp.K / t10[9] + np.eye(gp.n))                      # B^-1, B = I + K / sn2
+        r = ys - gp.K @ gp.Alpha
+        g9 = -float((Q / t10[9] * gp.K).sum()) - float(r @ r) / t10[9] + gp.n   # SURVEY.md section 8(a) row H
+        assert abs(g[9] - g9) <= 1e-7 * max(1.0, abs(g9))
+        assert abs(g[8] - float(np.trace(Q / t10[9] - np.outer(gp.Alpha, gp.Alpha)))) <= 1e-7 * max(1.0, np.abs(g).max())
+    m.set_white(0.0)
+    m.close()

@@ -196,3 +196,24 @@ def test_lean_baseline_matches_oracle():
     assert abs(a - 2e-6) < 1e-9 and abs(b - 1e-11) < 1e-14
     a, b = LB.fit_n2_n3([1000, 2000], [3e-6 * n * n + 1e-11 * n ** 3 for n in (1000, 2000)], b_fixed=1e-11)
     assert abs(a - 3e-6) < 1e-12 and b == 1e-11
+
+
+def test_oracle_white_member_matches_reference():
+    """Kern_White (Kernel.cpp:180-270) in the oracle against the unmodified reference (tests/golden/ref_white_n300.npz, made with
+    GPSS_REF_NOGRAD=1: the reference cannot differentiate a kernel with a White member): objective, Alpha, predictions on a foreign
+    test set and on the training set itself (cross-covariance diagonal quirk)."""
+    z = np.load(os.path.join(GOLD, "ref_white_n300.npz"))
+    Xs, ys = z["Xs"], z["ys"].ravel()
+    for tag, k, t10, white in O.white_fixture_cases(z):
+        gp = O.OracleGP(Xs, ys, t10, dist="blas", literal=True, white=white)
+        L = gp.log_likelihood()
+        Lr = float(z["%s_foreign_nlml_%d" % (tag, k)])
+        assert abs(L - Lr) <= 2e-7 * abs(Lr)
+        a = z["%s_foreign_alpha_%d" % (tag, k)].ravel()
+        assert np.abs(gp.Alpha - a).max() <= 5e-7 * np.abs(a).max()
+        assert np.abs(np.diag(gp.K) - z["%s_foreign_K_diag_%d" % (tag, k)].ravel()).max() <= 1e-6
+        for tset, Xq in (("foreign", z["Xt"]), ("self", Xs)):
+            mu, var = gp.predict(Xq)
+            assert np.abs(mu - z["%s_%s_mu_%d" % (tag, tset, k)].ravel()).max() <= 5e-7
+            assert np.abs(var - z["%s_%s_var_%d" % (tag, tset, k)].ravel()).max() <= 1e-7
+    assert int(z["cli_w_rc"]) != 0 and int(z["cli_ew_rc"]) != 0          # the reference dies in the first gradient (Kernel.h:56-59)
