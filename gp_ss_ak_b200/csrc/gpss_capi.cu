@@ -347,27 +347,34 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     ncclResult_t nr = g_nccl.CommInitRank(&c->comm, part_world, id, part_rank);
     if (nr != ncclSuccess) return fail(fail_nccl(nr, "ncclCommInitRank", __FILE__, __LINE__));
   }
-  // int8 tensor-core path of the three long-k contractions (gpss_ozaki.cuh), single-GPU handles only.
-  //   GPSS_OZAKI unset : 8 slices (operands carried to 2^-55 of their a-priori bound: at or below the rounding of the DMMA
-  //                      path) for 8192 < n_pad <= 57 344, i.e. where an evaluation is GEMM-bound and the two extra
-  //                      n_pad^2-byte x 8 plane buffers still fit beside L, U and B^-1 in 180 GB; the DMMA path otherwise
+  // int8 tensor-core path of the three long-k contractions (gpss_ozaki.cuh).
+  //   GPSS_OZAKI unset : 7 slices of 8 bits (base-256 signed digits: operands carried to 2^-55 of their a-priori bound, at or below the
+  //                      rounding of the DMMA path; 28 int8 products per FP64 product) for 8192 < n_pad <= 57 344, i.e. where an
+  //                      evaluation is GEMM-bound and the two extra 7 n_pad^2-byte plane buffers still fit beside L, U and B^-1 in
+  //                      180 GB; the DMMA path otherwise.  Measured at n = 50 000 against the DMMA path: nlml 1e-13, g 8e-12, alpha
+  //                      4e-11 (profiles/r02_ozaki_digits_n50k.log) -- closer than 8 slices of 7 bits (36 products), and 12 % faster.
   //   GPSS_OZAKI=0     : always the FP64 DMMA path
-  //   GPSS_OZAKI=6|7|8 : that many 7-bit slices, for every n (7: 1.3x faster than 8; nlml 1e-11, alpha 4e-10 at n = 5 000..50 000)
+  //   GPSS_OZAKI=6|7|8 : that many slices for every n; 7-bit digits unless GPSS_OZAKI_BITS=8 (then 6 or 7 slices)
+  //   GPSS_OZAKI_BITS=7 without GPSS_OZAKI: the size rule with 8 slices of 7 bits (the round-1 default)
   if (part_world <= 1) {
-    int v = (c->n_pad > 8192 && c->n_pad <= 57344) ? 8 : 0;
+    int v = (c->n_pad > 8192 && c->n_pad <= 57344) ? 7 : 0;
+    int bits_default = 8;
     c->oz_auto = true;
+    if (const char* eb = getenv("GPSS_OZAKI_BITS")) { if (atoi(eb) == 7 && v) { v = 8; bits_default = 7; } }
     if (const char* e = getenv("GPSS_OZAKI")) {
       c->oz_auto = false;
+      bits_default = 7;
       v = atoi(e);
-      if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (7-bit slices per operand)"));
+      if (v != 0 && (v < 6 || v > 8)) return fail(fail_arg("GPSS_OZAKI must be 0 (FP64 DMMA path), 6, 7 or 8 (slices per operand)"));
       // |G_g| <= S n_pad 64^2 must stay below 2^31 (S = 8: n_pad < 65 536)
       const char* eb = getenv("GPSS_OZAKI_BITS");
       if (v != 0 && !(eb && atoi(eb) == 8) && (long long)v * c->n_pad * 4096 >= (1ll << 31)) return fail(fail_arg("GPSS_OZAKI: n too large for exact int32 accumulation with this many slices"));
     }
+    c->oz_bits = bits_default;
     if (v != 0) {
       c->oz_s = v;
       if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;
-      if (const char* e = getenv("GPSS_OZAKI_GRAD")) { const int sg = atoi(e); if (sg >= 6 && sg < v) c->oz_s_grad = sg; }
+      if (const char* e = getenv("GPSS_OZAKI_GRAD")) { const int sg = atoi(e); if (sg >= 5 && sg < v) c->oz_s_grad = sg; }
       if (const char* e = getenv("GPSS_OZAKI_BITS")) {
         if (atoi(e) != 7 && atoi(e) != 8) return fail(fail_arg("GPSS_OZAKI_BITS must be 7 or 8"));
         if (atoi(e) == 8 && v == 8) return fail(fail_arg("GPSS_OZAKI_BITS=8 takes GPSS_OZAKI=6 or 7 (7 x 8 bits already exceed FP64)"));

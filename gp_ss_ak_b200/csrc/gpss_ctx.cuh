@@ -214,6 +214,7 @@ static int oz_active(const gpss_ctx* c)
 
 static int oz_configure()
 {
+  CU(oz::configure<5>());
   CU(oz::configure<6>());
   CU(oz::configure<7>());
   CU(oz::configure<8>());
@@ -258,6 +259,7 @@ static int oz_gemm_on(gpss_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb,
     a.k1 = (s0 + seg < k1) ? s0 + seg : k1;
     if (!first) a.accumulate = 1;
     switch (s_use) {
+      case 5: oz::launch<5>(ta, tb, a, st); break;
       case 6: oz::launch<6>(ta, tb, a, st); break;
       case 7: oz::launch<7>(ta, tb, a, st); break;
       case 8: oz::launch<8>(ta, tb, a, st); break;

@@ -377,7 +377,7 @@ __global__ void oz_slice_kernel(const double* __restrict__ X, long ldx, int row0
       // |x| <= 2^e holds when B = I + K / sn2 >= I, i.e. for a positive semi-definite K; nothing constrains theta (Sigma_Bias enters
       // raw), so an operand that exceeds its a-priori bound by more than rounding noise (2^-40 relative) raises the flag the host reads
       // at the end of the evaluation, which is then repeated on the DMMA path (gpss_capi.cu: oz_blocked).  NaN raises it too.
-      if (viol && !(fabs(sc) <= lim * (1.0 + 0x1p-40))) *viol = 1;
+      if (viol && !(fabs(sc) <= (double)vmax * (1.0 + 0x1p-40))) *viol = 1;      // vmax: the largest value the digits can hold (= lim with 7-bit digits)
       sc = fmin(fmax(sc, -lim), lim);                                  // rounding excess only
       long long v = __double2ll_rn(sc);
       v = v > vmax ? vmax : (v < -vmax ? -vmax : v);

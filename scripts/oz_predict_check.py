@@ -14,14 +14,19 @@ from gp_ss_ak_b200 import datagen
 
 base = np.array([np.pi / 3.1, 1.5, np.pi / 3.1, 1.5, np.pi / 3.1, 1.3, 0.9, 0.6, 0.2, 0.016])
 rc = 0
-for n, s in [(int(a), 8) for a in sys.argv[1:]] or [(2000, 8), (5000, 7), (20000, 8), (50000, 8)]:
+for n, s in [(int(a), 7) for a in sys.argv[1:]] or [(2000, 7), (5000, 7), (20000, 7), (50000, 7)]:
     X, y = datagen.drillholes(n, 0)
     Xs, ys, _ = datagen.standardise_symmetric(X, y)
     m_test = 8192 if n >= 20000 else 1000
     Xt = np.concatenate([Xs[:100], np.random.default_rng(1).uniform(-1, 1, (m_test - 100, 3))])
     out = {}
     for pred in (0, 1):
-        os.environ["GPSS_OZAKI"] = str(s)
+        if n > 8192:
+            os.environ.pop("GPSS_OZAKI", None)                    # the library's size rule: 7 slices of 8 bits
+            os.environ.pop("GPSS_OZAKI_BITS", None)
+        else:
+            os.environ["GPSS_OZAKI"] = str(s)
+            os.environ["GPSS_OZAKI_BITS"] = "8"
         os.environ["GPSS_OZAKI_PREDICT"] = str(pred)
         m = G.GpssModel(Xs, ys)
         m.set_theta(base)

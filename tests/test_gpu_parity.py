@@ -369,7 +369,7 @@ def test_large_n_properties(gpss):
     Xs, ys, _ = datagen.standardise_symmetric(X, y)
     th = O.THETA0.copy()
     m = gpss.GpssModel(Xs, ys)
-    assert m.ozaki_slices() == 8          # n_pad > 8192: the long-k contractions run on the int8 tensor cores (csrc/gpss_ozaki.cuh)
+    assert (m.ozaki_slices(), m.ozaki_digit_bits()) == (7, 8)   # n_pad > 8192: the long-k contractions run on the int8 tensor cores (csrc/gpss_ozaki.cuh)
     m.set_theta(th)
     L, g = m.nlml_grad()
     a, f = m.alpha(), m.yhat()
@@ -391,18 +391,20 @@ def test_large_n_properties(gpss):
     m.close()
 
 
-@pytest.mark.parametrize("slices,n,seed", [(8, 2000, 0), (7, 2000, 0), (8, 700, 4), (8, 2100, 6)])
-def test_int8_tensor_core_path_parity_with_oracle(gpss, monkeypatch, slices, n, seed):
+@pytest.mark.parametrize("slices,bits,n,seed", [(8, 7, 2000, 0), (7, 7, 2000, 0), (8, 7, 700, 4), (8, 7, 2100, 6), (7, 8, 2000, 0), (7, 8, 2100, 6),
+                                                (6, 8, 700, 4)])
+def test_int8_tensor_core_path_parity_with_oracle(gpss, monkeypatch, slices, bits, n, seed):
     """The int8 tensor-core evaluation of the three long-k contractions (csrc/gpss_ozaki.cuh: Ozaki splitting into 7-bit slices,
     tcgen05 kind::i8, exact int32 accumulation) is the default for 8192 < n_pad <= 57 344; GPSS_OZAKI forces it at sizes the
     oracle finishes in seconds.  Same tolerances as the FP64 DMMA path (which the same sizes run by default, above)."""
     monkeypatch.setenv("GPSS_OZAKI", str(slices))
+    monkeypatch.setenv("GPSS_OZAKI_BITS", str(bits))        # 7 slices of 8 bits is what the size rule selects above n_pad = 8192
     X, y = datagen.drillholes(n, seed)
     Xs, ys, params = datagen.standardise_symmetric(X, y)
     Xt_raw, _ = datagen.drillholes(150, seed + 100)
     Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
     m = gpss.GpssModel(Xs, ys)
-    assert m.ozaki_slices() == slices
+    assert (m.ozaki_slices(), m.ozaki_digit_bits()) == (slices, bits)
     m.close()
     _check_against_oracle(gpss, Xs, ys, O.THETA0.copy(), Xt)
     monkeypatch.setenv("GPSS_OZAKI", "0")
@@ -411,17 +413,16 @@ def test_int8_tensor_core_path_parity_with_oracle(gpss, monkeypatch, slices, n, 
     m.close()
 
 
-@pytest.mark.parametrize("slices", [7, 8])
-def test_int8_gemm_bit_exact_against_numpy_restatement(gpss, slices):
-    """Integer work is exact, the FP64 recombination has a fixed order: the kernel must equal oracle/ozaki_oracle.py bit for bit."""
+@pytest.mark.parametrize("slices,bits", [(7, 7), (8, 7), (7, 8), (6, 8)])
+def test_int8_gemm_bit_exact_against_numpy_restatement(gpss, monkeypatch, slices, bits):
+    """Integer work is exact, the FP64 recombination has a fixed order: the kernel must equal oracle/ozaki_oracle.py bit for bit,
+    with 7-bit digits (one launch) and with 8-bit digits (the shipped default: 7 slices; k cut into int32-exact segments)."""
     from oracle import ozaki_oracle as Z
+    monkeypatch.setenv("GPSS_OZAKI_BITS", str(bits))
     rng = np.random.default_rng(slices)
     A = rng.uniform(-1, 1, (256, 512)) * 2.0 ** -rng.integers(0, 20, (256, 512))
     B = rng.uniform(-1, 1, (192, 512)) * 2.0 ** -rng.integers(0, 20, (192, 512))
     C0 = rng.uniform(-1, 1, (256, 192))
-    bits = 8 if os.environ.get("GPSS_OZAKI_BITS") == "8" else 7
-    if bits == 8 and slices == 8:
-        pytest.skip("8-bit digits take at most 7 slices")
     e = Z.oz_exponent(Z.SCALE_UNIT, bits=bits)          # 0, or 1 with 8-bit digits (the widened unit bound)
     C, _ = gpss.test_oz_gemm(A, B, slices=slices)
     assert np.array_equal(C, Z.oz_gemm_nt(A, B, slices, e, e, bits=bits))
@@ -451,8 +452,34 @@ def test_int8_gemm_exact_at_the_int32_bound(gpss):
     C, _ = gpss.test_oz_gemm(A, B, slices=S)
     ref = Z.oz_gemm_nt(A, B, S, 0, 0)
     assert np.array_equal(C, ref)
-    assert C[0, 0] == -C[0, 1]
+    assert abs(C[0, 0] + C[0, 1]) <= 1e-15 * K                      # (+x and -x have different digit strings: equal to rounding only)
     assert abs(C[0, 0] - K * x * x) <= 1e-15 * K                    # and it is the FP64 product to rounding
+
+
+def test_int8_gemm_exact_at_the_int32_bound_8bit_digits(gpss, monkeypatch):
+    """The shipped default (7 slices of 8 bits): digits span [-128, 127], so ONE int32 accumulation may cover at most
+    oz_kseg = 18 688 bytes of k (7 x 18 688 x 128^2 = 0.998 x 2^31); longer ranges run as several launches that accumulate in FP64.
+    Operands whose digits are [-126, -128, ..., -128] reach 0.9936 x 2^31 in group 6 of every segment; K = 3 segments."""
+    from oracle import ozaki_oracle as Z
+    monkeypatch.setenv("GPSS_OZAKI_BITS", "8")
+    S, bits = 7, 8
+    e = Z.oz_exponent(Z.SCALE_UNIT, bits=bits)
+    seg = Z.oz_kseg(S, bits)
+    assert e == 1 and seg == 18688
+    K = 3 * seg
+    v = -(126 * 256 ** 6 + 128 * (256 ** 6 - 1) // 255)
+    x = float(v) * 2.0 ** (e - (bits * S - 1))
+    assert int(x * 2.0 ** (bits * S - 1 - e)) == v
+    d = Z.oz_digits(np.array([[x]]), e, S, bits)[:, 0, 0]
+    assert d.tolist() == [-126] + [-128] * 6
+    A = np.full((128, K), x)
+    B = np.full((64, K), x)
+    B[1::2] = -x
+    G = Z.oz_groups(Z.oz_digits(A[:1, :seg], e, S, bits), Z.oz_digits(B[:1, :seg], e, S, bits))
+    assert int(G[6][0, 0]) > 0.99 * 2 ** 31 and int(G[6][0, 0]) < 2 ** 31
+    C, _ = gpss.test_oz_gemm(A, B, slices=S)
+    assert np.array_equal(C, Z.oz_gemm_nt(A, B, S, e, e, bits=bits))
+    assert abs(C[0, 0] - K * x * x) <= 4e-15 * K * x * x
 
 
 @pytest.mark.parametrize("n,seed", [(10000, 3)])
@@ -468,7 +495,7 @@ def test_default_pipe_above_8192_against_oracle_and_dmma(gpss, monkeypatch, n, s
     Xt = (np.concatenate([Xt_raw, X[:20]]) - params[1:, 0]) / params[1:, 1]
     th = O.THETA0.copy()
     m = gpss.GpssModel(Xs, ys)
-    assert m.padded_n() > 8192 and m.ozaki_slices() == 8
+    assert m.padded_n() > 8192 and (m.ozaki_slices(), m.ozaki_digit_bits()) == (7, 8)
     m.set_theta(th)
     L, g = m.nlml_grad()
     a = m.alpha()
@@ -506,7 +533,7 @@ def test_config2_n20000_default_pipe_against_dmma(gpss, monkeypatch):
         if env is not None:
             monkeypatch.setenv("GPSS_OZAKI", env)
         m = gpss.GpssModel(Xs, ys)
-        assert m.ozaki_slices() == (8 if env is None else 0)
+        assert m.ozaki_slices() == (7 if env is None else 0)
         res = []
         for th in (O.THETA0, O.THETA0 * np.array([1.05, 0.9, 0.97, 1.1, 1.02, 0.85, 1.1, 1.0, 0.7, 1.3])):
             m.set_theta(th)
