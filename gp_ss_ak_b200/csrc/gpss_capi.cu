@@ -373,7 +373,8 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
     c->oz_bits = bits_default;
     if (v != 0) {
       c->oz_s = v;
-      if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;
+      c->oz_predict = true;                                   // the variance GEMM V = W (Sw o k*) on the same pipe (41.1 k vs 14.2 k points/s at
+      if (const char* e = getenv("GPSS_OZAKI_PREDICT")) c->oz_predict = atoi(e) != 0;   // n = 50 000, var within 2e-12: profiles/r02_int8_predict.log)
       if (const char* e = getenv("GPSS_OZAKI_GRAD")) { const int sg = atoi(e); if (sg >= 5 && sg < v) c->oz_s_grad = sg; }
       if (const char* e = getenv("GPSS_OZAKI_BITS")) {
         if (atoi(e) != 7 && atoi(e) != 8) return fail(fail_arg("GPSS_OZAKI_BITS must be 7 or 8"));
@@ -628,8 +629,9 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
+  c->oz_dist = true;                                     // the int8 pipe stays on (measured: profiles/r02_dist_int8_2gpu.log); GPSS_OZAKI_DIST=0: DMMA
   if (const char* e = getenv("GPSS_OZAKI_DIST")) c->oz_dist = atoi(e) != 0;
-  if (!c->oz_dist) {                                     // the int8 path is single-GPU by default (oz_active): give its planes back
+  if (!c->oz_dist) {                                     // asked for the DMMA pipe on this multi-GPU handle: give the planes back
     c->oz_s = 0;
     if (c->ozL) { cudaFree(c->ozL); c->ozL = nullptr; }
     if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
@@ -739,12 +741,18 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
     if (var) {
       PhaseTimer t(c, 7);
       // V = L^-1 (Sw o kX): A = W (lower), B = Bm (test index contiguous)
+      if (oz_active(c) && c->oz_predict && !c->ozW) {
+        // the planes of W = L^-1 and of one batch: if they do not fit beside L, U, W and the planes of L and U, predict on the DMMA pipe
+        const size_t wb = (size_t)c->oz_s * n_pad * n_pad, bb = (size_t)c->oz_s * cap * n_pad;
+        if (cudaMalloc(&c->ozW, wb) != cudaSuccess) { cudaGetLastError(); c->ozW = nullptr; c->oz_predict = false; }
+        else if (cudaMalloc(&c->ozB, bb) != cudaSuccess) { cudaGetLastError(); cudaFree(c->ozW); c->ozW = nullptr; c->ozB = nullptr; c->oz_predict = false; }
+        else c->oz_w_fresh = true;
+      }
       if (oz_active(c) && c->oz_predict) {
-        // opt-in: the same product on the int8 tensor cores -- planes of W once per factor, planes of the batch per batch
-        if (!c->ozW) {
-          const size_t wb = (size_t)c->oz_s * n_pad * n_pad, bb = (size_t)c->oz_s * cap * n_pad;
-          CU(cudaMalloc(&c->ozW, wb));
-          CU(cudaMalloc(&c->ozB, bb));
+        // the same product on the int8 tensor cores -- planes of W once per factor, planes of the batch per batch
+        if (c->oz_w_fresh) {
+          const size_t bb = (size_t)c->oz_s * cap * n_pad;
+          c->oz_w_fresh = false;
           CU(cudaMemsetAsync(c->ozB, 0, bb, c->st));
           if (oz::make_plane_map(&c->oz_tmW[0], c->ozW, (long)c->oz_s * n_pad, n_pad, oz::BM) != 0 ||
               oz::make_plane_map(&c->oz_tmB[1], c->ozB, (long)c->oz_s * cap, n_pad, oz::BN) != 0)
@@ -1176,6 +1184,7 @@ int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A
   CU(cudaEventRecord(e0, 0));
   double* dparts = nullptr;
   if (tile == 0) rc = gemm_ws_on(&tmp, g, tmp.st);
+  else if (tile == 9) { tmp.dmma_coresident = true; rc = gemm_ws_on(&tmp, g, tmp.st); tmp.dmma_coresident = false; }   // the 2-stage ring (51 KB)
   else if (tile == 1) rc = gemm_legacy_on(&tmp, g, tmp.st);
   else {
     // tile = S in 2..8: the split-k form used by the distributed triangular inverse (S partial products + fixed-order sum)

@@ -127,6 +127,7 @@ struct gpss_ctx {
   int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
   bool oz_blocked = false;                                     // this theta stays on the DMMA path: Sigma_Bias < 0 or sn2 <= 0 (K not PSD, so |L^-1| <= 1 is not
                                                                // guaranteed), or dflag[1] was raised by the previous attempt at this theta
+  bool dmma_coresident = false;                                // set while an int8 bulk phase is in flight: main-stream DMMA GEMMs use the 2-stage ring (gemm_ws_on)
   long oz_fallbacks = 0;                                       // evaluations repeated on the DMMA path because dflag[1] was raised
   bool oz_auto = false;                                        // chosen by the size rule, not by GPSS_OZAKI: falls back to DMMA if the planes do not fit
   int8_t *ozL = nullptr, *ozU = nullptr;
@@ -136,7 +137,7 @@ struct gpss_ctx {
   // (cut once per factor) and of the cross-covariance batch (PRED_BATCH rows, cut per batch)
   // GPSS_OZAKI_DIST=1 (opt-in, not yet measured): keep the int8 path on replicated-layout multi-GPU handles (gpss_dist_init)
   bool oz_dist = false;
-  bool oz_predict = false, ozW_valid = false;
+  bool oz_predict = false, ozW_valid = false, oz_w_fresh = false;
   int8_t *ozW = nullptr, *ozB = nullptr;
   CUtensorMap oz_tmW[2], oz_tmB[2];
   // host state
@@ -166,6 +167,7 @@ struct gpss_ctx {
 static int configure_kernels()
 {
   CU(cudaFuncSetAttribute(gemm_nt_ws_kernel<GemmTileWideWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWideWS::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_nt_ws_kernel<GemmTileWideWS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWideWS2::SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_nt_kernel<GemmTileWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTileWide::SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   return GPSS_OK;
@@ -181,6 +183,17 @@ static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
   ga.mt = g.M / T::BM;
   ga.nt = g.N / T::BN;
   const int parts = ga.ksplit > 1 ? ga.ksplit : 1;
+  // While oz_gemm_kernel CTAs hold the SMs (one per SM, 169 KB of shared memory with 7 digit planes) the panel work of the main
+  // stream -- U2, the panel solves, the rank-128 updates, the diagonal blocks of the inverse -- would wait for whole SMs to drain.
+  // The same kernel with a 2-stage ring (51 KB, same registers, bitwise the same sums) fits NEXT TO a resident int8 CTA, on the
+  // FP64 pipe that CTA leaves idle.  (8 planes of 7 bits take 193 KB: no room, the hardware then simply queues these CTAs.)
+  if (c->dmma_coresident && stream == c->st && parts == 1) {
+    using T2 = GemmTileWideWS2;
+    gemm_nt_ws_kernel<T2><<<(unsigned)(ga.mt * ga.nt), T2::THREADS, T2::SMEM_BYTES, stream>>>(ga);
+    c->launches++;
+    CU(cudaGetLastError());
+    return GPSS_OK;
+  }
   gemm_nt_ws_kernel<T><<<(unsigned)(ga.mt * ga.nt * parts), T::THREADS, T::SMEM_BYTES, stream>>>(ga);
   c->launches++;
   CU(cudaGetLastError());

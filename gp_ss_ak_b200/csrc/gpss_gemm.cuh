@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_CTAS) gemm_nt_ws_kernel(con
 }
 
 using GemmTileWideWS = GemmTileWS<128, 64, 2, 2, 2>;
+// the same tile with a 2-stage ring: 51 KB of shared memory, so that a CTA fits on an SM NEXT TO a resident oz_gemm_kernel CTA (gemm_ws_on)
+using GemmTileWideWS2 = GemmTileWS<128, 64, 2, 2, 2, 2>;
 
 // 128x64 tile, 4 warps (64x32 each), 2 CTAs per SM: one CTA's prologue/epilogue hides behind the other's DMMA loop.
 using GemmTileWide = GemmTile<128, 64, 2, 2, 2>;

@@ -250,6 +250,7 @@ static int trtri_upper(gpss_ctx* c)
   // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
   const bool ozk = oz_active(c) && c->ozL && c->ozU && c->ozL_valid;
   c->ozU_valid = ozk;
+  c->dmma_coresident = ozk && c->oz_s <= 7 && !(getenv("GPSS_DMMA_CORESIDENT") && atoi(getenv("GPSS_DMMA_CORESIDENT")) == 0);   // see gemm_ws_on
   // the side stream must not start before the factor is complete on the main stream
   CU(cudaEventRecord(c->ev_main, c->st));
   CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
@@ -318,6 +319,7 @@ static int trtri_upper(gpss_ctx* c)
   }
   CU(cudaEventRecord(c->ev_side, c->st2));
   CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+  c->dmma_coresident = false;
   return GPSS_OK;
 }
 

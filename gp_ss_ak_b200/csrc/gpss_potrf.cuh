@@ -148,12 +148,18 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   const bool pipe_env = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
   const bool ozk = oz_active(c) && c->ozL && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
   if (A == c->Lm) c->ozL_valid = ozk;                          // every panel is cut below iff ozk; the inverse must not read stale planes
+  // main-stream DMMA GEMMs next to resident int8 CTAs (gemm_ws_on): only the 7-plane stage ring leaves the room
+  struct Coresident {
+    gpss_ctx* c;
+    Coresident(gpss_ctx* c_, bool on) : c(c_) { c->dmma_coresident = on; }
+    ~Coresident() { c->dmma_coresident = false; }
+  } coresident(c, ozk && c->oz_s <= 7 && !(getenv("GPSS_DMMA_CORESIDENT") && atoi(getenv("GPSS_DMMA_CORESIDENT")) == 0));
   auto update = [&](int T0, int nbT, int kbeg, int klen, cudaStream_t stream) -> int {
     // A[T0:, T0:T0+nbT] -= L[T0:, kbeg:kbeg+klen] L[T0:T0+nbT, kbeg:kbeg+klen]^T
     // (distributed: only the long chunks -- a single received panel, k = NBO, stays on DMMA)
-    // GPSS_OZ_U2=1 (single GPU): U2 (k = NBO, main stream) on the int8 kernel as well -- panel t-1 was cut into planes right after it was factored
-    static const bool oz_u2 = getenv("GPSS_OZ_U2") != nullptr && atoi(getenv("GPSS_OZ_U2")) != 0;
-    if (ozk && (stream != c->st || (oz_u2 && P == 1)) && (P == 1 || klen >= 4 * NBO)) {
+    // U2 (k = NBO, main stream) on the int8 kernel as well (GPSS_OZ_U2=0: DMMA) -- panel t-1 was cut into planes right after it was factored / received
+    static const bool oz_u2 = !(getenv("GPSS_OZ_U2") != nullptr && atoi(getenv("GPSS_OZ_U2")) == 0);   // default on (454 vs 468 ms potrf at n = 50 000)
+    if (ozk && ((stream != c->st && (P == 1 || klen >= 4 * NBO)) || (oz_u2 && stream == c->st))) {
       oz::Args a;
       memset(&a, 0, sizeof a);
       a.C = A + (long)T0 * ld + T0; a.ldc = ld; a.m = n_pad - T0; a.n = nbT;

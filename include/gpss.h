@@ -90,6 +90,8 @@ int gpss_get_yhat(gpss_handle h, double* yhat);
  * Cholesky factor are owned round-robin, the owner factors its panel and broadcasts it (ncclBroadcast over NVLink),
  * every rank updates only its own block columns; L^-T is computed in balanced row slices without communication and
  * gathered once; B^-1 and the gradient reductions are split by rows and summed with one small ncclAllReduce.
+ * The pipe of the long-k products is the handle's (gpss_get_ozaki): the int8 tensor-core pipe chosen at gpss_create stays on after
+ * gpss_dist_init (its digit planes are replicated like the factor); GPSS_OZAKI_DIST=0 switches a multi-GPU handle to the DMMA pipe.
  * The reference has no counterpart (single process, single thread). */
 int gpss_nccl_unique_id(void* id128);                           /* rank 0 creates it, the caller distributes the 128 bytes */
 int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
@@ -174,7 +176,8 @@ int gpss_get_ozaki_bits(gpss_handle h, int* bits);
 /* C(MxN) = A(MxK) * B(NxK)^T with host buffers, through the DMMA kernel; tile: 0 = the warp-specialised
  * bulk-copy/mbarrier kernel every product of the path uses, 1 = the legacy cp.async kernel (A/B baseline),
  * 2..8 = the same kernel in its split-k form (that many partial products summed in a fixed order), which the
- * distributed triangular inverse uses to fill the machine from a narrow row slice. */
+ * distributed triangular inverse uses to fill the machine from a narrow row slice, 9 = tile 0 with a 2-stage ring (the 51 KB
+ * variant that shares an SM with a resident int8 CTA). */
 int gpss_test_gemm_nt(int device, int tile, int M, int N, int K, const double* A, const double* B, double* C,
                       int subtract_from_C, double* ms_out);
 /* C(MxN) = A B^T, or C - A B^T, with host buffers through the int8 tensor-core kernel (csrc/gpss_ozaki.cuh) with `slices` in

@@ -42,7 +42,7 @@ def _check_against_oracle(G, Xs, ys, th, Xt=None):
 
 def test_gemm_nt_kernel_exact(gpss):
     rng = np.random.default_rng(0)
-    for tile in (0, 1):
+    for tile in (0, 1, 9):
         A = rng.integers(-8, 9, (256, 96)).astype(float)
         B = rng.integers(-8, 9, (384, 96)).astype(float)
         C0 = rng.integers(-8, 9, (256, 384)).astype(float)
