@@ -47,7 +47,11 @@ enum { MASK_NONE = 0, MASK_LOWER = 1, MASK_UPPER = 2 };
 //      read from shared memory 12 times instead of 36 (the round-1 kernel ran at the 128 B/clk shared-memory limit:
 //      36 x (4 KB + 2 KB) per 32 clk of tensor work)
 //   2: variant 1 with 32-byte stages (SWIZZLE_32B): twice the stages in the same shared memory, finer refill granularity
-enum { VAR_PAIR64 = 0, VAR_MERGE64 = 1, VAR_MERGE32 = 2, VAR_DEFAULT = VAR_MERGE64 };
+//   3: variant 1 with PER-PLANE barriers: a stage is S units {A_i, B_(S-1-i)} of 12 KB; step i of a chunk (A_i against B_0 .. B_(S-1-i))
+//      is the last reader of unit i, so the MMA warp hands each unit back right after its step and the producer refills it at once --
+//      the refill of a 2-stage ring starts (S - i) / S of a chunk earlier than with one barrier per stage.  With 7 planes a chunk is
+//      1792 clk of tensor work against ~2300 clk to land an 84 KB stage: the whole-stage ring left the pipe waiting (0.82 of peak).
+enum { VAR_PAIR64 = 0, VAR_MERGE64 = 1, VAR_MERGE32 = 2, VAR_UNIT64 = 3, VAR_DEFAULT = VAR_MERGE64 };
 
 template <int S, int BKB = BK>
 struct Cfg {
@@ -57,7 +61,8 @@ struct Cfg {
   static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = S * BN <= 64 ? 64 : S * BN <= 128 ? 128 : S * BN <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 1024 /* barriers: 2 x STAGES x S + 1 */;
+  static_assert((2 * STAGES * S + 2) * 8 <= 1024, "barrier area");
   static_assert(S >= 1 && S * BN <= 512, "S group accumulators of BN columns must fit the 512 TMEM columns");
   static_assert(STAGES >= 2, "need at least two stages");
 };
@@ -137,16 +142,18 @@ __device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr)
 __host__ __device__ constexpr uint32_t idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 constexpr uint32_t IDESC_I8 = idesc_i8(BN);
 
-template <int S, int BKB = BK, bool MERGE = false>
+template <int S, int BKB = BK, bool MERGE = false, bool UNIT = false>
 __global__ void __launch_bounds__(192, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g)
 {
   using T = Cfg<S, BKB>;
+  static_assert(!UNIT || (MERGE && BKB == 64), "per-plane barriers come with the merged 64-byte kernel");
+  constexpr int NBAR = UNIT ? T::STAGES * S : T::STAGES;        // full / empty barriers: per stage, or per stage and plane unit
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + T::STAGES;
-  uint64_t* acc_bar = empty_bar + T::STAGES;
+  uint64_t* empty_bar = full_bar + NBAR;
+  uint64_t* acc_bar = empty_bar + NBAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,7 +172,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (nk == 0 && g.accumulate) return;                                                      // nothing to add (k-segment launches of 8-bit digits)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T::STAGES; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < NBAR; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
     gpss::mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -184,15 +191,27 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < nk; kc++) {
         const int st = kc % T::STAGES;
         const uint32_t ph = (uint32_t)(kc / T::STAGES) & 1u;
-        gpss::mbar_wait(empty_bar + st, ph ^ 1u);
-        gpss::mbar_arrive_expect_tx(full_bar + st, (uint32_t)T::STAGE_BYTES);
         uint8_t* sa = smem + st * T::STAGE_BYTES;
         uint8_t* sb = sa + S * T::A_BYTES;
         const int kq = kb + kc * BKB;
+        if constexpr (UNIT) {
+          // unit u = {A_u, B_(S-1-u)}: freed by step u of the chunk that used this stage last, refilled here in the same order
 #pragma unroll
-        for (int p = 0; p < S; p++) {
-          tma_load_2d(sa + p * T::A_BYTES, &tmA, full_bar + st, kq, p * g.a_rows + g.a_row0 + tile_m * BM);
-          tma_load_2d(sb + p * T::B_BYTES, &tmB, full_bar + st, kq, p * g.b_rows + g.b_row0 + tile_n * BN);
+          for (int u = 0; u < S; u++) {
+            uint64_t* fb = full_bar + st * S + u;
+            gpss::mbar_wait(empty_bar + st * S + u, ph ^ 1u);
+            gpss::mbar_arrive_expect_tx(fb, (uint32_t)(T::A_BYTES + T::B_BYTES));
+            tma_load_2d(sa + u * T::A_BYTES, &tmA, fb, kq, u * g.a_rows + g.a_row0 + tile_m * BM);
+            tma_load_2d(sb + (S - 1 - u) * T::B_BYTES, &tmB, fb, kq, (S - 1 - u) * g.b_rows + g.b_row0 + tile_n * BN);
+          }
+        } else {
+          gpss::mbar_wait(empty_bar + st, ph ^ 1u);
+          gpss::mbar_arrive_expect_tx(full_bar + st, (uint32_t)T::STAGE_BYTES);
+#pragma unroll
+          for (int p = 0; p < S; p++) {
+            tma_load_2d(sa + p * T::A_BYTES, &tmA, full_bar + st, kq, p * g.a_rows + g.a_row0 + tile_m * BM);
+            tma_load_2d(sb + p * T::B_BYTES, &tmB, full_bar + st, kq, p * g.b_rows + g.b_row0 + tile_n * BN);
+          }
         }
       }
     }
@@ -202,10 +221,36 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < nk; kc++) {
         const int st = kc % T::STAGES;
         const uint32_t ph = (uint32_t)(kc / T::STAGES) & 1u;
-        gpss::mbar_wait(full_bar + st, ph);
-        tc_fence_after();
         const uint32_t sa = gpss::smem_u32(smem + st * T::STAGE_BYTES);
         const uint32_t sb = sa + S * T::A_BYTES;
+        if constexpr (UNIT) {
+          // step 0 reads every B plane, i.e. every unit of the stage: all of them must have landed; step i is the last reader of unit i
+#pragma unroll
+          for (int u = 0; u < S; u++) gpss::mbar_wait(full_bar + st * S + u, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < S; i++) {
+#pragma unroll
+            for (int ks = 0; ks < BKB / UMMA_K; ks++) {
+              const uint64_t ad = smem_desc_k<BKB>(sa + i * T::A_BYTES + ks * UMMA_K);
+              const uint32_t acc = (kc > 0 || ks > 0 || i > 0) ? 1u : 0u;
+              constexpr int MAXP = 256 / BN;
+              const int cnt = S - i, nm = (cnt + MAXP - 1) / MAXP;
+              int j0 = 0;
+#pragma unroll
+              for (int q = 0; q < nm; q++) {
+                const int len = (cnt - j0 + (nm - q) - 1) / (nm - q);
+                const uint64_t bd = smem_desc_k<BKB>(sb + j0 * T::B_BYTES + ks * UMMA_K);
+                mma_i8(tmem_base + (uint32_t)((i + j0) * BN), ad, bd, idesc_i8(len * BN), acc);
+                j0 += len;
+              }
+            }
+            tc_commit(empty_bar + st * S + i);         // A_i and B_(S-1-i) have no reader left in this chunk
+          }
+          continue;
+        }
+        gpss::mbar_wait(full_bar + st, ph);
+        tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKB / UMMA_K; ks++) {
 #pragma unroll
@@ -426,7 +471,7 @@ static inline int variant()
   static int v = -1;
   if (v < 0) {
     v = VAR_DEFAULT;
-    if (const char* e = getenv("GPSS_OZ_VARIANT")) { const int x = atoi(e); if (x >= VAR_PAIR64 && x <= VAR_MERGE32) v = x; }
+    if (const char* e = getenv("GPSS_OZ_VARIANT")) { const int x = atoi(e); if (x >= VAR_PAIR64 && x <= VAR_UNIT64) v = x; }
   }
   return v;
 }
@@ -453,6 +498,7 @@ static inline cudaError_t configure()
   cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel<S, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 64>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<S, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 64>::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<S, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 32>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<S, 64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<S, 64>::SMEM_BYTES);
   return e;
 }
 
@@ -463,7 +509,8 @@ static inline void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Ar
   switch (variant()) {
     case VAR_PAIR64: oz_gemm_kernel<S, 64, false><<<grid, 192, Cfg<S, 64>::SMEM_BYTES, st>>>(ta, tb, g); break;
     case VAR_MERGE64: oz_gemm_kernel<S, 64, true><<<grid, 192, Cfg<S, 64>::SMEM_BYTES, st>>>(ta, tb, g); break;
-    default: oz_gemm_kernel<S, 32, true><<<grid, 192, Cfg<S, 32>::SMEM_BYTES, st>>>(ta, tb, g); break;
+    case VAR_MERGE32: oz_gemm_kernel<S, 32, true><<<grid, 192, Cfg<S, 32>::SMEM_BYTES, st>>>(ta, tb, g); break;
+    default: oz_gemm_kernel<S, 64, true, true><<<grid, 192, Cfg<S, 64>::SMEM_BYTES, st>>>(ta, tb, g); break;
   }
 }
 

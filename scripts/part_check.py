@@ -33,14 +33,21 @@ for n in sizes:
     n_pad = m.padded_n()
     ref = None
     if rank == 0 and n <= 20000:
-        # same pipe for the long-k products as the multi-GPU handle (DMMA unless GPSS_OZAKI_DIST=1 kept the int8 path)
+        # same pipe for the long-k products as the multi-GPU handle (the int8 pipe unless GPSS_OZAKI_DIST=0 asked for DMMA)
         prev = os.environ.get("GPSS_OZAKI")
         os.environ["GPSS_OZAKI"] = str(m.ozaki_slices())
+        prev_bits = os.environ.get("GPSS_OZAKI_BITS")
+        if m.ozaki_slices():
+            os.environ["GPSS_OZAKI_BITS"] = str(m.ozaki_digit_bits())      # same digits as the multi-GPU handle (7 slices of 8 bits by default)
         ms = G.GpssModel(Xs, ys, device=local)
         if prev is None:
             os.environ.pop("GPSS_OZAKI", None)
         else:
             os.environ["GPSS_OZAKI"] = prev
+        if prev_bits is None:
+            os.environ.pop("GPSS_OZAKI_BITS", None)
+        else:
+            os.environ["GPSS_OZAKI_BITS"] = prev_bits
         ms.set_theta(base)
         ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1])
         ms.close()
