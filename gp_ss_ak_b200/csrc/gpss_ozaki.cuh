@@ -62,7 +62,7 @@ struct Cfg {
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = S * BN <= 64 ? 64 : S * BN <= 128 ? 128 : S * BN <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 1024 /* barriers: 2 x STAGES x S + 1 */;
-  static_assert((2 * STAGES * S + 2) * 8 <= 1024, "barrier area");
+  static_assert((2 * STAGES * S + 3) * 8 <= 1024, "barrier area");
   static_assert(S >= 1 && S * BN <= 512, "S group accumulators of BN columns must fit the 512 TMEM columns");
   static_assert(STAGES >= 2, "need at least two stages");
 };
@@ -81,7 +81,10 @@ struct Args {
   int accumulate;                // 0: C = sign * A B^T, 1: C += sign * A B^T
   double sign;
   int a_kind, b_kind;            // SCALE_*: which power of two each operand was divided by before slicing
-  int digit_bits;                // 0 or 7: base-128 digits in [-64, 64] (default); 8: base-256 digits in [-128, 127] (GPSS_OZAKI_BITS=8)
+  int digit_bits;                // 0 or 7: base-128 digits in [-64, 64]; 8: base-256 digits in [-128, 127] (the default of the size rule)
+  int kseg;                      // 0: the whole k-range is ONE int32 accumulation; > 0 (multiple of 64): the accumulators are drained into C at
+                                 // every absolute multiple of kseg (8-bit digits: 18 688 at S = 7) and restarted -- exact int32 sums per
+                                 // segment, FP64 sums across segments, all inside one launch
   const gpss::DevParams* dP;     // device parameters (theta-dependent scale: never a launch argument, so launches can sit in a graph)
   int32_t* dbg;                  // test hook: raw int32 group accumulators, [S][m][n] row-major (else nullptr)
 };
@@ -154,7 +157,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NBAR;
   uint64_t* acc_bar = empty_bar + NBAR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* free_bar = acc_bar + 1;                               // epilogue -> MMA warp: the accumulators of a k-segment have been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // rasterisation as in gemm_nt_ws_kernel: super-columns of RASTER_W tile columns, tile column fastest, so that one wave of
@@ -169,11 +173,17 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   int ke = g.k1;
   if (g.kend_row) { const int kr = g.a_row0 + tile_m * BM + BM; if (kr < ke) ke = kr; }
   const int nk = ke > kb ? (ke - kb) / BKB : 0;
-  if (nk == 0 && g.accumulate) return;                                                      // nothing to add (k-segment launches of 8-bit digits)
+  if (nk == 0 && g.accumulate) return;                                                      // nothing to add
+  // k-segments (absolute multiples of kseg, so that every tile cuts at the same k whatever its own range): chunk kc is the last of its
+  // segment when the next chunk starts on a boundary
+  const int kseg = g.kseg > 0 ? g.kseg : (1 << 30);
+  const int nseg = nk > 0 ? ((ke - 1) / kseg - kb / kseg + 1) : 1;
+  auto seg_ends_after = [&](int kc) { return kc == nk - 1 || (kb + (kc + 1) * BKB) % kseg == 0; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NBAR; s++) { gpss::mbar_init(full_bar + s, 1); gpss::mbar_init(empty_bar + s, 1); }
     gpss::mbar_init(acc_bar, 1);
+    gpss::mbar_init(free_bar, 4);                                 // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 5) {
@@ -218,11 +228,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && nk > 0) {
+      bool seg_first = true;                 // the next chunk opens a k-segment: its first products overwrite the accumulators
+      int seg = 0;
       for (int kc = 0; kc < nk; kc++) {
         const int st = kc % T::STAGES;
         const uint32_t ph = (uint32_t)(kc / T::STAGES) & 1u;
         const uint32_t sa = gpss::smem_u32(smem + st * T::STAGE_BYTES);
         const uint32_t sb = sa + S * T::A_BYTES;
+        const bool opens = seg_first, closes = seg_ends_after(kc);
+        if (opens && seg > 0) {              // the epilogue warps must have drained the previous segment out of TMEM
+          gpss::mbar_wait(free_bar, (uint32_t)(seg - 1) & 1u);
+          tc_fence_after();
+        }
+        seg_first = closes;
         if constexpr (UNIT) {
           // step 0 reads every B plane, i.e. every unit of the stage: all of them must have landed; step i is the last reader of unit i
 #pragma unroll
@@ -233,7 +251,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int ks = 0; ks < BKB / UMMA_K; ks++) {
               const uint64_t ad = smem_desc_k<BKB>(sa + i * T::A_BYTES + ks * UMMA_K);
-              const uint32_t acc = (kc > 0 || ks > 0 || i > 0) ? 1u : 0u;
+              const uint32_t acc = (!opens || ks > 0 || i > 0) ? 1u : 0u;
               constexpr int MAXP = 256 / BN;
               const int cnt = S - i, nm = (cnt + MAXP - 1) / MAXP;
               int j0 = 0;
@@ -247,6 +265,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_commit(empty_bar + st * S + i);         // A_i and B_(S-1-i) have no reader left in this chunk
           }
+          if (closes) { tc_commit(acc_bar); seg++; }   // the segment's accumulators are complete
           continue;
         }
         gpss::mbar_wait(full_bar + st, ph);
@@ -256,8 +275,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < S; i++) {
             const uint64_t ad = smem_desc_k<BKB>(sa + i * T::A_BYTES + ks * UMMA_K);
-            // group i + j: the first product that reaches it (i == 0 of the first k-step) overwrites, the rest accumulate
-            const uint32_t acc = (kc > 0 || ks > 0 || i > 0) ? 1u : 0u;
+            // group i + j: the first product that reaches it (i == 0 of the first k-step of a segment) overwrites, the rest accumulate
+            const uint32_t acc = (!opens || ks > 0 || i > 0) ? 1u : 0u;
             if constexpr (MERGE) {
               // B planes 0 .. S-1-i are 64 (S - i) consecutive rows of shared memory and their groups i .. S-1 are 64 (S - i)
               // consecutive TMEM columns: ceil((S - i) / 4) instructions of N <= 256, planes split as evenly as possible
@@ -281,61 +300,69 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_commit(empty_bar + st);         // stage reusable once these MMAs have read it
+        if (closes) { tc_commit(acc_bar); seg++; }     // the segment's accumulators are complete
       }
-      tc_commit(acc_bar);                  // accumulators complete
     }
   } else {
     // ------------------------------------------------ epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows of the tile
-    if (nk > 0) {
-      gpss::mbar_wait(acc_bar, 0);
-      tc_fence_after();
-    }
     const int row = tile_m * BM + warp * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int bits = g.digit_bits ? g.digit_bits : DIGIT_BITS;
     const double w = ldexp(1.0, -bits);
     const double scale = g.sign * ldexp(1.0, oz_exponent(g.a_kind, g.dP, bits) + oz_exponent(g.b_kind, g.dP, bits) - 2 * (bits - 1));
-    // C is read-modify-written in place: the 8 loads of a column group are issued together, BEFORE the TMEM read-back and the Horner
-    // sums, and the next group's loads before this group's stores (one round trip to L2 / HBM per group instead of one per column --
-    // the first version's 64 dependent load -> FMA -> store chains cost ~30 us per tile, profiles/r02_oz_gemm_variants.txt)
     double* const crow = g.C + row + (size_t)(tile_n * BN) * g.ldc;
-    double cin[8], cnx[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) cnx[c] = g.accumulate ? __ldcg(crow + (size_t)c * g.ldc) : 0.0;
-    for (int c0 = 0; c0 < BN; c0 += 8) {
-      uint32_t v[S][8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) cin[c] = cnx[c];
-      if (g.accumulate && c0 + 8 < BN) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) cnx[c] = __ldcg(crow + (size_t)(c0 + 8 + c) * g.ldc);
-      }
+    for (int seg = 0; seg < nseg; seg++) {
       if (nk > 0) {
-#pragma unroll
-        for (int gi = 0; gi < S; gi++) tmem_ld8(lane_base + (uint32_t)(gi * BN + c0), v[gi]);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int gi = 0; gi < S; gi++)
-#pragma unroll
-          for (int c = 0; c < 8; c++) v[gi][c] = 0u;
+        gpss::mbar_wait(acc_bar, (uint32_t)seg & 1u);
+        tc_fence_after();
       }
-      if (g.dbg) {
+      const bool rmw = g.accumulate || seg > 0;        // later segments add to what the first one wrote
+      // C is read-modify-written in place: the 8 loads of a column group are issued together, BEFORE the TMEM read-back and the Horner
+      // sums, and the next group's loads before this group's stores (one round trip to L2 / HBM per group instead of one per column --
+      // the first version's 64 dependent load -> FMA -> store chains cost ~30 us per tile, profiles/r02_oz_gemm_variants.txt)
+      double cin[8], cnx[8];
 #pragma unroll
-        for (int gi = 0; gi < S; gi++)
+      for (int c = 0; c < 8; c++) cnx[c] = rmw ? __ldcg(crow + (size_t)c * g.ldc) : 0.0;
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        uint32_t v[S][8];
 #pragma unroll
-          for (int c = 0; c < 8; c++) g.dbg[((size_t)gi * g.m + row) * g.n + tile_n * BN + c0 + c] = (int32_t)v[gi][c];
+        for (int c = 0; c < 8; c++) cin[c] = cnx[c];
+        if (rmw && c0 + 8 < BN) {
+#pragma unroll
+          for (int c = 0; c < 8; c++) cnx[c] = __ldcg(crow + (size_t)(c0 + 8 + c) * g.ldc);
+        }
+        if (nk > 0) {
+#pragma unroll
+          for (int gi = 0; gi < S; gi++) tmem_ld8(lane_base + (uint32_t)(gi * BN + c0), v[gi]);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int gi = 0; gi < S; gi++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[gi][c] = 0u;
+        }
+        if (g.dbg) {
+#pragma unroll
+          for (int gi = 0; gi < S; gi++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) g.dbg[((size_t)gi * g.m + row) * g.n + tile_n * BN + c0 + c] = (int32_t)v[gi][c];
+        }
+        double outv[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int gi = S - 1; gi >= 0; gi--) acc = acc * w + (double)(int32_t)v[gi][c];     // sum_g 2^(-7g) G_g, smallest first
+          outv[c] = rmw ? (cin[c] + scale * acc) : (scale * acc);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) crow[(size_t)(c0 + c) * g.ldc] = outv[c];
       }
-      double outv[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int gi = S - 1; gi >= 0; gi--) acc = acc * w + (double)(int32_t)v[gi][c];     // sum_g 2^(-7g) G_g, smallest first
-        outv[c] = g.accumulate ? (cin[c] + scale * acc) : (scale * acc);
+      if (seg + 1 < nseg) {                            // hand the accumulators back: every lane's TMEM loads have completed (wait::ld above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) gpss::mbar_arrive(free_bar);
       }
-#pragma unroll
-      for (int c = 0; c < 8; c++) crow[(size_t)(c0 + c) * g.ldc] = outv[c];
     }
     tc_fence_before();
   }
