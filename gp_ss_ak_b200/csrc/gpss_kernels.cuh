@@ -31,6 +31,8 @@ struct DevParams {
   double var2;        // Sigma_ExpAns^2 (Kernel.cpp:861)
   double bias;        // Sigma_Bias (Kernel.cpp:366)
   double white;       // Sigma_White, summed over the White members: added to K_ii of the training covariance only (Kernel.cpp:257-264)
+  double var2x;       // Sigma^2 of a SECOND distance-based member of the Hyb sum (0 without one; its own parameters live in a second
+                      // DevParams block with bias = white = 0 and the same sn2 fields): enters the a-priori bound of the int8 scaling
   double sn2;         // hyperlf(0) (GP_Utils.cpp:406)
   double inv_sn2;     // 1/sn2 = d2lp (GP_Utils.cpp:412-413)
   double sw;          // Sw = sqrt(d2lp) (GP_Utils.cpp:897)
@@ -75,16 +77,30 @@ __global__ void transform_kernel(const double* __restrict__ xs, long ldx, double
 //     (Kernel.cpp:881, 366, 140-154; GP_Utils.cpp:898-902).  One 128x128 tile per CTA, 256 threads,
 //     each thread owns 2 consecutive rows (16-byte coalesced stores down a column) x 32 columns.
 // ---------------------------------------------------------------------------------------------------
+// one member's covariance without the Bias term
+__device__ __forceinline__ double kern_main(double d2, const DevParams& P)
+{
+  if (P.kind == 2) return __dmul_rn(exp(__dmul_rn(P.rbf_c, d2)), P.var2);   // RBF (Kernel.cpp:486)
+  return __dmul_rn(P.var2, exp(-sqrt(d2)));                                  // ExpAns, Exp (Kernel.cpp:881, 640)
+}
+// Hyb{member 1, member 2, Bias} (HybKerns::computeK, Kernel.cpp:140-154): the members' values added in order, then the bias
+__device__ __forceinline__ double kern_val2(double d2a, const DevParams& Pa, double d2b, const DevParams& Pb)
+{
+  return __dadd_rn(__dadd_rn(kern_main(d2a, Pa), kern_main(d2b, Pb)), Pa.bias);
+}
 __device__ __forceinline__ double kern_val(double d2, const DevParams& P)
 {
   if (P.kind == 2) return __dadd_rn(__dmul_rn(exp(__dmul_rn(P.rbf_c, d2)), P.var2), P.bias);   // RBF (Kernel.cpp:486)
   return __dadd_rn(__dmul_rn(P.var2, exp(-sqrt(d2))), P.bias);                                  // ExpAns, Exp (Kernel.cpp:881, 640)
 }
 
+template <bool TWO = false>
 __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ Bm, long ld, const double* __restrict__ zs, long ldz,
                                                            int n, const DevParams* __restrict__ Pp, int raw_K, int own_world, int own_rank,
-                                                           int own_width)
+                                                           int own_width, const double* __restrict__ zs2 = nullptr,
+                                                           const DevParams* __restrict__ P2p = nullptr)
 {
+  // TWO: a second distance-based member (its transformed coordinates zs2, its parameters P2p) is added to every element
   // own_world > 1: only the tile columns of the block columns (own_width tiles wide) this rank owns in the distributed
   // Cholesky are built -- every other block column arrives already factored with the owner's broadcast.
   // own_width < 0 (partitioned storage): Bm holds ONLY this rank's block columns, packed; blockIdx.y is the local tile column.
@@ -98,18 +114,25 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
   } else if (own_world > 1 && (tn / own_width) % own_world != own_rank) return;
   if (tn > tm) return;
   __shared__ double cz[NZ][NB];
-  __shared__ DevParams P;
+  __shared__ double cz2[TWO ? NZ : 1][TWO ? NB : 1];
+  __shared__ DevParams P, P2;
   const int tid = threadIdx.x;
-  if (tid == 0) P = *Pp;
+  if (tid == 0) { P = *Pp; if constexpr (TWO) P2 = *P2p; }
   const int r0 = tm * NB, c0 = tn * NB;
-  for (int idx = tid; idx < NZ * NB; idx += 256) cz[idx / NB][idx % NB] = zs[(long)(idx / NB) * ldz + c0 + idx % NB];
+  for (int idx = tid; idx < NZ * NB; idx += 256) {
+    cz[idx / NB][idx % NB] = zs[(long)(idx / NB) * ldz + c0 + idx % NB];
+    if constexpr (TWO) cz2[idx / NB][idx % NB] = zs2[(long)(idx / NB) * ldz + c0 + idx % NB];
+  }
   const int tx = tid & 63, ty = tid >> 6;
   const int i0 = r0 + 2 * tx;
-  double zi[2][NZ];
+  double zi[2][NZ], zi2[2][TWO ? NZ : 1];
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int q = 0; q < NZ; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+    for (int q = 0; q < NZ; q++) {
+      zi[e][q] = zs[(long)q * ldz + i0 + e];
+      if constexpr (TWO) zi2[e][q] = zs2[(long)q * ldz + i0 + e];
+    }
   __syncthreads();
 #pragma unroll 4
   for (int jj = ty; jj < NB; jj += 4) {
@@ -122,7 +145,12 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(double* __restrict__ 
       double v;
       if (i < n && j < n) {
         const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
-        v = kern_val(d2, P);
+        if constexpr (TWO) {
+          const double d2b = pair_d2(zi2[e][0], zi2[e][1], zi2[e][2], zi2[e][3], cz2[0][jj], cz2[1][jj], cz2[2][jj], cz2[3][jj], zi2[e][4], cz2[4][jj]);
+          v = kern_val2(d2, P, d2b, P2);
+        } else {
+          v = kern_val(d2, P);
+        }
         if (i == j) v = __dadd_rn(v, P.white);                 // Kern_White: K.diag() += Sigma_White (0 without a White member: v unchanged)
         if (!raw_K) {
           v = __dmul_rn(P.sww, v);
@@ -528,18 +556,23 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_part_kernel(const 
 // f = K * alpha with K regenerated from coordinates (mvmK_exact, GP_Utils.cpp:394-397, used at :1147).
 // 64 rows per CTA, 256 threads: thread (row, part) strides over columns, partials combined in smem.
 // ---------------------------------------------------------------------------------------------------
+template <bool TWO = false>
 __global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
-                                                      double* __restrict__ f, int n, const DevParams* __restrict__ Pp)
+                                                      double* __restrict__ f, int n, const DevParams* __restrict__ Pp,
+                                                      const double* __restrict__ zs2 = nullptr, const DevParams* __restrict__ P2p = nullptr)
 {
   __shared__ double cz[6][256];
+  __shared__ double cy[TWO ? 5 : 1][TWO ? 256 : 1];             // the second member's transformed coordinates of the column block
   __shared__ double part[4][64];
-  __shared__ DevParams P;
+  __shared__ DevParams P, P2;
   const int tid = threadIdx.x, rr = tid & 63, pp = tid >> 6;
-  if (tid == 0) P = *Pp;
+  if (tid == 0) { P = *Pp; if constexpr (TWO) P2 = *P2p; }
   const int i = blockIdx.x * 64 + rr;
   const bool vi = i < n;
   const int ic = vi ? i : 0;
   const double z0 = zs[ic], z1 = zs[ldz + ic], z2 = zs[2 * ldz + ic], ai = zs[3 * ldz + ic], z3 = zs[4 * ldz + ic];
+  double y0 = 0, y1 = 0, y2 = 0, bi = 0, y3 = 0;
+  if constexpr (TWO) { y0 = zs2[ic]; y1 = zs2[ldz + ic]; y2 = zs2[2 * ldz + ic]; bi = zs2[3 * ldz + ic]; y3 = zs2[4 * ldz + ic]; }
   double acc = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     __syncthreads();
@@ -547,12 +580,21 @@ __global__ void __launch_bounds__(256) kmatvec_kernel(const double* __restrict__
     if (j < n) {
       cz[0][tid] = zs[j]; cz[1][tid] = zs[ldz + j]; cz[2][tid] = zs[2 * ldz + j]; cz[3][tid] = zs[3 * ldz + j];
       cz[4][tid] = alpha[j]; cz[5][tid] = zs[4 * ldz + j];
-    } else { cz[0][tid] = cz[1][tid] = cz[2][tid] = cz[3][tid] = 0; cz[4][tid] = 0; cz[5][tid] = 0; }
+      if constexpr (TWO) { cy[0][tid] = zs2[j]; cy[1][tid] = zs2[ldz + j]; cy[2][tid] = zs2[2 * ldz + j]; cy[3][tid] = zs2[3 * ldz + j]; cy[4][tid] = zs2[4 * ldz + j]; }
+    } else {
+      cz[0][tid] = cz[1][tid] = cz[2][tid] = cz[3][tid] = 0; cz[4][tid] = 0; cz[5][tid] = 0;
+      if constexpr (TWO) { cy[0][tid] = cy[1][tid] = cy[2][tid] = cy[3][tid] = cy[4][tid] = 0; }
+    }
     __syncthreads();
 #pragma unroll 4
     for (int q = pp; q < 256; q += 4) {
       const double d2 = pair_d2(z0, z1, z2, ai, cz[0][q], cz[1][q], cz[2][q], cz[3][q], z3, cz[5][q]);
-      acc = fma(kern_val(d2, P), cz[4][q], acc);
+      if constexpr (TWO) {
+        const double d2b = pair_d2(y0, y1, y2, bi, cy[0][q], cy[1][q], cy[2][q], cy[3][q], y3, cy[4][q]);
+        acc = fma(kern_val2(d2, P, d2b, P2), cz[4][q], acc);
+      } else {
+        acc = fma(kern_val(d2, P), cz[4][q], acc);
+      }
     }
   }
   part[pp][rr] = acc;
@@ -618,10 +660,16 @@ __global__ void __launch_bounds__(256) lml_terms_kernel(const double* __restrict
 // ---------------------------------------------------------------------------------------------------
 constexpr int NGRAD = 13;
 
+// TWO: the Hyb sum holds a second distance-based member.  The pass is then run once per member (zs / Pp = the member whose entries are
+// being accumulated, zs2 / P2p = the other one): the ExpAns sums use the member's OWN distance (getGradients recomputes DD2 itself,
+// Kernel.cpp:925), the Exp / RBF sums use the D2 argument -- which HybKerns::computeK has SUMMED over the members (Kernel.cpp:140-154,
+// 646-695, 491-541: reproduced).  common != 0 (first member's pass): also tr QW and sum Q o K with the full covariance.
+template <bool TWO = false>
 __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict__ Qm, long ld, const double* __restrict__ zs, long ldz,
                                                         const double* __restrict__ xs, long ldx, const double* __restrict__ alpha,
                                                         int n, const DevParams* __restrict__ Pp, double* __restrict__ partial, int tm0,
-                                                        int tn0, int rmap_P, int rmap_me, int rmap_w)
+                                                        int tn0, int rmap_P, int rmap_me, int rmap_w, int common = 1,
+                                                        const double* __restrict__ zs2 = nullptr, const DevParams* __restrict__ P2p = nullptr)
 {
   // Qm points at the FIRST tile handed to this launch: tile (blockIdx.x, blockIdx.y) of the buffer is global tile (tm, tn) with
   //   tm = tm0 + blockIdx.x                      rows of a contiguous slice (single GPU, replicated layout), or, rmap_P > 1,
@@ -633,25 +681,32 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
   double* out = partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * NGRAD;
   if (tn > tm) { if (threadIdx.x < NGRAD) out[threadIdx.x] = 0.0; return; }
   __shared__ double cz[NZ][NB], cx[NX][NB], ca[NB];
-  __shared__ DevParams P;
+  __shared__ double cy[TWO ? NZ : 1][TWO ? NB : 1];
+  __shared__ DevParams P, P2;
   const int tid = threadIdx.x;
-  if (tid == 0) P = *Pp;
+  if (tid == 0) { P = *Pp; if constexpr (TWO) P2 = *P2p; }
   const int r0 = tm * NB, c0 = tn * NB;
   for (int idx = tid; idx < NB; idx += 256) {
     const int j = c0 + idx;
 #pragma unroll
-    for (int q = 0; q < NZ; q++) cz[q][idx] = zs[(long)q * ldz + j];
+    for (int q = 0; q < NZ; q++) {
+      cz[q][idx] = zs[(long)q * ldz + j];
+      if constexpr (TWO) cy[q][idx] = zs2[(long)q * ldz + j];
+    }
 #pragma unroll
     for (int q = 0; q < NX; q++) cx[q][idx] = xs[(long)q * ldx + j];
     ca[idx] = alpha[j];
   }
   const int tx = tid & 63, ty = tid >> 6;
   const int i0 = r0 + 2 * tx;
-  double zi[2][NZ], xi[2][NX], al[2];
+  double zi[2][NZ], xi[2][NX], al[2], yi[2][TWO ? NZ : 1];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
 #pragma unroll
-    for (int q = 0; q < NZ; q++) zi[e][q] = zs[(long)q * ldz + i0 + e];
+    for (int q = 0; q < NZ; q++) {
+      zi[e][q] = zs[(long)q * ldz + i0 + e];
+      if constexpr (TWO) yi[e][q] = zs2[(long)q * ldz + i0 + e];
+    }
 #pragma unroll
     for (int q = 0; q < NX; q++) xi[e][q] = xs[(long)q * ldx + i0 + e];
     al[e] = alpha[i0 + e];
@@ -667,7 +722,13 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
     for (int e = 0; e < 2; e++) {
       const int i = i0 + e;
       if (i < n && j < n && i >= j) {
-        const double d2 = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
+        const double d2own = pair_d2(zi[e][0], zi[e][1], zi[e][2], zi[e][3], cz[0][jj], cz[1][jj], cz[2][jj], cz[3][jj], zi[e][4], cz[4][jj]);
+        double d2 = d2own, Ktot = 0.0;
+        if constexpr (TWO) {
+          const double d2o = pair_d2(yi[e][0], yi[e][1], yi[e][2], yi[e][3], cy[0][jj], cy[1][jj], cy[2][jj], cy[3][jj], yi[e][4], cy[4][jj]);
+          if (P.kind != 0) d2 = __dadd_rn(d2own, d2o);                       // Exp / RBF: the D2 argument is the members' sum
+          if (common) Ktot = kern_val2(d2own, P, d2o, P2);
+        }
         const double QWij = qe[e] * P.inv_sn2 - al[e] * ca[jj];
         if (P.kind != 0) {
           // isotropic kernels: two pair sums each (slots G6 and RK), see combine_gradient_iso
@@ -687,20 +748,27 @@ __global__ void __launch_bounds__(256) grad_pass_kernel(const double* __restrict
           }
           g6 += mult * a;
           rk += mult * b;
-          if (i == j) tr += QWij;
-          qk += mult * (qe[e] * ((i == j) ? __dadd_rn(kern_val(d2, P), P.white) : kern_val(d2, P)));
+          if constexpr (TWO) {
+            if (common) {
+              if (i == j) tr += QWij;
+              qk += mult * (qe[e] * ((i == j) ? __dadd_rn(Ktot, P.white) : Ktot));
+            }
+          } else {
+            if (i == j) tr += QWij;
+            qk += mult * (qe[e] * ((i == j) ? __dadd_rn(kern_val(d2, P), P.white) : kern_val(d2, P)));
+          }
           continue;
         }
         const double s = sqrt(d2);
         const double es = exp(-s);
-        const double Kij = __dadd_rn(__dmul_rn(P.var2, es), P.bias);
+        const double Kij = TWO ? Ktot : __dadd_rn(__dmul_rn(P.var2, es), P.bias);
+        const bool cm = !TWO || common;
         if (i == j) {
           g6 += QWij * es;
-          tr += QWij;
-          qk += qe[e] * __dadd_rn(Kij, P.white);
+          if (cm) { tr += QWij; qk += qe[e] * __dadd_rn(Kij, P.white); }
         } else {
           g6 += 2.0 * (QWij * es);
-          qk += 2.0 * (qe[e] * Kij);
+          if (cm) qk += 2.0 * (qe[e] * Kij);
           const double dr = xi[e][3] - cx[3][jj];
           rk = fma(es, dr * dr, rk);
           if (s != 0.0) {
@@ -850,32 +918,42 @@ __global__ void zero_region_kernel(double* __restrict__ p, long ld, int rows, in
 //        predictive-mean partial sums fused in:  mu_part[tile_i][j] = sum_{i in tile} alpha_i K(x*_j,x_i)
 //        (GP_Utils.cpp:943-949, 958-972, 985-990).  grid = (m_pad/128, n_pad/128), 256 threads.
 // ---------------------------------------------------------------------------------------------------
+template <bool TWO = false>
 __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ Bm, long ldb, const double* __restrict__ zt, long ldzt,
                                                           const double* __restrict__ zs, long ldz, const double* __restrict__ alpha,
                                                           int m, int n, const DevParams* __restrict__ Pp,
-                                                          double* __restrict__ mu_part, long ldmu, int write_B, double white_x, long goff)
+                                                          double* __restrict__ mu_part, long ldmu, int write_B, double white_x, long goff,
+                                                          const double* __restrict__ zt2 = nullptr, const double* __restrict__ zs2 = nullptr,
+                                                          const DevParams* __restrict__ P2p = nullptr)
 {
   // white_x != 0: Kern_White::computeK's condition held for the whole call (X1(0) == X2(0) and equally many rows, Kernel.cpp:261-262),
   // so element (i, i) of the n x m cross-covariance carries Sigma_White; goff = global test index of this batch's column 0.
   __shared__ double cz[NZ][NB], ca[NB];
+  __shared__ double cy[TWO ? NZ : 1][TWO ? NB : 1];
   __shared__ double mred[4][NB];
-  __shared__ DevParams P;
+  __shared__ DevParams P, P2;
   const int tid = threadIdx.x;
-  if (tid == 0) P = *Pp;
+  if (tid == 0) { P = *Pp; if constexpr (TWO) P2 = *P2p; }
   const int j0t = blockIdx.x * NB, i0t = blockIdx.y * NB;
   for (int idx = tid; idx < NB; idx += 256) {
     const int i = i0t + idx;
 #pragma unroll
-    for (int q = 0; q < NZ; q++) cz[q][idx] = zs[(long)q * ldz + i];
+    for (int q = 0; q < NZ; q++) {
+      cz[q][idx] = zs[(long)q * ldz + i];
+      if constexpr (TWO) cy[q][idx] = zs2[(long)q * ldz + i];
+    }
     ca[idx] = (i < n) ? alpha[i] : 0.0;
   }
   const int tx = tid & 63, ty = tid >> 6;
   const int j0 = j0t + 2 * tx;
-  double zj[2][NZ];
+  double zj[2][NZ], yj[2][TWO ? NZ : 1];
 #pragma unroll
   for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int q = 0; q < NZ; q++) zj[e][q] = zt[(long)q * ldzt + j0 + e];
+    for (int q = 0; q < NZ; q++) {
+      zj[e][q] = zt[(long)q * ldzt + j0 + e];
+      if constexpr (TWO) yj[e][q] = zt2[(long)q * ldzt + j0 + e];
+    }
   __syncthreads();
   double mu[2] = {0, 0};
   for (int ii = ty; ii < NB; ii += 4) {
@@ -888,7 +966,13 @@ __global__ void __launch_bounds__(256) cross_build_kernel(double* __restrict__ B
       if (i < n && (j0 + e) < m) {
         // K(X_train, X_test)(i,j): first argument is the training point (GP_Utils.cpp:946-947)
         const double d2 = pair_d2(cz[0][ii], cz[1][ii], cz[2][ii], cz[3][ii], zj[e][0], zj[e][1], zj[e][2], zj[e][3], cz[4][ii], zj[e][4]);
-        double k = kern_val(d2, P);
+        double k;
+        if constexpr (TWO) {
+          const double d2b = pair_d2(cy[0][ii], cy[1][ii], cy[2][ii], cy[3][ii], yj[e][0], yj[e][1], yj[e][2], yj[e][3], cy[4][ii], yj[e][4]);
+          k = kern_val2(d2, P, d2b, P2);
+        } else {
+          k = kern_val(d2, P);
+        }
         if (white_x != 0.0 && (long)i == goff + j0 + e) k = __dadd_rn(k, white_x);
         mu[e] = fma(ca[ii], k, mu[e]);
         v = __dmul_rn(k, P.sw);
