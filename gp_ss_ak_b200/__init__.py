@@ -78,6 +78,9 @@ def load_library():
         "gpss_debug_fetch": (I, [H, I, P, L]),
         "gpss_padded_n": (I, [H, ctypes.POINTER(I)]),
         "gpss_set_white": (I, [H, D, I]),
+        "gpss_set_kernel2": (I, [H, I]),
+        "gpss_set_theta2": (I, [H, P]),
+        "gpss_get_grad2": (I, [H, P]),
         "gpss_get_ozaki": (I, [H, ctypes.POINTER(I)]),
         "gpss_get_ozaki_fallbacks": (I, [H, ctypes.POINTER(L)]),
         "gpss_get_ozaki_bits": (I, [H, ctypes.POINTER(I)]),
@@ -235,6 +238,20 @@ class GpssModel:
         v = ctypes.c_int(0)
         _check(self._lib.gpss_get_ozaki(self._h, ctypes.byref(v)))
         return v.value
+
+    def set_member2(self, kind2, theta2=None):
+        """Second distance-based member of the Hyb sum: kind2 = -1 (none) | 0 ExpAns | 1 Exp | 2 RBF, theta2 = its own parameters."""
+        _check(self._lib.gpss_set_kernel2(self._h, int(kind2)))
+        if theta2 is not None:
+            t = np.zeros(8)
+            t[:len(theta2)] = theta2
+            _check(self._lib.gpss_set_theta2(self._h, _dp(t)))
+
+    def grad2(self):
+        """Gradient entries of the second member from the last nlml_grad() (8 slots, the member's own parameter order)."""
+        g = np.zeros(8)
+        _check(self._lib.gpss_get_grad2(self._h, _dp(g)))
+        return g
 
     def set_white(self, sigma_white, cross_diagonal=False):
         """Sum of the White members' Sigma_White (Kernel.cpp:180-270); cross_diagonal: see include/gpss.h."""

@@ -15,12 +15,31 @@ __global__ void scale_copy_kernel(double* __restrict__ dst, const double* __rest
 // ---------------------------------------------------------------------------------------------------
 // objective pieces
 // ---------------------------------------------------------------------------------------------------
+// the second member's parameters in the 10-slot layout of ITS kind: [own parameters ..., Sigma_Bias = 0, sn2]
+static void member2_theta(const gpss_ctx* c, double t2[GPSS_NPAR])
+{
+  for (int i = 0; i < GPSS_NPAR; i++) t2[i] = 0.0;
+  const int np = kernel_npar(c->kind2);
+  for (int i = 0; i < np - 2; i++) t2[i] = c->theta2[i];
+  t2[np - 2] = 0.0;
+  t2[np - 1] = theta_sn2(c->kind, c->theta);
+}
+
 static int upload_params(gpss_ctx* c, int slot, const double* centre)
 {
-  DevParams P;
-  fill_params(c->theta, centre, P, c->d, c->kind, c->white);
+  DevParams P, P2;
+  double var2x = 0.0;
+  if (c->kind2 >= 0) {
+    // the second member's block: its own parameters in the 10-slot layout of its kind (bias 0), the same sn2
+    double t2[GPSS_NPAR];
+    member2_theta(c, t2);
+    fill_params(t2, centre, P2, c->d, c->kind2, 0.0);
+    var2x = P2.var2;
+    CU(cudaMemcpyAsync(c->dP + 2 + slot, &P2, sizeof P2, cudaMemcpyHostToDevice, c->st));
+  }
+  fill_params(c->theta, centre, P, c->d, c->kind, c->white, var2x);
   CU(cudaMemcpyAsync(c->dP + slot, &P, sizeof P, cudaMemcpyHostToDevice, c->st));
-  CU(cudaStreamSynchronize(c->st));   // P is a stack object
+  CU(cudaStreamSynchronize(c->st));   // P, P2 are stack objects
   return GPSS_OK;
 }
 
@@ -48,7 +67,12 @@ static int enqueue_factor(gpss_ctx* c)
   {
     PhaseTimer t(c, 0);
     transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs, ld, c->n, n_pad, c->dP);
-    if (c->partitioned)
+    if (c->kind2 >= 0) {
+      transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, ld, c->zs2, ld, c->n, n_pad, c->dP + 2);
+      kbuild_lower_kernel<true><<<dim3(c->nblk, c->nblk), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank, NBO / NB,
+                                                                          c->zs2, c->dP + 2);
+      c->launches++;
+    } else if (c->partitioned)
       kbuild_lower_kernel<<<dim3(c->nblk, (unsigned)(c->lcols / NB)), 256, 0, c->st>>>(c->Lm, ld, c->zs, ld, c->n, c->dP, 0, c->world, c->rank,
                                                                                       -(NBO / NB));
     else
@@ -79,7 +103,8 @@ static int enqueue_solves(gpss_ctx* c)
     c->launches++;
     if (c->partitioned) RET(potrs_vec_partitioned(c));
     else RET(potrs_vec(c));
-    kmatvec_kernel<<<(c->n + 63) / 64, 256, 0, c->st>>>(c->zs, n_pad, c->alpha, c->fvec, c->n, c->dP);
+    if (c->kind2 >= 0) kmatvec_kernel<true><<<(c->n + 63) / 64, 256, 0, c->st>>>(c->zs, n_pad, c->alpha, c->fvec, c->n, c->dP, c->zs2, c->dP + 2);
+    else kmatvec_kernel<<<(c->n + 63) / 64, 256, 0, c->st>>>(c->zs, n_pad, c->alpha, c->fvec, c->n, c->dP);
     lml_terms_kernel<<<1, 256, 0, c->st>>>(c->y, c->alpha, c->fvec, c->n, c->dP, c->logdet_parts, c->nblk, c->red);
     c->launches += 2;
     CU(cudaGetLastError());
@@ -236,7 +261,7 @@ int gpss_destroy(gpss_handle c)
   cudaSetDevice(c->device);
   double** bufs[] = {&c->xs, &c->y, &c->zs, &c->Lm, &c->Um, &c->Qm, &c->Winv, &c->logdet_parts, &c->rvec, &c->zvec, &c->alpha,
                      &c->fvec, &c->Tpanel, &c->Wjj, &c->partial, &c->red, &c->xt, &c->zt, &c->zsp, &c->Bm, &c->Vm, &c->mu_part,
-                     &c->dmu, &c->dvar};
+                     &c->dmu, &c->dvar, &c->zs2, &c->zsp2, &c->zt2, &c->partial2};
   for (auto b : bufs) if (*b) cudaFree(*b);
   if (c->dP) cudaFree(c->dP);
   if (c->dflag) cudaFree(c->dflag);
@@ -329,8 +354,8 @@ static int create_impl(int device, int n, int d, const double* X, const double* 
   CUF(cudaMalloc(&c->zvec, sizeof(double) * np));
   CUF(cudaMalloc(&c->alpha, sizeof(double) * np));
   CUF(cudaMalloc(&c->fvec, sizeof(double) * np));
-  CUF(cudaMalloc(&c->red, sizeof(double) * 32));
-  CUF(cudaMalloc(&c->dP, sizeof(DevParams) * 2));
+  CUF(cudaMalloc(&c->red, sizeof(double) * 64));
+  CUF(cudaMalloc(&c->dP, sizeof(DevParams) * 4));
   CUF(cudaMalloc(&c->dflag, 2 * sizeof(int)));
   CUF(cudaMemsetAsync(c->dflag, 0, 2 * sizeof(int), c->st));
   CUF(cudaMemsetAsync(c->alpha, 0, sizeof(double) * np, c->st));
@@ -441,6 +466,41 @@ int gpss_set_white(gpss_handle c, double sigma_white, int cross_diagonal)
   return GPSS_OK;
 }
 
+// A SECOND distance-based member of the additive covariance (HybKerns with two of ExpAns | Exp | RBF, gp_ss_ak.cpp:146-175;
+// HybKerns::computeK / getGradients, Kernel.cpp:140-169).  kind2 < 0 removes it.
+int gpss_set_kernel2(gpss_handle c, int kind2)
+{
+  if (!c || kind2 > 2) return fail_arg("gpss_set_kernel2: kind must be -1 (none), GPSS_KERNEL_EXPANS, _EXP or _RBF");
+  if (kind2 < 0) kind2 = -1;
+  if (kind2 >= 0 && c->partitioned) return fail_arg("gpss_set_kernel2: not supported on partitioned handles");
+  if (kind2 == c->kind2) return GPSS_OK;
+  CU(cudaSetDevice(c->device));
+  if (kind2 >= 0) RET(ensure_lazy(&c->zs2, (size_t)NZ * c->n_pad));
+  c->kind2 = kind2;
+  // captured graphs hold the kernel instantiations and pointer arguments of the old member set
+  CU(cudaStreamSynchronize(c->st));
+  for (int w = 0; w < 2; w++) if (c->graph[w]) { cudaGraphExecDestroy(c->graph[w]); c->graph[w] = nullptr; }
+  c->have_factor = c->have_alpha = c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_set_theta2(gpss_handle c, const double* theta2)
+{
+  if (!c || !theta2) return fail_arg("gpss_set_theta2: null argument");
+  memcpy(c->theta2, theta2, sizeof c->theta2);
+  c->have_factor = c->have_alpha = c->have_U = false;
+  c->qstate = Q_NONE;
+  return GPSS_OK;
+}
+
+int gpss_get_grad2(gpss_handle c, double g2[8])
+{
+  if (!c || !g2) return fail_arg("gpss_get_grad2: null argument");
+  memcpy(g2, c->g2, sizeof c->g2);
+  return GPSS_OK;
+}
+
 int gpss_get_theta(gpss_handle c, double theta[GPSS_NPAR])
 {
   if (!c || !theta) return fail_arg("gpss_get_theta: null argument");
@@ -504,9 +564,9 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
       }
     }
     if (!replayed) RET(enqueue_gradient(c));
-    double red[NGRAD];
+    double red[2 * NGRAD];
     int viol = 0;
-    CU(cudaMemcpyAsync(red, c->red + 8, sizeof red, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(red, c->red + 8, sizeof(double) * (c->kind2 >= 0 ? 2 : 1) * NGRAD, cudaMemcpyDeviceToHost, c->st));
     if (oz_active(c)) CU(cudaMemcpyAsync(&viol, c->dflag + 1, sizeof viol, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     if (viol && attempt == 0) {
@@ -526,6 +586,16 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
     }
     if (c->kind == 0) combine_gradient(c->theta, red, c->s3, g, c->d, c->n);
     else { for (int i = 0; i < GPSS_NPAR; i++) g[i] = 0.0; combine_gradient_iso(c->kind, c->theta, red, c->s3, g); }
+    if (c->kind2 >= 0) {
+      // the second member's entries from ITS pass (its own 10-slot layout; the bias / sn2 slots of that result are meaningless: tr QW and
+      // sum Q o K were accumulated in the first pass only)
+      double t2[GPSS_NPAR], gm[GPSS_NPAR];
+      member2_theta(c, t2);
+      for (int i = 0; i < GPSS_NPAR; i++) gm[i] = 0.0;
+      if (c->kind2 == 0) combine_gradient(t2, red + NGRAD, c->s3, gm, c->d, c->n);
+      else combine_gradient_iso(c->kind2, t2, red + NGRAD, c->s3, gm);
+      for (int i = 0; i < 8; i++) c->g2[i] = (i < kernel_npar(c->kind2) - 2) ? gm[i] : 0.0;
+    }
     return GPSS_OK;
   }
 }
@@ -551,8 +621,10 @@ static int ensure_gradient_buffers(gpss_ctx* c)
     if (c->partial) cudaFree(c->partial);
     c->partial = nullptr;
     CU(cudaMalloc(&c->partial, sizeof(double) * (nblocks > 0 ? nblocks : 1) * NGRAD));
+    if (c->partial2) { cudaFree(c->partial2); c->partial2 = nullptr; }
     c->partial_blocks = nblocks;
   }
+  if (c->kind2 >= 0 && !c->partial2) CU(cudaMalloc(&c->partial2, sizeof(double) * (nblocks > 0 ? nblocks : 1) * NGRAD));
   return GPSS_OK;
 }
 
@@ -569,15 +641,26 @@ static int enqueue_gradient(gpss_ctx* c)
   const long nblocks = (long)ntm * c->nblk;
   {
     PhaseTimer t(c, 5);
-    if (ntm > 0) {
+    if (ntm > 0 && c->kind2 >= 0) {
+      // one pass per distance-based member (grad_pass_kernel<true>): the first also carries tr QW and sum Q o K
+      grad_pass_kernel<true><<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm + (long)tm0 * NB, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha,
+                                                                   c->n, c->dP, c->partial, tm0, 0, 0, 0, 1, 1, c->zs2, c->dP + 2);
+      grad_pass_kernel<true><<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm + (long)tm0 * NB, c->n_pad, c->zs2, c->n_pad, c->xs, c->n_pad, c->alpha,
+                                                                   c->n, c->dP + 2, c->partial2, tm0, 0, 0, 0, 1, 0, c->zs, c->dP);
+      c->launches += 2;
+    } else if (ntm > 0) {
       grad_pass_kernel<<<dim3(ntm, c->nblk), 256, 0, c->st>>>(c->Qm + (long)tm0 * NB, c->n_pad, c->zs, c->n_pad, c->xs, c->n_pad, c->alpha, c->n,
                                                              c->dP, c->partial, tm0, 0, 0, 0, 1);
       c->launches++;
     }
     sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial, nblocks, c->red + 8);
     c->launches++;
+    if (c->kind2 >= 0) {
+      sum_partials_kernel<NGRAD><<<1, 256, 0, c->st>>>(c->partial2, nblocks, c->red + 8 + NGRAD);
+      c->launches++;
+    }
     CU(cudaGetLastError());
-    if (c->world > 1) NC(g_nccl.AllReduce(c->red + 8, c->red + 8, NGRAD, ncclDouble, ncclSum, c->comm, c->st));
+    if (c->world > 1) NC(g_nccl.AllReduce(c->red + 8, c->red + 8, (c->kind2 >= 0 ? 2 : 1) * NGRAD, ncclDouble, ncclSum, c->comm, c->st));
     if (c->world > 1 && oz_active(c)) NC(g_nccl.AllReduce(c->dflag + 1, c->dflag + 1, 1, ncclInt, ncclMax, c->comm, c->st));   // all ranks take the same branch
   }
   return GPSS_OK;
@@ -719,8 +802,15 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
   RET(upload_params(c, 1, centre));
   transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp, n_pad, c->n, n_pad, c->dP + 1);
   c->launches++;
+  if (c->kind2 >= 0) {
+    RET(ensure_lazy(&c->zsp2, (size_t)NZ * n_pad));
+    RET(ensure_lazy(&c->zt2, (size_t)NZ * cap));
+    transform_kernel<<<(n_pad + 255) / 256, 256, 0, c->st>>>(c->xs, n_pad, c->zsp2, n_pad, c->n, n_pad, c->dP + 3);
+    c->launches++;
+  }
   const double sig_k = theta_sigma(c->kind, c->theta);
-  const double kD = sig_k * sig_k + theta_bias(c->kind, c->theta) + c->white;   // diag_Compute (Kernel.cpp:782, 449, 594, 331, 222-225, 127-136)
+  double kD = sig_k * sig_k + theta_bias(c->kind, c->theta) + c->white;   // diag_Compute (Kernel.cpp:782, 449, 594, 331, 222-225, 127-136)
+  if (c->kind2 >= 0) { double t2[GPSS_NPAR]; member2_theta(c, t2); const double s2 = theta_sigma(c->kind2, t2); kD += s2 * s2; }
   const double white_x = (c->white_cross && m_total == c->n) ? c->white : 0.0;   // Kern_White::computeK on (X_train, X_test), Kernel.cpp:257-264
   for (long off = 0; off < count; off += cap) {
     const int mb = (int)((count - off < cap) ? (count - off) : cap);
@@ -729,8 +819,14 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
     for (int j = 0; j < c->d; j++)
       CU(cudaMemcpyAsync(c->xt + (long)j * cap, Xs + (long)j * ldx + off, sizeof(double) * mb, cudaMemcpyHostToDevice, c->st));
     transform_kernel<<<(m_pad + 255) / 256, 256, 0, c->st>>>(c->xt, cap, c->zt, cap, mb, m_pad, c->dP + 1);
+    if (c->kind2 >= 0) transform_kernel<<<(m_pad + 255) / 256, 256, 0, c->st>>>(c->xt, cap, c->zt2, cap, mb, m_pad, c->dP + 3);
     {
       PhaseTimer t(c, 6);
+      if (c->kind2 >= 0)
+        cross_build_kernel<true><<<dim3(m_pad / NB, c->nblk), 256, 0, c->st>>>(c->Bm, m_pad, c->zt, cap, c->zsp, n_pad, c->alpha, mb, c->n,
+                                                                            c->dP + 1, c->mu_part, cap, var ? 1 : 0, white_x, shard_off + off,
+                                                                            c->zt2, c->zsp2, c->dP + 3);
+      else
       cross_build_kernel<<<dim3(m_pad / NB, c->nblk), 256, 0, c->st>>>(c->Bm, m_pad, c->zt, cap, c->zsp, n_pad, c->alpha, mb, c->n,
                                                                     c->dP + 1, c->mu_part, cap, var ? 1 : 0, white_x, shard_off + off);
       mean_finish_kernel<<<(mb + 255) / 256, 256, 0, c->st>>>(c->mu_part, cap, c->nblk, mb, c->dmu);

@@ -140,6 +140,12 @@ struct gpss_ctx {
   bool oz_predict = false, ozW_valid = false, oz_w_fresh = false;
   int8_t *ozW = nullptr, *ozB = nullptr;
   CUtensorMap oz_tmW[2], oz_tmB[2];
+  // a SECOND distance-based member of the Hyb sum (gpss_set_kernel2 / gpss_set_theta2; kind2 < 0: none).  Its transformed coordinates
+  // and its parameter blocks (dP[2] training, dP[3] prediction) sit beside the first member's; the kernels that evaluate K take both.
+  int kind2 = -1;
+  double theta2[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // the member's own parameters, in its own order (Kernel.h)
+  double g2[8] = {0, 0, 0, 0, 0, 0, 0, 0};                     // its gradient entries from the last gpss_nlml_grad
+  double *zs2 = nullptr, *zsp2 = nullptr, *zt2 = nullptr, *partial2 = nullptr;
   // host state
   double white = 0.0;                                          // sum of the White members' Sigma_White (gpss_set_white); 0 without one
   int white_cross = 0;                                         // the next gpss_predict adds it on the cross-covariance diagonal (Kernel.cpp:261-262)
@@ -332,7 +338,8 @@ struct PhaseTimer {
 // ---------------------------------------------------------------------------------------------------
 // parameters -> device
 // ---------------------------------------------------------------------------------------------------
-static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0, double white = 0.0)
+static void fill_params(const double theta[GPSS_NPAR], const double* centre, DevParams& P, int dim = 3, int kind = 0, double white = 0.0,
+                        double var2x = 0.0)
 {
   memset(&P, 0, sizeof P);
   for (int j = 0; j < dim; j++) P.c[j] = centre[j];
@@ -352,6 +359,7 @@ static void fill_params(const double theta[GPSS_NPAR], const double* centre, Dev
   P.var2 = sig * sig;
   P.bias = theta_bias(kind, theta);
   P.white = white;
+  P.var2x = var2x;
   P.sn2 = sn2;
   P.inv_sn2 = 1 / sn2;
   P.sw = std::sqrt(P.inv_sn2);

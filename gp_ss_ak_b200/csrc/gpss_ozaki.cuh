@@ -97,8 +97,8 @@ __device__ __forceinline__ int oz_exponent(int kind, const gpss::DevParams* P, i
 {
   if (bits != 8 && (kind == SCALE_UNIT || P == nullptr)) return 0;
   double bound = 1.0;
-  if (kind == SCALE_CROSS && P) bound = P->sw * (P->var2 + P->bias + P->white);
-  else if (kind == SCALE_CHOL && P) bound = sqrt(1.0 + P->sww * (P->var2 + P->bias + P->white));
+  if (kind == SCALE_CROSS && P) bound = P->sw * (P->var2 + P->var2x + P->bias + P->white);
+  else if (kind == SCALE_CHOL && P) bound = sqrt(1.0 + P->sww * (P->var2 + P->var2x + P->bias + P->white));
   if (bits == 8) bound *= 128.0 / 127.5;
   int e;
   frexp(bound, &e);                                           // bound = f 2^e, f in [0.5, 1)

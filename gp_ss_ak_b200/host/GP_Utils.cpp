@@ -54,6 +54,8 @@ void GP_utils::_init()
   handle = 0;
   handle_n = -1;
   kind_dev = -1;
+  kind2_dev = -1;
+  for (int i = 0; i < 8; i++) theta2_dev[i] = 0.0;
   white_cross = 0;
   data_stale = true;
   dirty = true;
@@ -135,14 +137,17 @@ void GP_utils::device_failure(const char* what) const
 // Members of the Hyb covariance as the device sees them: at most one distance-based member (the "main" kernel of the C ABI),
 // any number of Bias members (their parameters add up in the Sigma_Bias slot) and of White members (gpss_set_white).
 struct MemberMap {
-  int main_member;          // index of the ExpAns | Exp | RBF member, -1 if none
+  int main_member;          // index of the first ExpAns | Exp | RBF member, -1 if none
   int main_first;           // its first parameter in the concatenated vector
   int kind;                 // GPSS_KERNEL_* of it (ExpAns with Sigma = 0 stands in when there is none)
-  bool ok;                  // false: something this build does not evaluate (two distance members, an unknown member)
+  int second_member;        // index of a second distance-based member, -1 if none (gpss_set_kernel2)
+  int second_first;
+  int kind2;
+  bool ok;                  // false: something this build does not evaluate (three distance members, an unknown member)
 };
 static MemberMap map_members(const Kernels* K)
 {
-  MemberMap m = {-1, 0, GPSS_KERNEL_EXPANS, true};
+  MemberMap m = {-1, 0, GPSS_KERNEL_EXPANS, -1, 0, -1, true};
   const mainKernel* hyb = dynamic_cast<const mainKernel*>(K);
   if (!hyb || K->getKerName() != "Hyb" || hyb->getNumKerns() < 1) { m.ok = false; return m; }
   int first = 0;
@@ -150,8 +155,9 @@ static MemberMap map_members(const Kernels* K)
     const string name = hyb->getKern(i)->getKerName();
     const int kind = name == "ExpAns" ? GPSS_KERNEL_EXPANS : name == "Exp" ? GPSS_KERNEL_EXP : name == "RBF" ? GPSS_KERNEL_RBF : -1;
     if (kind >= 0) {
-      if (m.main_member >= 0) m.ok = false;                  // a sum of two distance-based kernels
-      m.main_member = (int)i; m.main_first = first; m.kind = kind;
+      if (m.main_member < 0) { m.main_member = (int)i; m.main_first = first; m.kind = kind; }
+      else if (m.second_member < 0) { m.second_member = (int)i; m.second_first = first; m.kind2 = kind; }
+      else m.ok = false;                                     // a sum of three distance-based kernels
     } else if (name != "Bias" && name != "White Noise") {
       m.ok = false;
     }
@@ -165,8 +171,8 @@ void GP_utils::check_supported() const
   const char* why = 0;
   if (!KerenlW) why = "no kernel";
   else if (!map_members(KerenlW).ok)
-    why = "the kernel must be Hyb{at most one of ExpAns | Exp | RBF, any number of Bias and White members} (-k ExpAns|Exp|RBF|Bias|White, -kn 0|1); "
-          "a sum of two distance-based kernels is not evaluated by this build";
+    why = "the kernel must be Hyb{at most two of ExpAns | Exp | RBF, any number of Bias and White members} (-k ExpAns|Exp|RBF|Bias|White, -kn 0|1); "
+          "a sum of three distance-based kernels is not evaluated by this build";
   else if (Xinp.n_cols != 3 && Xinp.n_cols != 4) why = "inputs must have 3 columns, or 4 with the rock-type column";
   else if (yTarg.n_cols != 1 || getOutDim() != 1) why = "exactly one output column is supported";
   else if (likelihoodType_ != likeL_Gaussian || getNumlikfpar() != 1) why = "only the Gaussian likelihood is supported";
@@ -247,6 +253,7 @@ void GP_utils::sync_device() const
     }
     handle_n = n;
     kind_dev = GPSS_KERNEL_EXPANS;       // a new handle starts with the default kernel
+    kind2_dev = -1;
     data_stale = false;
     dirty = true;
   } else if (data_stale) {
@@ -260,6 +267,24 @@ void GP_utils::sync_device() const
     dirty = true;
   }
   if (gpss_set_white(handle, white_now(), white_cross) != GPSS_OK) device_failure("gpss_set_white");   // invalidates only on change
+  {
+    // second distance-based member (gpss_set_kernel2 / gpss_set_theta2): sent when it changes
+    const MemberMap mm = map_members(KerenlW);
+    const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
+    double t2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (mm.second_member >= 0)
+      for (unsigned int i = 0; i < hyb->getKern(mm.second_member)->getNPars() && i < 8; i++) t2[i] = KerenlW->getParam(mm.second_first + i);
+    if (mm.kind2 != kind2_dev) {
+      if (gpss_set_kernel2(handle, mm.kind2) != GPSS_OK) device_failure("gpss_set_kernel2");
+      kind2_dev = mm.kind2;
+      dirty = true;
+    }
+    if (mm.second_member >= 0 && (dirty || std::memcmp(t2, theta2_dev, sizeof t2) != 0)) {
+      if (gpss_set_theta2(handle, t2) != GPSS_OK) device_failure("gpss_set_theta2");
+      std::memcpy(theta2_dev, t2, sizeof t2);
+      dirty = true;
+    }
+  }
   double theta[GPSS_NPAR];
   theta_now(theta);
   if (dirty || std::memcmp(theta, theta_dev, sizeof theta) != 0) {
@@ -318,11 +343,14 @@ double GP_utils::GradLL(mat& g) const
   const mainKernel* hyb = dynamic_cast<const mainKernel*>(KerenlW);
   const MemberMap mm = map_members(KerenlW);
   const unsigned int nk = (mm.main_member >= 0) ? hyb->getKern(mm.main_member)->getNPars() : Kern_ExpAnisotropic().getNPars();
+  double gv2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (mm.second_member >= 0 && gpss_get_grad2(handle, gv2) != GPSS_OK) device_failure("gpss_get_grad2");
   g_param.set_size(1, KerenlW->getNPars());
   unsigned int at = 0;
   for (unsigned int i = 0; i < hyb->getNumKerns(); i++) {
     const Kernels* k = hyb->getKern(i);
     if ((int)i == mm.main_member) for (unsigned int q = 0; q < nk; q++) g_param(at + q) = gv[q];
+    else if ((int)i == mm.second_member) for (unsigned int q = 0; q < k->getNPars(); q++) g_param(at + q) = gv2[q];
     else if (k->getKerName() == "Bias") g_param(at) = gv[nk];
     else g_param(at) = 0.0;                                  // White: getGradParam (Kernel.cpp:265-269); see Kernel.h on the reference's crash
     at += k->getNPars();

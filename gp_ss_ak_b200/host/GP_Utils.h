@@ -93,6 +93,8 @@ class GP_utils : public Modeling, public Main_Opt_Algs, public StreamIntfce {
   void check_supported() const;
   void theta_now(double theta[GPSS_NPAR]) const;
   double white_now() const;                        // sum of the White members' Sigma_White (gpss_set_white)
+  mutable int kind2_dev;                           // second distance-based member last sent to the device (-1: none)
+  mutable double theta2_dev[8];
   mutable int white_cross;                         // Kern_White's cross-covariance condition for the next prediction
   void sync_device() const;                        // create the handle / push data and parameters if stale
   [[noreturn]] void device_failure(const char* what) const;

@@ -59,6 +59,15 @@ int gpss_set_theta(gpss_handle h, const double theta[GPSS_NPAR]);
  * (gpss_predict only; gpss_predict_shard callers own the offset bookkeeping and do not get this quirk).  The gradient entry of a
  * White member is 0 (getGradParam, :266-270).  Invalidates the factorisation when the value changes. */
 int gpss_set_white(gpss_handle h, double sigma_white, int cross_diagonal);
+/* A SECOND distance-based member of the additive covariance: `gp_ss_ak train -k ExpAns -k RBF ...` builds Hyb{ExpAns, RBF[, Bias]}
+ * (gp_ss_ak.cpp:146-175), HybKerns::computeK adds the members' K AND their D2 (Kernel.cpp:140-154), HybKerns::getGradients hands
+ * every member the SUMMED D2 (:156-169) -- which Exp / RBF use as their distance (Kernel.cpp:646-695, 491-541) while ExpAns
+ * recomputes its own (:925).  All of that is reproduced.  kind2 = -1 (none) | GPSS_KERNEL_EXPANS | _EXP | _RBF; theta2 = the member's
+ * own parameters in its own order (8 slots read: ExpAns 8, Exp 2, RBF 3); its gradient entries come back through gpss_get_grad2
+ * after gpss_nlml_grad.  The first member, Sigma_Bias and sn2 stay in gpss_set_kernel / gpss_set_theta.  Not on partitioned handles. */
+int gpss_set_kernel2(gpss_handle h, int kind2);
+int gpss_set_theta2(gpss_handle h, const double* theta2);
+int gpss_get_grad2(gpss_handle h, double g2[8]);
 int gpss_get_theta(gpss_handle h, double theta[GPSS_NPAR]);
 /* The main kernel of the Hyb{main, Bias} covariance -- the reference's `-k` choice (gp_ss_ak.cpp:146-170; HybKerns,
  * Kernel.cpp:140-169).  theta and g keep their 10-slot arrays; the slots in use are

@@ -344,7 +344,11 @@ def sign_ref(v):
 class OracleGP:
     """State-carrying restatement of GP_utils for Gaussian likelihood, zero mean (GP_Utils.cpp)."""
 
-    def __init__(self, X, y, theta=None, dist="defined", literal=True, white=0.0):
+    def __init__(self, X, y, theta=None, dist="defined", literal=True, white=0.0, member2=None):
+        # member2: a SECOND distance-based member of the Hyb sum (gp_ss_ak.cpp:146-175), as a parameter vector in the single-kernel
+        # layout of its own kind (10 ExpAns / 4 Exp / 5 RBF) with the Sigma_Bias slot 0 and the sn2 slot ignored.  HybKerns::computeK adds
+        # the members' K and D2 (Kernel.cpp:140-154); getGradients hands every member the SUMMED D2 (:156-169).
+        self.member2 = None if member2 is None else np.array(member2, dtype=np.float64)
         # white: sum of the White members' Sigma_White (Kern_White, Kernel.cpp:180-270): K.diag() += white when computeK sees the same
         # point set twice (`X1(0) == X2(0) && X1.n_rows == X2.n_rows`, :261-262), prior variance += white (:222-225), gradient 0
         self.white = float(white)
@@ -379,6 +383,10 @@ class OracleGP:
     def update_kernel(self):
         if not self.K_ok:
             self.K, self.D2 = compute_K(self.X, self.X, self.theta, self.dist)
+            if self.member2 is not None:
+                K2, D2b = compute_K(self.X, self.X, self.member2, self.dist)
+                self.K = self.K + K2
+                self.D2 = self.D2 + D2b
             if self.white != 0.0:
                 self.K[np.diag_indices(self.n)] += self.white
             self.K_ok = True
@@ -597,6 +605,14 @@ class OracleGP:
         else:
             g[0:3] = rbf_gradients_literal(self.theta, QW, self.D2)
         g[npar - 2] = bias_gradient_literal(QW)
+        if self.member2 is not None:
+            k2 = kernel_of(self.member2)
+            if k2 == "ExpAns":
+                self.g2 = expans_gradients_literal(self.X, self.member2, QW, self.dist)
+            elif k2 == "Exp":
+                self.g2 = exp_gradients_literal(self.member2, QW, self.D2)
+            else:
+                self.g2 = rbf_gradients_literal(self.member2, QW, self.D2)
         # likelihood hyper-parameter (GP_Utils.cpp:1222-1235, 846-871)
         sn2 = self.sn2
         ymmu = self.y - self.yhat
@@ -617,11 +633,15 @@ class OracleGP:
     def predict(self, Xs):
         Xs = np.ascontiguousarray(Xs, dtype=np.float64)
         kX, _ = compute_K(self.X, Xs, self.theta, self.dist)      # n x m, centre uses BOTH sets (Kernel.cpp:1391)
+        if self.member2 is not None:
+            kX = kX + compute_K(self.X, Xs, self.member2, self.dist)[0]
         if self.white != 0.0 and Xs.shape[0] == self.n and Xs[0, 0] == self.X[0, 0]:      # Kern_White::computeK(X_train, X_test), Kernel.cpp:261-262
             kX[np.diag_indices(self.n)] += self.white
         self.update_alpha()
         mu = kX.T @ self.Alpha
         kD = np.full(Xs.shape[0], sigma_of(self.theta) ** 2 + self.theta[-2] + self.white)      # diag_Compute (Kernel.cpp:782, 331, 449, 594, 222-225)
+        if self.member2 is not None:
+            kD = kD + sigma_of(self.member2) ** 2
         self.log_likelihood()                                         # GP_Utils.cpp:980
         Wh = np.sqrt(self.d2lp)
         LKs = kX * Wh[:, None]
@@ -863,3 +883,18 @@ def white_fixture_cases(z):
             else:
                 out.append((tag, k, np.concatenate([th[:8], th[9:]]), float(th[8])))
     return out
+
+
+NPAR_MEMBER = {"ExpAns": 8, "Exp": 2, "RBF": 3}
+KIND_CODE = {"ExpAns": 0, "Exp": 1, "RBF": 2}
+
+
+def split_sum2_theta(combo, th):
+    """Parameter vector of Hyb{a, b, Bias} in the reference's order [a's parameters, b's parameters, Sigma_Bias, sn2] ->
+    (theta of member a in its single-kernel layout [.., Sigma_Bias, sn2], member b in its layout with the bias slot 0, names)."""
+    a, b = combo.split("+")
+    na, nb = NPAR_MEMBER[a], NPAR_MEMBER[b]
+    th = np.asarray(th, dtype=np.float64).ravel()
+    t1 = np.concatenate([th[:na], th[na + nb:]])
+    t2 = np.concatenate([th[na:na + nb], [0.0, th[-1]]])
+    return t1, t2, a, b

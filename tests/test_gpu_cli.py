@@ -126,9 +126,9 @@ def test_cli_baseline_config0_n2000(tmp_path):
 def test_cli_rejects_configurations_outside_the_hot_path(tmp_path):
     z = np.load(os.path.join(GOLD, "ref_n300.npz"))
     (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
-    # a sum of two distance-based members is the one additive combination this build does not evaluate (GP_utils::check_supported)
-    out = subprocess.run([CLI, "train", "-k", "ExpAns", "-k", "RBF", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True, text=True,
-                         stdin=subprocess.DEVNULL, cwd=tmp_path)
+    # a sum of THREE distance-based members is the one additive combination this build does not evaluate (GP_utils::check_supported)
+    out = subprocess.run([CLI, "train", "-k", "ExpAns", "-k", "RBF", "-k", "Exp", str(tmp_path / "train.txt"), str(tmp_path / "m")], capture_output=True,
+                         text=True, stdin=subprocess.DEVNULL, cwd=tmp_path)
     assert out.returncode == 1 and "outside the B200 hot path" in (out.stdout + out.stderr) and "no CPU fallback" in (out.stdout + out.stderr)
 
 
@@ -227,3 +227,28 @@ def test_cli_white_member_trains_where_the_reference_crashes(tmp_path):
         te = subprocess.run([CLI, "-v", "1", "-pm", "1", "test", str(tmp_path / "train.txt"), model, str(tmp_path / "train.txt")],
                             capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path)
         assert te.returncode == 1 and "Unknown kernel type" in (te.stdout + te.stderr)
+
+
+@pytest.mark.parametrize("a,b", [("ExpAns", "RBF"), ("RBF", "Exp")])
+def test_cli_sum_of_two_kernels_matches_reference_run(tmp_path, a, b):
+    """`gp_ss_ak -v 3 -pm 1 train -k a -k b -kn 1 -o LBFGS -# 2` (Hyb{a, b, Bias}): the printed objective of the initial model and of
+    the fitted one, and the written model file, against the unmodified reference's run on the same file (ref_sum2_n300.npz)."""
+    z = np.load(os.path.join(GOLD, "ref_sum2_n300.npz"))
+    (tmp_path / "train.txt").write_text(str(z["train_file_text"]))
+    tag = a + "_" + b
+    model = str(tmp_path / "m")
+    tr = subprocess.run([CLI, "-v", "3", "-pm", "1", "train", "-k", a, "-k", b, "-kn", "1", "-o", "LBFGS", "-#", "2", str(tmp_path / "train.txt"), model],
+                        capture_output=True, text=True, stdin=subprocess.DEVNULL, cwd=tmp_path)
+    assert tr.returncode == 0, tr.stdout + tr.stderr
+    ref_ll = _floats_after(str(z[tag + "_cli_train_stdout"]), "Log likelihood:")
+    mine_ll = _floats_after(tr.stdout, "Log likelihood:")
+    assert len(mine_ll) == len(ref_ll) and np.allclose(mine_ll, ref_ll, rtol=5e-5)
+    ref_model = [l for l in str(z[tag + "_cli_model_text"]).splitlines()]
+    mine_model = open(model).read().splitlines()
+    assert len(ref_model) == len(mine_model)
+    for lr, lm in zip(ref_model, mine_model):
+        if "=" in lr and not lr.startswith("Hyperparams"):
+            assert lr == lm
+        elif not lr.startswith("#"):
+            assert np.allclose([float(v) for v in lm.replace("Hyperparams_likelihood=", "").split()],
+                               [float(v) for v in lr.replace("Hyperparams_likelihood=", "").split()], rtol=2e-4, atol=2e-6)

@@ -623,3 +623,44 @@ def test_white_member_against_oracle_and_reference(gpss):
         assert abs(g[8] - float(np.trace(Q / t10[9] - np.outer(gp.Alpha, gp.Alpha)))) <= 1e-7 * max(1.0, np.abs(g).max())
     m.set_white(0.0)
     m.close()
+
+
+@pytest.mark.parametrize("combo", ["ExpAns+RBF", "Exp+ExpAns", "RBF+Exp"])
+def test_sum_of_two_distance_members_against_oracle_and_reference(gpss, combo):
+    """Hyb{a, b, Bias} with two distance-based members through gpss_set_kernel2 / gpss_set_theta2 (reference gp_ss_ak.cpp:146-175,
+    HybKerns Kernel.cpp:140-169): K and D2 summed over the members, ExpAns entries from its own distance, Exp / RBF entries from the
+    summed D2.  Against the oracle at the header's tolerances and the unmodified reference's dumps at the reference floor."""
+    z = np.load(os.path.join(GOLD, "ref_sum2_n300.npz"))
+    Xs, ys = z["Xs"], z["ys"].ravel()
+    tag = combo.replace("+", "_")
+    m = gpss.GpssModel(Xs, ys)
+    for k in range(2):
+        t1, t2, a, b = O.split_sum2_theta(combo, z["%s_theta_%d" % (tag, k)])
+        na, nb = O.NPAR_MEMBER[a], O.NPAR_MEMBER[b]
+        m.set_kernel(a)
+        m.set_member2(O.KIND_CODE[b], t2[:nb])
+        m.set_theta(t1)
+        L, g = m.nlml_grad()
+        g2 = m.grad2()
+        gcat = np.concatenate([g[:na], g2[:nb], g[na:]])
+        a_dev = m.alpha()
+        mu, var = m.predict(z["Xt"])
+        gp = O.OracleGP(Xs, ys, t1, literal=True, member2=t2)
+        Lo, go = gp.grad_ll()
+        gocat = np.concatenate([go[:na], gp.g2, go[na:]])
+        mu_o, var_o = gp.predict(z["Xt"])
+        assert abs(L - Lo) <= TOL_NLML * abs(Lo)
+        ok = np.isfinite(gocat)                               # Exp's own gradient is NaN for duplicate points in the reference too
+        assert np.abs(gcat[ok] - gocat[ok]).max() <= TOL_G * np.abs(gocat[ok]).max()
+        assert np.linalg.norm(a_dev - gp.Alpha) <= TOL_ALPHA * np.linalg.norm(gp.Alpha)
+        assert np.abs(mu - mu_o).max() <= TOL_MU and np.abs(var - var_o).max() <= TOL_VAR
+        gr, Lr = z["%s_g_%d" % (tag, k)].ravel(), float(z["%s_nlml_%d" % (tag, k)])
+        assert abs(L - Lr) <= 5e-7 * abs(Lr)
+        assert np.abs(gcat - gr).max() <= 5e-6 * np.abs(gr).max()
+        assert np.abs(mu - z["%s_mu_%d" % (tag, k)].ravel()).max() <= 5e-7
+        assert np.abs(var - z["%s_var_%d" % (tag, k)].ravel()).max() <= 1e-7
+    m.set_member2(-1)
+    m.set_kernel("ExpAns")
+    m.set_theta(O.THETA0)
+    assert np.isfinite(m.nlml())
+    m.close()

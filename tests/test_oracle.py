@@ -217,3 +217,29 @@ def test_oracle_white_member_matches_reference():
             assert np.abs(mu - z["%s_%s_mu_%d" % (tag, tset, k)].ravel()).max() <= 5e-7
             assert np.abs(var - z["%s_%s_var_%d" % (tag, tset, k)].ravel()).max() <= 1e-7
     assert int(z["cli_w_rc"]) != 0 and int(z["cli_ew_rc"]) != 0          # the reference dies in the first gradient (Kernel.h:56-59)
+
+
+def test_oracle_sum_of_two_distance_members_matches_reference():
+    """Hyb{a, b, Bias} with two distance-based members (gp_ss_ak.cpp:146-175, Kernel.cpp:140-169) against the unmodified reference
+    (tests/golden/ref_sum2_n300.npz: ExpAns+RBF, Exp+ExpAns, RBF+Exp): objective, all gradient entries in the reference's parameter
+    order, Alpha, predictions.  The isotropic members' gradients use the D2 summed over the members, as HybKerns hands it to them."""
+    z = np.load(os.path.join(GOLD, "ref_sum2_n300.npz"))
+    Xs, ys = z["Xs"], z["ys"].ravel()
+    for combo in [str(c) for c in z["combos"]]:
+        tag = combo.replace("+", "_")
+        for k in range(2):
+            t1, t2, a, b = O.split_sum2_theta(combo, z["%s_theta_%d" % (tag, k)])
+            gp = O.OracleGP(Xs, ys, t1, dist="blas", literal=True, member2=t2)
+            L, g = gp.grad_ll()
+            na = O.NPAR_MEMBER[a]
+            gcat = np.concatenate([g[:na], gp.g2, g[na:]])
+            gr, Lr = z["%s_g_%d" % (tag, k)].ravel(), float(z["%s_nlml_%d" % (tag, k)])
+            assert gcat.shape == gr.shape
+            assert abs(L - Lr) <= 5e-7 * abs(Lr)
+            assert np.abs(gcat - gr).max() <= 5e-6 * np.abs(gr).max()
+            ar = z["%s_alpha_%d" % (tag, k)].ravel()
+            assert np.abs(gp.Alpha - ar).max() <= 2e-6 * np.abs(ar).max()
+            mu, var = gp.predict(z["Xt"])
+            assert np.abs(mu - z["%s_mu_%d" % (tag, k)].ravel()).max() <= 5e-7
+            assert np.abs(var - z["%s_var_%d" % (tag, k)].ravel()).max() <= 1e-7
+        assert int(z[tag + "_cli_rc"]) == 0
