@@ -261,7 +261,7 @@ int gpss_destroy(gpss_handle c)
   cudaSetDevice(c->device);
   double** bufs[] = {&c->xs, &c->y, &c->zs, &c->Lm, &c->Um, &c->Qm, &c->Winv, &c->logdet_parts, &c->rvec, &c->zvec, &c->alpha,
                      &c->fvec, &c->Tpanel, &c->Wjj, &c->partial, &c->red, &c->xt, &c->zt, &c->zsp, &c->Bm, &c->Vm, &c->mu_part,
-                     &c->dmu, &c->dvar, &c->zs2, &c->zsp2, &c->zt2, &c->partial2};
+                     &c->dmu, &c->dvar, &c->zs2, &c->zsp2, &c->zt2, &c->partial2, &c->Wpan};
   for (auto b : bufs) if (*b) cudaFree(*b);
   if (c->dP) cudaFree(c->dP);
   if (c->dflag) cudaFree(c->dflag);

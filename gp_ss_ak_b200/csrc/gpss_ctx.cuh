@@ -92,6 +92,11 @@ struct gpss_ctx {
   cudaStream_t st3 = nullptr;                                 // second look-ahead stream: consecutive bulk updates alternate so
                                                               // the tail wave of one is filled by the head of the next
   cudaStream_t st4 = nullptr;                                 // communication stream of the pipelined panel broadcast (highest priority)
+  cudaStream_t st5 = nullptr;                                 // distributed Cholesky: the full-height part of U2 runs here (highest priority) WHILE the main
+                                                              // stream factors the 512 x 512 diagonal block of the same block column
+  cudaStream_t st6 = nullptr;                                 // distributed Cholesky: digit planes of a received panel (they gate bulk updates only)
+  cudaEvent_t ev_u2 = nullptr, ev_unpacked = nullptr;         // st5 / st6 dependencies of the above
+  double* Wpan = nullptr;                                     // 2 x NBO x NBO: inverse of the current diagonal block (transposed scratch | lower, column-major)
   std::vector<cudaEvent_t> ev_pipe;                           // per 128-column sub-panel: [2 i] factored on the owner, [2 i + 1] received
   cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead
   std::vector<cudaEvent_t> ev_pool;                           // per-panel events of the look-ahead Cholesky / inverse
@@ -193,7 +198,7 @@ static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
   // stream -- U2, the panel solves, the rank-128 updates, the diagonal blocks of the inverse -- would wait for whole SMs to drain.
   // The same kernel with a 2-stage ring (51 KB, same registers, bitwise the same sums) fits NEXT TO a resident int8 CTA, on the
   // FP64 pipe that CTA leaves idle.  (8 planes of 7 bits take 193 KB: no room, the hardware then simply queues these CTAs.)
-  if (c->dmma_coresident && stream == c->st && parts == 1) {
+  if (c->dmma_coresident && (stream == c->st || (c->st5 && stream == c->st5)) && parts == 1) {
     using T2 = GemmTileWideWS2;
     gemm_nt_ws_kernel<T2><<<(unsigned)(ga.mt * ga.nt), T2::THREADS, T2::SMEM_BYTES, stream>>>(ga);
     c->launches++;

@@ -174,7 +174,12 @@ static void destroy_streams(gpss_ctx* c)
   for (auto e : c->ev_pipe) cudaEventDestroy(e);
   c->ev_pipe.clear();
   if (c->st4) cudaStreamDestroy(c->st4);
-  c->st4 = nullptr;
+  if (c->st5) cudaStreamDestroy(c->st5);
+  if (c->st6) cudaStreamDestroy(c->st6);
+  if (c->ev_u2) cudaEventDestroy(c->ev_u2);
+  if (c->ev_unpacked) cudaEventDestroy(c->ev_unpacked);
+  c->st4 = c->st5 = c->st6 = nullptr;
+  c->ev_u2 = c->ev_unpacked = nullptr;
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
   if (c->st) cudaStreamDestroy(c->st);

@@ -119,6 +119,48 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
   return potrf_panel(c, A, ld, n_pad, K0, nbk, Winv, logdet_parts, dflag, [](int) { return (int)GPSS_OK; });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Distributed critical path, fused form.  A block column is factored in two parts with different latencies:
+//   (1) potrf_diag_chain: ONLY the nbk x nbk diagonal block D -- the 128-steps of potrf_panel with every GEMM cut down to the rows of
+//       D (<= 384), then W = inv(L_D) as one nbk x nbk lower-triangular matrix (trtri_diag_block + a transpose).  ~30 dependent launches
+//       on <= 2 MB of data: pure latency, independent of n.
+//   (2) ONE full-height GEMM  A[below D, block column] <- A[below D, block column] W^T  (k = nbk, triangular k-range), written
+//       out of place -- straight into the broadcast buffer, so the pack kernel disappears too.
+// The old panel made the full height wait for each of the four diagonal steps (16 dependent full-height launches, 0.73 ms at n = 50 000);
+// here the full-height work is one launch after the chain, and the owner applies the full-height part of U2 on a second stream WHILE the
+// chain runs (potrf_blocked).  Same flops (m x 512^2 / 2 x 2 against m x 163 840 x 2).
+// ---------------------------------------------------------------------------------------------------
+static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj);
+static int potrf_diag_chain(gpss_ctx* c, double* A, long ld, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
+{
+  for (int k = K0; k < K0 + nbk; k += NB) {
+    double* Akk = A + (long)k * ld + k;
+    double* Wk = Winv + (long)(k / NB) * NB * NB;
+    potrf_diag_inv_kernel<<<1, DIAG_THREADS, DIAG_SMEM, c->st>>>(Akk, ld, Wk, logdet_parts + k / NB, dflag);
+    c->launches++;
+    CU(cudaGetLastError());
+    const int m = K0 + nbk - k - NB;                    // rows of D below this step
+    if (m <= 0) continue;
+    double* A21 = A + (long)k * ld + (k + NB);
+    GemmArgs g1 = gemm_args(A21, ld, Wk + 64, NB, A21 + 64 * ld, ld, m, 64, NB);
+    RET(gemm(c, g1));
+    GemmArgs g2 = gemm_args(A21, ld, Wk, NB, A21, ld, m, 64, 64);
+    RET(gemm(c, g2));
+    double* A22 = A + (long)(k + NB) * ld + (k + NB);
+    GemmArgs g = gemm_args(A21, ld, A21, ld, A22, ld, m, m, NB);
+    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = k + NB; g.gcol0 = k + NB;
+    RET(gemm(c, g));
+  }
+  // W = inv(L_D): the transposed inverse in 128-steps (as the diagonal blocks of U = L^-T), then transposed into column-major lower form
+  double* Ud = c->Wpan;
+  double* Wd = c->Wpan + (size_t)NBO * NBO;
+  RET(trtri_diag_block(c, Ud - ((long)K0 * NBO + K0), NBO, A, ld, K0, nbk));
+  transpose_kernel<<<dim3(nbk / 32, nbk / 32), 256, 0, c->st>>>(Wd, NBO, Ud, NBO, 1);
+  c->launches++;
+  CU(cudaGetLastError());
+  return GPSS_OK;
+}
+
 // LEFT-looking blocked Cholesky with look-ahead.  Block column T (width NBO) receives
 //     U1(T):  A[T:, T] -= L[T:, 0:T-1] L[T, 0:T-1]^T     (panels 0..T-2: one long-k DMMA GEMM, side stream)
 //     U2(T):  A[T:, T] -= L[T:, T-1]   L[T, T-1]^T       (panel T-1, k = NBO, main stream)
@@ -171,6 +213,32 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     const double* Lp = A + (long)kbeg * ld + T0;
     GemmArgs g = gemm_args(Lp, ld, Lp, ld, A + (long)T0 * ld + T0, ld, n_pad - T0, nbT, klen);
     g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
+    return gemm_ws_on(c, g, stream);
+  };
+  // fused distributed panel (default for P > 1; GPSS_DIST_PANEL=0: the 16-launch panel with U2 in front of it)
+  const bool fused = P > 1 && !pipe_env && Winv == c->Winv && !(getenv("GPSS_DIST_PANEL") && atoi(getenv("GPSS_DIST_PANEL")) == 0);
+  // GPSS_DIST_U2=int8: the full-height part of U2 on the int8 kernel (its CTAs need whole SMs, which the bulk updates hold) instead of the
+  // co-resident DMMA kernel
+  const bool u2_int8 = fused && ozk && getenv("GPSS_DIST_U2") && !strcmp(getenv("GPSS_DIST_U2"), "int8");
+  if (fused) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (!c->st5) CU(cudaStreamCreateWithPriority(&c->st5, cudaStreamNonBlocking, hi));
+    if (!c->st6) CU(cudaStreamCreateWithPriority(&c->st6, cudaStreamNonBlocking, hi));
+    if (!c->ev_u2) CU(cudaEventCreateWithFlags(&c->ev_u2, cudaEventDisableTiming));
+    if (!c->ev_unpacked) CU(cudaEventCreateWithFlags(&c->ev_unpacked, cudaEventDisableTiming));
+    if (!c->Wpan) CU(cudaMalloc(&c->Wpan, sizeof(double) * 2 * NBO * NBO));
+  }
+  const bool fused1 = P == 1 && la && Winv == c->Winv && getenv("GPSS_PANEL") && !strcmp(getenv("GPSS_PANEL"), "fused");
+  if (fused1) {
+    if (!c->Wpan) CU(cudaMalloc(&c->Wpan, sizeof(double) * 2 * NBO * NBO));
+    RET(ensure_stage(c, (size_t)n_pad * NBO));
+  }
+  // rows [T0 + r0, T0 + r0 + rows) of block column T0 -= L[same rows, kbeg : kbeg + klen] L[T0 : T0 + nbT, kbeg : kbeg + klen]^T  (DMMA)
+  auto update_rows = [&](int T0, int nbT, int r0, int rows, int kbeg, int klen, cudaStream_t stream) -> int {
+    if (rows <= 0) return GPSS_OK;
+    GemmArgs g = gemm_args(A + (long)kbeg * ld + T0 + r0, ld, A + (long)kbeg * ld + T0, ld, A + (long)T0 * ld + T0 + r0, ld, rows, nbT, klen);
+    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0 + r0; g.gcol0 = T0;
     return gemm_ws_on(c, g, stream);
   };
   if (P > 1) {
@@ -251,6 +319,68 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
         }
         continue;
       }
+      if (fused && op.kind != DIST_WAIT_SIDE && op.kind != DIST_UPDATE_SIDE) {
+        const long rows = n_pad - T0;
+        const size_t n_panel = (size_t)rows * nbT, n_w = (size_t)(nbT / NB) * NB * NB, n_l = nbT / NB;
+        double* Wt = Winv + (size_t)(T0 / NB) * NB * NB;
+        if (op.kind == DIST_UPDATE_MAIN) {
+          // U2 = panel T-1 (unpacked on this stream just before).  Its rows of the diagonal block first, on the main stream, so that the
+          // latency chain can start; everything below on st5, concurrently with the chain.
+          const int kb = op.pbeg * NBO, kl = op.pcnt * NBO;
+          if (u2_int8) {
+            RET(update(T0, nbT, kb, kl, c->st));                           // needs the planes of panel T-1: cut on this stream in DIST_BCAST
+          } else {
+            CU(cudaEventRecord(c->ev_main, c->st));
+            CU(cudaStreamWaitEvent(c->st5, c->ev_main, 0));
+            RET(update_rows(T0, nbT, 0, nbT, kb, kl, c->st));
+            RET(update_rows(T0, nbT, nbT, (int)rows - nbT, kb, kl, c->st5));
+            CU(cudaEventRecord(c->ev_u2, c->st5));
+          }
+          mark(1);
+        } else if (op.kind == DIST_FACTOR) {
+          RET(potrf_diag_chain(c, A, ld, T0, nbT, Winv, logdet_parts, dflag));
+          mark(2);
+          if (!u2_int8 && op.col >= 1) CU(cudaStreamWaitEvent(c->st, c->ev_u2, 0));
+          // the solved rows below D go straight into the broadcast buffer: stage(r, j) = sum_{k <= j} A(T0 + nbT + r, T0 + k) W(j, k)
+          if (rows > nbT) {
+            GemmArgs g = gemm_args(A + (long)T0 * ld + T0 + nbT, ld, c->Wpan + (size_t)NBO * NBO, NBO, c->stage + nbT, rows, (int)rows - nbT, nbT, nbT);
+            g.kend_col = 1;
+            RET(gemm_ws_on(c, g, c->st));
+          }
+          copy2d_kernel<<<64, 256, 0, c->st>>>(c->stage, rows, A + (long)T0 * ld + T0, ld, nbT, nbT);
+          CU(cudaMemcpyAsync(c->stage + n_panel, Wt, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+          CU(cudaMemcpyAsync(c->stage + n_panel + n_w, logdet_parts + T0 / NB, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+          c->launches++;
+          mark(3);
+        } else {   // DIST_BCAST
+          const bool mine = op.root == me;
+          NC(g_nccl.Broadcast(c->stage, c->stage, n_panel + n_w + n_l, ncclDouble, op.root, c->comm, c->st));
+          mark(mine ? 4 : 5);
+          if (mine) {                                                      // D is in place already; the rows below it come back from the buffer
+            if (rows > nbT) {
+              copy2d_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0 + nbT, ld, c->stage + nbT, rows, rows - nbT, nbT);
+              c->launches++;
+            }
+          } else {
+            unpack_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0, ld, c->stage, rows, nbT);
+            CU(cudaMemcpyAsync(Wt, c->stage + n_panel, n_w * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaMemcpyAsync(logdet_parts + T0 / NB, c->stage + n_panel + n_w, n_l * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            c->launches++;
+          }
+          mark(6);
+          if (ozk && !u2_int8) {
+            // digit planes of the panel: read by the bulk updates only, so they are cut beside the critical path
+            CU(cudaEventRecord(c->ev_unpacked, c->st));
+            CU(cudaStreamWaitEvent(c->st6, c->ev_unpacked, 0));
+            RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st6));
+            CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st6));
+          } else {
+            if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));
+            CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));
+          }
+        }
+        continue;
+      }
       switch (op.kind) {
         case DIST_WAIT_SIDE:                                               // every side-stream update of my column
           CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * op.col + 1], 0));
@@ -307,10 +437,19 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
       }
     }
     if (pipe) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * (nblk_o - 1)], 0));   // the last panel has arrived on the comm stream
+    if (fused && ozk && !u2_int8) {                                              // every plane cut on st6 is complete before anything that follows
+      CU(cudaEventRecord(c->ev_unpacked, c->st6));
+      CU(cudaStreamWaitEvent(c->st, c->ev_unpacked, 0));
+    }
     if (trace) {
       CU(cudaStreamSynchronize(c->st));
-      static const char* names[7] = {"wait for look-ahead updates", "U2 (panel j-1 -> my column)", "panel factorisation", "pack", "broadcast (as root)",
-                                     "broadcast (as receiver, incl. waiting for the owner)", "unpack"};
+      const char* names[7] = {"wait for look-ahead updates", "U2 (panel j-1 -> my column)", "panel factorisation", "pack", "broadcast (as root)",
+                              "broadcast (as receiver, incl. waiting for the owner)", "unpack"};
+      if (fused) {
+        names[1] = "U2 rows of the diagonal block (the rest runs beside the chain)";
+        names[2] = "diagonal-block chain + inverse";
+        names[3] = "wait for U2 + full-height solve into the broadcast buffer";
+      }
       double sum[7] = {0, 0, 0, 0, 0, 0, 0};
       int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
       for (size_t i = 1; i < marks.size(); i++) {
@@ -336,6 +475,17 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     cudaEvent_t evP = c->ev_pool[2 * t], evU = c->ev_pool[2 * t + 1];
     if (t >= 2) CU(cudaStreamWaitEvent(c->st, evU, 0));              // U1(t) was issued on the side stream below
     if (t >= 1) RET(update(T0, nbT, T0 - NBO, NBO, c->st));          // U2(t)
+    if (fused1) {                                                    // GPSS_PANEL=fused: the distributed path's panel on one GPU (tests, A/B timing)
+      const long rows = n_pad - T0;
+      RET(potrf_diag_chain(c, A, ld, T0, nbT, Winv, logdet_parts, dflag));
+      if (rows > nbT) {
+        GemmArgs g = gemm_args(A + (long)T0 * ld + T0 + nbT, ld, c->Wpan + (size_t)NBO * NBO, NBO, c->stage, rows - nbT, (int)rows - nbT, nbT, nbT);
+        g.kend_col = 1;
+        RET(gemm_ws_on(c, g, c->st));
+        copy2d_kernel<<<592, 256, 0, c->st>>>(A + (long)T0 * ld + T0 + nbT, ld, c->stage, rows - nbT, rows - nbT, nbT);
+        c->launches++;
+      }
+    } else
     RET(potrf_panel(c, A, ld, n_pad, T0, nbT, Winv, logdet_parts, dflag));
     if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));   // planes of panel t
     CU(cudaEventRecord(evP, c->st));

@@ -664,3 +664,33 @@ def test_sum_of_two_distance_members_against_oracle_and_reference(gpss, combo):
     m.set_theta(O.THETA0)
     assert np.isfinite(m.nlml())
     m.close()
+
+
+@pytest.mark.parametrize("n,ozaki", [(3000, "0"), (9000, None)])
+def test_fused_panel_of_the_distributed_path_on_one_gpu(gpss, monkeypatch, n, ozaki):
+    """The multi-GPU Cholesky factors a block column as (1) a latency chain on its 512 x 512 diagonal block that ends in inv(L_D) and
+    (2) ONE full-height GEMM with that inverse (potrf_diag_chain, gpss_potrf.cuh).  GPSS_PANEL=fused runs the same panel on a single-GPU
+    handle, so its numerics are pinned here without a second GPU: every output against the default handle (16-launch panel), which the
+    tests above hold against the oracle and the compiled reference (chol: GP_Utils.cpp:881,903)."""
+    if ozaki is None:
+        monkeypatch.delenv("GPSS_OZAKI", raising=False)
+    else:
+        monkeypatch.setenv("GPSS_OZAKI", ozaki)
+    monkeypatch.setenv("GPSS_NO_GRAPH", "1")
+    X, y = datagen.drillholes(n, 11)
+    Xs, ys, params = datagen.standardise_symmetric(X, y)
+    Xt = Xs[:: max(1, n // 100)][:64] + 0.01
+    out = []
+    for panel in (None, "fused"):
+        if panel:
+            monkeypatch.setenv("GPSS_PANEL", panel)
+        m = gpss.GpssModel(Xs, ys)
+        m.set_theta(O.THETA0)
+        L, g = m.nlml_grad()
+        out.append((L, g, m.alpha(), *m.predict(Xt)))
+        m.close()
+    (L0, g0, a0, mu0, v0), (L, g, a, mu, v) = out
+    assert np.isfinite(L) and abs(L - L0) <= 1e-11 * abs(L0)
+    assert np.abs(g - g0).max() <= 1e-9 * np.abs(g0).max()
+    assert np.linalg.norm(a - a0) <= 1e-10 * np.linalg.norm(a0)
+    assert np.abs(mu - mu0).max() <= 1e-10 and np.abs(v - v0).max() <= 1e-9
