@@ -171,6 +171,10 @@ static int run_graph(gpss_ctx* c, int which)
 
 static int ensure_objective(gpss_ctx* c)
 {
+  if (c->solve_pending) {                              // an overlapped evaluation that ended early (error path): order the main stream after its solves
+    CU(cudaStreamWaitEvent(c->st, c->ev_solved, 0));
+    c->solve_pending = false;
+  }
   if (!c->have_factor && graphs_enabled(c)) {
     const int nblk_o = (c->n_pad + NBO - 1) / NBO;
     RET(ensure_event_pool(c, 2 * nblk_o + 2));
@@ -205,6 +209,53 @@ static int ensure_objective(gpss_ctx* c)
   }
   c->have_alpha = true;
   return GPSS_OK;
+}
+
+// gpss_nlml_grad on a theta that has no factor yet (every optimiser probe, every bench step): the vector solves for alpha are a chain of
+// 2 x n/128 dependent HBM-bound step launches (24 ms at n = 50 000, the same on every rank of a multi-GPU handle) that need only L, like
+// the inverse.  They are enqueued on their own stream and run BESIDE the tensor-bound inverse; the gradient pass waits for both, and the
+// objective's scalars travel to the host with the gradient sums (one synchronisation per evaluation instead of two).
+// Not for graph-replayed sizes, partitioned storage or while phase timers are on; GPSS_NO_SOLVE_OVERLAP=1 restores the serial order.
+static bool solve_overlap_enabled(const gpss_ctx* c)
+{
+  if (c->have_factor || c->partitioned || c->profiling || !c->st2 || graphs_enabled(c)) return false;
+  return getenv("GPSS_NO_SOLVE_OVERLAP") == nullptr;
+}
+
+static int enqueue_objective_overlapped(gpss_ctx* c)
+{
+  if (!c->st7) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&c->st7, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&c->ev_factored, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_solved, cudaEventDisableTiming));
+  }
+  RET(upload_train_params(c));
+  RET(enqueue_factor(c));
+  CU(cudaEventRecord(c->ev_factored, c->st));
+  CU(cudaStreamWaitEvent(c->st7, c->ev_factored, 0));
+  cudaStream_t main_stream = c->st;
+  c->st = c->st7;                                     // enqueue_solves launches on the handle's stream
+  const int rc = enqueue_solves(c);
+  c->st = main_stream;
+  RET(rc);
+  CU(cudaEventRecord(c->ev_solved, c->st7));
+  c->solve_pending = true;
+  return GPSS_OK;
+}
+
+// after the synchronisation that follows an overlapped evaluation: what ensure_objective does with the scalars
+static void finish_objective(gpss_ctx* c, const double red[4], int flag)
+{
+  c->chol_fail = flag;
+  if (flag) {
+    c->nlml = std::numeric_limits<double>::quiet_NaN();
+  } else {
+    c->nlml = red[0] - red[1] + red[3];
+    c->s3 = red[2];
+  }
+  c->have_alpha = true;
 }
 
 static int ensure_lazy(double** p, size_t count)
@@ -525,11 +576,16 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
   CallTimer ct(c);
-  RET(ensure_objective(c));
-  *nlml = c->nlml;
-  if (c->chol_fail) {
-    for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
-    return GPSS_NOT_POSDEF;
+  const bool overlapped = solve_overlap_enabled(c);
+  if (overlapped) {
+    RET(enqueue_objective_overlapped(c));            // no host synchronisation: nlml and the failure flag are read below, with the gradient sums
+  } else {
+    RET(ensure_objective(c));
+    *nlml = c->nlml;
+    if (c->chol_fail) {
+      for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
+      return GPSS_NOT_POSDEF;
+    }
   }
   if (c->partitioned) {
     RET(part_buffers(c));
@@ -568,7 +624,23 @@ int gpss_nlml_grad(gpss_handle c, double* nlml, double g[GPSS_NPAR])
     int viol = 0;
     CU(cudaMemcpyAsync(red, c->red + 8, sizeof(double) * (c->kind2 >= 0 ? 2 : 1) * NGRAD, cudaMemcpyDeviceToHost, c->st));
     if (oz_active(c)) CU(cudaMemcpyAsync(&viol, c->dflag + 1, sizeof viol, cudaMemcpyDeviceToHost, c->st));
+    double red_obj[4];
+    int flag_obj = 0;
+    if (overlapped && attempt == 0) {
+      CU(cudaMemcpyAsync(red_obj, c->red, sizeof red_obj, cudaMemcpyDeviceToHost, c->st));
+      CU(cudaMemcpyAsync(&flag_obj, c->dflag, sizeof flag_obj, cudaMemcpyDeviceToHost, c->st));
+    }
     CU(cudaStreamSynchronize(c->st));
+    if (overlapped && attempt == 0) {
+      finish_objective(c, red_obj, flag_obj);
+      *nlml = c->nlml;
+      if (c->chol_fail) {                              // the inverse above ran on a failed factor: nothing of it is kept
+        c->have_U = false;
+        c->qstate = Q_NONE;
+        for (int i = 0; i < GPSS_NPAR; i++) g[i] = std::numeric_limits<double>::quiet_NaN();
+        return GPSS_NOT_POSDEF;
+      }
+    }
     if (viol && attempt == 0) {
       // an operand of the int8 products left its a-priori bound (oz_slice_kernel): U, B^-1 and the sums above are not trustworthy.
       // Repeat this theta on the FP64 DMMA path (oz_active() is 0 while oz_blocked is set; gpss_set_theta clears it).
@@ -639,6 +711,10 @@ static int enqueue_gradient(gpss_ctx* c)
   }
   const int tm0 = c->qrow0 / NB, ntm = (c->qrow1 - c->qrow0) / NB;
   const long nblocks = (long)ntm * c->nblk;
+  if (c->solve_pending) {                              // alpha comes from the solve stream (enqueue_objective_overlapped)
+    CU(cudaStreamWaitEvent(c->st, c->ev_solved, 0));
+    c->solve_pending = false;
+  }
   {
     PhaseTimer t(c, 5);
     if (ntm > 0 && c->kind2 >= 0) {

@@ -96,6 +96,10 @@ struct gpss_ctx {
                                                               // stream factors the 512 x 512 diagonal block of the same block column
   cudaStream_t st6 = nullptr;                                 // distributed Cholesky: digit planes of a received panel (they gate bulk updates only)
   cudaEvent_t ev_u2 = nullptr, ev_unpacked = nullptr;         // st5 / st6 dependencies of the above
+  cudaStream_t st7 = nullptr;                                 // gpss_nlml_grad on a fresh theta: the vector solves for alpha run here beside the inverse
+  cudaEvent_t ev_factored = nullptr, ev_solved = nullptr;
+  bool solve_pending = false;                                 // the solves were enqueued on st7: the gradient pass must wait for ev_solved, and the
+                                                              // objective's scalars are read together with the gradient sums
   double* Wpan = nullptr;                                     // 2 x NBO x NBO: inverse of the current diagonal block (transposed scratch | lower, column-major)
   std::vector<cudaEvent_t> ev_pipe;                           // per 128-column sub-panel: [2 i] factored on the owner, [2 i + 1] received
   cudaEvent_t ev_main = nullptr, ev_side = nullptr;           // cross-stream dependencies of the look-ahead

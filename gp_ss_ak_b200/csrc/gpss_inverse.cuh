@@ -178,8 +178,11 @@ static void destroy_streams(gpss_ctx* c)
   if (c->st6) cudaStreamDestroy(c->st6);
   if (c->ev_u2) cudaEventDestroy(c->ev_u2);
   if (c->ev_unpacked) cudaEventDestroy(c->ev_unpacked);
-  c->st4 = c->st5 = c->st6 = nullptr;
-  c->ev_u2 = c->ev_unpacked = nullptr;
+  if (c->st7) cudaStreamDestroy(c->st7);
+  if (c->ev_factored) cudaEventDestroy(c->ev_factored);
+  if (c->ev_solved) cudaEventDestroy(c->ev_solved);
+  c->st4 = c->st5 = c->st6 = c->st7 = nullptr;
+  c->ev_u2 = c->ev_unpacked = c->ev_factored = c->ev_solved = nullptr;
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
   if (c->st) cudaStreamDestroy(c->st);

@@ -145,8 +145,15 @@ __device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr)
 __host__ __device__ constexpr uint32_t idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 constexpr uint32_t IDESC_I8 = idesc_i8(BN);
 
+// Registers: capped at OZ_MAXNREG so that the critical-path DMMA kernel (gemm_nt_ws_kernel, 2-stage ring: 168 x 160 threads, 51 KB) fits on
+// an SM NEXT TO a resident CTA of this kernel (6 warps x 168 x 32 = 32 256 of 65 536 registers, 175 of 227 KB).  Uncapped, ptxas gave the
+// epilogue's batched loads 222 registers: 43 008 + 26 880 > 65 536, i.e. every panel GEMM of the Cholesky waited for an SM to drain a bulk
+// CTA (~1 ms long) -- 30-45 us per dependent launch in the GPSS_DIST_TRACE logs of round 2.
+#ifndef OZ_MAXNREG
+#define OZ_MAXNREG 168
+#endif
 template <int S, int BKB = BK, bool MERGE = false, bool UNIT = false>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __maxnreg__(OZ_MAXNREG)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g)
 {
   using T = Cfg<S, BKB>;

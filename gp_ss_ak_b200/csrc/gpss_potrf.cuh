@@ -215,8 +215,10 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1; g.lower_only = 1; g.grow0 = T0; g.gcol0 = T0;
     return gemm_ws_on(c, g, stream);
   };
-  // fused distributed panel (default for P > 1; GPSS_DIST_PANEL=0: the 16-launch panel with U2 in front of it)
-  const bool fused = P > 1 && !pipe_env && Winv == c->Winv && !(getenv("GPSS_DIST_PANEL") && atoi(getenv("GPSS_DIST_PANEL")) == 0);
+  // fused distributed panel: OPT-IN (GPSS_DIST_PANEL=fused).  Measured on 2 GPUs at n = 50 000 (profiles/r02_dist_fused_panel_2gpu.log): correct
+  // (same results as one GPU to 1e-14 / 1e-12), but the chain is ~27 dependent launches of 10-17 us GEMMs + 4 x the diagonal kernel =
+  // 0.94 ms per panel against 0.72 ms for the whole 16-launch panel, so an evaluation takes 759-769 ms against 744 ms.
+  const bool fused = P > 1 && !pipe_env && Winv == c->Winv && getenv("GPSS_DIST_PANEL") && !strcmp(getenv("GPSS_DIST_PANEL"), "fused");
   // GPSS_DIST_U2=int8: the full-height part of U2 on the int8 kernel (its CTAs need whole SMs, which the bulk updates hold) instead of the
   // co-resident DMMA kernel
   const bool u2_int8 = fused && ozk && getenv("GPSS_DIST_U2") && !strcmp(getenv("GPSS_DIST_U2"), "int8");

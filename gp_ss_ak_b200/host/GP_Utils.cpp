@@ -3,6 +3,7 @@
 #include "DistHost.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -294,6 +295,18 @@ void GP_utils::sync_device() const
   }
 }
 
+// GPSS_TIMING: how many evaluations an optimiser run asked of the device, and their device time (reported by OptimisePars on rank 0)
+namespace {
+struct EvalStats { unsigned long objective = 0, gradient = 0; double device_ms = 0.0; } g_eval_stats;
+void count_eval(gpss_handle h, bool gradient)
+{
+  double ms = 0.0;
+  if (h) gpss_get_last_call_ms(h, &ms);
+  (gradient ? g_eval_stats.gradient : g_eval_stats.objective)++;
+  g_eval_stats.device_ms += ms;
+}
+}  // namespace
+
 double GP_utils::lastDeviceMs() const
 {
   double ms = 0.0;
@@ -310,6 +323,7 @@ double GP_utils::logLikelihood() const
   double nlml = 0.0;
   const int rc = gpss_nlml(handle, &nlml);
   if (rc < 0) device_failure("gpss_nlml");
+  count_eval(handle, false);
   Chol_fail = (rc == GPSS_NOT_POSDEF);
   if (Chol_fail) return std::numeric_limits<double>::quiet_NaN();       // GP_Utils.cpp:1145-1146, 1155-1158
   L.zeros(1, 1);
@@ -334,6 +348,7 @@ double GP_utils::GradLL(mat& g) const
   double nlml = 0.0, gv[GPSS_NPAR];
   const int rc = gpss_nlml_grad(handle, &nlml, gv);
   if (rc < 0) device_failure("gpss_nlml_grad");
+  count_eval(handle, true);
   Chol_fail = (rc == GPSS_NOT_POSDEF);
   if (Chol_fail) return std::numeric_limits<double>::quiet_NaN();       // g is left untouched, as in the reference (:1175-1176)
   L.zeros(1, 1);
@@ -413,7 +428,12 @@ void GP_utils::OptimisePars(unsigned int iters)
   }
   // [quirk] the iteration count only takes effect at verbosity > 2: a dangling `if` guards setMaxIters (GP_Utils.cpp:1295-1296)
   if (getVerbose() > 2 && getNumPars() < 40) setMaxIters(iters);
+  const EvalStats before = g_eval_stats;
   Optimise();
+  if (std::getenv("GPSS_TIMING") && gpss_host::rank() == 0)
+    std::fprintf(stderr, "[gpss timing] optimiser: %lu objective + %lu objective-and-gradient calls to the device, %.3f s of device time\n",
+                 g_eval_stats.objective - before.objective, g_eval_stats.gradient - before.gradient,
+                 (g_eval_stats.device_ms - before.device_ms) * 1e-3);
   if (getVerbose() > 0) ShowKernelPars(cout);
 }
 

@@ -694,3 +694,38 @@ def test_fused_panel_of_the_distributed_path_on_one_gpu(gpss, monkeypatch, n, oz
     assert np.abs(g - g0).max() <= 1e-9 * np.abs(g0).max()
     assert np.linalg.norm(a - a0) <= 1e-10 * np.linalg.norm(a0)
     assert np.abs(mu - mu0).max() <= 1e-10 and np.abs(v - v0).max() <= 1e-9
+
+
+def test_solves_beside_the_inverse_give_the_serial_results(gpss, monkeypatch):
+    """Above the graph-replayed sizes, gpss_nlml_grad on a fresh theta runs the vector solves for alpha on their own stream beside the
+    inverse and reads the objective's scalars together with the gradient sums (enqueue_objective_overlapped, gpss_capi.cu).  Same kernels,
+    same operands: nlml, g and alpha must equal the serial order BITWISE (ObjVal first, then Grad_Values at the same theta --
+    Opt_pars.cpp:179-332 calls them in both orders), a failed Cholesky must still give NaN (GP_Utils.cpp:881-888) and leave the handle usable."""
+    monkeypatch.delenv("GPSS_OZAKI", raising=False)
+    n = 9000
+    X, y = datagen.drillholes(n, 21)
+    Xs, ys, _ = datagen.standardise_symmetric(X, y)
+    m = gpss.GpssModel(Xs, ys)
+    assert m.padded_n() > 8192
+    th = O.THETA0.copy()
+    m.set_theta(th)
+    L_s = m.nlml()                       # serial: objective, then gradient with the factor in place
+    L_s2, g_s = m.nlml_grad()
+    a_s = m.alpha()
+    m.set_theta(th * 1.01)
+    m.nlml_grad()
+    m.set_theta(th)
+    L_o, g_o = m.nlml_grad()             # overlapped: fresh theta, gradient asked for at once
+    a_o = m.alpha()
+    assert L_s == L_s2 == L_o and np.array_equal(g_s, g_o) and np.array_equal(a_s, a_o)
+    assert m.nlml() == L_o
+    bad = th.copy()
+    bad[6] = 3.0
+    bad[9] = -0.5
+    m.set_theta(bad)
+    L, g = m.nlml_grad()
+    assert np.isnan(L) and np.all(np.isnan(g))
+    m.set_theta(th)
+    L_r, g_r = m.nlml_grad()
+    assert L_r == L_o and np.array_equal(g_r, g_o)
+    m.close()
