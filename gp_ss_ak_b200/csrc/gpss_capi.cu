@@ -63,6 +63,13 @@ static int enqueue_factor(gpss_ctx* c)
 {
   const int n_pad = c->n_pad;
   const long ld = n_pad;
+  if (c->trtri_inflight) {                             // an inverse issued beside the previous factorisation was never collected: L is about to change
+    c->trtri_inflight = false;
+    CU(cudaEventRecord(c->ev_side, c->st9));
+    CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+    CU(cudaEventRecord(c->ev_side, c->st8));
+    CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+  }
   CU(cudaMemsetAsync(c->dflag, 0, 2 * sizeof(int), c->st));
   {
     PhaseTimer t(c, 0);
@@ -232,7 +239,13 @@ static int enqueue_objective_overlapped(gpss_ctx* c)
     CU(cudaEventCreateWithFlags(&c->ev_solved, cudaEventDisableTiming));
   }
   RET(upload_train_params(c));
-  RET(enqueue_factor(c));
+  if (c->world > 1 && oz_active(c)) {                 // multi-GPU int8 handle: the inverse is issued inside the factorisation (potrf_blocked)
+    RET(ensure_gradient_buffers(c));
+    c->want_trtri_interleaved = true;
+  }
+  const int rc_f = enqueue_factor(c);
+  c->want_trtri_interleaved = false;
+  RET(rc_f);
   CU(cudaEventRecord(c->ev_factored, c->st));
   CU(cudaStreamWaitEvent(c->st7, c->ev_factored, 0));
   cudaStream_t main_stream = c->st;

@@ -96,6 +96,9 @@ struct gpss_ctx {
                                                               // stream factors the 512 x 512 diagonal block of the same block column
   cudaStream_t st6 = nullptr;                                 // distributed Cholesky: digit planes of a received panel (they gate bulk updates only)
   cudaEvent_t ev_u2 = nullptr, ev_unpacked = nullptr;         // st5 / st6 dependencies of the above
+  cudaStream_t st8 = nullptr, st9 = nullptr;                  // inverse issued DURING the distributed Cholesky: diagonal blocks (highest priority) / bulk (lowest)
+  bool want_trtri_interleaved = false;                        // set by the overlapped gpss_nlml_grad before the factorisation is enqueued
+  bool trtri_inflight = false;                                // potrf_blocked issued every step of the inverse: trtri_upper only joins the streams
   cudaStream_t st7 = nullptr;                                 // gpss_nlml_grad on a fresh theta: the vector solves for alpha run here beside the inverse
   cudaEvent_t ev_factored = nullptr, ev_solved = nullptr;
   bool solve_pending = false;                                 // the solves were enqueued on st7: the gradient pass must wait for ev_solved, and the
@@ -178,6 +181,13 @@ struct gpss_ctx {
   long launches = 0;
 };
 
+// streams and events of one pass of the triangular inverse (gpss_inverse.cuh: trtri_step)
+struct TrtriRun {
+  cudaStream_t sm, ss;
+  std::vector<cudaEvent_t>* evs;
+  bool ozk;
+};
+
 // ---------------------------------------------------------------------------------------------------
 static int configure_kernels()
 {
@@ -202,7 +212,7 @@ static int gemm_ws_on(gpss_ctx* c, const GemmArgs& g, cudaStream_t stream)
   // stream -- U2, the panel solves, the rank-128 updates, the diagonal blocks of the inverse -- would wait for whole SMs to drain.
   // The same kernel with a 2-stage ring (51 KB, same registers, bitwise the same sums) fits NEXT TO a resident int8 CTA, on the
   // FP64 pipe that CTA leaves idle.  (8 planes of 7 bits take 193 KB: no room, the hardware then simply queues these CTAs.)
-  if (c->dmma_coresident && (stream == c->st || (c->st5 && stream == c->st5)) && parts == 1) {
+  if (c->dmma_coresident && (stream == c->st || (c->st5 && stream == c->st5) || (c->st8 && stream == c->st8)) && parts == 1) {
     using T2 = GemmTileWideWS2;
     gemm_nt_ws_kernel<T2><<<(unsigned)(ga.mt * ga.nt), T2::THREADS, T2::SMEM_BYTES, stream>>>(ga);
     c->launches++;

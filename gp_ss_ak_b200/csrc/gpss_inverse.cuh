@@ -158,8 +158,11 @@ static int create_streams(gpss_ctx* c)
   int lo = 0, hi = 0;
   CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (largest number), hi = greatest
   CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, hi));
-  CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, lo));
-  CU(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, lo));
+  // the bulk updates of the Cholesky sit one level above the lowest priority when the device has one to spare, so that the inverse the
+  // distributed factorisation issues beside them (st9, lowest) only takes the CTA slots they leave
+  const int bulk = (hi <= lo - 2) ? lo - 1 : lo;
+  CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, bulk));
+  CU(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, bulk));
   CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
   return GPSS_OK;
@@ -179,6 +182,9 @@ static void destroy_streams(gpss_ctx* c)
   if (c->ev_u2) cudaEventDestroy(c->ev_u2);
   if (c->ev_unpacked) cudaEventDestroy(c->ev_unpacked);
   if (c->st7) cudaStreamDestroy(c->st7);
+  if (c->st8) cudaStreamDestroy(c->st8);
+  if (c->st9) cudaStreamDestroy(c->st9);
+  c->st8 = c->st9 = nullptr;
   if (c->ev_factored) cudaEventDestroy(c->ev_factored);
   if (c->ev_solved) cudaEventDestroy(c->ev_solved);
   c->st4 = c->st5 = c->st6 = c->st7 = nullptr;
@@ -214,11 +220,11 @@ static int pick_ksplit(int tiles, int klen, long part_doubles, size_t cap_double
 // the side stream, which runs the bulk GEMMs back to back.
 // The diagonal block U[J0:J0+nbj, J0:J0+nbj] = inv(L[J0.., J0..])^T in 128-steps from the stored 128 x 128 inverses (main stream).
 // U and L are addressed by GLOBAL row / column (callers with packed storage pass suitably shifted base pointers).
-static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj)
+static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj, cudaStream_t sm)
 {
   for (int i0 = J0; i0 < J0 + nbj; i0 += NB) {
     const double* Wi = c->Winv + (long)(i0 / NB) * NB * NB;
-    put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, c->st>>>(U + (long)i0 * ldu + i0, ldu, Wi);
+    put_transposed_block_kernel<<<dim3(NB / 32, NB / 32), 256, 0, sm>>>(U + (long)i0 * ldu + i0, ldu, Wi);
     c->launches++;
     CU(cudaGetLastError());
     const int mr = i0 - J0;
@@ -226,68 +232,61 @@ static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, l
       double* Uc = U + (long)i0 * ldu + J0;                 // U[J0:i0, i0:i0+128]
       GemmArgs g = gemm_args(U + (long)J0 * ldu + J0, ldu, L + (long)J0 * ldl + i0, ldl, Uc, ldu, mr, NB, mr);
       g.kbeg_row = 1;
-      RET(gemm(c, g));
+      RET(gemm_ws_on(c, g, sm));
       // Uc <- -Uc Wi^T in place: columns 64..127 first (all 128 inputs), then 0..63 (inputs 0..63 only)
       GemmArgs g1 = gemm_args(Uc, ldu, Wi + 64, NB, Uc + 64 * ldu, ldu, mr, 64, NB);
       g1.negate_out = 1;
-      RET(gemm(c, g1));
+      RET(gemm_ws_on(c, g1, sm));
       GemmArgs g2 = gemm_args(Uc, ldu, Wi, NB, Uc, ldu, mr, 64, 64);
       g2.negate_out = 1;
-      RET(gemm(c, g2));
+      RET(gemm_ws_on(c, g2, sm));
     }
   }
   return GPSS_OK;
 }
+static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj)
+{
+  return trtri_diag_block(c, U, ldu, L, ldl, J0, nbj, c->st);
+}
 
-static int trtri_upper(gpss_ctx* c)
+// One block column of the inverse.  sm: stream of the small diagonal-block launches, ss: stream of the bulk products, evs: the events that
+// order ss after sm (entry 2 t belongs to step t).  trtri_upper runs all steps on (st, st2) after the factorisation; the distributed int8
+// Cholesky issues step t on (st8, st9) as soon as panel t is complete on the rank (potrf_blocked), so that the inverse fills the time the
+// tensor pipe spends waiting for the next panel.
+static int trtri_step(gpss_ctx* c, const TrtriRun& R, int t)
 {
   const long ld = c->n_pad;
   const int n_pad = c->n_pad;
   double *L = c->Lm, *U = c->Um;
-  const int nblk_o = (n_pad + NBO - 1) / NBO;
-  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev_pool.push_back(e);
-  }
-  // Distributed: every row of U depends only on L and on the SAME row of earlier block columns, so a rank computes
-  // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
-  // rank needs as right factors, are cheap and computed redundantly).
   const int R0 = c->urow0, R1 = c->urow1;
-  // opt-in int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
-  // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
-  const bool ozk = oz_active(c) && c->ozL && c->ozU && c->ozL_valid;
-  c->ozU_valid = ozk;
-  c->dmma_coresident = ozk && c->oz_s <= 7 && !(getenv("GPSS_DMMA_CORESIDENT") && atoi(getenv("GPSS_DMMA_CORESIDENT")) == 0);   // see gemm_ws_on
-  // the side stream must not start before the factor is complete on the main stream
-  CU(cudaEventRecord(c->ev_main, c->st));
-  CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
-  for (int t = 0; t < nblk_o; t++) {
+  const bool ozk = R.ozk;
+  std::vector<cudaEvent_t>& ev = *R.evs;
+  {
     const int J0 = t * NBO;
     const int nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
     double* Wjj = c->Wjj + (size_t)t * NBO * NBO;
     // (1) the diagonal NBO-block of U in 128-steps
-    RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj));
+    RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj, R.sm));
     // rows of block column t this rank reads as digit planes later: its own rows above the block and its share of the diagonal block
     const int sr0 = R0, sr1 = (R1 < J0 + nbj) ? R1 : (J0 + nbj);
     if (t == 0) {
       if (ozk && sr1 > sr0) {                                // digit planes of block column 0 (only its diagonal block)
-        CU(cudaEventRecord(c->ev_pool[0], c->st));
-        CU(cudaStreamWaitEvent(c->st2, c->ev_pool[0], 0));
-        RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
+        CU(cudaEventRecord(ev[0], R.sm));
+        CU(cudaStreamWaitEvent(R.ss, ev[0], 0));
+        RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, R.ss));
       }
-      continue;
+      return GPSS_OK;
     }
     // (2) W_JJ = U_JJ^T into this block's scratch
-    transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, c->st>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
+    transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, R.sm>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev_pool[2 * t], c->st));
-    CU(cudaStreamWaitEvent(c->st2, c->ev_pool[2 * t], 0));
+    CU(cudaEventRecord(ev[2 * t], R.sm));
+    CU(cudaStreamWaitEvent(R.ss, ev[2 * t], 0));
     const int ra = R0, rb = (R1 < J0) ? R1 : J0;             // my rows above this block column
     if (rb <= ra) {                                          // no rows above this block column: only my share of the diagonal block
-      if (ozk && sr1 > sr0) RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));
-      continue;
+      if (ozk && sr1 > sr0) RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, R.ss));
+      return GPSS_OK;
     }
     // (3) T[ra:rb] = U[ra:rb, 0:J0] * L[Jblk, 0:J0]^T      (k starts at each tile's own row: U is upper triangular)
     GemmArgs g = gemm_args(U + ra, ld, L + J0, ld, c->Tpanel + ra, ld, rb - ra, nbj, J0);
@@ -301,55 +300,133 @@ static int trtri_upper(gpss_ctx* c)
       a.C = c->Tpanel + ra; a.ldc = ld; a.m = rb - ra; a.n = nbj;
       a.a_row0 = ra; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
       a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
-      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, c->st2, c->oz_s_grad));
+      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, R.ss, c->oz_s_grad));
       GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
       g2.negate_out = 1; g2.kend_col = 1;
-      RET(gemm_ws_on(c, g2, c->st2));
-      RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, c->st2));   // planes of block column t
-      continue;
+      RET(gemm_ws_on(c, g2, R.ss));
+      RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, R.ss));   // planes of block column t
+      return GPSS_OK;
     }
     int S = 1;
     if (c->world > 1) S = pick_ksplit((rb - ra) / GemmTileWideWS::BM * (nbj / GemmTileWideWS::BN), J0 - ra, (long)(rb - ra) * nbj, c->Tsplit_cap);
     if (S > 1) {
       const int rows = rb - ra;
       g.C = c->Tsplit; g.ldc = rows; g.ksplit = S; g.csplit = (long)rows * nbj;
-      RET(gemm_ws_on(c, g, c->st2));
-      split_sum_kernel<<<296, 256, 0, c->st2>>>(c->Tpanel + ra, ld, c->Tsplit, rows, nbj, S);
+      RET(gemm_ws_on(c, g, R.ss));
+      split_sum_kernel<<<296, 256, 0, R.ss>>>(c->Tpanel + ra, ld, c->Tsplit, rows, nbj, S);
       c->launches++;
       CU(cudaGetLastError());
     } else {
-      RET(gemm_ws_on(c, g, c->st2));
+      RET(gemm_ws_on(c, g, R.ss));
     }
     // (4) U[ra:rb, Jblk] = -T * W_JJ^T
     GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
     g2.negate_out = 1; g2.kend_col = 1;
-    RET(gemm_ws_on(c, g2, c->st2));
+    RET(gemm_ws_on(c, g2, R.ss));
   }
+  return GPSS_OK;
+}
+
+static int trtri_upper(gpss_ctx* c)
+{
+  const int n_pad = c->n_pad;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  if (c->trtri_inflight) {
+    // the distributed Cholesky issued every step on (st8, st9) while it ran (potrf_blocked): only the join is left
+    c->trtri_inflight = false;
+    CU(cudaEventRecord(c->ev_side, c->st9));
+    CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+    CU(cudaEventRecord(c->ev_side, c->st8));
+    CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+    return GPSS_OK;
+  }
+  while ((int)c->ev_pool.size() < 2 * nblk_o + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  // Distributed: every row of U depends only on L and on the SAME row of earlier block columns, so a rank computes
+  // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
+  // rank needs as right factors, are cheap and computed redundantly).
+  // opt-in int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
+  // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
+  const bool ozk = oz_active(c) && c->ozL && c->ozU && c->ozL_valid;
+  c->ozU_valid = ozk;
+  c->dmma_coresident = ozk && c->oz_s <= 7 && !(getenv("GPSS_DMMA_CORESIDENT") && atoi(getenv("GPSS_DMMA_CORESIDENT")) == 0);   // see gemm_ws_on
+  // the side stream must not start before the factor is complete on the main stream
+  CU(cudaEventRecord(c->ev_main, c->st));
+  CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
+  const TrtriRun R = {c->st, c->st2, &c->ev_pool, ozk};
+  for (int t = 0; t < nblk_o; t++) RET(trtri_step(c, R, t));
   CU(cudaEventRecord(c->ev_side, c->st2));
   CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
   c->dmma_coresident = false;
   return GPSS_OK;
 }
 
-// Distributed: every rank has computed its rows of U; B^-1 = U U^T and W = U^T need all of them.  Each rank's slice
-// (rows [b_k, b_k+1) x columns b_k..n, a strided region of the column-major buffer) is packed, broadcast and unpacked.
+// Distributed: every rank has computed its rows of U; B^-1 = U U^T and W = U^T need all of them.  A rank's slice is sent WITHOUT the
+// diagonal 512-blocks (every rank computed those itself) and without the zeros below them (uslice_copy_kernel): at 2 GPUs and n = 50 000
+// that is 8.3 GB instead of 16.7 GB.  All ranks pack their own slice at once; the broadcasts follow each other on the main stream while a
+// helper stream unpacks the previous slice into U (two receive buffers).  35 ms -> see profiles/ for the measured time.
+static long uslice_count(int n_pad, int r0, int rows)
+{
+  long cnt = 0;
+  for (int b = 0; b * NBO < n_pad; b++) {
+    long len = (long)b * NBO - r0;
+    len = len < 0 ? 0 : (len > rows ? rows : len);
+    const int w = (n_pad - b * NBO < NBO) ? (n_pad - b * NBO) : NBO;
+    cnt += len * w;
+  }
+  return cnt;
+}
+
 static int allgather_U(gpss_ctx* c)
 {
   if (c->world == 1) return GPSS_OK;
   const long ld = c->n_pad;
+  const int P = c->world, me = c->rank;
   std::vector<int> b;
-  balanced_rows(c->n_pad, c->world, 0, b);
-  size_t need = 0;
-  for (int k = 0; k < c->world; k++) need = std::max(need, (size_t)(b[k + 1] - b[k]) * (size_t)(c->n_pad - b[k]));
-  RET(ensure_stage(c, need));
-  for (int k = 0; k < c->world; k++) {
-    const long rows = b[k + 1] - b[k], cols = c->n_pad - b[k];
-    if (rows <= 0) continue;
-    double* slice = c->Um + (long)b[k] * ld + b[k];
-    if (k == c->rank) { pack_kernel<<<1184, 256, 0, c->st>>>(c->stage, slice, ld, rows, cols); c->launches++; }
-    NC(g_nccl.Broadcast(c->stage, c->stage, (size_t)rows * cols, ncclDouble, k, c->comm, c->st));
-    if (k != c->rank) { unpack_kernel<<<1184, 256, 0, c->st>>>(slice, ld, c->stage, rows, cols); c->launches++; }
+  balanced_rows(c->n_pad, P, 0, b);
+  std::vector<long> cnt(P);
+  long mx = 0;
+  for (int k = 0; k < P; k++) { cnt[k] = uslice_count(c->n_pad, b[k], b[k + 1] - b[k]); mx = std::max(mx, cnt[k]); }
+  if (mx == 0) return GPSS_OK;
+  RET(ensure_stage(c, (size_t)3 * mx));                        // [my packed slice | receive buffer 0 | receive buffer 1]
+  if (!c->st5) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&c->st5, cudaStreamNonBlocking, hi));
   }
+  if (!c->ev_u2) CU(cudaEventCreateWithFlags(&c->ev_u2, cudaEventDisableTiming));
+  while ((int)c->ev_pool.size() < 2 * P + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_pool.push_back(e);
+  }
+  double* mine = c->stage;
+  if (cnt[me] > 0) {
+    uslice_copy_kernel<<<1184, 256, 0, c->st>>>(mine, c->Um, ld, c->n_pad, b[me], b[me + 1] - b[me], NBO, 0);
+    c->launches++;
+  }
+  CU(cudaEventRecord(c->ev_u2, c->st));                        // the helper stream starts after everything the main stream holds so far
+  CU(cudaStreamWaitEvent(c->st5, c->ev_u2, 0));
+  int nrecv = 0;
+  for (int k = 0; k < P; k++) {
+    if (cnt[k] == 0) continue;
+    double* rbuf = c->stage + (size_t)(1 + (nrecv & 1)) * mx;
+    if (k != me && nrecv >= 2) CU(cudaStreamWaitEvent(c->st, c->ev_pool[2 * ((nrecv - 2) & 1) + 1], 0));   // that buffer's previous slice is unpacked
+    NC(g_nccl.Broadcast(k == me ? mine : rbuf, k == me ? mine : rbuf, (size_t)cnt[k], ncclDouble, k, c->comm, c->st));
+    if (k != me) {
+      CU(cudaEventRecord(c->ev_pool[2 * (nrecv & 1)], c->st));
+      CU(cudaStreamWaitEvent(c->st5, c->ev_pool[2 * (nrecv & 1)], 0));
+      uslice_copy_kernel<<<1184, 256, 0, c->st5>>>(rbuf, c->Um, ld, c->n_pad, b[k], b[k + 1] - b[k], NBO, 1);
+      c->launches++;
+      CU(cudaEventRecord(c->ev_pool[2 * (nrecv & 1) + 1], c->st5));
+      nrecv++;
+    }
+  }
+  CU(cudaEventRecord(c->ev_u2, c->st5));
+  CU(cudaStreamWaitEvent(c->st, c->ev_u2, 0));
   CU(cudaGetLastError());
   return GPSS_OK;
 }

@@ -900,6 +900,38 @@ __global__ void unpack_kernel(double* __restrict__ dst, long ld, const double* _
     dst[(idx / rows) * ld + (idx % rows)] = src[idx];
 }
 
+// Row slice [r0, r0 + rows) of the upper-triangular U = L^-T, WITHOUT what every rank already holds: a rank needs from another rank's
+// slice only the entries strictly above the w-wide diagonal blocks (the diagonal blocks themselves are computed redundantly everywhere,
+// everything below them is zero).  Column j (global) contributes its rows r0 .. min(r0 + rows, w floor(j / w)) - 1, columns packed one
+// after the other.  One CTA per column (grid-stride); dir = 0: pack (dst = contiguous buffer), 1: unpack (src = buffer).
+__device__ __forceinline__ long uslice_offset(int j, int r0, int rows, int w)
+{
+  // sum over the columns before j of clamp(w floor(j' / w) - r0, 0, rows): whole block columns first, then the columns of j's own block
+  long off = 0;
+  const int J = j / w;
+  for (int b = 0; b < J; b++) {
+    int len = b * w - r0;
+    len = len < 0 ? 0 : (len > rows ? rows : len);
+    off += (long)len * w;
+  }
+  int len = J * w - r0;
+  len = len < 0 ? 0 : (len > rows ? rows : len);
+  return off + (long)len * (j - J * w);
+}
+__global__ void __launch_bounds__(256) uslice_copy_kernel(double* __restrict__ buf, double* __restrict__ U, long ld, int n_pad, int r0, int rows,
+                                                          int w, int dir)
+{
+  for (int j = r0 + blockIdx.x; j < n_pad; j += gridDim.x) {
+    int len = (j / w) * w - r0;
+    len = len < 0 ? 0 : (len > rows ? rows : len);
+    if (len == 0) continue;
+    double* b = buf + uslice_offset(j, r0, rows, w);
+    double* u = U + (long)j * ld + r0;
+    if (dir == 0) for (int i = threadIdx.x; i < len; i += blockDim.x) b[i] = u[i];
+    else          for (int i = threadIdx.x; i < len; i += blockDim.x) u[i] = b[i];
+  }
+}
+
 __global__ void fill_kernel(double* __restrict__ p, long count, double v)
 {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) p[i] = v;

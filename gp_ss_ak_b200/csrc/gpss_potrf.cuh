@@ -131,6 +131,7 @@ static int potrf_panel(gpss_ctx* c, double* A, long ld, int n_pad, int K0, int n
 // chain runs (potrf_blocked).  Same flops (m x 512^2 / 2 x 2 against m x 163 840 x 2).
 // ---------------------------------------------------------------------------------------------------
 static int trtri_diag_block(gpss_ctx* c, double* U, long ldu, const double* L, long ldl, int J0, int nbj);
+static int trtri_step(gpss_ctx* c, const TrtriRun& R, int t);
 static int potrf_diag_chain(gpss_ctx* c, double* A, long ld, int K0, int nbk, double* Winv, double* logdet_parts, int* dflag)
 {
   for (int k = K0; k < K0 + nbk; k += NB) {
@@ -236,6 +237,32 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
     if (!c->Wpan) CU(cudaMalloc(&c->Wpan, sizeof(double) * 2 * NBO * NBO));
     RET(ensure_stage(c, (size_t)n_pad * NBO));
   }
+  // The inverse INSIDE the distributed factorisation.  With P ranks the tensor pipe of a rank has 1/P of a panel period's bulk work but waits
+  // a whole period for the next panel (8 GPUs, n = 50 000: ~0.5 ms of updates per ~1.5 ms period).  Block column t of U = L^-T needs only
+  // panels <= t, and a rank's rows of it need nothing from other ranks, so step t of the inverse is issued on two streams of its own (st8:
+  // diagonal blocks, st9: bulk, lowest priority) the moment panel t is complete here.  Asked for by the overlapped gpss_nlml_grad
+  // (want_trtri_interleaved; the buffers exist then); trtri_upper later only joins the streams.  GPSS_TRTRI_INTERLEAVE=0 switches it off.
+  const bool inter = P > 1 && ozk && c->want_trtri_interleaved && c->ozU && c->Um && c->Tpanel && c->Wjj && A == c->Lm && !pipe_env &&
+                     !(getenv("GPSS_TRTRI_INTERLEAVE") && atoi(getenv("GPSS_TRTRI_INTERLEAVE")) == 0);
+  TrtriRun inv_run = {nullptr, nullptr, &c->ev_pipe, true};
+  if (inter) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (!c->st8) CU(cudaStreamCreateWithPriority(&c->st8, cudaStreamNonBlocking, hi));
+    if (!c->st9) CU(cudaStreamCreateWithPriority(&c->st9, cudaStreamNonBlocking, lo));
+    while ((int)c->ev_pipe.size() < 2 * nblk_o + 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->ev_pipe.push_back(e);
+    }
+    inv_run.sm = c->st8; inv_run.ss = c->st9;
+    c->ozU_valid = true;
+  }
+  auto inverse_step = [&](int col) -> int {                  // panel `col` is complete on this rank (ev_pool[2 col])
+    if (!inter) return GPSS_OK;
+    CU(cudaStreamWaitEvent(c->st8, c->ev_pool[2 * col], 0));
+    return trtri_step(c, inv_run, col);
+  };
   // rows [T0 + r0, T0 + r0 + rows) of block column T0 -= L[same rows, kbeg : kbeg + klen] L[T0 : T0 + nbT, kbeg : kbeg + klen]^T  (DMMA)
   auto update_rows = [&](int T0, int nbT, int r0, int rows, int kbeg, int klen, cudaStream_t stream) -> int {
     if (rows <= 0) return GPSS_OK;
@@ -380,6 +407,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
             if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));
             CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));
           }
+          RET(inverse_step(op.col));
         }
         continue;
       }
@@ -421,6 +449,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
           if (ozk) RET(oz_slice_on(c, A, ld, T0, n_pad - T0, T0, nbT, oz::SCALE_CHOL, oz::MASK_LOWER, c->ozL, c->st));   // planes of panel op.col
           CU(cudaEventRecord(c->ev_pool[2 * op.col], c->st));            // panel op.col is complete on this rank
           if (!mine) mark(6);
+          RET(inverse_step(op.col));
           break;
         }
         case DIST_UPDATE_SIDE: {                                           // look-ahead: panels pbeg .. pbeg+pcnt-1 -> my column
@@ -505,6 +534,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   if (P > 1) {   // a failed pivot anywhere must be seen everywhere
     NC(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMax, c->comm, c->st));
   }
+  if (inter) c->trtri_inflight = true;                       // st8 / st9 still hold work: trtri_upper (or the next factorisation) joins them
   return GPSS_OK;
 }
 
