@@ -863,13 +863,23 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
 {
   if (!c || !sums_total || (count > 0 && (!Xs || !mu))) return fail_arg("gpss_predict_shard: null argument");
   if (m_total < 1 || count < 0) return fail_arg("gpss_predict_shard: bad sizes");
-  if (c->partitioned && var) { g_last_error = "gpss_predict: the predictive variance needs L^-1, which partitioned storage does not hold yet (pass var = NULL for the mean)"; return GPSS_ERR_STATE; }
+  if (c->partitioned && var && count != m_total) {
+    g_last_error = "gpss_predict_shard: on a partitioned handle the variance is a collective over the SAME test points on every rank (use gpss_predict)";
+    return GPSS_ERR_STATE;
+  }
   CU(cudaSetDevice(c->device));
   if (c->profiling) memset(c->phase_ms, 0, sizeof c->phase_ms);
   CallTimer ct(c);
   RET(ensure_objective(c));          // _postMean -> updateAlpha (GP_Utils.cpp:961)
   if (c->chol_fail) return GPSS_NOT_POSDEF;
-  if (var) RET(ensure_W(c));
+  if (var && c->partitioned) {                         // U = L^-T as cyclic block rows (variance_partitioned streams its strips)
+    RET(part_buffers(c));
+    if (!c->have_U) {
+      PhaseTimer t(c, 3);
+      RET(trtri_partitioned(c));
+      c->have_U = true;
+    }
+  } else if (var) RET(ensure_W(c));
   const int n_pad = c->n_pad;
   const int cap = PRED_BATCH;
   if (!c->pred_cap) {
@@ -923,7 +933,13 @@ static int predict_core(gpss_ctx* c, long m_total, const double* sums_total, lon
       CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(mu + off, c->dmu, sizeof(double) * mb, cudaMemcpyDeviceToHost, c->st));
-    if (var) {
+    if (var && c->partitioned) {
+      PhaseTimer t(c, 7);
+      RET(variance_partitioned(c, mb, m_pad));
+      CU(cudaMemcpyAsync(var + off, c->dvar, sizeof(double) * mb, cudaMemcpyDeviceToHost, c->st));
+      CU(cudaStreamSynchronize(c->st));
+      for (int j = 0; j < mb; j++) var[off + j] = kD - var[off + j];      // raw variance, as var_finish_kernel
+    } else if (var) {
       PhaseTimer t(c, 7);
       // V = L^-1 (Sw o kX): A = W (lower), B = Bm (test index contiguous)
       if (oz_active(c) && c->oz_predict && !c->ozW) {
@@ -1008,7 +1024,9 @@ int gpss_predict(gpss_handle c, long m, const double* Xs, double* mu, double* va
   if (m < 1) return fail_arg("gpss_predict: m must be >= 1");
   double sums[4];
   seq_colsums(Xs, m, sums, c->d);
-  if (c->world == 1) {
+  if (c->world == 1 || (c->partitioned && var)) {
+    // (partitioned storage with the variance: the factor is spread over the ranks, so every rank works on ALL test points -- the call is
+    //  a collective inside predict_core and returns the same vectors everywhere)
     RET(predict_core(c, m, sums, m, Xs, m, mu, var));
   } else {
     // Distributed handle (collective call, same Xs on every rank): the test points are split over the ranks -- L and alpha

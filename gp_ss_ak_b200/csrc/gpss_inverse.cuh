@@ -153,6 +153,49 @@ static int gradient_partitioned(gpss_ctx* c)
   return GPSS_OK;
 }
 
+// PARTITIONED storage, predictive variance:  var_j = kD - || L^-1 b_j ||^2 = kD - || U^T b_j ||^2  with b_j = Sw k(X, x*_j) (GP_Utils.cpp:985-998).
+// U = L^-T lives as cyclic block ROWS (trtri_partitioned); v = U^T b is needed by COLUMNS of U: rank r accumulates the block columns K it
+// owns, v[K] = sum_{J <= K} U[J, K]^T b[J].  For every block row J the owner broadcasts the strip U[J, J0:] (transposed on the way, so
+// that it is the NT product's B operand), and every rank adds its columns' share with ONE k = 512 DMMA launch over all of them (the cyclic
+// column map of gemm_nt_ws_kernel, as in the partitioned Cholesky).  Then a sum of squares over the rank's columns and one all-reduce of
+// m doubles.  Bm: the scaled cross-covariance batch, m_pad x n_pad, test index contiguous; result: c->dvar[0..mb) = || U^T b_j ||^2.
+// The whole of U crosses NVLink once per batch of PRED_BATCH test points (4 n^2 bytes): a first version, sized for config 5's use
+// (a trained n = 200 000 model queried at ~10^4 points), not for block models.
+static int variance_partitioned(gpss_ctx* c, int mb, int m_pad)
+{
+  const int P = c->world, me = c->rank, n_pad = c->n_pad;
+  const long ldu = (long)(c->nq > 0 ? c->nq : 1) * NBO;
+  const int nblk_o = (n_pad + NBO - 1) / NBO;
+  double* strip = c->stage;                                       // U[J, J0:]^T as (n_pad - J0) x nbj, contiguous
+  double* Vt = c->Vm;                                             // -(U^T b)^T for my block columns: m_pad x lcols
+  RET(ensure_stage(c, (size_t)n_pad * NBO));
+  CU(cudaMemsetAsync(Vt, 0, sizeof(double) * (size_t)m_pad * c->lcols, c->st));
+  for (int J = 0; J < nblk_o; J++) {
+    const int J0 = J * NBO, nbj = (n_pad - J0 < NBO) ? (n_pad - J0) : NBO;
+    const int owner = J % P;
+    const long cols = n_pad - J0;
+    if (owner == me) {
+      transpose_kernel<<<dim3(nbj / 32, (unsigned)(cols / 32)), 256, 0, c->st>>>(strip, cols, c->Um + (long)J0 * ldu + (long)(J / P) * NBO, ldu, 0);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
+    NC(g_nccl.Broadcast(strip, strip, (size_t)nbj * cols, ncclDouble, owner, c->comm, c->st));
+    int q0 = 0;                                                   // my first block column K >= J
+    while (q0 < c->nq && q0 * P + me < J) q0++;
+    const long ncols = c->lcols - (long)q0 * NBO;
+    if (ncols <= 0) continue;
+    GemmArgs g = gemm_args(c->Bm + (long)J0 * m_pad, m_pad, strip, cols, Vt + (long)q0 * NBO * m_pad, m_pad, m_pad, (int)ncols, nbj);
+    g.init_mode = GEMM_INIT_NEGC; g.negate_out = 1;               // Vt <- Vt - b[J]^T U[J, my columns]: the sign does not matter for the norm
+    g.cyc_P = P; g.cyc_me = me; g.cyc_w = NBO; g.cyc_lcol0 = q0 * NBO; g.cyc_boff = J0;
+    RET(gemm(c, g));
+  }
+  rowsumsq_kernel<<<(mb + 255) / 256, 256, 0, c->st>>>(Vt, m_pad, mb, c->lcols, c->dvar);
+  c->launches++;
+  CU(cudaGetLastError());
+  NC(g_nccl.AllReduce(c->dvar, c->dvar, (size_t)mb, ncclDouble, ncclSum, c->comm, c->st));
+  return GPSS_OK;
+}
+
 static int create_streams(gpss_ctx* c)
 {
   int lo = 0, hi = 0;

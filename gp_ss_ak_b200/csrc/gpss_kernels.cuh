@@ -1051,4 +1051,20 @@ __global__ void __launch_bounds__(256) var_finish_kernel(const double* __restric
   if (lane == 0) var[j] = kD - s;
 }
 
+// out[j] = sum_k V(j, k)^2 over `cols` columns of an m x cols column-major matrix (row index contiguous): one thread per row, fixed order
+__global__ void __launch_bounds__(256) rowsumsq_kernel(const double* __restrict__ V, long ld, int m, long cols, double* __restrict__ out)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s0 = 0, s1 = 0;
+  long k = 0;
+  for (; k + 1 < cols; k += 2) {
+    const double a = V[j + k * ld], b = V[j + (k + 1) * ld];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (k < cols) { const double a = V[j + k * ld]; s0 = fma(a, a, s0); }
+  out[j] = s0 + s1;
+}
+
 }  // namespace gpss

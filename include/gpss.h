@@ -106,8 +106,9 @@ int gpss_nccl_unique_id(void* id128);                           /* rank 0 create
 int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
 /* PARTITIONED storage for n too large to replicate (n = 200 000: n^2 doubles = 320 GB; 8 x B200 hold 40 GB of block columns
  * each): collective constructor, every rank passes the same data.  The handle supports gpss_set_theta, gpss_nlml,
- * gpss_nlml_grad, gpss_get_alpha, gpss_get_yhat and gpss_predict with var == NULL (mean); the predictive variance needs L^-1
- * replicated and returns GPSS_ERR_STATE.  Right-looking block-column-cyclic Cholesky: the owner's NCCL panel broadcast buffer is
+ * gpss_nlml_grad, gpss_get_alpha, gpss_get_yhat and gpss_predict (mean, and mean + variance: the variance is a collective over the
+ * SAME test points on every rank -- strips of U = L^-T are broadcast and every rank accumulates || U^T b ||^2 over the block columns
+ * it owns; gpss_predict_shard with a variance on a slice of the points returns GPSS_ERR_STATE).  Right-looking block-column-cyclic Cholesky: the owner's NCCL panel broadcast buffer is
  * itself the DMMA operand of every rank's trailing update; the triangular solves pass the right-hand side around; for the gradient
  * U = L^-T is held as block rows owned cyclically and B^-1 is produced one 512-wide strip at a time and consumed by the fused
  * gradient reductions without ever being stored. */

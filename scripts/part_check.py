@@ -49,7 +49,8 @@ for n in sizes:
         else:
             os.environ["GPSS_OZAKI_BITS"] = prev_bits
         ms.set_theta(base)
-        ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1])
+        ref = (ms.nlml(), ms.alpha(), ms.yhat(), ms.predict(Xs[:512] * 0.99, want_var=False)[0], ms.nlml_grad()[1],
+               ms.predict(Xs[:700] * 0.99, want_var=True))
         ms.close()
     times = []
     for rep in range(3 if n <= 60000 else 1):
@@ -114,12 +115,29 @@ for n in sizes:
                 print("   vs single GPU: g rel %.2e   (ref g = %s)" % (eg, " ".join("%.6e" % v for v in ref[4])), flush=True)
                 ok &= eg < 1e-9
             print("PART_GRAD_RESULT " + json.dumps({"n": n, "world": world, "grad_ms": dtg * 1e3, "trtri_ms": float(phg[3]), "binv_grad_ms": float(phg[4])}), flush=True)
-    try:
-        m.predict(Xs[:256], want_var=True)
-        ok = False
-        print("   ERROR: the variance call should have been refused", flush=True)
-    except G.GpssError:
-        pass
+    # predictive variance from the partitioned factor (variance_partitioned: strips of U = L^-T broadcast, k = 512 products per strip);
+    # a collective over the same test points on every rank
+    if os.environ.get("GPSS_PART_VAR", "1") != "0":
+        mt = 700 if n <= 60000 else 4096
+        Xv = Xs[:mt] * 0.99
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mu_v, var_v = m.predict(Xv, want_var=True)
+        torch.cuda.synchronize(); dist.barrier()
+        dtv = time.perf_counter() - t0
+        tv = torch.tensor(np.concatenate([mu_v, var_v]), device="cuda")
+        tvl = [torch.zeros_like(tv) for _ in range(world)]
+        dist.all_gather(tvl, tv)
+        same_v = all(torch.equal(tvl[0], v) for v in tvl)
+        if rank == 0:
+            print("   predictive mean + variance of %d points: %.1f ms (device %.1f ms)  identical across ranks: %s  var in [%.4g, %.4g]"
+                  % (mt, dtv * 1e3, m.last_call_ms(), same_v, var_v.min(), var_v.max()), flush=True)
+            ok &= same_v and bool(np.all(np.isfinite(var_v)))
+            if ref is not None:
+                emu = np.abs(mu_v - ref[5][0]).max(); ev = np.abs(var_v - ref[5][1]).max()
+                print("   vs single GPU: mean abs %.2e  variance abs %.2e" % (emu, ev), flush=True)
+                ok &= emu < 1e-9 and ev < 1e-9
+            print("PART_VAR_RESULT " + json.dumps({"n": n, "world": world, "points": mt, "ms": dtv * 1e3}), flush=True)
     m.close()
 if rank == 0:
     print("PART CHECK", "OK" if ok else "FAILED", flush=True)
