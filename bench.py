@@ -222,6 +222,26 @@ def ref_samples_once(sizes):
     return out
 
 
+def recorded_fits():
+    """BASELINE configs[2] (LBFGS fit at n = 50 000 through the reference's command line) is minutes of GPU time per run, so the bench line carries
+    the RECORDED runs of scripts/fit_n50k.py (profiles/r02_fit_n50k_<N>gpu.json) instead of repeating them: not measured in this run."""
+    runs = []
+    for g in (1, 2, 4, 8):
+        path = os.path.join(ROOT, "profiles", "r02_fit_n50k_%dgpu.json" % g)
+        if not os.path.exists(path):
+            continue
+        try:
+            with open(path) as f:
+                r = json.loads(f.readline())
+        except (OSError, ValueError):
+            continue
+        runs.append({k: r.get(k) for k in ("gpus", "iters", "wall_s", "device_s", "objective_calls", "gradient_calls", "nlml_first", "nlml_last")})
+    if not runs:
+        return None
+    return {"what": "gp_ss_ak -v 3 -pm 1 train -k ExpAns -kn 1 -o LBFGS -# ITERS on a synthetic n = 50 000 file, end to end (scripts/fit_n50k.py)",
+            "recorded": True, "source": "profiles/r02_fit_n50k_<N>gpu.json", "runs": runs}
+
+
 def run_reference_arm(args, rank, world):
     """bench.py --impl reference: the reference's own CPU implementation on the host cores.  Each of the W + K steps is ONE
     LML+gradient evaluation of the compiled reference at one of REF_SIZES (cycled); the K timed ones are averaged per size, fitted
@@ -251,10 +271,33 @@ def run_reference_arm(args, rank, world):
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." from C when NCCL_DEBUG=VERSION is in the
+# environment, as on the GPU boxes of round 2), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -489,10 +532,16 @@ def main():
                                "e2e": {"value": m_total / pred[1], "unit": "preds/s", "h2d_bytes": 24 * m_total, "d2h_bytes": 16 * m_total},
                                "roofline": pred_roof,
                                "sharding": "test points split over %d GPUs, L / alpha replicated" % world}
+        fit = recorded_fits()
+        if fit:
+            line["fit"] = fit
+        line["phases_note"] = ("phases_ms come from one PROFILED evaluation after the timed region: phase timers synchronise the host after every phase, "
+                               "so the solves do not overlap the inverse there (and, on multi-GPU handles, the inverse is not issued inside the Cholesky); "
+                               "their sum exceeds ms_per_step by what those overlaps save")
         if not args.no_cpu_baseline:
             lean_sizes = LEAN_SIZES + ((args.cpu_lean_max,) if args.cpu_lean_max > LEAN_SIZES[-1] else ())
             line["cpu_baseline"] = cpu_baseline_block(n, ref_samples_once(REF_SIZES), lean_sizes, os.cpu_count())
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.close()
     if world > 1:
         dist.destroy_process_group()

@@ -809,7 +809,10 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
     if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
   }
   std::vector<int> b;
-  balanced_rows(c->n_pad, world, 0, b);
+  // rows of the inverse: flop-balanced on the DMMA pipe (split-k fills the waves there), wave-aware on the int8 pipe (GPSS_UROW_KIND=0|2 overrides)
+  c->urow_kind = (c->oz_s > 0) ? 2 : 0;
+  if (const char* e = getenv("GPSS_UROW_KIND")) c->urow_kind = (atoi(e) == 2) ? 2 : 0;
+  balanced_rows(c->n_pad, world, c->urow_kind, b);
   c->urow0 = b[rank]; c->urow1 = b[rank + 1];
   balanced_rows(c->n_pad, world, 1, b);
   c->qrow0 = b[rank]; c->qrow1 = b[rank + 1];
@@ -834,7 +837,7 @@ int gpss_dist_potrf_schedule(int nblk, int world, int rank, int* ops6, int cap, 
 
 int gpss_dist_partition(int n_pad, int world, int kind, int* bounds)
 {
-  if (!bounds || world < 1 || n_pad < NB || n_pad % NB || (kind != 0 && kind != 1)) return fail_arg("gpss_dist_partition: bad argument");
+  if (!bounds || world < 1 || n_pad < NB || n_pad % NB || (kind != 0 && kind != 1 && kind != 2)) return fail_arg("gpss_dist_partition: bad argument");
   std::vector<int> b;
   balanced_rows(n_pad, world, kind, b);
   for (int k = 0; k <= world; k++) bounds[k] = b[k];

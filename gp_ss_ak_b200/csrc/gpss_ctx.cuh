@@ -130,13 +130,14 @@ struct gpss_ctx {
   bool partitioned = false;                                    // Lm holds only my block columns, packed (n too large to replicate)
   int nq = 0; long lcols = 0;                                  //   number of own block columns / local column count
   int urow0 = 0, urow1 = 0;                                    // my rows of U = L^-T
+  int urow_kind = 0;                                           // which partition of balanced_rows they come from (0: flops, 2: int8 wave model)
   int qrow0 = 0, qrow1 = 0;                                    // my rows of B^-1
-  // opt-in int8 tensor-core path (GPSS_OZAKI = 6 | 7 | 8, gpss_ozaki.cuh): signed base-128 digit planes of L and of U = L^-T,
+  // int8 tensor-core path (the default above n_pad = 8192; GPSS_OZAKI, gpss_ozaki.cuh): signed digit planes of L and of U = L^-T,
   // [oz_s][n_pad rows][n_pad bytes of k] each, and their TMA descriptors ([0] 128-row box = A operand, [1] 64-row box = B operand)
   int oz_s = 0;
-  int oz_s_grad = 0;                                           // GPSS_OZAKI_GRAD=6|7 (opt-in, not yet measured): fewer slices for the inverse / B^-1
+  int oz_s_grad = 0;                                           // GPSS_OZAKI_GRAD=6 (measured, NOT adopted: -10 % time, gradient 1e-8): fewer slices for the inverse / B^-1
                                                                // products (they feed the gradient only), read from the TOP planes of the same tensors
-  int oz_bits = 7;                                             // digit width: 7 (default) or 8 (GPSS_OZAKI_BITS=8, opt-in, not yet measured)
+  int oz_bits = 7;                                             // digit width: 8 with the size rule's 7 slices (default), 7 with a forced GPSS_OZAKI unless GPSS_OZAKI_BITS=8
   bool oz_blocked = false;                                     // this theta stays on the DMMA path: Sigma_Bias < 0 or sn2 <= 0 (K not PSD, so |L^-1| <= 1 is not
                                                                // guaranteed), or dflag[1] was raised by the previous attempt at this theta
   bool dmma_coresident = false;                                // set while an int8 bulk phase is in flight: main-stream DMMA GEMMs use the 2-stage ring (gemm_ws_on)
@@ -145,9 +146,9 @@ struct gpss_ctx {
   int8_t *ozL = nullptr, *ozU = nullptr;
   bool ozL_valid = false, ozU_valid = false;                   // the planes hold the CURRENT factor / inverse (set by the drivers that cut them)
   CUtensorMap oz_tmL[2], oz_tmU[2];
-  // GPSS_OZAKI_PREDICT=1 (opt-in, not yet measured): the prediction GEMM V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
+  // the prediction GEMM on the int8 kernel too (default; GPSS_OZAKI_PREDICT=0: DMMA): V = W (Sw o k*)^T on the same kernel -- planes of W = L^-1
   // (cut once per factor) and of the cross-covariance batch (PRED_BATCH rows, cut per batch)
-  // GPSS_OZAKI_DIST=1 (opt-in, not yet measured): keep the int8 path on replicated-layout multi-GPU handles (gpss_dist_init)
+  // the int8 path on replicated-layout multi-GPU handles (gpss_dist_init; default, GPSS_OZAKI_DIST=0: DMMA)
   bool oz_dist = false;
   bool oz_predict = false, ozW_valid = false, oz_w_fresh = false;
   int8_t *ozW = nullptr, *ozB = nullptr;

@@ -343,6 +343,18 @@ static int trtri_step(gpss_ctx* c, const TrtriRun& R, int t)
       a.C = c->Tpanel + ra; a.ldc = ld; a.m = rb - ra; a.n = nbj;
       a.a_row0 = ra; a.b_row0 = J0; a.k0 = 0; a.k1 = J0; a.kbeg_row = 1;
       a.accumulate = 0; a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
+      // Issued inside the distributed Cholesky (R.ss == st9), a CTA of this product would hold its SM for up to ~2 ms (k up to n) while the
+      // panel kernels of the critical path -- the diagonal-block kernel cannot share an SM with it -- wait for one to drain.  GPSS_INV_KCHUNK
+      // cuts the k-range into launches of that length (later ones accumulate), so SMs come free every fraction of a millisecond.
+      const int inv_kchunk = [] { const char* e = getenv("GPSS_INV_KCHUNK"); const int v = e ? atoi(e) : 0; return v >= 1024 ? (v / 64) * 64 : 0; }();
+      if (inv_kchunk > 0 && R.ss == c->st9 && J0 > inv_kchunk) {
+        for (int k0 = (ra / inv_kchunk) * inv_kchunk; k0 < J0; k0 += inv_kchunk) {     // tiles start at their own row: nothing before ra
+          oz::Args ac = a;
+          ac.k0 = k0; ac.k1 = (k0 + inv_kchunk < J0) ? k0 + inv_kchunk : J0;
+          ac.accumulate = (k0 > (ra / inv_kchunk) * inv_kchunk) ? 1 : 0;
+          RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], ac, R.ss, c->oz_s_grad));
+        }
+      } else
       RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, R.ss, c->oz_s_grad));
       GemmArgs g2 = gemm_args(c->Tpanel + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
       g2.negate_out = 1; g2.kend_col = 1;
@@ -391,7 +403,7 @@ static int trtri_upper(gpss_ctx* c)
   // Distributed: every row of U depends only on L and on the SAME row of earlier block columns, so a rank computes
   // the rows [urow0, urow1) of its balanced slice with no communication (the 128-step diagonal blocks, which every
   // rank needs as right factors, are cheap and computed redundantly).
-  // opt-in int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
+  // int8 path (gpss_ozaki.cuh): the long-k product (3) reads digit planes of U (cut block column by block column on the
   // side stream, right after (4) has written the column) and of L (cut by the factorisation); (4) and the diagonal blocks stay DMMA
   const bool ozk = oz_active(c) && c->ozL && c->ozU && c->ozL_valid;
   c->ozU_valid = ozk;
@@ -429,7 +441,7 @@ static int allgather_U(gpss_ctx* c)
   const long ld = c->n_pad;
   const int P = c->world, me = c->rank;
   std::vector<int> b;
-  balanced_rows(c->n_pad, P, 0, b);
+  balanced_rows(c->n_pad, P, c->urow_kind, b);
   std::vector<long> cnt(P);
   long mx = 0;
   for (int k = 0; k < P; k++) { cnt[k] = uslice_count(c->n_pad, b[k], b[k + 1] - b[k]); mx = std::max(mx, cnt[k]); }

@@ -6,8 +6,9 @@
 // 83.7 FP64-equivalent TFLOP/s with S = 7 slices, 69.0 with S = 8, against 35.9 for gemm_nt_ws_kernel; error of S = 8
 // against a long-double reference 1.3e-15 (DMMA: 1.4e-14).  Numerics of the whole path: scripts/ozaki_numerics.py.
 //
-// (GPSS_OZAKI_BITS=8, opt-in and not yet measured: base-256 digits in [-128, 127] -- 7 slices then carry the 55 bits that take 8 slices
-//  of 7 bits, 28 products instead of 36; the k-range of one int32 accumulation shrinks to 18 688, see kseg.)
+// Digits: 7 slices of 8 bits by default (base-256 digits in [-128, 127]: the 55 bits that take 8 slices of 7 bits, 28 products instead
+// of 36; the k-range of one int32 accumulation shrinks to 18 688, see kseg).  The formulas below are written for 7-bit digits
+// (GPSS_OZAKI_BITS=7); with b-bit digits read 2^b for 128 and 2^(b-1) for 64.
 //   operand x -> t = x / 2^e (ONE a-priori exponent per operand kind, see oz_exponent), v = rint(t 2^(7S-1)),
 //   signed base-128 digits d_0 .. d_{S-1} in [-64, 64]:  t = sum_p d_p 2^-(7p+6)          (oz_slice_kernel, K-major int8 planes)
 //   A B^T = 2^(eA+eB-12) sum_g 2^(-7g) G_g,  G_g = sum_{i+j=g} A_i B_j^T  exact in int32 (|G_g| <= (g+1) k 2^12 < 2^31 for

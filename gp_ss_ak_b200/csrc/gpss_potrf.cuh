@@ -22,10 +22,57 @@ static int ensure_stage(gpss_ctx* c, size_t count)
 // Row boundaries (multiples of 128) that give every rank the same share of work:
 //   kind 0: rows of U = L^-T in the block-column inverse, cost(row i) ~ (n - i)^2 / 2   -> (n - r_k)^3 = n^3 (1 - k/P)
 //   kind 1: rows of B^-1 = U U^T (lower),                 cost(row i) ~ (i + 1)(n - i)  -> n x^2/2 - x^3/3 = (k/P) n^3/6
+//   kind 2: rows of U = L^-T when the bulk product of the inverse runs on oz_gemm_kernel (ONE CTA per SM, 128 x 64 tiles, NBO / 64 = 8 tile
+//           columns per step).  A slice of t tile rows is 8 t CTAs per step: up to 18 tile rows it is one partial wave whose length is its
+//           LONGEST k-range, 19 tile rows are two waves -- the flop-balanced partition of kind 0 gives ranks 1-4 of 8 exactly such slices at
+//           n = 50 000 (measured: 94 / 85 / 78 / 69 ms against 58 ms for rank 0, profiles/r02_dist_8gpu.log).  Model of a step at block column
+//           J0 for rows [a, a + t): its CTAs run in waves of 148, each wave as long as its first (longest) k-range, summed over the steps;
+//           the boundaries minimise the largest rank cost (bisection on the cost, greedy assignment).
+static double inv_slice_cost(int a_t, int t, int ntile)
+{
+  const int tpb = NBO / NB;                                  // tile rows per block column
+  const int tc = NBO / 64;                                   // tile columns per step
+  double cost = 0.0;
+  for (int J0t = tpb; J0t < ntile; J0t += tpb) {             // block columns 1 .. : rows above the block are [0, J0t)
+    const int r1 = (a_t + t < J0t) ? a_t + t : J0t;
+    if (r1 <= a_t) continue;
+    // CTAs are scheduled in row order, longest k-range first (row a_t), 148 at a time: wave w lasts as long as its first CTA, which
+    // belongs to tile row a_t + floor(148 w / tc)
+    const int jobs = (r1 - a_t) * tc;
+    for (int w = 0; w * 148 < jobs; w++) cost += J0t - (a_t + (w * 148) / tc);
+  }
+  return cost;
+}
+
 static void balanced_rows(int n_pad, int world, int kind, std::vector<int>& bounds)
 {
   bounds.assign(world + 1, 0);
   bounds[world] = n_pad;
+  if (kind == 2) {
+    const int ntile = n_pad / NB;
+    double lo = 0.0, hi = inv_slice_cost(0, ntile, ntile);
+    std::vector<int> best(world + 1, 0);
+    best[world] = ntile;
+    for (int k = 1; k < world; k++) best[k] = (int)((long)ntile * k / world);
+    for (int it = 0; it < 60; it++) {
+      const double C = 0.5 * (lo + hi);
+      std::vector<int> b(world + 1, 0);
+      int a = 0;
+      for (int k = 0; k + 1 < world; k++) {                  // the most tile rows whose cost stays within C (the cost grows with t)
+        int t_lo = 0, t_hi = ntile - a;
+        while (t_lo < t_hi) {
+          const int mid = (t_lo + t_hi + 1) / 2;
+          if (inv_slice_cost(a, mid, ntile) <= C) t_lo = mid; else t_hi = mid - 1;
+        }
+        a += t_lo;
+        b[k + 1] = a;
+      }
+      b[world] = ntile;
+      if (inv_slice_cost(a, ntile - a, ntile) <= C) { hi = C; best = b; } else lo = C;
+    }
+    for (int k = 0; k <= world; k++) bounds[k] = best[k] * NB;
+    return;
+  }
   const double n = n_pad;
   for (int k = 1; k < world; k++) {
     const double f = (double)k / world;
@@ -186,7 +233,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   // staging layout of one broadcast: [panel rows T0.. x nbT | the panel's 128x128 diagonal inverses | their log-dets]
   const size_t stage_need = (size_t)n_pad * NBO + (size_t)(NBO / NB) * NB * NB + NBO / NB;
   if (P > 1) RET(ensure_stage(c, stage_need));
-  // opt-in int8 path (gpss_ozaki.cuh): every finished block column is cut into digit planes on the main stream, and the long-k
+  // int8 path (gpss_ozaki.cuh): every finished block column is cut into digit planes on the main stream, and the long-k
   // look-ahead update U1 reads those planes through the tcgen05 kernel; U2 (k = NBO, critical path) and the panel stay on DMMA
   const bool pipe_env = getenv("GPSS_DIST_PIPE") != nullptr && atoi(getenv("GPSS_DIST_PIPE")) != 0;
   const bool ozk = oz_active(c) && c->ozL && la && A == c->Lm && n_pad == c->n_pad && ld == (long)c->n_pad && !(P > 1 && pipe_env);
@@ -241,9 +288,13 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   // a whole period for the next panel (8 GPUs, n = 50 000: ~0.5 ms of updates per ~1.5 ms period).  Block column t of U = L^-T needs only
   // panels <= t, and a rank's rows of it need nothing from other ranks, so step t of the inverse is issued on two streams of its own (st8:
   // diagonal blocks, st9: bulk, lowest priority) the moment panel t is complete here.  Asked for by the overlapped gpss_nlml_grad
-  // (want_trtri_interleaved; the buffers exist then); trtri_upper later only joins the streams.  GPSS_TRTRI_INTERLEAVE=0 switches it off.
-  const bool inter = P > 1 && ozk && c->want_trtri_interleaved && c->ozU && c->Um && c->Tpanel && c->Wjj && A == c->Lm && !pipe_env &&
-                     !(getenv("GPSS_TRTRI_INTERLEAVE") && atoi(getenv("GPSS_TRTRI_INTERLEAVE")) == 0);
+  // (want_trtri_interleaved; the buffers exist then); trtri_upper later only joins the streams.  GPSS_TRTRI_INTERLEAVE=0 / 1 forces it off / on.
+  // Measured (profiles/r02_dist_8gpu.log, r02_dist_4gpu.log, r02_dist_interleaved_inverse_2gpu.log): 327.5 -> 304 ms per evaluation at 8 GPUs,
+  // 436 -> 440 ms at 4, 731 -> 728 ms at 2 -- with few ranks the pipe has little idle time and the resident bulk CTAs of the inverse delay the
+  // panel kernels (the diagonal-block kernel cannot share an SM with an int8 CTA) by as much as they hide.  Default: on from 6 ranks up.
+  const char* inter_env = getenv("GPSS_TRTRI_INTERLEAVE");
+  const bool inter_wanted = inter_env ? atoi(inter_env) != 0 : P >= 6;
+  const bool inter = P > 1 && ozk && c->want_trtri_interleaved && c->ozU && c->Um && c->Tpanel && c->Wjj && A == c->Lm && !pipe_env && inter_wanted;
   TrtriRun inv_run = {nullptr, nullptr, &c->ev_pipe, true};
   if (inter) {
     int lo = 0, hi = 0;

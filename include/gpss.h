@@ -114,7 +114,8 @@ int gpss_dist_init(gpss_handle h, int rank, int world, const void* id128);
  * gradient reductions without ever being stored. */
 int gpss_create_partitioned(int device, int rank, int world, const void* id128, int n, int d, const double* X_colmajor,
                             const double* y, gpss_handle* out);
-/* The balanced row partitions used above (kind 0: rows of L^-T, kind 1: rows of B^-1): bounds[0..world], multiples of 128. */
+/* The balanced row partitions used above (kind 0: rows of L^-T by flops, kind 1: rows of B^-1, kind 2: rows of L^-T for the int8 pipe --
+ * narrow slices are whole waves of one CTA per SM, so their cost is their longest k-range): bounds[0..world], multiples of 128. */
 int gpss_dist_partition(int n_pad, int world, int kind, int* bounds);
 /* The operation list one rank executes for a factor of `nblk` 512-wide block columns (pure host logic, no device needed):
  * 6 ints per operation {kind, column, first panel, panel count, broadcast root, side stream}; kind 0 = main stream waits

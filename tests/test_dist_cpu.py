@@ -102,6 +102,38 @@ def test_balanced_row_partitions(gpss, world):
         assert w.max() / w.mean() < 1.05
 
 
+def _inverse_step_model(a_t, t, ntile, tile_cols=8, slots=148, tpb=4):
+    """The cost model behind kind 2 (gpss_potrf.cuh: inv_slice_cost), restated: per block column the CTAs of the rows [a_t, a_t + t) above
+    it (tile_cols per row, longest k-range first) run in waves of `slots`, each wave as long as its first CTA."""
+    cost = 0.0
+    for J0t in range(tpb, ntile, tpb):
+        r1 = min(a_t + t, J0t)
+        if r1 <= a_t:
+            continue
+        jobs = (r1 - a_t) * tile_cols
+        w = 0
+        while w * slots < jobs:
+            cost += J0t - (a_t + (w * slots) // tile_cols)
+            w += 1
+    return cost
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_wave_aware_row_partition_of_the_int8_inverse(gpss, world):
+    """kind 2 (rows of U = L^-T on the int8 pipe, one CTA per SM): a valid partition whose largest rank cost under the model is not above the
+    flop-balanced partition's (kind 0), and clearly below it at 8 ranks, where kind 0 hands ranks 1-4 slices of 19-24 tile rows = two waves per step."""
+    n_pad = 50048
+    ntile = n_pad // 128
+    cost = {}
+    for kind in (0, 2):
+        b = gpss.dist_partition(n_pad, world, kind)
+        assert b[0] == 0 and b[-1] == n_pad and all(x % 128 == 0 for x in b) and all(b[i] <= b[i + 1] for i in range(world))
+        cost[kind] = max(_inverse_step_model(b[k] // 128, (b[k + 1] - b[k]) // 128, ntile) for k in range(world))
+    assert cost[2] <= cost[0] * 1.0001
+    if world == 8:
+        assert cost[2] < 0.85 * cost[0]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
