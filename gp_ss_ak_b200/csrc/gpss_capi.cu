@@ -809,8 +809,10 @@ int gpss_dist_init(gpss_handle c, int rank, int world, const void* id128)
     if (c->ozU) { cudaFree(c->ozU); c->ozU = nullptr; }
   }
   std::vector<int> b;
-  // rows of the inverse: flop-balanced on the DMMA pipe (split-k fills the waves there), wave-aware on the int8 pipe (GPSS_UROW_KIND=0|2 overrides)
-  c->urow_kind = (c->oz_s > 0) ? 2 : 0;
+  // rows of the inverse: flop-balanced (kind 0).  The wave-aware partition (kind 2, GPSS_UROW_KIND=2) is faster when the inverse runs AFTER the
+  // factorisation (8 GPUs, n = 50 000: 326 -> 310.5 ms) but not when it is issued inside it, where other work fills the partial waves
+  // (300 ms with kind 0, 306 ms with kind 2: profiles/r02_dist_row_partition_8gpu.log) -- and that is the default from 6 ranks up.
+  c->urow_kind = 0;
   if (const char* e = getenv("GPSS_UROW_KIND")) c->urow_kind = (atoi(e) == 2) ? 2 : 0;
   balanced_rows(c->n_pad, world, c->urow_kind, b);
   c->urow0 = b[rank]; c->urow1 = b[rank + 1];
