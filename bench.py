@@ -46,8 +46,10 @@ BF16_SUSTAINED_FALLBACK_TFLOPS = 1400.0   # /opt/skills/guides/B200_PROFILING.md
 INT8_PEAK_FALLBACK_TOPS = 3796.9   # profiles/r02_int8_peak_microbench.txt (sustained, N = 256 shape) -- used only if the live measurement fails
 
 # DRAM bytes (read + write) of the B^-1 = U U^T launch of oz_gemm_kernel at n_pad = 50 048, from the ncu capture of the bench command
-# (profiles/r02_oz_gemm_dram_per_launch_n50k.txt); filled in by the round's GPU job, None until then
-OZ_LAUUM_TRAFFIC_BYTES = None
+# with the 7 x 8-bit default: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:oz_gemm_kernel` over
+# scripts/profile_target.py 50000 (scripts/gpu_job_r2_m.sh; profiles/r02_oz_gemm_dram_per_launch_n50k.txt, r02_oz_gemm_dram_n50k_7x8bit.csv.gz):
+# 360.9 GB read + 17.04 GB written in 351 ms
+OZ_LAUUM_TRAFFIC_BYTES = 360.9e9 + 17.04e9
 
 
 def int8_tensor_peak(device):
@@ -469,8 +471,9 @@ def main():
             lau_tops = lau_ops / (float(ph[4]) * 1e-3) * 1e-12
             roofline = {"bound": "tensor", "achieved": lau_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
                         "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES,
-                        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from the ncu pass over the bench "
-                                        "command (profiles/r02_oz_gemm_dram_per_launch_n50k.txt); algorithmic: the digit planes of U (upper triangle, %d planes) read "
+                        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from an ncu pass over one evaluation "
+                                        "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 % of the HBM peak -- every A row panel is "
+                                        "re-read once per super-column of 8 tile columns, every B column panel once per wave); algorithmic: the digit planes of U (upper triangle, %d planes) read "
                                         "once + the lower triangle of B^-1 written = %.1f GB" % (oz_s, (oz_s * n_pad * n_pad / 2 + 4.0 * n_pad * n_pad) / 1e9),
                         "kernel": "oz_gemm_kernel<%d, 64, merged> (tcgen05.mma kind::i8 M 128 N <= 256, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; "
                                   "%d int8 products per FP64 product)" % (oz_s, pairs),
