@@ -1,7 +1,7 @@
 """Multi-GPU parity (needs >= 2 devices; skipped on a one-GPU box -- run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`).
 One evaluation spread over the GPUs must return what a single GPU returns, on every rank: the replicated-factor layout
 (scripts/dist_check.py: objective, gradient, alpha, sharded prediction) and the partitioned-storage layout of BASELINE config 5
-(scripts/part_check.py: objective, alpha, K alpha, predictive mean, residual against the definition)."""
+(scripts/part_check.py: objective, alpha, K alpha, gradient, predictive mean and variance, residual against the definition)."""
 import os
 import socket
 import subprocess
@@ -28,9 +28,11 @@ def _ngpu():
     return G.device_count()
 
 
-@pytest.mark.parametrize("script,token", [("dist_check.py", "DIST CHECK OK"), ("part_check.py", "PART CHECK OK")])
-def test_two_gpu_evaluation_matches_single_gpu(script, token):
+@pytest.mark.parametrize("script,token,sizes", [("dist_check.py", "DIST CHECK OK", (1100, 3000, 9000)), ("part_check.py", "PART CHECK OK", (1100, 3000))])
+def test_two_gpu_evaluation_matches_single_gpu(script, token, sizes):
+    """n = 9000 (n_pad > 8192) puts the replicated handle on the int8 tensor-core pipe, the default at the sizes multi-GPU runs are for;
+    part_check.py also compares the partitioned handle's predictive variance (variance_partitioned) with the single-GPU one."""
     if _ngpu() < 2:
         pytest.skip("needs 2 CUDA devices")
-    out = _torchrun(script, 2, 1100, 3000)
+    out = _torchrun(script, 2, *sizes)
     assert out.returncode == 0 and token in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
