@@ -541,7 +541,7 @@ def main():
         line["phases_note"] = ("phases_ms come from one PROFILED evaluation after the timed region: phase timers synchronise the host after every phase, "
                                "so the solves do not overlap the inverse there (and, on multi-GPU handles, the inverse is not issued inside the Cholesky); "
                                "their sum exceeds ms_per_step by what those overlaps save")
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU legs run on rank 0 at N = 1 only (other ranks would sit in NCCL teardown meanwhile)
             lean_sizes = LEAN_SIZES + ((args.cpu_lean_max,) if args.cpu_lean_max > LEAN_SIZES[-1] else ())
             line["cpu_baseline"] = cpu_baseline_block(n, ref_samples_once(REF_SIZES), lean_sizes, os.cpu_count())
         emit(line)

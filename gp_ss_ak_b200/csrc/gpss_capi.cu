@@ -285,6 +285,7 @@ static int ensure_U(gpss_ctx* c)
   RET(ensure_lazy(&c->Um, nn));
   if (oz_active(c)) RET(oz_ensure_planes(c, &c->ozU, c->oz_tmU));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
+  if (oz_active(c)) RET(ensure_lazy(&c->Tpanel2, (size_t)c->n_pad * NBO));
   RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
   if (c->world > 1 && !c->Tsplit) {
     const size_t cap = (size_t)24576 * NBO;                    // S * rows <= 24k rows of a 512-wide block column
@@ -325,7 +326,7 @@ int gpss_destroy(gpss_handle c)
   cudaSetDevice(c->device);
   double** bufs[] = {&c->xs, &c->y, &c->zs, &c->Lm, &c->Um, &c->Qm, &c->Winv, &c->logdet_parts, &c->rvec, &c->zvec, &c->alpha,
                      &c->fvec, &c->Tpanel, &c->Wjj, &c->partial, &c->red, &c->xt, &c->zt, &c->zsp, &c->Bm, &c->Vm, &c->mu_part,
-                     &c->dmu, &c->dvar, &c->zs2, &c->zsp2, &c->zt2, &c->partial2, &c->Wpan};
+                     &c->dmu, &c->dvar, &c->zs2, &c->zsp2, &c->zt2, &c->partial2, &c->Wpan, &c->Tpanel2};
   for (auto b : bufs) if (*b) cudaFree(*b);
   if (c->dP) cudaFree(c->dP);
   if (c->dflag) cudaFree(c->dflag);
@@ -694,6 +695,7 @@ static int ensure_gradient_buffers(gpss_ctx* c)
   RET(ensure_lazy(&c->Um, nn));
   if (oz_active(c)) RET(oz_ensure_planes(c, &c->ozU, c->oz_tmU));
   RET(ensure_lazy(&c->Tpanel, (size_t)c->n_pad * NBO));
+  if (oz_active(c)) RET(ensure_lazy(&c->Tpanel2, (size_t)c->n_pad * NBO));
   RET(ensure_lazy(&c->Wjj, (size_t)NBO * NBO * ((c->n_pad + NBO - 1) / NBO)));
   if (c->world > 1 && !c->Tsplit) {
     const size_t cap = (size_t)24576 * NBO;                    // S * rows <= 24k rows of a 512-wide block column

@@ -114,6 +114,7 @@ struct gpss_ctx {
   double *logdet_parts = nullptr;                              // nblk
   double *rvec = nullptr, *zvec = nullptr, *alpha = nullptr, *fvec = nullptr;   // n_pad each
   double *Tpanel = nullptr, *Wjj = nullptr;                    // n_pad x NBO, NBO x NBO (lazily)
+  double *Tpanel2 = nullptr;                                   // second product buffer of the two-stream inverse (int8 path)
   double *partial = nullptr; long partial_blocks = 0;          // gradient partial sums
   double *red = nullptr;                                       // 32 doubles of reduced scalars
   DevParams* dP = nullptr;                                     // [0] training, [1] prediction
@@ -185,8 +186,10 @@ struct gpss_ctx {
 // streams and events of one pass of the triangular inverse (gpss_inverse.cuh: trtri_step)
 struct TrtriRun {
   cudaStream_t sm, ss;
-  std::vector<cudaEvent_t>* evs;
+  std::vector<cudaEvent_t>* evs;     // [2 t]: diagonal block t ready (sm -> bulk stream); [2 t + 1]: digit planes of block column t cut
   bool ozk;
+  cudaStream_t ss2;                  // second bulk stream (nullptr: none): consecutive block columns alternate between ss and ss2
+  double* T2;                        // second n_pad x NBO product buffer for the steps on ss2
 };
 
 // ---------------------------------------------------------------------------------------------------

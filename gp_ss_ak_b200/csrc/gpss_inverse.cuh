@@ -312,6 +312,54 @@ static int trtri_step(gpss_ctx* c, const TrtriRun& R, int t)
     RET(trtri_diag_block(c, U, ld, L, ld, J0, nbj, R.sm));
     // rows of block column t this rank reads as digit planes later: its own rows above the block and its share of the diagonal block
     const int sr0 = R0, sr1 = (R1 < J0 + nbj) ? R1 : (J0 + nbj);
+    if (ozk && R.ss2) {
+      // TWO bulk streams: block column t runs on A = (t odd ? ss2 : ss).  Its long product is cut at k = J0 - NBO: the part below the cut
+      // needs only block columns <= t - 2 of U, so it starts while the OTHER stream still finishes column t - 1 (its k = NBO product, the
+      // DMMA product with W_JJ and the digit planes, ~0.3 ms during which the int8 pipe used to idle, and the tail wave of a narrow slice);
+      // the k = NBO rest follows when column t - 1 has been cut.  ev[2 t + 1] = digit planes of block column t complete.
+      cudaStream_t A = (t & 1) ? R.ss2 : R.ss;
+      double* Tb = (t & 1) ? R.T2 : c->Tpanel;
+      if (t == 0) {
+        CU(cudaEventRecord(ev[0], R.sm));
+        CU(cudaStreamWaitEvent(A, ev[0], 0));
+        if (sr1 > sr0) RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, 0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, A));
+        CU(cudaEventRecord(ev[1], A));
+        return GPSS_OK;
+      }
+      transpose_kernel<<<dim3(nbj / 32, nbj / 32), 256, 0, R.sm>>>(Wjj, NBO, U + (long)J0 * ld + J0, ld, 1);
+      c->launches++;
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(ev[2 * t], R.sm));
+      const int ra = R0, rb = (R1 < J0) ? R1 : J0;           // my rows above this block column
+      if (rb <= ra) {
+        CU(cudaStreamWaitEvent(A, ev[2 * t], 0));
+        if (sr1 > sr0) RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, A));
+        CU(cudaEventRecord(ev[2 * t + 1], A));
+        return GPSS_OK;
+      }
+      oz::Args a;
+      memset(&a, 0, sizeof a);
+      a.C = Tb + ra; a.ldc = ld; a.m = rb - ra; a.n = nbj;
+      a.a_row0 = ra; a.b_row0 = J0; a.kbeg_row = 1;
+      a.sign = 1.0; a.a_kind = oz::SCALE_UNIT; a.b_kind = oz::SCALE_CHOL;
+      const int kcut = J0 - NBO;                             // columns of U below the cut were cut into planes by steps <= t - 2
+      const bool has_bulk = kcut > (ra & ~(oz::BK - 1));
+      if (has_bulk) {
+        if (t >= 2) CU(cudaStreamWaitEvent(A, ev[2 * (t - 2) + 1], 0));      // (same stream: in order anyway; it also covers t - 3, see above)
+        a.k0 = 0; a.k1 = kcut; a.accumulate = 0;
+        RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, A, c->oz_s_grad));
+      }
+      CU(cudaStreamWaitEvent(A, ev[2 * (t - 1) + 1], 0));                    // block column t - 1 of U is in planes
+      a.k0 = has_bulk ? kcut : 0; a.k1 = J0; a.accumulate = has_bulk ? 1 : 0;
+      RET(oz_gemm_on(c, c->oz_tmU[0], c->oz_tmL[1], a, A, c->oz_s_grad));
+      CU(cudaStreamWaitEvent(A, ev[2 * t], 0));                              // W_JJ
+      GemmArgs g2 = gemm_args(Tb + ra, ld, Wjj, NBO, U + (long)J0 * ld + ra, ld, rb - ra, nbj, nbj);
+      g2.negate_out = 1; g2.kend_col = 1;
+      RET(gemm_ws_on(c, g2, A));
+      RET(oz_slice_on(c, U, ld, sr0, sr1 - sr0, J0, nbj, oz::SCALE_UNIT, oz::MASK_UPPER, c->ozU, A));
+      CU(cudaEventRecord(ev[2 * t + 1], A));
+      return GPSS_OK;
+    }
     if (t == 0) {
       if (ozk && sr1 > sr0) {                                // digit planes of block column 0 (only its diagonal block)
         CU(cudaEventRecord(ev[0], R.sm));
@@ -411,10 +459,19 @@ static int trtri_upper(gpss_ctx* c)
   // the side stream must not start before the factor is complete on the main stream
   CU(cudaEventRecord(c->ev_main, c->st));
   CU(cudaStreamWaitEvent(c->st2, c->ev_main, 0));
-  const TrtriRun R = {c->st, c->st2, &c->ev_pool, ozk};
+  // int8 path, OPT-IN (GPSS_INV_TWO_STREAMS=1): consecutive block columns alternate between the two look-ahead streams (trtri_step).  Measured
+  // on one B200 (profiles/r02_inverse_two_streams.log): correct, but SLOWER -- trtri 421 vs 410 ms at n = 50 000, 32.0 vs 31.1 ms at 20 000: with
+  // >= 1000 CTAs per launch there is no idle pipe to fill on one GPU, and the cut costs every tile a second epilogue.
+  const bool two = ozk && c->st3 && c->Tpanel2 && getenv("GPSS_INV_TWO_STREAMS") && atoi(getenv("GPSS_INV_TWO_STREAMS")) != 0;
+  if (two) CU(cudaStreamWaitEvent(c->st3, c->ev_main, 0));
+  const TrtriRun R = {c->st, c->st2, &c->ev_pool, ozk, two ? c->st3 : nullptr, two ? c->Tpanel2 : nullptr};
   for (int t = 0; t < nblk_o; t++) RET(trtri_step(c, R, t));
   CU(cudaEventRecord(c->ev_side, c->st2));
   CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+  if (two) {
+    CU(cudaEventRecord(c->ev_side, c->st3));
+    CU(cudaStreamWaitEvent(c->st, c->ev_side, 0));
+  }
   c->dmma_coresident = false;
   return GPSS_OK;
 }

@@ -295,7 +295,7 @@ static int potrf_blocked(gpss_ctx* c, double* A, long ld, int n_pad, double* Win
   const char* inter_env = getenv("GPSS_TRTRI_INTERLEAVE");
   const bool inter_wanted = inter_env ? atoi(inter_env) != 0 : P >= 6;
   const bool inter = P > 1 && ozk && c->want_trtri_interleaved && c->ozU && c->Um && c->Tpanel && c->Wjj && A == c->Lm && !pipe_env && inter_wanted;
-  TrtriRun inv_run = {nullptr, nullptr, &c->ev_pipe, true};
+  TrtriRun inv_run = {nullptr, nullptr, &c->ev_pipe, true, nullptr, nullptr};
   if (inter) {
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
