@@ -63,6 +63,7 @@ def load_library():
         "gpss_dist_init": (I, [H, I, I, ctypes.c_void_p]),
         "gpss_create_partitioned": (I, [I, I, I, ctypes.c_void_p, I, I, P, P, ctypes.POINTER(H)]),
         "gpss_dist_partition": (I, [I, I, I, ctypes.POINTER(I)]),
+        "gpss_dist_uslice_layout": (I, [I, I, I, ctypes.POINTER(L), ctypes.POINTER(I), ctypes.POINTER(L)]),
         "gpss_dist_potrf_schedule": (I, [I, I, I, ctypes.POINTER(I), I, ctypes.POINTER(I)]),
         "gpss_predict": (I, [H, L, P, P, P]),
         "gpss_predict_shard": (I, [H, L, P, L, P, P, P]),
@@ -298,6 +299,16 @@ def dist_partition(n_pad, world, kind):
     b = (ctypes.c_int * (world + 1))()
     _check(load_library().gpss_dist_partition(n_pad, world, kind, b))
     return list(b)
+
+
+def dist_uslice_layout(n_pad, r0, rows):
+    """(offsets, lens, count) of the packed exchange layout of the U = L^-T row slice [r0, r0 + rows) (host logic only)."""
+    ncol = n_pad - r0
+    off = (ctypes.c_long * ncol)()
+    lens = (ctypes.c_int * ncol)()
+    cnt = ctypes.c_long(0)
+    _check(load_library().gpss_dist_uslice_layout(n_pad, r0, rows, off, lens, ctypes.byref(cnt)))
+    return list(off), list(lens), cnt.value
 
 
 def dist_potrf_schedule(nblk, world, rank):

@@ -839,6 +839,21 @@ int gpss_dist_potrf_schedule(int nblk, int world, int rank, int* ops6, int cap, 
   return GPSS_OK;
 }
 
+// The packed layout of one rank's slice of U = L^-T in the exchange of allgather_U (host logic only, for the CPU tests): offsets[j - r0] =
+// position of column j's first kept entry, lens[j - r0] = how many rows of it travel, *count = doubles allocated for the slice.
+int gpss_dist_uslice_layout(int n_pad, int r0, int rows, long* offsets, int* lens, long* count)
+{
+  if (!offsets || !lens || !count || n_pad < NB || n_pad % NB || r0 < 0 || rows < 0 || r0 + rows > n_pad) return fail_arg("gpss_dist_uslice_layout: bad argument");
+  for (int j = r0; j < n_pad; j++) {
+    int len = (j / NBO) * NBO - r0;
+    len = len < 0 ? 0 : (len > rows ? rows : len);
+    lens[j - r0] = len;
+    offsets[j - r0] = uslice_offset(j, r0, rows, NBO);
+  }
+  *count = uslice_count(n_pad, r0, rows);
+  return GPSS_OK;
+}
+
 int gpss_dist_partition(int n_pad, int world, int kind, int* bounds)
 {
   if (!bounds || world < 1 || n_pad < NB || n_pad % NB || (kind != 0 && kind != 1 && kind != 2)) return fail_arg("gpss_dist_partition: bad argument");

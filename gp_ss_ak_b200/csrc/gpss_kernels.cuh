@@ -904,7 +904,7 @@ __global__ void unpack_kernel(double* __restrict__ dst, long ld, const double* _
 // slice only the entries strictly above the w-wide diagonal blocks (the diagonal blocks themselves are computed redundantly everywhere,
 // everything below them is zero).  Column j (global) contributes its rows r0 .. min(r0 + rows, w floor(j / w)) - 1, columns packed one
 // after the other.  One CTA per column (grid-stride); dir = 0: pack (dst = contiguous buffer), 1: unpack (src = buffer).
-__device__ __forceinline__ long uslice_offset(int j, int r0, int rows, int w)
+__host__ __device__ __forceinline__ long uslice_offset(int j, int r0, int rows, int w)
 {
   // sum over the columns before j of clamp(w floor(j' / w) - r0, 0, rows): whole block columns first, then the columns of j's own block
   long off = 0;

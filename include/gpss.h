@@ -117,6 +117,10 @@ int gpss_create_partitioned(int device, int rank, int world, const void* id128, 
 /* The balanced row partitions used above (kind 0: rows of L^-T by flops, kind 1: rows of B^-1, kind 2: rows of L^-T for the int8 pipe --
  * narrow slices are whole waves of one CTA per SM, so their cost is their longest k-range): bounds[0..world], multiples of 128. */
 int gpss_dist_partition(int n_pad, int world, int kind, int* bounds);
+/* Host logic of the exchange of the L^-T row slices between ranks (no counterpart in the reference): the packed position and length of
+ * every column j = r0 .. n_pad-1 of the slice [r0, r0 + rows), and the buffer size -- entries inside and below the 512-wide diagonal
+ * blocks do not travel (every rank computes the diagonal blocks itself; below them U is zero). */
+int gpss_dist_uslice_layout(int n_pad, int r0, int rows, long* offsets, int* lens, long* count);
 /* The operation list one rank executes for a factor of `nblk` 512-wide block columns (pure host logic, no device needed):
  * 6 ints per operation {kind, column, first panel, panel count, broadcast root, side stream}; kind 0 = main stream waits
  * for the column's look-ahead updates, 1 = update on the main stream, 2 = factor the column, 3 = broadcast it from root,

@@ -134,6 +134,27 @@ def test_wave_aware_row_partition_of_the_int8_inverse(gpss, world):
         assert cost[2] < 0.85 * cost[0]
 
 
+@pytest.mark.parametrize("n_pad,world", [(50048, 8), (50048, 2), (20096, 4), (3072, 2), (1152, 3)])
+def test_exchange_layout_of_the_inverse_slices(gpss, n_pad, world):
+    """allgather_U sends a rank's rows of U = L^-T without the 512-wide diagonal blocks and the zeros below them (uslice_copy_kernel).  The
+    packed layout must be a bijection onto [0, count): offsets increase by exactly the column lengths, the last column ends at the allocated
+    size, a column keeps exactly its rows strictly above its own diagonal block, and the slices of all ranks together cover every entry of
+    the strict block-upper triangle once."""
+    b = gpss.dist_partition(n_pad, world, 0)
+    covered = 0
+    for k in range(world):
+        r0, rows = b[k], b[k + 1] - b[k]
+        off, lens, count = gpss.dist_uslice_layout(n_pad, r0, rows)
+        off, lens = np.array(off), np.array(lens)
+        j = np.arange(r0, n_pad)
+        expect = np.clip((j // 512) * 512 - r0, 0, rows)
+        assert np.array_equal(lens, expect)
+        assert off[0] == 0 and np.array_equal(np.diff(off), lens[:-1]) and off[-1] + lens[-1] == count
+        covered += count
+    jj = np.arange(n_pad)
+    assert covered == int(((jj // 512) * 512).sum())          # rows strictly above the diagonal block of every column
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
