@@ -472,7 +472,7 @@ def main():
             roofline = {"bound": "tensor", "achieved": lau_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
                         "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES,
                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from an ncu pass over one evaluation "
-                                        "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 % of the HBM peak -- every A row panel is "
+                                        "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 %% of the HBM peak -- every A row panel is "
                                         "re-read once per super-column of 8 tile columns, every B column panel once per wave); algorithmic: the digit planes of U (upper triangle, %d planes) read "
                                         "once + the lower triangle of B^-1 written = %.1f GB" % (oz_s, (oz_s * n_pad * n_pad / 2 + 4.0 * n_pad * n_pad) / 1e9),
                         "kernel": "oz_gemm_kernel<%d, 64, merged> (tcgen05.mma kind::i8 M 128 N <= 256, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; "
