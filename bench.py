@@ -470,7 +470,7 @@ def main():
             lau_ops = 2.0 * int8_macs_lauum(n_pad) * pairs / share
             lau_tops = lau_ops / (float(ph[4]) * 1e-3) * 1e-12
             roofline = {"bound": "tensor", "achieved": lau_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
-                        "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES,
+                        "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES if share == 1 else None,    # measured for the one-GPU launch only
                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from an ncu pass over one evaluation "
                                         "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 %% of the HBM peak -- every A row panel is "
                                         "re-read once per super-column of 8 tile columns, every B column panel once per wave); algorithmic: the digit planes of U (upper triangle, %d planes) read "
