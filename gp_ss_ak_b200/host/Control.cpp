@@ -5,7 +5,10 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <cstdio>
 #include <iostream>
+#include <thread>
+#include <vector>
 
 using namespace arma;
 using std::cerr;
@@ -307,4 +310,53 @@ void Control::postData_var(mat& X, bool& yscale, string ModelN)
 {
   if (getMode() == "test") loadStatistics(ModelN, X.n_cols);
   if (yscale) X = sqrt(X * std::pow(params(0, 1), 2));
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Prediction table writer.  The reference inserts value by value into an ofstream (gp_ss_ak.cpp:470-481): at 10 M rows x 7 columns
+// that is 70 M conversions on one core -- 10 s of the 65 s of BASELINE configs[3] on 8 GPUs (profiles/r02_predict_10m_8gpu.log), more than
+// reading and standardising the input.  The conversions are independent per row: rows are cut into contiguous chunks, one per worker,
+// each formatted with snprintf("%g\t") (= the default ostream format) into its own buffer; the buffers are written in order.
+// ---------------------------------------------------------------------------------------------------
+bool Control::writePredictTable(const std::string& path, const arma::mat& regr, int threads)
+{
+  FILE* out = std::fopen(path.c_str(), "w");
+  if (!out) return false;
+  std::fputs("# SampleNo, Y,  Yh, StdYh, Inputs\n", out);
+  const size_t rows = regr.n_rows, cols = regr.n_cols;
+  if (threads <= 0) {
+    threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if (threads > 16) threads = 16;
+  }
+  if ((size_t)threads > rows / 4096 + 1) threads = (int)(rows / 4096 + 1);      // small tables: no point in spawning workers
+  const size_t piece = (size_t)1 << 13;                                         // rows per work item (bounds the buffers: ~2 MB each, allocated once)
+  std::vector<std::vector<char> > bufs((size_t)threads);
+  std::vector<size_t> used((size_t)threads, 0);
+  for (size_t base = 0; base < rows; base += piece * (size_t)threads) {
+    auto work = [&](int t) {
+      const size_t r0 = base + piece * (size_t)t, r1 = (r0 + piece < rows) ? r0 + piece : rows;
+      used[t] = 0;
+      if (r0 >= rows) return;
+      std::vector<char>& b = bufs[t];
+      if (b.size() < piece * (32 * cols + 1)) b.resize(piece * (32 * cols + 1));
+      size_t u = 0;
+      for (size_t i = r0; i < r1; i++) {
+        for (size_t j = 0; j < cols; j++) u += (size_t)std::snprintf(b.data() + u, 32, "%g\t", regr(i, j));
+        b[u++] = '\n';
+      }
+      used[t] = u;
+    };
+    if (threads == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; t++) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
+    }
+    for (int t = 0; t < threads; t++)
+      if (used[t]) std::fwrite(bufs[t].data(), 1, used[t], out);
+  }
+  return std::fclose(out) == 0;
 }

@@ -49,6 +49,11 @@ class Control {
   void postData(arma::mat& X, bool& yscale, std::string ModelN);
   void postData_var(arma::mat& X, bool& yscale, std::string ModelN);
 
+  // ---- <model>_predict.txt (gp_ss_ak.cpp:470-481): one row per line, every value followed by a tab, formatted like `ostream << double`
+  //      with the default format ("%g").  Rows are formatted by `threads` workers into private buffers and written in row order
+  //      (0 = as many as the host has cores, capped at 16); the bytes do not depend on the thread count.  false: file not writable.
+  static bool writePredictTable(const std::string& path, const arma::mat& regr, int threads = 0);
+
   void ErrorTermination(const std::string error);
   void Helping();
   void NormalTermination();

@@ -290,22 +290,9 @@ void GP_Cntrl::test()
   if (base.find("train")) plotName += "_train";
   if (base.find("test")) plotName += "_test";
 
-  // Buffered writer: "%g" is exactly what `ostream << double` prints with the default format (6 significant digits), which is
-  // what the reference's loop does value by value (gp_ss_ak.cpp:470-481); 1 MiB blocks instead of one stream insertion per number.
-  {
-    FILE* outputs = std::fopen(gpss_host::out_path(PredictOut).c_str(), "w");
-    if (!outputs) ErrorTermination("File is " + PredictOut + " not writable");
-    std::fputs("# SampleNo, Y,  Yh, StdYh, Inputs\n", outputs);
-    std::vector<char> block(1 << 20);
-    size_t used = 0;
-    for (uword i = 0; i < regr.n_rows; i++) {
-      if (used + 32 * (regr.n_cols + 1) > block.size()) { std::fwrite(block.data(), 1, used, outputs); used = 0; }
-      for (uword j = 0; j < regr.n_cols; j++) used += (size_t)std::snprintf(block.data() + used, 32, "%g\t", regr(i, j));
-      block[used++] = '\n';
-    }
-    std::fwrite(block.data(), 1, used, outputs);
-    std::fclose(outputs);
-  }
+  // "%g" is exactly what `ostream << double` prints with the default format (6 significant digits), which is what the reference's loop
+  // does value by value (gp_ss_ak.cpp:470-481); here the rows are formatted by several host threads (Control::writePredictTable)
+  if (!Control::writePredictTable(gpss_host::out_path(PredictOut), regr)) ErrorTermination("File is " + PredictOut + " not writable");
   clk.mark("sort by y + write predict file");
 
   // gnuplot script (gp_ss_ak.cpp:482-505); gnuplot itself is run only when GPSS_RUN_GNUPLOT is set
