@@ -52,6 +52,14 @@ INT8_PEAK_FALLBACK_TOPS = 3796.9   # profiles/r02_int8_peak_microbench.txt (sust
 OZ_LAUUM_TRAFFIC_BYTES = 360.9e9 + 17.04e9
 
 
+def oz_traffic_note(oz_s, n_pad):
+    """Where roofline.traffic of the int8 kernel comes from, and the algorithmic bytes beside it."""
+    return ("dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from an ncu pass over one evaluation "
+            "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 %% of the HBM peak -- every A row panel is "
+            "re-read once per super-column of 8 tile columns, every B column panel once per wave); algorithmic: the digit planes of U (upper triangle, "
+            "%d planes) read once + the lower triangle of B^-1 written = %.1f GB" % (oz_s, (oz_s * n_pad * n_pad / 2 + 4.0 * n_pad * n_pad) / 1e9))
+
+
 def int8_tensor_peak(device):
     """int8 tensor-pipe micro-peak in TOP/s measured live (gpss_measure_int8_peak: tcgen05.mma kind::i8 M 128 N 256 K 32 from resident
     shared-memory operands on all SMs).  MEASURED_PEAKS.json has no int8 entry.  The kernel is timed inside a long step, so the
@@ -471,10 +479,7 @@ def main():
             lau_tops = lau_ops / (float(ph[4]) * 1e-3) * 1e-12
             roofline = {"bound": "tensor", "achieved": lau_tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor pipe)",
                         "frac": lau_tops / i8_peak, "traffic": OZ_LAUUM_TRAFFIC_BYTES if share == 1 else None,    # measured for the one-GPU launch only
-                        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the B^-1 = U U^T launch at n_pad = 50048 from an ncu pass over one evaluation "
-                                        "(profiles/r02_oz_gemm_dram_per_launch_n50k.txt: ~20x the algorithmic bytes, at 1.08 TB/s = 16 %% of the HBM peak -- every A row panel is "
-                                        "re-read once per super-column of 8 tile columns, every B column panel once per wave); algorithmic: the digit planes of U (upper triangle, %d planes) read "
-                                        "once + the lower triangle of B^-1 written = %.1f GB" % (oz_s, (oz_s * n_pad * n_pad / 2 + 4.0 * n_pad * n_pad) / 1e9),
+                        "traffic_note": oz_traffic_note(oz_s, n_pad),
                         "kernel": "oz_gemm_kernel<%d, 64, merged> (tcgen05.mma kind::i8 M 128 N <= 256, TMA SWIZZLE_64B operand planes, int32 accumulators in TMEM; "
                                   "%d int8 products per FP64 product)" % (oz_s, pairs),
                         "launch": "B^-1 = U U^T (lauum phase: oz_gemm_kernel launches only), %.3e int8 op in %.1f ms, CUDA events on the handle's stream"
