@@ -5,9 +5,11 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <cstdio>
 #include <iostream>
 #include <thread>
+#include <utility>
 #include <vector>
 
 using namespace arma;
@@ -359,4 +361,46 @@ bool Control::writePredictTable(const std::string& path, const arma::mat& regr, 
       if (used[t]) std::fwrite(bufs[t].data(), 1, used[t], out);
   }
   return std::fclose(out) == 0;
+}
+
+
+// Sorting 10 M observed values through an index comparator is 23 passes of random reads; (value, row) pairs sort with sequential
+// access, have a total order (so the result does not depend on how the work is cut) and the chunks sort in parallel.
+arma::uvec Control::sortedOrder(const arma::mat& y, int threads)
+{
+  typedef std::pair<double, arma::uword> Item;
+  const size_t n = y.n_elem;
+  if (threads <= 0) {
+    threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if (threads > 16) threads = 16;
+  }
+  if ((size_t)threads > n / 65536 + 1) threads = (int)(n / 65536 + 1);
+  std::vector<Item> v(n);
+  for (size_t i = 0; i < n; i++) v[i] = Item(y[i], (arma::uword)i);
+  std::vector<size_t> cut((size_t)threads + 1);
+  for (int t = 0; t <= threads; t++) cut[t] = n * (size_t)t / (size_t)threads;
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back([&v, &cut, t] { std::sort(v.begin() + cut[t], v.begin() + cut[t + 1]); });
+    for (auto& th : pool) th.join();
+  }
+  // pairwise merges of neighbouring runs, each round in parallel, ping-pong between two buffers (std::inplace_merge would allocate and
+  // fault in a temporary of half the range at every call)
+  std::vector<Item> w(threads > 1 ? n : 0);
+  std::vector<Item>* src = &v;
+  std::vector<Item>* dst = &w;
+  for (int width = 1; width < threads; width *= 2) {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t += 2 * width) {
+      const size_t a = cut[t], m = cut[(t + width < threads) ? t + width : threads], b = cut[(t + 2 * width < threads) ? t + 2 * width : threads];
+      pool.emplace_back([src, dst, a, m, b] { std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a); });
+    }
+    for (auto& th : pool) th.join();
+    std::swap(src, dst);
+  }
+  if (src != &v) v.swap(*src);
+  arma::uvec order(n);
+  for (size_t i = 0; i < n; i++) order[i] = v[i].second;
+  return order;
 }

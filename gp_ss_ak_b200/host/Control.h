@@ -53,6 +53,9 @@ class Control {
   //      with the default format ("%g").  Rows are formatted by `threads` workers into private buffers and written in row order
   //      (0 = as many as the host has cores, capped at 16); the bytes do not depend on the thread count.  false: file not writable.
   static bool writePredictTable(const std::string& path, const arma::mat& regr, int threads = 0);
+  // Row numbers of y in ascending order of the value, ties by row number -- what `sort_index(y, "ascend")` gives with a stable sort, one of
+  // the orders Armadillo's sort_index may produce (gp_ss_ak.cpp:434-436).  (value, row) pairs are sorted in `threads` chunks and merged.
+  static arma::uvec sortedOrder(const arma::mat& y, int threads = 0);
 
   void ErrorTermination(const std::string error);
   void Helping();

@@ -271,7 +271,7 @@ void GP_Cntrl::test()
 
   clk.mark("de-standardise, error report");
   // <model>_predict.txt: rows sorted by the observed value (gp_ss_ak.cpp:434-481)
-  const uvec order = sort_index(y, "ascend");
+  const uvec order = Control::sortedOrder(y);                // = sort_index(y, "ascend") with a stable sort, in parallel chunks
   mat regr(y.n_rows, 4 + X.n_cols);
   for (uword i = 0; i < y.n_rows; i++) {
     const uword s = order[i];

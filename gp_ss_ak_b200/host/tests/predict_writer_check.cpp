@@ -47,6 +47,23 @@ int main(int argc, char** argv)
     regr(3, 3) = std::numeric_limits<double>::quiet_NaN();
   }
   typedef std::chrono::steady_clock clk;
+  {
+    // Control::sortedOrder against sort_index (stable) on a column with many ties
+    mat yv(rows, 1);
+    for (size_t i = 0; i < rows; i++) yv[i] = std::floor(regr(i, 4) * 1e-3) + (double)(i % 7 == 0);
+    auto s0 = clk::now();
+    const uvec ref = sort_index(yv, "ascend");
+    auto s1 = clk::now();
+    const uvec o1 = Control::sortedOrder(yv, 1), o5 = Control::sortedOrder(yv, 5);
+    auto s2 = clk::now();
+    const uvec o0 = Control::sortedOrder(yv, 0);
+    auto s3 = clk::now();
+    bool same_order = ref.n_elem == o1.n_elem;
+    for (size_t i = 0; same_order && i < rows; i++) same_order = ref[i] == o1[i] && ref[i] == o5[i] && ref[i] == o0[i];
+    std::printf("sorted order identical %d  sort_index %.3f s  1 + 5 workers %.3f s  default workers %.3f s\n", (int)same_order,
+                std::chrono::duration<double>(s1 - s0).count(), std::chrono::duration<double>(s2 - s1).count(), std::chrono::duration<double>(s3 - s2).count());
+    if (!same_order) return 4;
+  }
   auto t0 = clk::now();
   {
     std::ofstream outputs((dir + "/ref_loop.txt").c_str());

@@ -159,8 +159,9 @@ def test_bfgs_and_scg_replay_reference_traces(host_built, tmp_path, opt):
 def test_threaded_predict_table_writer_writes_the_reference_loops_bytes(host_built, tmp_path, rows):
     """`<model>_predict.txt` (gp_ss_ak.cpp:470-481: every value inserted into an ofstream, a tab after each, a line per row) is written by
     several host threads since round 2 (Control::writePredictTable; 10 M rows are BASELINE configs[3]).  The bytes must equal the
-    reference loop's for every thread count -- magnitudes 1e-9..1e9, both signs, exact integers, +-0, inf and nan included."""
+    reference loop's for every thread count -- magnitudes 1e-9..1e9, both signs, exact integers, +-0, inf and nan included.  The same
+    harness checks Control::sortedOrder (rows by ascending observed value, gp_ss_ak.cpp:434-436) against a stable sort_index on a column full of ties."""
     out = subprocess.run([os.path.join(host_built, "tests", "predict_writer_check"), str(rows), str(tmp_path)], capture_output=True, text=True)
-    assert out.returncode == 0 and "identical 1" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "identical 1" in out.stdout and "sorted order identical 1" in out.stdout, out.stdout + out.stderr
     lines = (tmp_path / "w7.txt").read_text().splitlines()
     assert len(lines) == rows + 1 and lines[0] == "# SampleNo, Y,  Yh, StdYh, Inputs" and all(l.endswith("\t") for l in lines[1:4])
