@@ -377,7 +377,9 @@ arma::uvec Control::sortedOrder(const arma::mat& y, int threads)
   }
   if ((size_t)threads > n / 65536 + 1) threads = (int)(n / 65536 + 1);
   std::vector<Item> v(n);
-  for (size_t i = 0; i < n; i++) v[i] = Item(y[i], (arma::uword)i);
+  bool has_nan = false;
+  for (size_t i = 0; i < n; i++) { v[i] = Item(y[i], (arma::uword)i); has_nan = has_nan || (y[i] != y[i]); }
+  if (has_nan) return arma::sort_index(y, "ascend");          // no total order on the pairs: leave it to the library call the reference makes
   std::vector<size_t> cut((size_t)threads + 1);
   for (int t = 0; t <= threads; t++) cut[t] = n * (size_t)t / (size_t)threads;
   {
